@@ -1,0 +1,154 @@
+"""CPU: pin the oracle against (a) the reference's own doctest vectors, (b) golden vectors
+produced by the imported reference modules (oracle/gen_golden.py), (c) the reference's own
+knn_cpu.cpp binary when oracle/_ref is present."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import clib, densefusion as odf, icp as oicp, pose_math as pm, synth
+
+
+def _g(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+# ---- (a) known-answer vectors from DenseFusion/lib/transformations.py doctests
+def test_quaternion_matrix_doctests():
+    # transformations.py:1257-1265
+    M = pm.quaternion_matrix([0.99810947, 0.06146124, 0, 0])
+    c, s = math.cos(0.123), math.sin(0.123)
+    assert np.allclose(M[:3, :3], [[1, 0, 0], [0, c, -s], [0, s, c]])
+    assert np.allclose(pm.quaternion_matrix([1, 0, 0, 0]), np.identity(4))
+    assert np.allclose(pm.quaternion_matrix([0, 1, 0, 0]), np.diag([1, -1, -1, 1]))
+
+
+def test_quaternion_from_matrix_doctests():
+    # transformations.py:1287-1295
+    assert np.allclose(pm.quaternion_from_matrix_precise(np.identity(4)), [1, 0, 0, 0])
+    ax = np.array([1.0, 2.0, 3.0]); ax /= np.linalg.norm(ax)
+    a = 0.123
+    K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    R = np.identity(4); R[:3, :3] = np.identity(3) + math.sin(a) * K + (1 - math.cos(a)) * K @ K
+    assert np.allclose(pm.quaternion_from_matrix_precise(R), [0.9981095, 0.0164262, 0.0328524, 0.0492786])
+
+
+def test_kabsch_doctest():
+    # transformations.py:909-917 (affine_matrix_from_points, shear=False, scale=False -> rigid)
+    v0 = np.array([[0, 1031, 1031, 0], [0, 0, 1600, 1600]], float).T
+    v1 = np.array([[675, 826, 826, 677], [55, 52, 281, 277]], float).T
+    # rigid 2-D fit embedded in 3-D; the doctest's affine answer is not rigid, so pin instead
+    # the defining property on a synthetic rigid motion (:1009-1020 superimposition_matrix)
+    rng = np.random.RandomState(0)
+    P = rng.rand(20, 3) - 0.5
+    R = synth.random_rotation(rng, 1.0); t = rng.rand(3)
+    T = oicp.kabsch_umeyama(P, P @ R.T + t)
+    assert np.allclose(T[:3, :3], R, atol=1e-12) and np.allclose(T[:3, 3], t, atol=1e-12)
+    Pm = P.copy(); Pm[:, 2] = 0          # planar (rank-2) input must still give a proper rotation
+    T = oicp.kabsch_umeyama(Pm, Pm @ R.T + t)
+    assert np.linalg.det(T[:3, :3]) > 0.999
+    assert v0.shape == v1.shape
+
+
+# ---- (b) golden vectors from the imported reference
+def test_pose_math_golden(golden_dir):
+    g = _g(golden_dir, 'pose_math.npz')
+    for q, M in zip(g['quats'], g['quat_mats']):
+        assert np.array_equal(pm.quaternion_matrix(q), M)
+    for R, q in zip(g['rots'], g['rot_quats']):
+        assert np.allclose(pm.quaternion_from_matrix_precise(R), q, rtol=0, atol=1e-15)
+    for i in range(len(g['r2'])):
+        q, t = pm.refined_prediction(g['r2'][i], g['t2'][i], g['my_r'][i], g['my_t'][i])
+        assert np.allclose(q, g['refined_q'][i], atol=1e-12) and np.allclose(t, g['refined_t'][i], atol=1e-12)
+    i, r, t = pm.estimator_prediction(g['pr'][0], g['pt'][0], g['pc'][0, :, 0], g['pts'][0])
+    assert np.allclose(r, g['est_r'], atol=1e-7) and np.allclose(t, g['est_t'], atol=1e-7)
+    npn = pm.new_points(g['pr'][0], g['pt'][0], g['pc'][0, :, 0], g['pts'][0])
+    assert np.allclose(npn, g['new_points'][0], atol=2e-6)
+
+
+@pytest.mark.parametrize('case', [0, 1, 2])
+def test_densefusion_golden(golden_dir, case):
+    g = _g(golden_dir, 'densefusion_case%d.npz' % case)
+    seed, npts, nobj = int(g['seed']), int(g['npts']), int(g['nobj'])
+    hw = tuple(int(v) for v in g['hw'])
+    sd_e = synth.to_torch(synth.posenet_state_dict(seed, nobj))
+    sd_r = synth.to_torch(synth.refiner_state_dict(seed + 1000, nobj))
+    out_img, cloud, choose, idx = (torch.from_numpy(a) for a in synth.posenet_inputs(seed, npts, hw, nobj))
+    torch.set_num_threads(4)
+    with torch.no_grad():
+        r, t, c, emb = odf.posenet_geometry(sd_e, out_img, cloud, choose, idx, nobj)
+        assert np.allclose(r.numpy(), g['r'], atol=1e-5, rtol=1e-5)
+        assert np.allclose(t.numpy(), g['t'], atol=1e-5, rtol=1e-5)
+        assert np.allclose(c.numpy(), g['c'], atol=1e-6)
+        assert np.allclose(emb.numpy().sum(axis=1), g['emb_sum'], atol=1e-4)
+        res = odf.live_prediction(sd_e, sd_r, out_img, cloud, choose, idx, nobj)
+    assert np.allclose(res['my_r'], g['my_r'], atol=1e-6) and np.allclose(res['my_t'], g['my_t'], atol=1e-6)
+    assert np.allclose(res['r2'], g['r2'][0], atol=1e-5) and np.allclose(res['t2'], g['t2'][0], atol=1e-5)
+    assert pm.rotation_angle_between(res['q'], g['final_q']) < 1e-5
+    assert np.allclose(res['t'], g['final_t'], atol=1e-6)
+
+
+def test_losses_golden(golden_dir):
+    g = _g(golden_dir, 'losses.npz')
+    T = lambda k: torch.from_numpy(g[k])
+    for tag, sym in (('sym', [0]), ('nosym', [])):
+        dis, npn, ntg, pred = odf.loss_refine(T('pr1'), T('pt1'), T('target'), T('model'), torch.LongTensor([[0]]), T('points'), sym)
+        assert np.allclose(dis.numpy(), g['lr_dis_' + tag], atol=1e-7)
+        assert np.allclose(npn.numpy(), g['lr_newp_' + tag], atol=1e-6)
+        assert np.allclose(ntg.numpy(), g['lr_newt_' + tag], atol=1e-6)
+        assert np.allclose(pred.numpy(), g['lr_pred_' + tag], atol=1e-6)
+        # C restatement of the metric (what the CUDA kernel is checked against)
+        d_c = clib.add_metric(g['pr1'][0], g['pt1'][0], g['model'][0], g['target'][0], bool(sym))
+        assert abs(d_c - float(g['lr_dis_' + tag][0])) < 1e-6
+    for tag, sym, refine in (('sym', [0], False), ('nosym', [], False), ('symrefine', [0], True)):
+        lo, dis, npn, ntg, _ = odf.loss_estimator(T('pr_n'), T('pt_n'), T('pc_n'), T('target'), T('model'),
+                                                  torch.LongTensor([[0]]), T('points'), 0.015, refine, sym)
+        assert np.allclose(lo.numpy(), g['l_loss_' + tag], atol=1e-6)
+        assert np.allclose(dis.numpy(), g['l_dis_' + tag], atol=1e-6)
+        assert np.allclose(npn.numpy(), g['l_newp_' + tag], atol=1e-6)
+        assert np.allclose(ntg.numpy(), g['l_newt_' + tag], atol=1e-6)
+
+
+def test_knn_golden(golden_dir):
+    g = _g(golden_dir, 'knn.npz')
+    assert np.array_equal(clib.knn(g['ref'], g['qry'], 1, 0), g['idx_k1'])
+    assert np.array_equal(clib.knn(g['ref'], g['qry'], 4, 0), g['idx_k4'])
+    assert np.array_equal(clib.knn(g['refd'], g['qryd'], 2, 0), g['idxd_k2'])
+    # numpy restatement used inside the loss oracle
+    j = odf.knn_top1_np(g['ref'][0].T, g['qry'][0].T)
+    assert np.array_equal(j + 1, g['idx_k1'][0, 0])
+    # exact tie: query 3 equals ref 5 and ref 17 -> lowest index (1-based 6)
+    assert g['idx_k1'][0, 0, 3] == 6
+
+
+# ---- (c) live against the reference's own compiled knn_cpu.cpp (dev container / travels in oracle/_ref)
+def test_knn_against_reference_binary():
+    rng = np.random.RandomState(5)
+    ref = rng.rand(1, 3, 150).astype(np.float32); qry = rng.rand(1, 3, 40).astype(np.float32)
+    out = clib.ref_knn_cpu(ref, qry, 3)
+    if out is None:
+        pytest.skip('oracle/_ref not built (reference tree absent)')
+    assert np.array_equal(out, clib.knn(ref, qry, 3, 0))
+
+
+# ---- ICP restatement self-consistency (parity unpinned at the open3d boundary)
+def test_icp_oracle_recovers_known_motion():
+    rng = np.random.RandomState(7)
+    tgt = synth.ellipsoid_cloud(rng, 1500)
+    R = synth.random_rotation(rng, math.radians(6)); t = np.array([1.5, -2.0, 1.0])
+    src = (tgt[rng.choice(1500, 900, replace=False)] - t) @ R     # R^T (q - t)
+    T, info = oicp.registration_icp_p2p(src, tgt, 10.0, return_info=True)
+    assert info['fitness'] > 0.99 and info['inlier_rmse'] < 2.0
+    T2 = oicp.registration_icp_p2p(src, tgt, 10.0, use_kdtree=True)
+    assert np.allclose(T, T2, atol=1e-9)
+    # criteria semantics: stops well before max_iteration
+    assert info['iterations'] < 100
+
+
+def test_voxel_down_sample_oracle():
+    p = np.array([[0.1, 0.1, 0.1], [0.2, 0.3, 0.1], [4.2, 4.1, 4.3], [4.4, 4.5, 4.6], [9.9, 0.0, 0.0]])
+    v = oicp.voxel_down_sample(p, 2.0)
+    assert v.shape == (3, 3)
+    assert np.allclose(sorted(v[:, 0]), sorted([0.15, 4.3, 9.9]))
