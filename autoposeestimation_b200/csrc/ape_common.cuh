@@ -1,0 +1,73 @@
+// Shared helpers for the sm_100a kernels behind include/ape_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include "../../include/ape_b200.h"
+
+namespace ape {
+
+// ---- error reporting (thread-local message behind ape_last_error) -------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int  check_launch(const char* what);     // cudaGetLastError -> APE_OK / APE_ERR_CUDA
+int  sm_count();
+
+#define APE_REQUIRE(cond, ...)                                   \
+    do {                                                         \
+        if (!(cond)) {                                           \
+            ::ape::set_error(__VA_ARGS__);                       \
+            return APE_ERR_INVALID;                              \
+        }                                                        \
+    } while (0)
+
+#define APE_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t e__ = (call);                                                   \
+        if (e__ != cudaSuccess) {                                                   \
+            ::ape::set_error("%s failed: %s", #call, cudaGetErrorString(e__));      \
+            return APE_ERR_CUDA;                                                    \
+        }                                                                           \
+    } while (0)
+
+// ---- device helpers ------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// streaming 16-byte load that does not allocate in L1 (inputs that are read exactly once)
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// Row-major 3x3 "base" of a normalised quaternion (w,x,y,z), fp32, written as in
+// DenseFusion/tools/utils.py:46-67 / lib/loss_refiner.py:19-29.
+__device__ __forceinline__ void quat_to_base(float w, float x, float y, float z, float* R) {
+    R[0] = 1.0f - 2.0f * (y * y + z * z);
+    R[1] = 2.0f * x * y - 2.0f * w * z;
+    R[2] = 2.0f * w * y + 2.0f * x * z;
+    R[3] = 2.0f * x * y + 2.0f * z * w;
+    R[4] = 1.0f - 2.0f * (x * x + z * z);
+    R[5] = -2.0f * w * x + 2.0f * y * z;
+    R[6] = -2.0f * w * y + 2.0f * x * z;
+    R[7] = 2.0f * w * x + 2.0f * y * z;
+    R[8] = 1.0f - 2.0f * (x * x + y * y);
+}
+
+}  // namespace ape

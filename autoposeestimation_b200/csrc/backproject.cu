@@ -1,0 +1,207 @@
+// Depth -> point cloud back-projection kernels (sm_100a).
+//   ape_backproject_choose   : gather at fixed sampling indices, fp32 bit-exact with
+//                              pipeline/utils.py:542-553
+//   ape_surface_backproject  : masked scan with ordered stream compaction + fp64 rigid
+//                              transform, replaces pc_reconstruction/open3d_utils.py:172-192
+// Both are HBM-bound integer/byte scans; the second is the 921 600 B/frame kernel whose
+// roofline is reported.
+#include "ape_common.cuh"
+
+namespace ape {
+
+// ---------------------------------------------------------------------------------- a3
+__global__ void __launch_bounds__(256)
+backproject_choose_kernel(const uint16_t* __restrict__ depth, int n_frames, int H, int W,
+                          const int32_t* __restrict__ frame_of, const int32_t* __restrict__ bbox,
+                          const int64_t* __restrict__ choose, const float* __restrict__ cam,
+                          int n_points, float* __restrict__ cloud)
+{
+    const int b = blockIdx.y;
+    const int f = frame_of ? frame_of[b] : b;
+    const int rmin = bbox[4 * b + 0], cmin = bbox[4 * b + 2], cmax = bbox[4 * b + 3];
+    const int cw = cmax - cmin;
+    const float ppx = cam[5 * b + 0], ppy = cam[5 * b + 1], fx = cam[5 * b + 2], fy = cam[5 * b + 3],
+                scale = cam[5 * b + 4];
+    const uint16_t* d = depth + (size_t)f * H * W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_points; i += gridDim.x * blockDim.x) {
+        const int64_t c = choose[(size_t)b * n_points + i];
+        const int r = rmin + (int)(c / cw);
+        const int col = cmin + (int)(c % cw);
+        float z = 0.f, x = 0.f, y = 0.f;
+        if (r >= 0 && r < H && col >= 0 && col < W) {
+            // numpy order (pipeline/utils.py:549-551): pt2 = d*scale; pt0 = ((col-ppx)*pt2)/fx;
+            // pt1 = ((row-ppy)*pt2)/fy -- every op rounded to fp32, no contraction.
+            z = __fmul_rn((float)d[r * W + col], scale);
+            x = __fdiv_rn(__fmul_rn(__fsub_rn((float)col, ppx), z), fx);
+            y = __fdiv_rn(__fmul_rn(__fsub_rn((float)r, ppy), z), fy);
+        }
+        float* o = cloud + ((size_t)b * n_points + i) * 3;
+        o[0] = x; o[1] = y; o[2] = z;
+    }
+}
+
+// ---------------------------------------------------------------------------------- a4
+// One CTA per view.  The CTA walks the frame in chunks of kThreads*32 pixels; each thread owns
+// 32 consecutive pixels (2 x 16 B of label, 4 x 16 B of depth, all in flight together, next
+// chunk prefetched before the scan of the current one), builds a 32-bit validity mask, and a
+// block-wide exclusive scan of the pop-counts gives every thread its ordered output slot.
+constexpr int kSurfThreads = 512;
+constexpr int kSurfPix = 32;                       // pixels per thread per chunk
+constexpr int kSurfChunk = kSurfThreads * kSurfPix;
+
+struct SurfRegs { uint4 l0, l1, d0, d1, d2, d3; };
+
+__device__ __forceinline__ void surf_load(SurfRegs& r, const uint8_t* lab, const uint16_t* dep, int p, int npix) {
+    if (p + kSurfPix <= npix) {
+        r.l0 = ld_stream16(lab + p);      r.l1 = ld_stream16(lab + p + 16);
+        r.d0 = ld_stream16(dep + p);      r.d1 = ld_stream16(dep + p + 8);
+        r.d2 = ld_stream16(dep + p + 16); r.d3 = ld_stream16(dep + p + 24);
+    } else {                              // ragged tail (or past the end): scalar, zero-filled
+        uint8_t lb[32]; uint16_t db[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const bool in = p + i < npix;
+            lb[i] = in ? lab[p + i] : (uint8_t)0;
+            db[i] = in ? dep[p + i] : (uint16_t)0;
+        }
+        const uint32_t* lw = reinterpret_cast<const uint32_t*>(lb);
+        const uint32_t* dw = reinterpret_cast<const uint32_t*>(db);
+        r.l0 = make_uint4(lw[0], lw[1], lw[2], lw[3]);   r.l1 = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+        r.d0 = make_uint4(dw[0], dw[1], dw[2], dw[3]);   r.d1 = make_uint4(dw[4], dw[5], dw[6], dw[7]);
+        r.d2 = make_uint4(dw[8], dw[9], dw[10], dw[11]); r.d3 = make_uint4(dw[12], dw[13], dw[14], dw[15]);
+    }
+}
+
+__device__ __forceinline__ uint32_t label_bits(uint32_t w, uint32_t want) {
+    // 4 label bytes -> 4 bits (bit i set when byte i matches: !=0 if want==0 else ==want)
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t b = (w >> (8 * i)) & 0xffu;
+        m |= (uint32_t)(want ? (b == want) : (b != 0u)) << i;
+    }
+    return m;
+}
+__device__ __forceinline__ uint32_t depth_bits(uint32_t w) {
+    return (uint32_t)((w & 0xffffu) != 0u) | ((uint32_t)((w >> 16) != 0u) << 1);
+}
+
+__global__ void __launch_bounds__(kSurfThreads)
+surface_backproject_kernel(const uint8_t* __restrict__ label, const uint16_t* __restrict__ depth, int H, int W,
+                           const int32_t* __restrict__ frame_of, const uint8_t* __restrict__ label_value,
+                           const double* __restrict__ cam, const double* __restrict__ robot2cam, int capacity,
+                           double* __restrict__ points, int32_t* __restrict__ pixel_index,
+                           int32_t* __restrict__ counts)
+{
+    __shared__ int warp_tot[2][kSurfThreads / 32];
+    const int v = blockIdx.x;
+    const int f = frame_of ? frame_of[v] : v;
+    const uint32_t want = label_value ? label_value[v] : 0u;
+    const int npix = H * W;
+    const uint8_t* lab = label + (size_t)f * npix;
+    const uint16_t* dep = depth + (size_t)f * npix;
+    const double ppx = cam[4 * v + 0], ppy = cam[4 * v + 1], fx = cam[4 * v + 2], fy = cam[4 * v + 3];
+    double T[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) T[i] = robot2cam[16 * v + i];
+    double* out = points + (size_t)v * capacity * 3;
+    int32_t* opix = pixel_index ? pixel_index + (size_t)v * capacity : nullptr;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int base = 0;                                          // valid pixels emitted before this chunk
+    SurfRegs cur, nxt = {};
+    surf_load(cur, lab, dep, threadIdx.x * kSurfPix, npix);
+    int it = 0;
+    for (int c0 = 0; c0 < npix; c0 += kSurfChunk, ++it) {
+        const int p = c0 + threadIdx.x * kSurfPix;
+        if (c0 + kSurfChunk < npix) surf_load(nxt, lab, dep, p + kSurfChunk, npix);
+
+        const uint32_t lw[8] = {cur.l0.x, cur.l0.y, cur.l0.z, cur.l0.w, cur.l1.x, cur.l1.y, cur.l1.z, cur.l1.w};
+        const uint32_t dw[16] = {cur.d0.x, cur.d0.y, cur.d0.z, cur.d0.w, cur.d1.x, cur.d1.y, cur.d1.z, cur.d1.w,
+                                 cur.d2.x, cur.d2.y, cur.d2.z, cur.d2.w, cur.d3.x, cur.d3.y, cur.d3.z, cur.d3.w};
+        uint32_t mask = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mask |= label_bits(lw[i], want) << (4 * i);
+        uint32_t dmask = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dmask |= depth_bits(dw[i]) << (2 * i);
+        mask &= dmask;
+
+        const int cnt = __popc(mask);
+        int incl = cnt;                                    // warp inclusive scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[it & 1][warp] = incl;
+        __syncthreads();                                   // one barrier per chunk (ping-pong buffer)
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kSurfThreads / 32; ++w) {
+            const int t = warp_tot[it & 1][w];
+            before += (w < warp) ? t : 0;
+            total += t;
+        }
+        int slot = base + before + incl - cnt;
+        uint32_t m = mask;
+        while (m) {
+            const int i = __ffs(m) - 1;
+            m &= m - 1;
+            if (slot < capacity) {
+                const int pix = p + i;
+                const int r = pix / W, col = pix - r * W;
+                const double z = (double)dep[pix];   // rare (valid pixels only): L2 hit, keeps dw[] in registers
+                // open3d_utils.py:185-189: p0 = ((px-ppx)*z)/fx, p1 = ((py-ppy)*z)/fy (fp64, rounded per op)
+                const double x = __ddiv_rn(__dmul_rn(__dsub_rn((double)col, ppx), z), fx);
+                const double y = __ddiv_rn(__dmul_rn(__dsub_rn((double)r, ppy), z), fy);
+                // robot2cam * [x y z 1]^T (:190-192)
+                double* o = out + (size_t)slot * 3;
+                o[0] = fma(T[0], x, fma(T[1], y, fma(T[2], z, T[3])));
+                o[1] = fma(T[4], x, fma(T[5], y, fma(T[6], z, T[7])));
+                o[2] = fma(T[8], x, fma(T[9], y, fma(T[10], z, T[11])));
+                if (opix) opix[slot] = pix;
+            }
+            ++slot;
+        }
+        base += total;
+        cur = nxt;
+    }
+    if (threadIdx.x == 0) counts[v] = base;
+}
+
+}  // namespace ape
+
+extern "C" __attribute__((visibility("default"))) int ape_backproject_choose(const uint16_t* depth, int n_frames, int height, int width,
+                                      const int32_t* frame_of, const int32_t* bbox, const int64_t* choose,
+                                      const float* cam, int n_obj, int n_points, float* cloud, void* stream)
+{
+    APE_REQUIRE(depth && bbox && choose && cam && cloud, "ape_backproject_choose: null pointer");
+    APE_REQUIRE(n_frames > 0 && height > 0 && width > 0 && n_obj >= 0 && n_points >= 0,
+                "ape_backproject_choose: bad sizes");
+    if (n_obj == 0 || n_points == 0) return APE_OK;
+    APE_REQUIRE(n_obj <= 65535, "ape_backproject_choose: n_obj > 65535 (split the batch)");
+    dim3 grid((n_points + 255) / 256, n_obj);
+    ape::backproject_choose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(depth, n_frames, height, width, frame_of,
+                                                                          bbox, choose, cam, n_points, cloud);
+    ape::count_launch();
+    return ape::check_launch("ape_backproject_choose");
+}
+
+extern "C" __attribute__((visibility("default"))) int ape_surface_backproject(const uint8_t* label, const uint16_t* depth, int n_frames, int height,
+                                       int width, const int32_t* frame_of, const uint8_t* label_value,
+                                       const double* cam, const double* robot2cam, int n_views, int capacity,
+                                       double* points, int32_t* pixel_index, int32_t* counts, void* stream)
+{
+    APE_REQUIRE(label && depth && cam && robot2cam && points && counts, "ape_surface_backproject: null pointer");
+    APE_REQUIRE(n_frames > 0 && height > 0 && width > 0 && n_views >= 0 && capacity > 0,
+                "ape_surface_backproject: bad sizes");
+    APE_REQUIRE(((size_t)height * width) % 16 == 0, "ape_surface_backproject: height*width must be a multiple of 16");
+    APE_REQUIRE((((uintptr_t)label) & 15) == 0 && (((uintptr_t)depth) & 15) == 0,
+                "ape_surface_backproject: label/depth must be 16-byte aligned");
+    if (n_views == 0) return APE_OK;
+    ape::surface_backproject_kernel<<<n_views, ape::kSurfThreads, 0, (cudaStream_t)stream>>>(
+        label, depth, height, width, frame_of, label_value, cam, robot2cam, capacity, points, pixel_index, counts);
+    ape::count_launch();
+    return ape::check_launch("ape_surface_backproject");
+}

@@ -1,0 +1,408 @@
+// Point-to-point ICP: one whole registration per CTA, all iterations inside one persistent kernel
+// (sm_100a).  Replaces o3d.registration.registration_icp(..., PointToPoint, criteria) as called at
+// pc_reconstruction/open3d_utils.py:76-104 (open3d 0.9.0 semantics restated in oracle/icp.py).
+//
+// Per registration:
+//   build   : uniform grid over the (fixed) target cloud, cell >= threshold, counting sort of the
+//             target into cell order (scratch in global memory: read-only afterwards, L1/L2-resident)
+//   iterate : [apply update to the working source cloud] -> nearest target point in the 27
+//             neighbouring cells (fp64, d2=(dx*dx+dy*dy)+dz*dz, strict d2<r2, lowest original index on
+//             exact ties) -> block reduction of n, sum d2, sum p, sum q -> fitness / rmse / stop rule
+//             -> centred 3x3 covariance (second pass over the stored correspondences) -> one-thread
+//             fp64 Jacobi SVD (Kabsch / Eigen::umeyama without scaling) -> T = update * T
+// Reductions use a fixed tree, so results are run-to-run reproducible.
+#include "ape_common.cuh"
+#include <cfloat>
+
+namespace ape {
+
+constexpr int kIcpThreads = 512;
+constexpr int kIcpWarps = kIcpThreads / 32;
+constexpr int kIcpMaxCells = 4096;
+
+struct IcpSmem {
+    int cell_start[kIcpMaxCells + 1];
+    int cell_fill[kIcpMaxCells];
+    double red[kIcpWarps][12];
+    double out[12];
+    double U[12];          // current update (3x4 row-major)
+    double T[12];          // accumulated transform (3x4 row-major)
+    double bbmin[3], bbmax[3];
+    int scan_carry;
+};
+
+template <int K>
+__device__ __forceinline__ void block_sum(double (&v)[K], IcpSmem& s) {
+    // result in s.out[0..K); safe to call back-to-back (leading barrier protects s.out readers)
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) s.red[threadIdx.x >> 5][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        double a = 0.0;
+#pragma unroll
+        for (int w = 0; w < kIcpWarps; ++w) a += s.red[w][threadIdx.x];
+        s.out[threadIdx.x] = a;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double det3(const double* M) {
+    return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+}
+
+// Kabsch rotation from sigma = (1/n) sum (q-qm)(p-pm)^T via one-sided Jacobi SVD (fp64).
+// R = U diag(1,1,det(U)det(V)) V^T with singular values sorted descending (Eigen::umeyama Eq. 39-40).
+__device__ void kabsch_rotation(const double* sigma, double* R) {
+    double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) A[i] = sigma[i];
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        bool rotated = false;
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+            double alpha = 0, beta = 0, gamma = 0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                alpha += A[3 * k + p] * A[3 * k + p];
+                beta += A[3 * k + q] * A[3 * k + q];
+                gamma += A[3 * k + p] * A[3 * k + q];
+            }
+            if (fabs(gamma) > 1e-17 * sqrt(alpha * beta) && gamma != 0.0) {
+                rotated = true;
+                const double zeta = (beta - alpha) / (2.0 * gamma);
+                const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double ap = A[3 * k + p], aq = A[3 * k + q];
+                    A[3 * k + p] = c * ap - s * aq; A[3 * k + q] = s * ap + c * aq;
+                    const double vp = V[3 * k + p], vq = V[3 * k + q];
+                    V[3 * k + p] = c * vp - s * vq; V[3 * k + q] = s * vp + c * vq;
+                }
+            }
+        }
+        if (!rotated) break;
+    }
+    double sv[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) sv[j] = sqrt(A[j] * A[j] + A[3 + j] * A[3 + j] + A[6 + j] * A[6 + j]);
+    // sort columns by singular value, descending (3-element network)
+#define APE_SWAPCOL(a, b)                                                                     \
+    if (sv[a] < sv[b]) {                                                                      \
+        double tmp = sv[a]; sv[a] = sv[b]; sv[b] = tmp;                                       \
+        for (int k = 0; k < 3; ++k) {                                                         \
+            tmp = A[3 * k + a]; A[3 * k + a] = A[3 * k + b]; A[3 * k + b] = tmp;              \
+            tmp = V[3 * k + a]; V[3 * k + a] = V[3 * k + b]; V[3 * k + b] = tmp;              \
+        }                                                                                     \
+    }
+    APE_SWAPCOL(0, 1) APE_SWAPCOL(1, 2) APE_SWAPCOL(0, 1)
+#undef APE_SWAPCOL
+    double Um[9];
+    const double tiny = 1e-13 * sv[0];
+    if (!(sv[0] > 0.0)) {                         // sigma == 0: no information, identity
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        return;
+    }
+    for (int k = 0; k < 3; ++k) Um[3 * k] = A[3 * k] / sv[0];
+    if (sv[1] > tiny) {
+        for (int k = 0; k < 3; ++k) Um[3 * k + 1] = A[3 * k + 1] / sv[1];
+    } else {                                      // rank 1: any unit vector orthogonal to u0
+        const double ax = fabs(Um[0]), ay = fabs(Um[3]), az = fabs(Um[6]);
+        double e[3] = {0, 0, 0};
+        e[(ax <= ay && ax <= az) ? 0 : (ay <= az ? 1 : 2)] = 1.0;
+        double w[3] = {Um[3] * e[2] - Um[6] * e[1], Um[6] * e[0] - Um[0] * e[2], Um[0] * e[1] - Um[3] * e[0]};
+        const double n = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+        for (int k = 0; k < 3; ++k) Um[3 * k + 1] = w[k] / n;
+    }
+    if (sv[2] > tiny) {
+        for (int k = 0; k < 3; ++k) Um[3 * k + 2] = A[3 * k + 2] / sv[2];
+    } else {                                      // rank <= 2: complete to a right-handed frame
+        Um[2] = Um[3] * Um[7] - Um[6] * Um[4];
+        Um[5] = Um[6] * Um[1] - Um[0] * Um[7];
+        Um[8] = Um[0] * Um[4] - Um[3] * Um[1];
+    }
+    const double sgn = (det3(Um) * det3(V) < 0.0) ? -1.0 : 1.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            R[3 * i + j] = Um[3 * i] * V[3 * j] + Um[3 * i + 1] * V[3 * j + 1] + sgn * Um[3 * i + 2] * V[3 * j + 2];
+}
+
+__device__ __forceinline__ int cell_coord(double v, double lo, double inv_h) {
+    return (int)floor((v - lo) * inv_h);
+}
+
+__global__ void __launch_bounds__(kIcpThreads)
+icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ src_offset,
+               const double* __restrict__ target, const int32_t* __restrict__ tgt_offset, int n_reg,
+               double threshold, double rel_fitness, double rel_rmse, int max_iter,
+               const double* __restrict__ init, double* __restrict__ transform, double* __restrict__ info,
+               double* __restrict__ wrk_src, double* __restrict__ wrk_tgt, int32_t* __restrict__ wrk_tgt_orig,
+               int32_t* __restrict__ wrk_corr)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    IcpSmem& s = *reinterpret_cast<IcpSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const double r2 = threshold * threshold;
+
+    for (int reg = blockIdx.x; reg < n_reg; reg += gridDim.x) {
+        const int s0 = src_offset[reg], Ns = src_offset[reg + 1] - s0;
+        const int t0 = tgt_offset[reg], Nt = tgt_offset[reg + 1] - t0;
+        const double* src = source + 3 * (size_t)s0;
+        const double* tgt = target + 3 * (size_t)t0;
+        double* wsrc = wrk_src + 3 * (size_t)s0;
+        double* wtgt = wrk_tgt + 3 * (size_t)t0;
+        int32_t* worig = wrk_tgt_orig + t0;
+        int32_t* corr = wrk_corr + s0;
+
+        // ---------------- target bounding box
+        double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+        for (int j = tid; j < Nt; j += kIcpThreads) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const double v = tgt[3 * j + a];
+                lo[a] = fmin(lo[a], v); hi[a] = fmax(hi[a], v);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[a] = fmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+                hi[a] = fmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+            }
+        }
+        __syncthreads();
+        if ((tid & 31) == 0) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { s.red[tid >> 5][a] = lo[a]; s.red[tid >> 5][3 + a] = hi[a]; }
+        }
+        __syncthreads();
+        if (tid < 3) {
+            double l = DBL_MAX, h = -DBL_MAX;
+            for (int w = 0; w < kIcpWarps; ++w) { l = fmin(l, s.red[w][tid]); h = fmax(h, s.red[w][3 + tid]); }
+            s.bbmin[tid] = l; s.bbmax[tid] = h;
+        }
+        __syncthreads();
+        // grid geometry (uniform across the CTA)
+        double h = threshold;
+        int dim[3];
+        for (;;) {
+            long cells = 1;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const double ext = (Nt > 0) ? (s.bbmax[a] - s.bbmin[a]) : 0.0;
+                double d = floor(ext / h) + 1.0;
+                if (!(d < 1e6)) d = 1e6;
+                dim[a] = (int)d;
+                cells *= dim[a];
+            }
+            if (cells <= kIcpMaxCells) break;
+            h *= 1.25;
+        }
+        const double inv_h = 1.0 / h;
+        const int ncell = dim[0] * dim[1] * dim[2];
+        const double g0 = s.bbmin[0], g1 = s.bbmin[1], g2 = s.bbmin[2];
+
+        // ---------------- counting sort of the target into cell order
+        for (int c = tid; c <= ncell; c += kIcpThreads) { s.cell_start[c] = 0; if (c < ncell) s.cell_fill[c] = 0; }
+        __syncthreads();
+        for (int j = tid; j < Nt; j += kIcpThreads) {
+            const int cx = min(max(cell_coord(tgt[3 * j], g0, inv_h), 0), dim[0] - 1);
+            const int cy = min(max(cell_coord(tgt[3 * j + 1], g1, inv_h), 0), dim[1] - 1);
+            const int cz = min(max(cell_coord(tgt[3 * j + 2], g2, inv_h), 0), dim[2] - 1);
+            atomicAdd(&s.cell_start[(cz * dim[1] + cy) * dim[0] + cx + 1], 1);
+        }
+        __syncthreads();
+        // inclusive scan of cell_start[1..ncell] in chunks of kIcpThreads
+        if (tid == 0) s.scan_carry = 0;
+        __syncthreads();
+        for (int c0 = 1; c0 <= ncell; c0 += kIcpThreads) {
+            const int c = c0 + tid;
+            int v = (c <= ncell) ? s.cell_start[c] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((tid & 31) >= o) incl += t;
+            }
+            int* wtot = reinterpret_cast<int*>(&s.red[0][0]);
+            if ((tid & 31) == 31) wtot[tid >> 5] = incl;
+            __syncthreads();
+            int before = s.scan_carry;
+            for (int w = 0; w < (tid >> 5); ++w) before += wtot[w];
+            if (c <= ncell) s.cell_start[c] = before + incl;
+            __syncthreads();
+            if (tid == kIcpThreads - 1) s.scan_carry = before + incl;
+            __syncthreads();
+        }
+        for (int j = tid; j < Nt; j += kIcpThreads) {
+            const double x = tgt[3 * j], y = tgt[3 * j + 1], z = tgt[3 * j + 2];
+            const int cx = min(max(cell_coord(x, g0, inv_h), 0), dim[0] - 1);
+            const int cy = min(max(cell_coord(y, g1, inv_h), 0), dim[1] - 1);
+            const int cz = min(max(cell_coord(z, g2, inv_h), 0), dim[2] - 1);
+            const int c = (cz * dim[1] + cy) * dim[0] + cx;
+            const int pos = s.cell_start[c] + atomicAdd(&s.cell_fill[c], 1);
+            wtgt[3 * pos] = x; wtgt[3 * pos + 1] = y; wtgt[3 * pos + 2] = z;
+            worig[pos] = j;
+        }
+        // ---------------- initial transform
+        if (tid < 12) {
+            const double idv = (tid % 5 == 0) ? 1.0 : 0.0;        // 3x4 identity: entries 0,5,10
+            const double v = init ? init[16 * (size_t)reg + tid] : idv;
+            s.T[tid] = v; s.U[tid] = v;
+        }
+        __threadfence_block();
+        __syncthreads();
+
+        double fitness = 0.0, rmse = 0.0, ncorr = 0.0;
+        int it = 0;
+        bool first = true;
+        for (;;) {
+            // ---- (re)evaluate correspondences; the working cloud is updated in place by s.U
+            double U[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) U[k] = s.U[k];
+            double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};            // n, sum d2, sum p(3), sum q(3)
+            for (int i = tid; i < Ns; i += kIcpThreads) {
+                const double* pin = first ? (src + 3 * i) : (wsrc + 3 * i);
+                const double x0 = pin[0], y0 = pin[1], z0 = pin[2];
+                const double px = fma(U[0], x0, fma(U[1], y0, fma(U[2], z0, U[3])));
+                const double py = fma(U[4], x0, fma(U[5], y0, fma(U[6], z0, U[7])));
+                const double pz = fma(U[8], x0, fma(U[9], y0, fma(U[10], z0, U[11])));
+                wsrc[3 * i] = px; wsrc[3 * i + 1] = py; wsrc[3 * i + 2] = pz;
+                const int cx = cell_coord(px, g0, inv_h), cy = cell_coord(py, g1, inv_h), cz = cell_coord(pz, g2, inv_h);
+                double best = DBL_MAX; int bpos = -1, borig = 0x7fffffff;
+                if (Nt > 0 && cx >= -1 && cx <= dim[0] && cy >= -1 && cy <= dim[1] && cz >= -1 && cz <= dim[2]) {
+                    const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, dim[0] - 1);
+                    for (int zz = max(cz - 1, 0); zz <= min(cz + 1, dim[2] - 1); ++zz)
+                        for (int yy = max(cy - 1, 0); yy <= min(cy + 1, dim[1] - 1); ++yy) {
+                            if (x_lo > x_hi) continue;
+                            const int row = (zz * dim[1] + yy) * dim[0];
+                            const int jb = s.cell_start[row + x_lo], je = s.cell_start[row + x_hi + 1];   // x-run is contiguous
+                            for (int j = jb; j < je; ++j) {
+                                const double dx = px - wtgt[3 * j], dy = py - wtgt[3 * j + 1], dz = pz - wtgt[3 * j + 2];
+                                const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                                if (d < best) { best = d; bpos = j; borig = 0x7fffffff; }
+                                else if (d == best) {             // exact tie: lowest ORIGINAL index wins
+                                    if (borig == 0x7fffffff) borig = worig[bpos];
+                                    const int o = worig[j];
+                                    if (o < borig) { bpos = j; borig = o; }
+                                }
+                            }
+                        }
+                }
+                if (bpos >= 0 && best < r2) {
+                    corr[i] = bpos;
+                    acc[0] += 1.0; acc[1] += best;
+                    acc[2] += px; acc[3] += py; acc[4] += pz;
+                    acc[5] += wtgt[3 * bpos]; acc[6] += wtgt[3 * bpos + 1]; acc[7] += wtgt[3 * bpos + 2];
+                } else {
+                    corr[i] = -1;
+                }
+            }
+            block_sum<8>(acc, s);
+            const double n = s.out[0];
+            const double pfit = fitness, prmse = rmse;
+            ncorr = n;
+            if (n > 0.0) { fitness = n / (double)Ns; rmse = sqrt(s.out[1] / n); }
+            else { fitness = 0.0; rmse = 0.0; }
+            if (!first) {
+                ++it;
+                if ((fabs(pfit - fitness) < rel_fitness && fabs(prmse - rmse) < rel_rmse) || it >= max_iter) break;
+            } else {
+                first = false;
+                if (max_iter <= 0) break;
+            }
+            // ---- Kabsch update from the current correspondences
+            const double inv_n = n > 0.0 ? 1.0 / n : 0.0;
+            const double pm[3] = {s.out[2] * inv_n, s.out[3] * inv_n, s.out[4] * inv_n};
+            const double qm[3] = {s.out[5] * inv_n, s.out[6] * inv_n, s.out[7] * inv_n};
+            double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int i = tid; i < Ns; i += kIcpThreads) {
+                const int j = corr[i];
+                if (j >= 0) {
+                    const double p0 = wsrc[3 * i] - pm[0], p1 = wsrc[3 * i + 1] - pm[1], p2 = wsrc[3 * i + 2] - pm[2];
+                    const double q0 = wtgt[3 * j] - qm[0], q1 = wtgt[3 * j + 1] - qm[1], q2 = wtgt[3 * j + 2] - qm[2];
+                    cov[0] += q0 * p0; cov[1] += q0 * p1; cov[2] += q0 * p2;
+                    cov[3] += q1 * p0; cov[4] += q1 * p1; cov[5] += q1 * p2;
+                    cov[6] += q2 * p0; cov[7] += q2 * p1; cov[8] += q2 * p2;
+                }
+            }
+            block_sum<9>(cov, s);
+            if (tid == 0) {
+                double Um[12];
+                if (n > 0.0) {
+                    double sigma[9], R[9];
+                    for (int k = 0; k < 9; ++k) sigma[k] = s.out[k] * inv_n;
+                    kabsch_rotation(sigma, R);
+                    for (int a = 0; a < 3; ++a) {
+                        Um[4 * a] = R[3 * a]; Um[4 * a + 1] = R[3 * a + 1]; Um[4 * a + 2] = R[3 * a + 2];
+                        Um[4 * a + 3] = qm[a] - (R[3 * a] * pm[0] + R[3 * a + 1] * pm[1] + R[3 * a + 2] * pm[2]);
+                    }
+                } else {                                         // no correspondences: identity update
+                    for (int k = 0; k < 12; ++k) Um[k] = (k % 5 == 0) ? 1.0 : 0.0;
+                }
+                double Tn[12];
+                for (int a = 0; a < 3; ++a) {                    // T = update * T
+                    for (int b = 0; b < 4; ++b)
+                        Tn[4 * a + b] = Um[4 * a] * s.T[b] + Um[4 * a + 1] * s.T[4 + b] + Um[4 * a + 2] * s.T[8 + b]
+                                        + (b == 3 ? Um[4 * a + 3] : 0.0);
+                }
+                for (int k = 0; k < 12; ++k) { s.T[k] = Tn[k]; s.U[k] = Um[k]; }
+            }
+            __syncthreads();
+        }
+        if (tid < 16) transform[16 * (size_t)reg + tid] = tid < 12 ? s.T[tid] : (tid == 15 ? 1.0 : 0.0);
+        if (info && tid == 0) {
+            info[4 * (size_t)reg] = fitness; info[4 * (size_t)reg + 1] = rmse;
+            info[4 * (size_t)reg + 2] = (double)it; info[4 * (size_t)reg + 3] = ncorr;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace ape
+
+extern "C" __attribute__((visibility("default"))) size_t ape_icp_work_bytes(int total_source_points, int total_target_points)
+{
+    const size_t s = (size_t)(total_source_points > 0 ? total_source_points : 0);
+    const size_t t = (size_t)(total_target_points > 0 ? total_target_points : 0);
+    return 24 * s + 24 * t + 4 * t + 4 * s + 64;
+}
+
+extern "C" __attribute__((visibility("default"))) int ape_icp_p2p(const double* source, const int32_t* src_offset, const double* target,
+                           const int32_t* tgt_offset, int n_reg, int total_source_points, int total_target_points,
+                           double threshold, double rel_fitness, double rel_rmse, int max_iter, const double* init,
+                           double* transform, double* info, void* work, void* stream)
+{
+    APE_REQUIRE(source && src_offset && target && tgt_offset && transform && work, "ape_icp_p2p: null pointer");
+    APE_REQUIRE(n_reg >= 0 && total_source_points >= 0 && total_target_points >= 0, "ape_icp_p2p: bad sizes");
+    APE_REQUIRE(threshold > 0.0, "ape_icp_p2p: threshold must be > 0 (open3d returns the identity otherwise)");
+    APE_REQUIRE((((uintptr_t)work) & 7) == 0, "ape_icp_p2p: work must be 8-byte aligned");
+    if (n_reg == 0) return APE_OK;
+    double* wsrc = reinterpret_cast<double*>(work);
+    double* wtgt = wsrc + 3 * (size_t)total_source_points;
+    int32_t* worig = reinterpret_cast<int32_t*>(wtgt + 3 * (size_t)total_target_points);
+    int32_t* wcorr = worig + total_target_points;
+    static bool attr_set = false;
+    const int smem = (int)sizeof(ape::IcpSmem);
+    if (!attr_set) {
+        APE_CUDA(cudaFuncSetAttribute(ape::icp_p2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    const int grid = n_reg < ape::sm_count() * 4 ? n_reg : ape::sm_count() * 4;
+    ape::icp_p2p_kernel<<<grid, ape::kIcpThreads, smem, (cudaStream_t)stream>>>(
+        source, src_offset, target, tgt_offset, n_reg, threshold, rel_fitness, rel_rmse, max_iter, init, transform, info,
+        wsrc, wtgt, worig, wcorr);
+    ape::count_launch();
+    return ape::check_launch("ape_icp_p2p");
+}

@@ -1,0 +1,242 @@
+// Brute-force nearest neighbours and the fused ADD / ADD-S metric (sm_100a).
+//   ape_knn          replaces knn() DenseFusion/lib/knn/src/knn.h:12 (kernels knn.cu:36, :113)
+//   ape_add_metric   replaces loss_refiner.py:39-49 / eval_linemod.py:118-130
+// The reference writes and re-reads an N x M fp32 distance matrix (10.4 MB per 500x2600
+// instance); here the reference points of one instance live in shared memory, each thread
+// keeps its queries in registers and the matrix is never materialised (compulsory traffic
+// only: ~41 KB per instance).  Arithmetic is selectable so indices are bit-exact with either
+// reference implementation (APE_KNN_ARITH_CPU / APE_KNN_ARITH_FMA).
+#include "ape_common.cuh"
+#include <cfloat>
+
+namespace ape {
+
+template <bool FMA>
+__device__ __forceinline__ float dist3(float rx, float ry, float rz, float qx, float qy, float qz) {
+    const float dx = __fsub_rn(rx, qx), dy = __fsub_rn(ry, qy), dz = __fsub_rn(rz, qz);
+    if (FMA) return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+constexpr int kKnnThreads = 256;
+constexpr int kKnnQ = 2;            // queries per thread (register tile)
+constexpr int kKnnRefTile = 2048;   // reference points staged per pass (float4 each: 32 KB)
+
+// Scan `n` staged reference points for kKnnQ queries.  Points are visited in ascending index and
+// replaced only on strict '<', so the lowest index wins exact ties (knn.cu:156-173, knn_cpu.cpp:30).
+// Groups of 4 references are reduced with min first; the index is resolved only when the group
+// beats the running best, which keeps the common path at one FMNMX per pair.
+template <bool FMA>
+__device__ __forceinline__ void scan_tile(const float4* __restrict__ s_ref, int n, int index0,
+                                          const float (&qx)[kKnnQ], const float (&qy)[kKnnQ], const float (&qz)[kKnnQ],
+                                          float (&best)[kKnnQ], int (&bidx)[kKnnQ])
+{
+    int j = 0;
+    for (; j + 4 <= n; j += 4) {
+        const float4 r0 = s_ref[j], r1 = s_ref[j + 1], r2 = s_ref[j + 2], r3 = s_ref[j + 3];
+#pragma unroll
+        for (int q = 0; q < kKnnQ; ++q) {
+            const float d0 = dist3<FMA>(r0.x, r0.y, r0.z, qx[q], qy[q], qz[q]);
+            const float d1 = dist3<FMA>(r1.x, r1.y, r1.z, qx[q], qy[q], qz[q]);
+            const float d2 = dist3<FMA>(r2.x, r2.y, r2.z, qx[q], qy[q], qz[q]);
+            const float d3 = dist3<FMA>(r3.x, r3.y, r3.z, qx[q], qy[q], qz[q]);
+            const float m = fminf(fminf(d0, d1), fminf(d2, d3));
+            if (m < best[q]) {
+                best[q] = m;
+                bidx[q] = index0 + j + (d0 == m ? 0 : (d1 == m ? 1 : (d2 == m ? 2 : 3)));
+            }
+        }
+    }
+    for (; j < n; ++j) {
+        const float4 r = s_ref[j];
+#pragma unroll
+        for (int q = 0; q < kKnnQ; ++q) {
+            const float d = dist3<FMA>(r.x, r.y, r.z, qx[q], qy[q], qz[q]);
+            if (d < best[q]) { best[q] = d; bidx[q] = index0 + j; }
+        }
+    }
+}
+
+// ref [B,3,N], query [B,3,M] (SoA rows as the reference lays them out), idx [B,1,M] 1-based.
+// grid = (ceil(M / (threads*Q)), B)
+template <bool FMA>
+__global__ void __launch_bounds__(kKnnThreads)
+knn3_top1_kernel(const float* __restrict__ ref, const float* __restrict__ query, int64_t* __restrict__ idx,
+                 int N, int M)
+{
+    __shared__ float4 s_ref[kKnnRefTile];
+    const int b = blockIdx.y;
+    const float* R = ref + (size_t)b * 3 * N;
+    const float* Q = query + (size_t)b * 3 * M;
+    const int q0 = (blockIdx.x * kKnnThreads + threadIdx.x) * kKnnQ;
+    float qx[kKnnQ], qy[kKnnQ], qz[kKnnQ], best[kKnnQ];
+    int bidx[kKnnQ];
+#pragma unroll
+    for (int q = 0; q < kKnnQ; ++q) {
+        const int m = min(q0 + q, M - 1);
+        qx[q] = Q[m]; qy[q] = Q[M + m]; qz[q] = Q[2 * M + m];
+        best[q] = FLT_MAX; bidx[q] = 0;
+    }
+    for (int t0 = 0; t0 < N; t0 += kKnnRefTile) {
+        const int n = min(kKnnRefTile, N - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += kKnnThreads)
+            s_ref[i] = make_float4(R[t0 + i], R[N + t0 + i], R[2 * N + t0 + i], 0.f);
+        __syncthreads();
+        scan_tile<FMA>(s_ref, n, t0, qx, qy, qz, best, bidx);
+    }
+#pragma unroll
+    for (int q = 0; q < kKnnQ; ++q)
+        if (q0 + q < M) idx[(size_t)b * M + q0 + q] = (int64_t)bidx[q] + 1;
+}
+
+// Generic shape: any D, 1 <= k <= kKnnMaxK.  One thread per query, sorted k-list per thread.
+constexpr int kKnnMaxK = 64;
+template <bool FMA>
+__global__ void __launch_bounds__(128)
+knn_generic_kernel(const float* __restrict__ ref, const float* __restrict__ query, int64_t* __restrict__ idx,
+                   int D, int N, int M, int k)
+{
+    const int b = blockIdx.y;
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const float* R = ref + (size_t)b * D * N;
+    const float* Q = query + (size_t)b * D * M;
+    float bd[kKnnMaxK];
+    int bi[kKnnMaxK];
+    int have = 0;
+    for (int r = 0; r < N; ++r) {
+        float acc = 0.f;
+        for (int d = 0; d < D; ++d) {
+            const float diff = __fsub_rn(R[(size_t)d * N + r], Q[(size_t)d * M + m]);
+            acc = FMA ? __fmaf_rn(diff, diff, acc) : __fadd_rn(acc, __fmul_rn(diff, diff));
+        }
+        if (have == k && !(acc < bd[k - 1])) continue;
+        int pos = have < k ? have : k - 1;
+        while (pos > 0 && acc < bd[pos - 1]) { bd[pos] = bd[pos - 1]; bi[pos] = bi[pos - 1]; --pos; }
+        bd[pos] = acc; bi[pos] = r + 1;
+        if (have < k) ++have;
+    }
+    for (int j = 0; j < k; ++j) idx[((size_t)b * k + j) * M + m] = bi[j];
+}
+
+// ------------------------------------------------------------------------------ ADD / ADD-S
+// One CTA per instance.  pred_i = model_i * R^T + t (row-major base of the normalised quaternion),
+// ADD-S: nearest target point per pred point (CPU arithmetic: the query is pred, the reference is
+// target, as knn(target, pred) in loss_refiner.py:44), distance = sqrt of the winning d2.
+// ADD: ||pred_i - target_i||.  dis = mean over model points (fp32, fixed-order block reduction).
+constexpr int kAddThreads = 256;
+__global__ void __launch_bounds__(kAddThreads)
+add_metric_kernel(const float* __restrict__ quat, const float* __restrict__ trans,
+                  const float* __restrict__ model, int64_t model_stride, int n_model,
+                  const float* __restrict__ target, int64_t target_stride, int n_target,
+                  const uint8_t* __restrict__ symmetric, float* __restrict__ dis, int32_t* __restrict__ nn_index)
+{
+    __shared__ float4 s_ref[kKnnRefTile];
+    __shared__ float s_part[kAddThreads / 32];
+    const int b = blockIdx.x;
+    const float* Mp = model + (size_t)b * model_stride;
+    const float* Tg = target + (size_t)b * target_stride;
+    float w = quat[4 * b], x = quat[4 * b + 1], y = quat[4 * b + 2], z = quat[4 * b + 3];
+    const float nrm = sqrtf(w * w + x * x + y * y + z * z);
+    w /= nrm; x /= nrm; y /= nrm; z /= nrm;
+    float R[9];
+    quat_to_base(w, x, y, z, R);
+    const float tx = trans[3 * b], ty = trans[3 * b + 1], tz = trans[3 * b + 2];
+    const bool sym = symmetric && symmetric[b];
+
+    float acc = 0.f;
+    for (int p0 = 0; p0 < n_model; p0 += kAddThreads * kKnnQ) {       // usually one pass (500 <= 512)
+        const int q0 = p0 + threadIdx.x * kKnnQ;
+        float qx[kKnnQ], qy[kKnnQ], qz[kKnnQ], best[kKnnQ];
+        int bidx[kKnnQ];
+#pragma unroll
+        for (int q = 0; q < kKnnQ; ++q) {
+            const int i = min(q0 + q, n_model - 1);
+            const float mx = Mp[3 * i], my = Mp[3 * i + 1], mz = Mp[3 * i + 2];
+            // model @ base^T + t  (loss_refiner.py:31, :39): pred_a = sum_k m_k * R[a][k] + t_a
+            qx[q] = (mx * R[0] + my * R[1] + mz * R[2]) + tx;
+            qy[q] = (mx * R[3] + my * R[4] + mz * R[5]) + ty;
+            qz[q] = (mx * R[6] + my * R[7] + mz * R[8]) + tz;
+            best[q] = FLT_MAX; bidx[q] = 0;
+        }
+        if (sym) {
+            for (int t0 = 0; t0 < n_target; t0 += kKnnRefTile) {
+                const int n = min(kKnnRefTile, n_target - t0);
+                __syncthreads();
+                for (int i = threadIdx.x; i < n; i += kAddThreads)
+                    s_ref[i] = make_float4(Tg[3 * (t0 + i)], Tg[3 * (t0 + i) + 1], Tg[3 * (t0 + i) + 2], 0.f);
+                __syncthreads();
+                scan_tile<false>(s_ref, n, t0, qx, qy, qz, best, bidx);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kKnnQ; ++q) {
+            if (q0 + q < n_model) {
+                float d;
+                if (sym) {
+                    d = sqrtf(best[q]);
+                    if (nn_index) nn_index[(size_t)b * n_model + q0 + q] = bidx[q];
+                } else {
+                    const int i = q0 + q;
+                    const float dx = qx[q] - Tg[3 * i], dy = qy[q] - Tg[3 * i + 1], dz = qz[q] - Tg[3 * i + 2];
+                    d = sqrtf(dx * dx + dy * dy + dz * dz);
+                    if (nn_index) nn_index[(size_t)b * n_model + i] = i;
+                }
+                acc += d;
+            }
+        }
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < kAddThreads / 32; ++i) s += s_part[i];
+        dis[b] = s / (float)n_model;
+    }
+}
+
+}  // namespace ape
+
+extern "C" __attribute__((visibility("default"))) int ape_knn(const float* ref, const float* query, int64_t* idx, int B, int D, int N, int M, int k,
+                       int arith, void* stream)
+{
+    APE_REQUIRE(ref && query && idx, "ape_knn: null pointer");
+    APE_REQUIRE(B >= 0 && D > 0 && N > 0 && M >= 0 && k > 0, "ape_knn: bad sizes");
+    APE_REQUIRE(k <= N, "ape_knn: k (%d) > number of reference points (%d)", k, N);
+    APE_REQUIRE(arith == APE_KNN_ARITH_CPU || arith == APE_KNN_ARITH_FMA, "ape_knn: unknown arithmetic mode");
+    if (B == 0 || M == 0) return APE_OK;
+    APE_REQUIRE(B <= 65535, "ape_knn: batch > 65535 (split the batch)");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (D == 3 && k == 1) {
+        dim3 grid((M + ape::kKnnThreads * ape::kKnnQ - 1) / (ape::kKnnThreads * ape::kKnnQ), B);
+        if (arith == APE_KNN_ARITH_FMA) ape::knn3_top1_kernel<true><<<grid, ape::kKnnThreads, 0, s>>>(ref, query, idx, N, M);
+        else ape::knn3_top1_kernel<false><<<grid, ape::kKnnThreads, 0, s>>>(ref, query, idx, N, M);
+    } else {
+        if (k > ape::kKnnMaxK) {
+            ape::set_error("ape_knn: k=%d > %d is not implemented", k, ape::kKnnMaxK);
+            return APE_ERR_UNSUPPORTED;
+        }
+        dim3 grid((M + 127) / 128, B);
+        if (arith == APE_KNN_ARITH_FMA) ape::knn_generic_kernel<true><<<grid, 128, 0, s>>>(ref, query, idx, D, N, M, k);
+        else ape::knn_generic_kernel<false><<<grid, 128, 0, s>>>(ref, query, idx, D, N, M, k);
+    }
+    ape::count_launch();
+    return ape::check_launch("ape_knn");
+}
+
+extern "C" __attribute__((visibility("default"))) int ape_add_metric(const float* quat, const float* trans, const float* model_points, int64_t model_stride,
+                              int n_model, const float* target, int64_t target_stride, int n_target,
+                              const uint8_t* symmetric, int B, float* dis, int32_t* nn_index, void* stream)
+{
+    APE_REQUIRE(quat && trans && model_points && target && dis, "ape_add_metric: null pointer");
+    APE_REQUIRE(B >= 0 && n_model > 0 && n_target > 0, "ape_add_metric: bad sizes");
+    APE_REQUIRE(symmetric || n_model == n_target, "ape_add_metric: ADD needs n_model == n_target");
+    if (B == 0) return APE_OK;
+    ape::add_metric_kernel<<<B, ape::kAddThreads, 0, (cudaStream_t)stream>>>(
+        quat, trans, model_points, model_stride, n_model, target, target_stride, n_target, symmetric, dis, nn_index);
+    ape::count_launch();
+    return ape::check_launch("ape_add_metric");
+}

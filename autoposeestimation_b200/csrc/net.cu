@@ -1,0 +1,669 @@
+// DenseFusion PoseNet (geometry side) and PoseRefineNet forward, batched over objects (sm_100a).
+// Replaces DenseFusion/lib/network.py:98-132 (PoseNet.forward after the colour encoder, with
+// PoseNetFeat.forward :53-68) and :187-206 (PoseRefineNet.forward, PoseRefineNetFeat.forward :151-168).
+//
+// Data layout (per call: B objects, N points, Np = N rounded up to 128, R = B*Np rows):
+//   PF  [R,384] split-bf16  = [conv1 64 | e_conv1 64 | conv2 128 | e_conv2 128]  (= pointfeat_1 | pointfeat_2,
+//                             the torch.cat's of network.py:56,:60,:160 become column slots)
+//   H5  [R,512], H1 [R,1920] (r|t|c), H2 [R,768], H3 [R,384]  split-bf16 activations
+//   CS  [R/128,1024] fp32 per-tile column sums of relu(conv6) -> AP [B,1024] = AvgPool1d (network.py:65)
+//   GB  [B,1920] fp32: conv1_{r,t,c} applied to the broadcast global feature (network.py:67-68) folded
+//                      into a per-object bias (it is identical for every point of an object)
+// Kernels: front-end (gather + K=3 / K=32 convs, SIMT), tcgen05 split-bf16 GEMM (gemm_tc.cuh) for every
+// K>=64 layer, small dense layers / heads (SIMT fp32), final conv4 + sigmoid + class select.
+#include "gemm_tc.cuh"
+#include <cstring>
+#include <vector>
+
+namespace ape {
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------------
+// Front end: one warp per point.  emb gather (network.py:100-102), conv1 (3->64), e_conv1 (32->64),
+// ReLU, written as split-bf16 into PF[:,0:128]; also emits emb [B,32,N] fp32 (PoseNet only).
+template <bool GATHER>
+__global__ void __launch_bounds__(256)
+frontend_kernel(const float* __restrict__ feat_src /*GATHER: out_img [B,32,hw]; else emb [B,32,N]*/, int hw,
+                const float* __restrict__ cloud, const int64_t* __restrict__ choose,
+                const float* __restrict__ w1, const float* __restrict__ b1,      // [64,3], [64]
+                const float* __restrict__ we1, const float* __restrict__ be1,    // [64,32], [64]
+                int N, int Np, bf16* __restrict__ pf_hi, bf16* __restrict__ pf_lo, int pf_ld,
+                float* __restrict__ emb_out)
+{
+    __shared__ float s_we1[32][65];          // [k][c], padded
+    __shared__ float s_w1[3][64];
+    __shared__ float s_b[128];
+    for (int i = threadIdx.x; i < 64 * 32; i += 256) s_we1[i & 31][i >> 5] = we1[i];       // we1[c][k]
+    for (int i = threadIdx.x; i < 64 * 3; i += 256) s_w1[i % 3][i / 3] = w1[i];
+    if (threadIdx.x < 64) s_b[threadIdx.x] = b1[threadIdx.x];
+    else if (threadIdx.x < 128) s_b[threadIdx.x] = be1[threadIdx.x - 64];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    for (int n = blockIdx.x * 8 + warp; n < Np; n += gridDim.x * 8) {
+        const size_t row = (size_t)b * Np + n;
+        bf16* oh = pf_hi + row * pf_ld;
+        bf16* ol = pf_lo + row * pf_ld;
+        if (n >= N) {                                   // padding row: zeros
+            for (int c = lane; c < 128; c += 32) { oh[c] = __float2bfloat16_rn(0.f); ol[c] = __float2bfloat16_rn(0.f); }
+            continue;
+        }
+        float e;                                        // lane k holds emb channel k of this point
+        if (GATHER) {
+            const int64_t ci = choose[(size_t)b * N + n];
+            e = feat_src[((size_t)b * 32 + lane) * hw + ci];
+            emb_out[((size_t)b * 32 + lane) * N + n] = e;
+        } else {
+            e = feat_src[((size_t)b * 32 + lane) * N + n];
+        }
+        const float px = cloud[((size_t)b * N + n) * 3], py = cloud[((size_t)b * N + n) * 3 + 1],
+                    pz = cloud[((size_t)b * N + n) * 3 + 2];
+        // each lane produces channels lane and lane+32 of both 64-wide outputs
+        float x0 = s_b[lane], x1 = s_b[lane + 32], e0 = s_b[64 + lane], e1 = s_b[96 + lane];
+        x0 = fmaf(s_w1[0][lane], px, x0); x0 = fmaf(s_w1[1][lane], py, x0); x0 = fmaf(s_w1[2][lane], pz, x0);
+        x1 = fmaf(s_w1[0][lane + 32], px, x1); x1 = fmaf(s_w1[1][lane + 32], py, x1); x1 = fmaf(s_w1[2][lane + 32], pz, x1);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const float ek = __shfl_sync(0xffffffffu, e, k);
+            e0 = fmaf(s_we1[k][lane], ek, e0);
+            e1 = fmaf(s_we1[k][lane + 32], ek, e1);
+        }
+        const float vals[4] = {fmaxf(x0, 0.f), fmaxf(x1, 0.f), fmaxf(e0, 0.f), fmaxf(e1, 0.f)};
+        const int cols[4] = {lane, lane + 32, 64 + lane, 96 + lane};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bf16 h = __float2bfloat16_rn(vals[j]);
+            oh[cols[j]] = h;
+            ol[cols[j]] = __float2bfloat16_rn(vals[j] - __bfloat162float(h));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT fp32 validation GEMM on the same split-bf16 buffers and with the same epilogues as the tcgen05
+// kernel (tests only: APE_GEMM_SIMT).  64x64 tile, 256 threads, 4x4 outputs per thread.
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const bf16* __restrict__ a_hi, const bf16* __restrict__ a_lo, int a_ld,
+                 const bf16* __restrict__ w_hi, const bf16* __restrict__ w_lo, const tc::Params p)
+{
+    __shared__ float sA[16][65], sW[16][65];
+    const int g = blockIdx.z, tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int row0 = blockIdx.y * 64, col0 = blockIdx.x * 64;
+    const int a_k = p.a_k0 + g * p.a_kg;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < p.K; k0 += 16) {
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            const int r = i >> 4, k = i & 15;
+            const size_t ia = (size_t)(row0 + r) * a_ld + a_k + k0 + k;
+            sA[k][r] = __bfloat162float(a_hi[ia]) + __bfloat162float(a_lo[ia]);
+            const size_t iw = (size_t)(g * p.N + col0 + r) * p.K + k0 + k;
+            sW[k][r] = __bfloat162float(w_hi[iw]) + __bfloat162float(w_lo[iw]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float a[4], w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = sA[k][ty * 4 + i]; w[i] = sW[k][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    const int GN = p.groups * p.N;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int cg = g * p.N + col0 + tx * 4 + j;
+        float csum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = row0 + ty * 4 + i;
+            const float bias = p.bias[(p.bias_obj_rows > 0 ? (size_t)(row / p.bias_obj_rows) * GN : 0) + cg];
+            const float v = fmaxf(acc[i][j] + bias, 0.f);
+            if (p.mode == tc::EPI_RELU_SPLIT) {
+                const bf16 h = __float2bfloat16_rn(v);
+                const size_t o = (size_t)row * p.o_ld + p.o_c0 + cg;
+                p.o_hi[o] = h;
+                p.o_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+            } else if ((row % p.rows_per_obj) < p.valid_rows) {
+                csum += v;
+            }
+        }
+        if (p.mode == tc::EPI_RELU_COLSUM) atomicAdd(&p.colsum[(size_t)(row0 / 128) * GN + cg], csum);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// AvgPool1d over the points of each object from the per-tile column sums: ap[b,c] = sum_t cs[b*tpo+t,c] / N
+__global__ void pool_finish_kernel(const float* __restrict__ cs, int tiles_per_obj, int C, float inv_n, float* __restrict__ ap)
+{
+    const int b = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f;
+    for (int t = 0; t < tiles_per_obj; ++t) s += cs[((size_t)b * tiles_per_obj + t) * C + c];
+    ap[(size_t)b * C + c] = s / inv_n;   // inv_n carries N: AvgPool1d divides
+}
+
+// Small dense layer over per-object vectors (fp32 SIMT): one warp per output, 8 objects per pass.
+//   out[b, g*npg + j] = act(bias[g*npg + j] + sum_k W[g*npg + j, k] * in[b, g*in_gs + k])
+constexpr int kDenseObj = 8;
+__global__ void __launch_bounds__(256)
+dense_small_kernel(const float* __restrict__ in, int in_ld, int in_gs, const float* __restrict__ W,
+                   const float* __restrict__ bias, float* __restrict__ out, int out_ld, int B, int K, int npg, int groups,
+                   int relu)
+{
+    const int lane = threadIdx.x & 31;
+    const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (o >= npg * groups) return;
+    const int g = o / npg;
+    const float* w = W + (size_t)o * K;
+    for (int b0 = blockIdx.y * kDenseObj; b0 < B; b0 += gridDim.y * kDenseObj) {
+        float acc[kDenseObj] = {};
+        for (int k = lane * 4; k < K; k += 128) {
+            const float4 wv = *reinterpret_cast<const float4*>(w + k);
+#pragma unroll
+            for (int j = 0; j < kDenseObj; ++j) {
+                if (b0 + j < B) {
+                    const float4 x = *reinterpret_cast<const float4*>(in + (size_t)(b0 + j) * in_ld + g * in_gs + k);
+                    acc[j] = fmaf(wv.x, x.x, fmaf(wv.y, x.y, fmaf(wv.z, x.z, fmaf(wv.w, x.w, acc[j]))));
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kDenseObj; ++j) {
+            const float s = warp_sum(acc[j]);
+            if (lane == 0 && b0 + j < B) {
+                const float v = s + bias[o];
+                out[(size_t)(b0 + j) * out_ld + o] = relu ? fmaxf(v, 0.f) : v;
+            }
+        }
+    }
+}
+
+// PoseNet last layer: conv4_{r,t,c} restricted to the object's class (network.py:119-130), sigmoid on c.
+// One warp per point; H3 row = [r128 | t128 | c128] split-bf16.
+__global__ void __launch_bounds__(256)
+posenet_out_kernel(const bf16* __restrict__ h_hi, const bf16* __restrict__ h_lo, int ld, int N, int Np,
+                   const float* __restrict__ w4r, const float* __restrict__ b4r, const float* __restrict__ w4t,
+                   const float* __restrict__ b4t, const float* __restrict__ w4c, const float* __restrict__ b4c,
+                   const int64_t* __restrict__ obj, int num_obj, float* __restrict__ pred_r, float* __restrict__ pred_t,
+                   float* __restrict__ pred_c)
+{
+    __shared__ float s_w[8][128];
+    __shared__ float s_b[8];
+    const int b = blockIdx.y;
+    int o = (int)obj[b];
+    o = o < 0 ? 0 : (o >= num_obj ? num_obj - 1 : o);
+    for (int i = threadIdx.x; i < 8 * 128; i += 256) {
+        const int j = i >> 7, k = i & 127;
+        s_w[j][k] = j < 4 ? w4r[(size_t)(o * 4 + j) * 128 + k] : (j < 7 ? w4t[(size_t)(o * 3 + j - 4) * 128 + k] : w4c[(size_t)o * 128 + k]);
+    }
+    if (threadIdx.x < 8) {
+        const int j = threadIdx.x;
+        s_b[j] = j < 4 ? b4r[o * 4 + j] : (j < 7 ? b4t[o * 3 + j - 4] : b4c[o]);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int n = blockIdx.x * 8 + warp; n < N; n += gridDim.x * 8) {
+        const size_t row = (size_t)b * Np + n;
+        float acc[8] = {};
+#pragma unroll
+        for (int h = 0; h < 3; ++h) {
+            // lane handles channels lane*4 .. lane*4+3 of head h
+            const uint2 hv = *reinterpret_cast<const uint2*>(h_hi + row * ld + h * 128 + lane * 4);
+            const uint2 lv = *reinterpret_cast<const uint2*>(h_lo + row * ld + h * 128 + lane * 4);
+            float x[4];
+            x[0] = __uint_as_float(hv.x << 16) + __uint_as_float(lv.x << 16);
+            x[1] = __uint_as_float(hv.x & 0xffff0000u) + __uint_as_float(lv.x & 0xffff0000u);
+            x[2] = __uint_as_float(hv.y << 16) + __uint_as_float(lv.y << 16);
+            x[3] = __uint_as_float(hv.y & 0xffff0000u) + __uint_as_float(lv.y & 0xffff0000u);
+            const int j0 = h == 0 ? 0 : (h == 1 ? 4 : 7), j1 = h == 0 ? 4 : (h == 1 ? 7 : 8);
+#pragma unroll
+            for (int j = j0; j < j1; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[j] = fmaf(s_w[j][lane * 4 + q], x[q], acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = warp_sum(acc[j]) + s_b[j];
+        if (lane == 0) {
+            float* r = pred_r + ((size_t)b * N + n) * 4;
+            r[0] = acc[0]; r[1] = acc[1]; r[2] = acc[2]; r[3] = acc[3];
+            float* t = pred_t + ((size_t)b * N + n) * 3;
+            t[0] = acc[4]; t[1] = acc[5]; t[2] = acc[6];
+            pred_c[(size_t)b * N + n] = 1.0f / (1.0f + expf(-acc[7]));
+        }
+    }
+}
+
+// PoseRefineNet last layer: conv3_{r,t} rows of the object's class (network.py:199-204); in = [r128 | t128] fp32
+__global__ void __launch_bounds__(256)
+refiner_out_kernel(const float* __restrict__ g2, const float* __restrict__ w3r, const float* __restrict__ b3r,
+                   const float* __restrict__ w3t, const float* __restrict__ b3t, const int64_t* __restrict__ obj,
+                   int num_obj, float* __restrict__ r2, float* __restrict__ t2)
+{
+    const int b = blockIdx.x, lane = threadIdx.x & 31, j = threadIdx.x >> 5;      // 8 warps, 7 outputs
+    if (j >= 7) return;
+    int o = (int)obj[b];
+    o = o < 0 ? 0 : (o >= num_obj ? num_obj - 1 : o);
+    const float* w = j < 4 ? w3r + (size_t)(o * 4 + j) * 128 : w3t + (size_t)(o * 3 + j - 4) * 128;
+    const float* x = g2 + (size_t)b * 256 + (j < 4 ? 0 : 128);
+    float acc = 0.f;
+#pragma unroll
+    for (int k = lane; k < 128; k += 32) acc = fmaf(w[k], x[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        if (j < 4) r2[b * 4 + j] = acc + b3r[o * 4 + j];
+        else t2[b * 3 + j - 4] = acc + b3t[o * 3 + j - 4];
+    }
+}
+
+}  // namespace ape
+
+// ================================================================================================
+// Host side: weights, workspace, tensor maps, layer sequencing
+// ================================================================================================
+using ape::bf16;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] tensor, box {64 cols, 128 rows}, 128-byte swizzle
+static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { ape::set_error("cuTensorMapEncodeTiled entry point not available"); return APE_ERR_CUDA; }
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld_elems * 2};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ape::set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return APE_ERR_CUDA; }
+    return APE_OK;
+}
+
+struct SplitMat {            // split-bf16 matrix with its TMA maps
+    bf16 *hi = nullptr, *lo = nullptr;
+    int rows = 0, cols = 0;
+    CUtensorMap map_hi, map_lo;
+};
+
+struct DevF32 { float* p = nullptr; size_t n = 0; };
+
+struct ape_net {
+    int kind = 0, num_obj = 0, max_batch = 0, max_points = 0, np_max = 0;
+    int gemm_impl = APE_GEMM_TCGEN05;
+    std::vector<void*> allocs;
+    // fp32 parameters
+    DevF32 w1, b1, we1, be1;                 // front end
+    DevF32 b_c2e2, b_c5, b_c6;               // GEMM biases
+    SplitMat W_c2e2, W_c5, W_c6;             // [256,64] (conv2 | e_conv2), [512,256|384], [1024,512]
+    // PoseNet heads
+    SplitMat W_h1, W_h2, W_h3;               // [1920,384], [768,640], [384,256]
+    DevF32 Wg, b_h1, b_h2, b_h3;             // global part of conv1_{r,t,c}: [1920,1024] fp32
+    DevF32 w4r, b4r, w4t, b4t, w4c, b4c;
+    // Refiner heads (fp32)
+    DevF32 Wr1, br1, Wr2, br2, w3r, b3r, w3t, b3t;
+    // workspace
+    SplitMat PF, H5, H1, H2, H3;
+    DevF32 CS, AP, GB, G1, G2;
+    // scratch of ape_pose_pipeline (PoseNet handle only)
+    DevF32 s_r, s_t, s_c, s_emb, s_newp, s_r2, s_t2, s_myr, s_myt;
+    double *s_pose_a = nullptr, *s_pose_b = nullptr;
+    int32_t* s_which = nullptr;
+};
+
+static int dev_alloc(ape_net* net, void** p, size_t bytes) {
+    APE_CUDA(cudaMalloc(p, bytes));
+    net->allocs.push_back(*p);
+    return APE_OK;
+}
+static int upload_f32(ape_net* net, DevF32& d, const float* host, size_t n) {
+    int rc = dev_alloc(net, (void**)&d.p, n * sizeof(float));
+    if (rc) return rc;
+    d.n = n;
+    APE_CUDA(cudaMemcpy(d.p, host, n * sizeof(float), cudaMemcpyHostToDevice));
+    return APE_OK;
+}
+static int alloc_f32(ape_net* net, DevF32& d, size_t n) {
+    int rc = dev_alloc(net, (void**)&d.p, n * sizeof(float));
+    if (rc) return rc;
+    d.n = n;
+    APE_CUDA(cudaMemset(d.p, 0, n * sizeof(float)));
+    return APE_OK;
+}
+static inline uint16_t f2bf(float f) {       // round-to-nearest-even, as __float2bfloat16_rn (finite inputs)
+    uint32_t u; memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static inline float bf2f(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
+
+static int upload_split(ape_net* net, SplitMat& m, const std::vector<float>& host, int rows, int cols) {
+    std::vector<uint16_t> hi(host.size()), lo(host.size());
+    for (size_t i = 0; i < host.size(); ++i) { hi[i] = f2bf(host[i]); lo[i] = f2bf(host[i] - bf2f(hi[i])); }
+    int rc;
+    if ((rc = dev_alloc(net, (void**)&m.hi, host.size() * 2))) return rc;
+    if ((rc = dev_alloc(net, (void**)&m.lo, host.size() * 2))) return rc;
+    APE_CUDA(cudaMemcpy(m.hi, hi.data(), host.size() * 2, cudaMemcpyHostToDevice));
+    APE_CUDA(cudaMemcpy(m.lo, lo.data(), host.size() * 2, cudaMemcpyHostToDevice));
+    m.rows = rows; m.cols = cols;
+    if ((rc = make_map(&m.map_hi, m.hi, rows, cols, cols))) return rc;
+    return make_map(&m.map_lo, m.lo, rows, cols, cols);
+}
+static int alloc_split(ape_net* net, SplitMat& m, size_t rows, int cols) {
+    int rc;
+    const size_t bytes = rows * (size_t)cols * 2;
+    if ((rc = dev_alloc(net, (void**)&m.hi, bytes))) return rc;
+    if ((rc = dev_alloc(net, (void**)&m.lo, bytes))) return rc;
+    APE_CUDA(cudaMemset(m.hi, 0, bytes));
+    APE_CUDA(cudaMemset(m.lo, 0, bytes));
+    m.rows = (int)rows; m.cols = cols;
+    if ((rc = make_map(&m.map_hi, m.hi, rows, cols, cols))) return rc;
+    return make_map(&m.map_lo, m.lo, rows, cols, cols);
+}
+
+// vertical concatenation of [rows_i, cols] fp32 host matrices, keeping columns [c0, c0+ncols) of each
+static std::vector<float> vcat(std::initializer_list<const float*> mats, std::initializer_list<int> rows, int cols, int c0, int ncols) {
+    std::vector<float> out;
+    auto r = rows.begin();
+    for (const float* m : mats) {
+        for (int i = 0; i < *r; ++i) out.insert(out.end(), m + (size_t)i * cols + c0, m + (size_t)i * cols + c0 + ncols);
+        ++r;
+    }
+    return out;
+}
+
+// Canonical weight order (DESIGN.md "weight order"); every entry is weight then bias:
+//  PoseNet : feat.conv1, feat.e_conv1, feat.conv2, feat.e_conv2, feat.conv5, feat.conv6,
+//            conv1_r, conv1_t, conv1_c, conv2_r, conv2_t, conv2_c, conv3_r, conv3_t, conv3_c,
+//            conv4_r, conv4_t, conv4_c                                             (36 tensors)
+//  Refiner : feat.conv1, feat.e_conv1, feat.conv2, feat.e_conv2, feat.conv5, feat.conv6,
+//            conv1_r, conv1_t, conv2_r, conv2_t, conv3_r, conv3_t                  (24 tensors)
+extern "C" __attribute__((visibility("default")))
+int ape_net_create(int kind, const float* const* w, int n_tensors, int num_obj, int max_batch, int max_points, ape_net** out)
+{
+    APE_REQUIRE(w && out, "ape_net_create: null pointer");
+    APE_REQUIRE(kind == APE_NET_POSENET || kind == APE_NET_REFINER, "ape_net_create: unknown kind");
+    APE_REQUIRE(n_tensors == (kind == APE_NET_POSENET ? 36 : 24), "ape_net_create: expected %d tensors, got %d",
+                kind == APE_NET_POSENET ? 36 : 24, n_tensors);
+    APE_REQUIRE(num_obj > 0 && max_batch > 0 && max_points > 0, "ape_net_create: bad sizes");
+    for (int i = 0; i < n_tensors; ++i) APE_REQUIRE(w[i], "ape_net_create: tensor %d is null", i);
+    int dev_count = 0;
+    if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) {
+        ape::set_error("ape_net_create: no CUDA device (there is no CPU fallback)");
+        return APE_ERR_CUDA;
+    }
+    ape_net* net = new ape_net();
+    net->kind = kind; net->num_obj = num_obj; net->max_batch = max_batch; net->max_points = max_points;
+    net->np_max = (max_points + 127) / 128 * 128;
+    const size_t R = (size_t)max_batch * net->np_max;
+    int rc = APE_OK;
+#define TRY(x) do { if ((rc = (x)) != APE_OK) { ape_net_destroy(net); return rc; } } while (0)
+    TRY(upload_f32(net, net->w1, w[0], 64 * 3));   TRY(upload_f32(net, net->b1, w[1], 64));
+    TRY(upload_f32(net, net->we1, w[2], 64 * 32)); TRY(upload_f32(net, net->be1, w[3], 64));
+    {   // conv2 | e_conv2 as two groups of a [256,64] matrix
+        std::vector<float> W = vcat({w[4], w[6]}, {128, 128}, 64, 0, 64);
+        TRY(upload_split(net, net->W_c2e2, W, 256, 64));
+        std::vector<float> b(w[5], w[5] + 128); b.insert(b.end(), w[7], w[7] + 128);
+        TRY(upload_f32(net, net->b_c2e2, b.data(), 256));
+    }
+    const int k5 = kind == APE_NET_POSENET ? 256 : 384;
+    TRY(upload_split(net, net->W_c5, std::vector<float>(w[8], w[8] + (size_t)512 * k5), 512, k5));
+    TRY(upload_f32(net, net->b_c5, w[9], 512));
+    TRY(upload_split(net, net->W_c6, std::vector<float>(w[10], w[10] + (size_t)1024 * 512), 1024, 512));
+    TRY(upload_f32(net, net->b_c6, w[11], 1024));
+    TRY(alloc_split(net, net->PF, R, 384));
+    TRY(alloc_split(net, net->H5, R, 512));
+    TRY(alloc_f32(net, net->CS, (R / 128) * 1024));
+    TRY(alloc_f32(net, net->AP, (size_t)max_batch * 1024));
+    if (kind == APE_NET_POSENET) {
+        TRY(upload_split(net, net->W_h1, vcat({w[12], w[14], w[16]}, {640, 640, 640}, 1408, 0, 384), 1920, 384));
+        {
+            std::vector<float> g = vcat({w[12], w[14], w[16]}, {640, 640, 640}, 1408, 384, 1024);
+            TRY(upload_f32(net, net->Wg, g.data(), g.size()));
+            std::vector<float> b(w[13], w[13] + 640); b.insert(b.end(), w[15], w[15] + 640); b.insert(b.end(), w[17], w[17] + 640);
+            TRY(upload_f32(net, net->b_h1, b.data(), 1920));
+        }
+        TRY(upload_split(net, net->W_h2, vcat({w[18], w[20], w[22]}, {256, 256, 256}, 640, 0, 640), 768, 640));
+        {
+            std::vector<float> b(w[19], w[19] + 256); b.insert(b.end(), w[21], w[21] + 256); b.insert(b.end(), w[23], w[23] + 256);
+            TRY(upload_f32(net, net->b_h2, b.data(), 768));
+        }
+        TRY(upload_split(net, net->W_h3, vcat({w[24], w[26], w[28]}, {128, 128, 128}, 256, 0, 256), 384, 256));
+        {
+            std::vector<float> b(w[25], w[25] + 128); b.insert(b.end(), w[27], w[27] + 128); b.insert(b.end(), w[29], w[29] + 128);
+            TRY(upload_f32(net, net->b_h3, b.data(), 384));
+        }
+        TRY(upload_f32(net, net->w4r, w[30], (size_t)num_obj * 4 * 128)); TRY(upload_f32(net, net->b4r, w[31], num_obj * 4));
+        TRY(upload_f32(net, net->w4t, w[32], (size_t)num_obj * 3 * 128)); TRY(upload_f32(net, net->b4t, w[33], num_obj * 3));
+        TRY(upload_f32(net, net->w4c, w[34], (size_t)num_obj * 128));     TRY(upload_f32(net, net->b4c, w[35], num_obj));
+        TRY(alloc_split(net, net->H1, R, 1920));
+        TRY(alloc_split(net, net->H2, R, 768));
+        TRY(alloc_split(net, net->H3, R, 384));
+        TRY(alloc_f32(net, net->GB, (size_t)max_batch * 1920));
+        const size_t BN_ = (size_t)max_batch * max_points;
+        TRY(alloc_f32(net, net->s_r, BN_ * 4)); TRY(alloc_f32(net, net->s_t, BN_ * 3)); TRY(alloc_f32(net, net->s_c, BN_));
+        TRY(alloc_f32(net, net->s_emb, BN_ * 32)); TRY(alloc_f32(net, net->s_newp, BN_ * 3));
+        TRY(alloc_f32(net, net->s_r2, (size_t)max_batch * 4)); TRY(alloc_f32(net, net->s_t2, (size_t)max_batch * 3));
+        TRY(alloc_f32(net, net->s_myr, (size_t)max_batch * 4)); TRY(alloc_f32(net, net->s_myt, (size_t)max_batch * 3));
+        TRY(dev_alloc(net, (void**)&net->s_pose_a, (size_t)max_batch * 7 * sizeof(double)));
+        TRY(dev_alloc(net, (void**)&net->s_pose_b, (size_t)max_batch * 7 * sizeof(double)));
+        TRY(dev_alloc(net, (void**)&net->s_which, (size_t)max_batch * sizeof(int32_t)));
+    } else {
+        {
+            std::vector<float> W1 = vcat({w[12], w[14]}, {512, 512}, 1024, 0, 1024);
+            TRY(upload_f32(net, net->Wr1, W1.data(), W1.size()));
+            std::vector<float> b(w[13], w[13] + 512); b.insert(b.end(), w[15], w[15] + 512);
+            TRY(upload_f32(net, net->br1, b.data(), 1024));
+            std::vector<float> W2 = vcat({w[16], w[18]}, {128, 128}, 512, 0, 512);
+            TRY(upload_f32(net, net->Wr2, W2.data(), W2.size()));
+            std::vector<float> b2(w[17], w[17] + 128); b2.insert(b2.end(), w[19], w[19] + 128);
+            TRY(upload_f32(net, net->br2, b2.data(), 256));
+        }
+        TRY(upload_f32(net, net->w3r, w[20], (size_t)num_obj * 4 * 128)); TRY(upload_f32(net, net->b3r, w[21], num_obj * 4));
+        TRY(upload_f32(net, net->w3t, w[22], (size_t)num_obj * 3 * 128)); TRY(upload_f32(net, net->b3t, w[23], num_obj * 3));
+        TRY(alloc_f32(net, net->G1, (size_t)max_batch * 1024));
+        TRY(alloc_f32(net, net->G2, (size_t)max_batch * 256));
+    }
+#undef TRY
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(ape::tc::gemm_split_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             ape::tc::kSmemBytes);
+        if (e != cudaSuccess) { ape::set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); ape_net_destroy(net); return APE_ERR_CUDA; }
+        attr_set = true;
+    }
+    *out = net;
+    return APE_OK;
+}
+
+extern "C" __attribute__((visibility("default")))
+int ape_net_destroy(ape_net* net)
+{
+    if (!net) return APE_OK;
+    for (void* p : net->allocs) cudaFree(p);
+    delete net;
+    return APE_OK;
+}
+
+extern "C" __attribute__((visibility("default")))
+int ape_net_set_gemm(ape_net* net, int gemm_impl)
+{
+    APE_REQUIRE(net, "ape_net_set_gemm: null handle");
+    APE_REQUIRE(gemm_impl == APE_GEMM_TCGEN05 || gemm_impl == APE_GEMM_SIMT, "ape_net_set_gemm: unknown implementation");
+    net->gemm_impl = gemm_impl;
+    return APE_OK;
+}
+
+// One GEMM layer: out = relu(A[:, a_k0 + g*a_kg : +K] * W_g^T + bias)
+static int run_gemm(ape_net* net, const SplitMat& A, const SplitMat& W, const ape::tc::Params& p, cudaStream_t s)
+{
+    if (net->gemm_impl == APE_GEMM_TCGEN05) {
+        dim3 grid(p.N / ape::tc::BN, p.M / ape::tc::BM, p.groups);
+        ape::tc::gemm_split_bf16_kernel<<<grid, ape::tc::kThreads, ape::tc::kSmemBytes, s>>>(A.map_hi, A.map_lo, W.map_hi,
+                                                                                           W.map_lo, p);
+    } else {
+        if (p.mode == ape::tc::EPI_RELU_COLSUM)
+            APE_CUDA(cudaMemsetAsync(p.colsum, 0, (size_t)(p.M / 128) * p.groups * p.N * sizeof(float), s));
+        dim3 grid(p.N / 64, p.M / 64, p.groups);
+        ape::gemm_simt_kernel<<<grid, 256, 0, s>>>(A.hi, A.lo, A.cols, W.hi, W.lo, p);
+    }
+    ape::count_launch();
+    return ape::check_launch("gemm layer");
+}
+
+static ape::tc::Params split_layer(int M, int N, int K, int groups, int a_k0, int a_kg, const float* bias, SplitMat& out, int o_c0)
+{
+    ape::tc::Params p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = N; p.K = K; p.groups = groups; p.a_k0 = a_k0; p.a_kg = a_kg; p.bias = bias; p.bias_obj_rows = 0;
+    p.mode = ape::tc::EPI_RELU_SPLIT; p.o_hi = out.hi; p.o_lo = out.lo; p.o_ld = out.cols; p.o_c0 = o_c0;
+    p.rows_per_obj = 1; p.valid_rows = 1;
+    return p;
+}
+
+// front end + conv2/e_conv2 + conv5 + conv6 (+AvgPool) shared by both networks; leaves AP [B,1024]
+static int run_trunk(ape_net* net, const float* feat_src, int hw, const float* cloud, const int64_t* choose, int B, int N,
+                     float* emb_out, cudaStream_t s)
+{
+    const int Np = (N + 127) / 128 * 128;
+    const int M = B * Np;
+    dim3 gf((Np + 63) / 64, B);
+    if (net->kind == APE_NET_POSENET)
+        ape::frontend_kernel<true><<<gf, 256, 0, s>>>(feat_src, hw, cloud, choose, net->w1.p, net->b1.p, net->we1.p, net->be1.p,
+                                                     N, Np, net->PF.hi, net->PF.lo, 384, emb_out);
+    else
+        ape::frontend_kernel<false><<<gf, 256, 0, s>>>(feat_src, hw, cloud, nullptr, net->w1.p, net->b1.p, net->we1.p,
+                                                      net->be1.p, N, Np, net->PF.hi, net->PF.lo, 384, nullptr);
+    ape::count_launch();
+    int rc = ape::check_launch("frontend");
+    if (rc) return rc;
+    // conv2 (PF[:,0:64] -> PF[:,128:256]) and e_conv2 (PF[:,64:128] -> PF[:,256:384]) as two groups
+    ape::tc::Params p = split_layer(M, 128, 64, 2, 0, 64, net->b_c2e2.p, net->PF, 128);
+    if ((rc = run_gemm(net, net->PF, net->W_c2e2, p, s))) return rc;
+    // conv5: PoseNet reads pointfeat_2 = PF[:,128:384] (network.py:62); refiner reads pointfeat_3 = PF[:,0:384] (:162)
+    const bool pn = net->kind == APE_NET_POSENET;
+    p = split_layer(M, 512, pn ? 256 : 384, 1, pn ? 128 : 0, 0, net->b_c5.p, net->H5, 0);
+    if ((rc = run_gemm(net, net->PF, net->W_c5, p, s))) return rc;
+    // conv6 + ReLU + AvgPool1d: masked per-tile column sums, never materialising [1024, N]
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = 1024; p.K = 512; p.groups = 1; p.bias = net->b_c6.p; p.mode = ape::tc::EPI_RELU_COLSUM;
+    p.colsum = net->CS.p; p.rows_per_obj = Np; p.valid_rows = N;
+    if ((rc = run_gemm(net, net->H5, net->W_c6, p, s))) return rc;
+    dim3 gp(1024 / 256, B);
+    ape::pool_finish_kernel<<<gp, 256, 0, s>>>(net->CS.p, Np / 128, 1024, (float)N, net->AP.p);
+    ape::count_launch();
+    return ape::check_launch("pool_finish");
+}
+
+static int dense(const float* in, int in_ld, int in_gs, const DevF32& W, const DevF32& bias, float* out, int out_ld, int B, int K,
+                 int npg, int groups, int relu, cudaStream_t s)
+{
+    dim3 grid((npg * groups + 7) / 8, (B + ape::kDenseObj - 1) / ape::kDenseObj);
+    if (grid.y > 64) grid.y = 64;
+    ape::dense_small_kernel<<<grid, 256, 0, s>>>(in, in_ld, in_gs, W.p, bias.p, out, out_ld, B, K, npg, groups, relu);
+    ape::count_launch();
+    return ape::check_launch("dense_small");
+}
+
+extern "C" __attribute__((visibility("default")))
+int ape_posenet_forward(ape_net* net, const float* out_img, int hw, const float* cloud, const int64_t* choose,
+                        const int64_t* obj, int B, int N, float* pred_r, float* pred_t, float* pred_c, float* emb,
+                        void* stream)
+{
+    APE_REQUIRE(net && net->kind == APE_NET_POSENET, "ape_posenet_forward: not a PoseNet handle");
+    APE_REQUIRE(out_img && cloud && choose && obj && pred_r && pred_t && pred_c && emb, "ape_posenet_forward: null pointer");
+    APE_REQUIRE(B > 0 && N > 0 && hw > 0, "ape_posenet_forward: bad sizes");
+    APE_REQUIRE(B <= net->max_batch && N <= net->max_points, "ape_posenet_forward: B=%d N=%d exceed the handle's workspace (%d, %d)",
+                B, N, net->max_batch, net->max_points);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int Np = (N + 127) / 128 * 128, M = B * Np;
+    int rc = run_trunk(net, out_img, hw, cloud, choose, B, N, emb, s);
+    if (rc) return rc;
+    // global-feature half of conv1_{r,t,c} folded into a per-object bias: GB = b + Wg * AP
+    if ((rc = dense(net->AP.p, 1024, 0, net->Wg, net->b_h1, net->GB.p, 1920, B, 1024, 1920, 1, 0, s))) return rc;
+    // conv1_{r,t,c} on [pointfeat_1 | pointfeat_2] (K=384), N = 3*640, per-object bias
+    ape::tc::Params p = split_layer(M, 1920, 384, 1, 0, 0, net->GB.p, net->H1, 0);
+    p.bias_obj_rows = Np;
+    if ((rc = run_gemm(net, net->PF, net->W_h1, p, s))) return rc;
+    p = split_layer(M, 256, 640, 3, 0, 640, net->b_h2.p, net->H2, 0);          // conv2_{r,t,c}
+    if ((rc = run_gemm(net, net->H1, net->W_h2, p, s))) return rc;
+    p = split_layer(M, 128, 256, 3, 0, 256, net->b_h3.p, net->H3, 0);          // conv3_{r,t,c}
+    if ((rc = run_gemm(net, net->H2, net->W_h3, p, s))) return rc;
+    dim3 go((N + 7) / 8 < 64 ? (N + 7) / 8 : 64, B);
+    ape::posenet_out_kernel<<<go, 256, 0, s>>>(net->H3.hi, net->H3.lo, 384, N, Np, net->w4r.p, net->b4r.p, net->w4t.p,
+                                              net->b4t.p, net->w4c.p, net->b4c.p, obj, net->num_obj, pred_r, pred_t, pred_c);
+    ape::count_launch();
+    return ape::check_launch("posenet_out");
+}
+
+extern "C" __attribute__((visibility("default")))
+int ape_refiner_forward(ape_net* net, const float* new_points, const float* emb, const int64_t* obj, int B, int N,
+                        float* r2, float* t2, void* stream)
+{
+    APE_REQUIRE(net && net->kind == APE_NET_REFINER, "ape_refiner_forward: not a PoseRefineNet handle");
+    APE_REQUIRE(new_points && emb && obj && r2 && t2, "ape_refiner_forward: null pointer");
+    APE_REQUIRE(B > 0 && N > 0, "ape_refiner_forward: bad sizes");
+    APE_REQUIRE(B <= net->max_batch && N <= net->max_points, "ape_refiner_forward: B=%d N=%d exceed the handle's workspace (%d, %d)",
+                B, N, net->max_batch, net->max_points);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = run_trunk(net, emb, 0, new_points, nullptr, B, N, nullptr, s);
+    if (rc) return rc;
+    if ((rc = dense(net->AP.p, 1024, 0, net->Wr1, net->br1, net->G1.p, 1024, B, 1024, 1024, 1, 1, s))) return rc;   // conv1_{r,t}
+    if ((rc = dense(net->G1.p, 1024, 512, net->Wr2, net->br2, net->G2.p, 256, B, 512, 128, 2, 1, s))) return rc;    // conv2_{r,t}
+    ape::refiner_out_kernel<<<B, 256, 0, s>>>(net->G2.p, net->w3r.p, net->b3r.p, net->w3t.p, net->b3t.p, obj, net->num_obj, r2, t2);
+    ape::count_launch();
+    return ape::check_launch("refiner_out");
+}
+
+// Whole option-6 geometry block for B objects in one call (graph-capturable, no host sync):
+// PoseNet -> arg-max / pose / new cloud -> `iterations` x (PoseRefineNet -> fp64 compose [-> next cloud]).
+//   canonical != 0 : DenseFusion/tools/eval_linemod.py:81-114 (cloud re-expressed in the composed pose each iteration)
+//   canonical == 0 : pipeline/utils.py:564-571 as written (the refiner input is never updated, so its
+//                    `iterations` calls are identical: it runs once and one composition follows)
+extern "C" __attribute__((visibility("default")))
+int ape_pose_pipeline(ape_net* est, ape_net* ref, const float* out_img, int hw, const float* cloud, const int64_t* choose,
+                      const int64_t* obj, int B, int N, int iterations, int canonical, double* poses, int32_t* which_max,
+                      void* stream)
+{
+    APE_REQUIRE(est && est->kind == APE_NET_POSENET, "ape_pose_pipeline: estimator handle required");
+    APE_REQUIRE(iterations == 0 || (ref && ref->kind == APE_NET_REFINER), "ape_pose_pipeline: refiner handle required");
+    APE_REQUIRE(poses, "ape_pose_pipeline: null output");
+    int rc = ape_posenet_forward(est, out_img, hw, cloud, choose, obj, B, N, est->s_r.p, est->s_t.p, est->s_c.p, est->s_emb.p, stream);
+    if (rc) return rc;
+    int32_t* wm = which_max ? which_max : est->s_which;
+    double* cur = iterations == 0 ? poses : est->s_pose_a;
+    rc = ape_pose_select(est->s_r.p, est->s_t.p, est->s_c.p, cloud, B, N, wm, est->s_myr.p, est->s_myt.p, est->s_newp.p, cur, stream);
+    if (rc) return rc;
+    const int n_eff = canonical ? iterations : (iterations > 0 ? 1 : 0);
+    for (int it = 0; it < n_eff; ++it) {
+        rc = ape_refiner_forward(ref, est->s_newp.p, est->s_emb.p, obj, B, N, est->s_r2.p, est->s_t2.p, stream);
+        if (rc) return rc;
+        const bool last = it == n_eff - 1;
+        double* nxt = last ? poses : (cur == est->s_pose_a ? est->s_pose_b : est->s_pose_a);
+        rc = ape_pose_compose(cur, est->s_r2.p, est->s_t2.p, B, nxt, last ? nullptr : cloud, last ? 0 : N,
+                              last ? nullptr : est->s_newp.p, stream);
+        if (rc) return rc;
+        cur = nxt;
+    }
+    return APE_OK;
+}

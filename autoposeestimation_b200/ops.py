@@ -1,0 +1,249 @@
+"""Tensor-level wrappers over the C-ABI (one function per entry point of include/ape_b200.h).
+
+Inputs are CUDA torch tensors (torch is only the allocator / stream provider here); every
+function launches on torch's current stream and returns device tensors.  There is no CPU path.
+"""
+import torch
+
+from . import _lib
+from ._lib import check, ptr, require_cuda, stream_ptr
+
+KNN_ARITH_CPU = 0
+KNN_ARITH_FMA = 1
+
+
+def _c(t, dtype):
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def backproject_choose(depth, bbox, choose, cam, frame_of=None):
+    """a3.  depth [F,H,W] uint16 (torch.int16/uint16 storage accepted), bbox [B,4] int32,
+    choose [B,N] int64, cam [B,5] fp32 (ppx,ppy,fx,fy,depth_scale) -> cloud [B,N,3] fp32."""
+    require_cuda(depth, bbox, choose, cam, frame_of)
+    assert depth.dtype in (torch.uint16, torch.int16) and depth.dim() == 3
+    depth = depth.contiguous(); bbox = _c(bbox, torch.int32); choose = _c(choose, torch.int64); cam = _c(cam, torch.float32)
+    if frame_of is not None:
+        frame_of = _c(frame_of, torch.int32)
+    B, N = choose.shape
+    F, H, W = depth.shape
+    cloud = torch.empty((B, N, 3), dtype=torch.float32, device=depth.device)
+    check(_lib.load().ape_backproject_choose(ptr(depth), F, H, W, ptr(frame_of), ptr(bbox), ptr(choose), ptr(cam),
+                                             B, N, ptr(cloud), stream_ptr()), 'ape_backproject_choose')
+    return cloud
+
+
+def surface_backproject(label, depth, cam, robot2cam, capacity, frame_of=None, label_value=None, want_pixels=True):
+    """a4.  label [F,H,W] uint8, depth [F,H,W] uint16, cam [V,4] fp64, robot2cam [V,4,4] fp64.
+    Returns (points [V,capacity,3] fp64, pixel_index [V,capacity] int32 or None, counts [V] int32)."""
+    require_cuda(label, depth, cam, robot2cam)
+    assert label.dtype == torch.uint8 and depth.dtype in (torch.uint16, torch.int16)
+    label = label.contiguous(); depth = depth.contiguous()
+    cam = _c(cam, torch.float64); robot2cam = _c(robot2cam, torch.float64)
+    F, H, W = label.shape
+    V = cam.shape[0]
+    if frame_of is not None:
+        frame_of = _c(frame_of, torch.int32)
+    if label_value is not None:
+        label_value = _c(label_value, torch.uint8)
+    dev = label.device
+    points = torch.empty((V, capacity, 3), dtype=torch.float64, device=dev)
+    pix = torch.empty((V, capacity), dtype=torch.int32, device=dev) if want_pixels else None
+    counts = torch.empty((V,), dtype=torch.int32, device=dev)
+    check(_lib.load().ape_surface_backproject(ptr(label), ptr(depth), F, H, W, ptr(frame_of), ptr(label_value), ptr(cam),
+                                              ptr(robot2cam), V, capacity, ptr(points), ptr(pix), ptr(counts),
+                                              stream_ptr()), 'ape_surface_backproject')
+    return points, pix, counts
+
+
+def knn(ref, query, k=1, arith=KNN_ARITH_CPU, out=None):
+    """a14.  ref [B,D,N], query [B,D,M] fp32 -> idx [B,k,M] int64, 1-based."""
+    require_cuda(ref, query)
+    ref = _c(ref, torch.float32); query = _c(query, torch.float32)
+    B, D, N = ref.shape
+    M = query.shape[2]
+    if out is None:
+        out = torch.empty((B, k, M), dtype=torch.int64, device=ref.device)
+    check(_lib.load().ape_knn(ptr(ref), ptr(query), ptr(out), B, D, N, M, k, arith, stream_ptr()), 'ape_knn')
+    return out
+
+
+def add_metric(quat, trans, model_points, target, symmetric, want_index=False):
+    """a13/a15.  quat [B,4], trans [B,3]; model_points [B,Mq,3] or [Mq,3] (shared); target [B,Nt,3] or
+    [Nt,3]; symmetric [B] uint8/bool.  Returns dis [B] fp32 (and nn_index [B,Mq] int32)."""
+    require_cuda(quat, trans, model_points, target)
+    quat = _c(quat, torch.float32); trans = _c(trans, torch.float32)
+    model_points = _c(model_points, torch.float32); target = _c(target, torch.float32)
+    B = quat.shape[0]
+    mq, nt = model_points.shape[-2], target.shape[-2]
+    ms = 0 if model_points.dim() == 2 else mq * 3
+    ts = 0 if target.dim() == 2 else nt * 3
+    sym = _c(symmetric.to(torch.uint8), torch.uint8)
+    dis = torch.empty((B,), dtype=torch.float32, device=quat.device)
+    nn = torch.empty((B, mq), dtype=torch.int32, device=quat.device) if want_index else None
+    check(_lib.load().ape_add_metric(ptr(quat), ptr(trans), ptr(model_points), ms, mq, ptr(target), ts, nt, ptr(sym), B,
+                                     ptr(dis), ptr(nn), stream_ptr()), 'ape_add_metric')
+    return (dis, nn) if want_index else dis
+
+
+def icp_p2p(source, src_offset, target, tgt_offset, threshold, rel_fitness=1e-2, rel_rmse=1e-2, max_iter=100, init=None):
+    """a5.  Ragged batch: source [S,3] fp64 with src_offset [R+1] int32, target [T,3] fp64 with tgt_offset [R+1].
+    Returns (transform [R,4,4] fp64, info [R,4] fp64 = fitness, rmse, iterations, n_corr)."""
+    require_cuda(source, target, src_offset, tgt_offset)
+    source = _c(source, torch.float64); target = _c(target, torch.float64)
+    src_offset = _c(src_offset, torch.int32); tgt_offset = _c(tgt_offset, torch.int32)
+    R = src_offset.numel() - 1
+    S, T = source.shape[0], target.shape[0]
+    dev = source.device
+    lib = _lib.load()
+    work = torch.empty((int(lib.ape_icp_work_bytes(S, T)) + 7) // 8, dtype=torch.float64, device=dev)
+    tf = torch.empty((R, 4, 4), dtype=torch.float64, device=dev)
+    info = torch.empty((R, 4), dtype=torch.float64, device=dev)
+    if init is not None:
+        init = _c(init, torch.float64)
+    check(lib.ape_icp_p2p(ptr(source), ptr(src_offset), ptr(target), ptr(tgt_offset), R, S, T, float(threshold),
+                          float(rel_fitness), float(rel_rmse), int(max_iter), ptr(init), ptr(tf), ptr(info), ptr(work),
+                          stream_ptr()), 'ape_icp_p2p')
+    return tf, info
+
+
+def voxel_down_sample(points, offset, voxel_size):
+    """a5/a6.  Ragged batch points [P,3] fp64, offset [C+1] int32 -> (out_points [P,3] fp64 (cloud c occupies
+    out[offset[c] : offset[c]+counts[c]]), counts [C] int32)."""
+    require_cuda(points, offset)
+    points = _c(points, torch.float64); offset = _c(offset, torch.int32)
+    C = offset.numel() - 1
+    out = torch.empty_like(points)
+    counts = torch.empty((C,), dtype=torch.int32, device=points.device)
+    check(_lib.load().ape_voxel_down_sample(ptr(points), ptr(offset), C, float(voxel_size), ptr(out), ptr(counts),
+                                            stream_ptr()), 'ape_voxel_down_sample')
+    return out, counts
+
+
+def pose_select(pred_r, pred_t, pred_c, cloud, want_new_points=True):
+    """a8/a9.  pred_r [B,N,4], pred_t [B,N,3], pred_c [B,N(,1)], cloud [B,N,3] fp32 ->
+    dict(which_max [B] int32, my_r [B,4], my_t [B,3], new_points [B,N,3] or None, pose [B,7] fp64)."""
+    require_cuda(pred_r, pred_t, pred_c, cloud)
+    pred_r = _c(pred_r, torch.float32); pred_t = _c(pred_t, torch.float32)
+    pred_c = _c(pred_c, torch.float32); cloud = _c(cloud, torch.float32)
+    B, N = pred_r.shape[0], pred_r.shape[1]
+    dev = pred_r.device
+    wm = torch.empty((B,), dtype=torch.int32, device=dev)
+    my_r = torch.empty((B, 4), dtype=torch.float32, device=dev)
+    my_t = torch.empty((B, 3), dtype=torch.float32, device=dev)
+    newp = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if want_new_points else None
+    pose = torch.empty((B, 7), dtype=torch.float64, device=dev)
+    check(_lib.load().ape_pose_select(ptr(pred_r), ptr(pred_t), ptr(pred_c), ptr(cloud), B, N, ptr(wm), ptr(my_r), ptr(my_t),
+                                      ptr(newp), ptr(pose), stream_ptr()), 'ape_pose_select')
+    return dict(which_max=wm, my_r=my_r, my_t=my_t, new_points=newp, pose=pose)
+
+
+def pose_compose(pose_in, r2, t2, cloud=None):
+    """a11.  pose_in [B,7] fp64, r2 [B,4] fp32, t2 [B,3] fp32 -> pose_out [B,7] fp64
+    (and next_points [B,N,3] if cloud [B,N,3] is given)."""
+    require_cuda(pose_in, r2, t2, cloud)
+    pose_in = _c(pose_in, torch.float64); r2 = _c(r2, torch.float32); t2 = _c(t2, torch.float32)
+    B = pose_in.shape[0]
+    out = torch.empty_like(pose_in)
+    nxt, N = None, 0
+    if cloud is not None:
+        cloud = _c(cloud, torch.float32)
+        N = cloud.shape[1]
+        nxt = torch.empty_like(cloud)
+    check(_lib.load().ape_pose_compose(ptr(pose_in), ptr(r2), ptr(t2), B, ptr(out), ptr(cloud), N, ptr(nxt), stream_ptr()),
+          'ape_pose_compose')
+    return (out, nxt) if cloud is not None else out
+
+
+# ------------------------------------------------------------------------------------------ networks
+NET_POSENET, NET_REFINER = 0, 1
+GEMM_TCGEN05, GEMM_SIMT = 0, 1
+
+_POSENET_ORDER = ['feat.conv1', 'feat.e_conv1', 'feat.conv2', 'feat.e_conv2', 'feat.conv5', 'feat.conv6',
+                  'conv1_r', 'conv1_t', 'conv1_c', 'conv2_r', 'conv2_t', 'conv2_c', 'conv3_r', 'conv3_t', 'conv3_c',
+                  'conv4_r', 'conv4_t', 'conv4_c']
+_REFINER_ORDER = ['feat.conv1', 'feat.e_conv1', 'feat.conv2', 'feat.e_conv2', 'feat.conv5', 'feat.conv6',
+                  'conv1_r', 'conv1_t', 'conv2_r', 'conv2_t', 'conv3_r', 'conv3_t']
+
+
+class NetHandle:
+    """Owns an `ape_net` (split-bf16 weights + activation workspace on the current CUDA device).
+
+    state_dict: reference-shaped tensors/arrays (DenseFusion/lib/network.py:74-91 or :139-183);
+    extra keys (e.g. the colour encoder `cnn.*`) are ignored."""
+
+    def __init__(self, kind, state_dict, num_obj, max_batch, max_points):
+        import ctypes
+        import numpy as np
+        if not torch.cuda.is_available():
+            raise _lib.ApeError('no CUDA device: the B200 path has no CPU fallback')
+        lib = _lib.load()
+        order = _POSENET_ORDER if kind == NET_POSENET else _REFINER_ORDER
+        host = []
+        for name in order:
+            for suffix in ('.weight', '.bias'):
+                v = state_dict[name + suffix]
+                if isinstance(v, torch.Tensor):
+                    v = v.detach().to('cpu', torch.float32).numpy()
+                host.append(np.ascontiguousarray(v, dtype=np.float32).reshape(-1))
+        arr = (ctypes.c_void_p * len(host))(*[h.ctypes.data for h in host])
+        out = ctypes.c_void_p()
+        check(lib.ape_net_create(kind, arr, len(host), int(num_obj), int(max_batch), int(max_points), ctypes.byref(out)),
+              'ape_net_create')
+        self._h = out
+        self.kind, self.num_obj, self.max_batch, self.max_points = kind, num_obj, max_batch, max_points
+        self.device = torch.device('cuda', torch.cuda.current_device())
+
+    def set_gemm(self, impl):
+        check(_lib.load().ape_net_set_gemm(self._h, impl), 'ape_net_set_gemm')
+
+    def close(self):
+        if getattr(self, '_h', None):
+            _lib.load().ape_net_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def posenet_forward(self, out_img, cloud, choose, obj):
+        """out_img [B,32,hw] (or [B,32,H,W]), cloud [B,N,3], choose [B,N] (or [B,1,N]) int64, obj [B] (or [B,1]) int64
+        -> pred_r [B,N,4], pred_t [B,N,3], pred_c [B,N,1], emb [B,32,N]"""
+        require_cuda(out_img, cloud, choose, obj)
+        B, N = cloud.shape[0], cloud.shape[1]
+        out_img = _c(out_img, torch.float32).reshape(B, 32, -1)
+        cloud = _c(cloud, torch.float32); choose = _c(choose, torch.int64).reshape(B, N); obj = _c(obj, torch.int64).reshape(B)
+        dev = cloud.device
+        r = torch.empty((B, N, 4), dtype=torch.float32, device=dev); t = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+        c = torch.empty((B, N, 1), dtype=torch.float32, device=dev); emb = torch.empty((B, 32, N), dtype=torch.float32, device=dev)
+        check(_lib.load().ape_posenet_forward(self._h, ptr(out_img), out_img.shape[2], ptr(cloud), ptr(choose), ptr(obj), B, N,
+                                              ptr(r), ptr(t), ptr(c), ptr(emb), stream_ptr()), 'ape_posenet_forward')
+        return r, t, c, emb
+
+    def refiner_forward(self, new_points, emb, obj):
+        """new_points [B,N,3], emb [B,32,N], obj [B] -> r2 [B,4], t2 [B,3]"""
+        require_cuda(new_points, emb, obj)
+        B, N = new_points.shape[0], new_points.shape[1]
+        new_points = _c(new_points, torch.float32); emb = _c(emb, torch.float32); obj = _c(obj, torch.int64).reshape(B)
+        r2 = torch.empty((B, 4), dtype=torch.float32, device=new_points.device)
+        t2 = torch.empty((B, 3), dtype=torch.float32, device=new_points.device)
+        check(_lib.load().ape_refiner_forward(self._h, ptr(new_points), ptr(emb), ptr(obj), B, N, ptr(r2), ptr(t2), stream_ptr()),
+              'ape_refiner_forward')
+        return r2, t2
+
+
+def pose_pipeline(est, ref, out_img, cloud, choose, obj, iterations=2, canonical=True, out=None):
+    """Whole option-6 geometry block: -> (poses [B,7] fp64 (wxyz, t), which_max [B] int32).  No host sync."""
+    require_cuda(out_img, cloud, choose, obj)
+    B, N = cloud.shape[0], cloud.shape[1]
+    out_img = _c(out_img, torch.float32).reshape(B, 32, -1)
+    cloud = _c(cloud, torch.float32); choose = _c(choose, torch.int64).reshape(B, N); obj = _c(obj, torch.int64).reshape(B)
+    poses = out if out is not None else torch.empty((B, 7), dtype=torch.float64, device=cloud.device)
+    wm = torch.empty((B,), dtype=torch.int32, device=cloud.device)
+    check(_lib.load().ape_pose_pipeline(est._h, ref._h if ref is not None else None, ptr(out_img), out_img.shape[2], ptr(cloud),
+                                        ptr(choose), ptr(obj), B, N, int(iterations), int(bool(canonical)), ptr(poses), ptr(wm),
+                                        stream_ptr()), 'ape_pose_pipeline')
+    return poses, wm

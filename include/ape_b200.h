@@ -1,0 +1,197 @@
+/* ape_b200.h -- C-ABI of the B200-native 6D-pose geometry hot path.
+ *
+ * Drop-in boundary for KochPJ/AutoPoseEstimation main.py options 4 ("Create Pose
+ * labels") and 6 ("Run Live Prediction").  The reference has one native entry point
+ * (`int knn(at::Tensor&, at::Tensor&, at::Tensor&)`, DenseFusion/lib/knn/src/knn.h:12,
+ * exported by src/vision.cpp:3-5); everything else on the path is Python that calls
+ * torch / numpy / open3d.  Each function below names the reference interface it
+ * replaces.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - calls are asynchronous on `stream`; the caller owns all buffers;
+ *   - return value: APE_OK or an APE_ERR_* code; ape_last_error() gives the message of
+ *     the last failing call on the calling thread.  Nothing aborts the process
+ *     (the reference's knn.h:41-46 printf + THError abort is replaced by a status).
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns
+ *     APE_ERR_CUDA.
+ */
+#ifndef APE_B200_H
+#define APE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    APE_OK = 0,
+    APE_ERR_INVALID = 1,      /* bad argument (null pointer, non-positive size, unsupported shape) */
+    APE_ERR_CUDA = 2,         /* CUDA runtime error (message in ape_last_error) */
+    APE_ERR_CAPACITY = 3,     /* an output/scratch capacity supplied by the caller is too small */
+    APE_ERR_UNSUPPORTED = 4   /* valid request outside what the kernels implement */
+};
+
+/* kNN distance arithmetic (both are fp32, summed in dimension order):
+ *   APE_KNN_ARITH_CPU  d += (r-q)*(r-q) with product and sum rounded separately
+ *                      = DenseFusion/lib/knn/src/cpu/knn_cpu.cpp:8-16 as gcc compiles it
+ *   APE_KNN_ARITH_FMA  d = fma(r-q, r-q, d)
+ *                      = DenseFusion/lib/knn/src/cuda/knn.cu:86-92 as nvcc compiles it   */
+enum { APE_KNN_ARITH_CPU = 0, APE_KNN_ARITH_FMA = 1 };
+
+int         ape_version(void);
+const char* ape_last_error(void);
+/* Number of kernel launches issued through this library by the calling process so far. */
+uint64_t    ape_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * a3. DenseFusion back-projection at fixed sampling indices.
+ * Replaces pipeline/utils.py:542-553 (= datasets/myDatasetAugmented/dataset.py:260-275).
+ *   depth      [n_frames,height,width] u16 raw sensor units
+ *   frame_of   [n_obj] frame index of each object, or NULL (object b reads frame b)
+ *   bbox       [n_obj,4] rmin,rmax,cmin,cmax from get_bbox (dataset.py:342-380)
+ *   choose     [n_obj,n_points] int64 flat indices into the bbox crop (width cmax-cmin)
+ *   cam        [n_obj,5] fp32 ppx,ppy,fx,fy,depth_scale (already rounded to fp32, as numpy does)
+ *   cloud      [n_obj,n_points,3] fp32 out: x=((col-ppx)*z)/fx, y=((row-ppy)*z)/fy, z=d*scale,
+ *              each operation rounded to fp32 in that order (bit-exact with the reference)  */
+int ape_backproject_choose(const uint16_t* depth, int n_frames, int height, int width,
+                           const int32_t* frame_of, const int32_t* bbox, const int64_t* choose,
+                           const float* cam, int n_obj, int n_points, float* cloud, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a4. Masked depth -> point cloud in the robot frame (ordered stream compaction).
+ * Replaces the per-pixel loop of pc_reconstruction/open3d_utils.py:172-192 (get_surface).
+ * A "view" is one (frame, label value) pair; pixels are emitted in row-major order
+ * (np.where order, :174) when label matches and depth != 0.
+ *   label        [n_frames,height,width] u8;  depth [n_frames,height,width] u16 (raw = mm)
+ *   frame_of     [n_views] frame index, or NULL (view v reads frame v)
+ *   label_value  [n_views] u8: 0 = "label != 0" (the reference's test), k>0 = "label == k"
+ *   cam          [n_views,4] fp64 ppx,ppy,fx,fy;  robot2cam [n_views,16] fp64 row-major 4x4
+ *   capacity     max points per view;  points [n_views,capacity,3] fp64 out
+ *   pixel_index  [n_views,capacity] int32 flat pixel index of every emitted point, or NULL
+ *   counts       [n_views] int32 out: number of valid pixels (may exceed capacity: the excess is dropped,
+ *                the caller checks)                                                              */
+int ape_surface_backproject(const uint8_t* label, const uint16_t* depth, int n_frames, int height, int width,
+                            const int32_t* frame_of, const uint8_t* label_value,
+                            const double* cam, const double* robot2cam, int n_views, int capacity,
+                            double* points, int32_t* pixel_index, int32_t* counts, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a14. Brute-force k nearest neighbours.
+ * Replaces `int knn(ref, query, idx)` DenseFusion/lib/knn/src/knn.h:12 (python:
+ * KNearestNeighbor.forward, lib/knn/__init__.py:15-23).
+ *   ref [B,D,N] fp32, query [B,D,M] fp32, idx [B,k,M] int64 out, 1-based, ascending distance,
+ *   lowest index first on exact ties.  No scratch (the reference's N*M distance matrix is
+ *   never materialised).  D==3,k==1 runs the tiled shared-memory kernel; other shapes run a
+ *   generic kernel (k <= 64).                                                                  */
+int ape_knn(const float* ref, const float* query, int64_t* idx, int B, int D, int N, int M, int k,
+            int arith, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a13/a15. ADD / ADD-S metric, fused (transform + top-1 NN + gather + mean norm).
+ * Replaces DenseFusion/lib/loss_refiner.py:39-49 and tools/eval_linemod.py:118-130.
+ *   quat [B,4] wxyz (normalised inside, fp32), trans [B,3]
+ *   model_points: instance b reads  model_points + b*model_stride  ([n_model,3] fp32; stride in floats, 0 = shared)
+ *   target:       instance b reads  target + b*target_stride      ([n_target,3] fp32)
+ *   symmetric [B] u8: 1 -> ADD-S (nearest target point per predicted point, APE_KNN_ARITH_CPU
+ *   arithmetic), 0 -> ADD (requires n_model == n_target)
+ *   dis [B] fp32 out; nn_index [B,n_model] int32 out (0-based) or NULL                          */
+int ape_add_metric(const float* quat, const float* trans, const float* model_points, int64_t model_stride,
+                   int n_model, const float* target, int64_t target_stride, int n_target,
+                   const uint8_t* symmetric, int B, float* dis, int32_t* nn_index, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a5. Point-to-point ICP, whole registration in one persistent kernel.
+ * Replaces o3d.registration.registration_icp(source, target, threshold, I,
+ * TransformationEstimationPointToPoint(), ICPConvergenceCriteria(rel_fitness, rel_rmse, max_iter))
+ * as called by pc_reconstruction/open3d_utils.py:76-104 (open3d 0.9.0 semantics, fp64).
+ * Registration r uses source points [src_offset[r], src_offset[r+1]) of `source` and target
+ * points [tgt_offset[r], tgt_offset[r+1]) of `target` (both [*,3] fp64, ragged batches).
+ *   init          [n_reg,16] fp64 row-major initial transforms, or NULL (identity)
+ *   transform     [n_reg,16] fp64 out (row-major 4x4)
+ *   info          [n_reg,4]  fp64 out: fitness, inlier_rmse, iterations, n_correspondences (or NULL)
+ *   work          scratch of ape_icp_work_bytes(total_source_points, total_target_points) bytes,
+ *                 8-byte aligned (working cloud, cell-sorted target, correspondences)            */
+size_t ape_icp_work_bytes(int total_source_points, int total_target_points);
+int ape_icp_p2p(const double* source, const int32_t* src_offset, const double* target, const int32_t* tgt_offset,
+                int n_reg, int total_source_points, int total_target_points,
+                double threshold, double rel_fitness, double rel_rmse, int max_iter,
+                const double* init, double* transform, double* info, void* work, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a5/a6. Voxel-grid down-sampling (open3d 0.9 PointCloud::voxel_down_sample semantics; output
+ * sorted by voxel index instead of hash-map order).  Replaces pcd.voxel_down_sample(voxel_size)
+ * at pc_reconstruction/open3d_utils.py:21, :198 and create_pointcloud.py:312.
+ * Ragged batch as above.  out_points has the same capacity/offsets as the input
+ * (cloud c writes at most its input count starting at offset[c]); out_counts [n_clouds].
+ * Clouds larger than APE_VOXEL_MAX_POINTS return APE_ERR_UNSUPPORTED.                           */
+#define APE_VOXEL_MAX_POINTS 16384
+int ape_voxel_down_sample(const double* points, const int32_t* offset, int n_clouds, double voxel_size,
+                          double* out_points, int32_t* out_counts, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a8/a9. Confidence arg-max, pose of the best point, cloud in the predicted frame.
+ * Replaces my_estimator_prediction + get_new_points (DenseFusion/tools/utils.py:7-18, :43-86).
+ *   pred_r [B,N,4], pred_t [B,N,3], pred_c [B,N], cloud [B,N,3] fp32
+ *   which_max [B] int32 (lowest index on ties), my_r [B,4] (normalised quaternion wxyz),
+ *   my_t [B,3], new_points [B,N,3] (may be NULL), pose [B,7] fp64 = (my_r, my_t) widened (may be NULL) */
+int ape_pose_select(const float* pred_r, const float* pred_t, const float* pred_c, const float* cloud,
+                    int B, int N, int32_t* which_max, float* my_r, float* my_t, float* new_points,
+                    double* pose, void* stream);
+
+/* a11. fp64 pose composition of one refinement step.
+ * Replaces my_refined_prediction (DenseFusion/tools/utils.py:20-40 -> transformations.py:1254, :1281).
+ *   pose_in [B,7] fp64 (wxyz,t); r2 [B,4] fp32 un-normalised; t2 [B,3] fp32; pose_out [B,7] fp64.
+ *   If next_points != NULL: cloud [B,N,3] re-expressed in the composed pose as in
+ *   tools/eval_linemod.py:92-97 (fp32 R and T) -> next_points [B,N,3].                           */
+int ape_pose_compose(const double* pose_in, const float* r2, const float* t2, int B, double* pose_out,
+                     const float* cloud, int N, float* next_points, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a7/a10. DenseFusion PoseNet (geometry side) and PoseRefineNet forward, batched over objects.
+ * Replaces PoseNet.forward after the colour encoder (DenseFusion/lib/network.py:98-132) and
+ * PoseRefineNet.forward (:187-206).  Weights are bound once per model with ape_net_create from
+ * the reference state_dict tensors (fp32, reference shapes); the handle owns split-bf16 copies.
+ */
+typedef struct ape_net ape_net;       /* opaque */
+
+enum { APE_NET_POSENET = 0, APE_NET_REFINER = 1 };
+enum { APE_GEMM_TCGEN05 = 0, APE_GEMM_SIMT = 1 };   /* SIMT = fp32 validation kernels (tests only) */
+
+/* weights_host: array of n_tensors host pointers to fp32 tensors in the canonical order listed in
+ * DESIGN.md ("weight order"); num_obj as in the reference constructor; max_batch/max_points size the
+ * activation workspace (allocated once, on the current device).                                  */
+int ape_net_create(int kind, const float* const* weights_host, int n_tensors, int num_obj,
+                   int max_batch, int max_points, ape_net** out);
+int ape_net_destroy(ape_net* net);
+int ape_net_set_gemm(ape_net* net, int gemm_impl);
+
+/* PoseNet geometry forward for B objects.
+ *   out_img [B,32,hw] fp32 colour-encoder output per object crop (hw = crop pixels, same for the batch)
+ *   cloud [B,N,3] fp32, choose [B,N] int64 (indices into hw), obj [B] int64 class ids
+ *   pred_r [B,N,4], pred_t [B,N,3], pred_c [B,N], emb [B,32,N] fp32 out                          */
+int ape_posenet_forward(ape_net* net, const float* out_img, int hw, const float* cloud, const int64_t* choose,
+                        const int64_t* obj, int B, int N, float* pred_r, float* pred_t, float* pred_c,
+                        float* emb, void* stream);
+
+/* PoseRefineNet forward: new_points [B,N,3], emb [B,32,N], obj [B] -> r2 [B,4], t2 [B,3] fp32 */
+int ape_refiner_forward(ape_net* net, const float* new_points, const float* emb, const int64_t* obj,
+                        int B, int N, float* r2, float* t2, void* stream);
+
+/* Whole option-6 geometry block for B objects in one call (no host synchronisation inside):
+ * PoseNet -> arg-max / pose / new cloud -> iterations x (PoseRefineNet -> fp64 compose -> next cloud).
+ * Replaces pipeline/utils.py:564-571.  canonical != 0 follows DenseFusion/tools/eval_linemod.py:81-114
+ * (cloud re-expressed in the composed pose every iteration); canonical == 0 reproduces pipeline/utils.py
+ * as written (the refiner input is never updated, so its calls are identical: one call, one composition).
+ *   poses [B,7] fp64 out (quaternion wxyz, translation); which_max [B] int32 out or NULL.             */
+int ape_pose_pipeline(ape_net* estimator, ape_net* refiner, const float* out_img, int hw, const float* cloud,
+                      const int64_t* choose, const int64_t* obj, int B, int N, int iterations, int canonical,
+                      double* poses, int32_t* which_max, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APE_B200_H */

@@ -1,0 +1,150 @@
+"""GPU parity: back-projection kernels vs the oracle (bit-exact indices / fp32, fp64 within 1e-9 mm)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import geometry as og, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def _u16(a):
+    return torch.from_numpy(a.astype(np.uint16).view(np.int16).copy()).cuda()   # same bits; kernel reads uint16
+
+
+@pytest.mark.parametrize('seed,num_points', [(0, 500), (1, 1000), (2, 20000)])
+def test_backproject_choose_bit_exact(seed, num_points):
+    from autoposeestimation_b200 import ops
+    fr = synth.render_ellipsoid_frame(seed)
+    depth, label = fr['depth'], fr['label']
+    bbox = og.get_bbox(label == 255)
+    cand = og.choose_candidates(label == 255, depth, bbox)
+    rng = np.random.RandomState(seed)
+    keep = og.make_keep(len(cand), num_points, rng) if len(cand) > num_points else None
+    choose = og.choose_fixed(cand, num_points, keep)            # num_points=20000 exercises the 'wrap' padding
+    intr = fr['intr']
+    ref = og.backproject_choose(depth, bbox, choose, intr['ppx'], intr['ppy'], intr['fx'], intr['fy'], synth.DEPTH_SCALE)
+    cam = np.array([[intr['ppx'], intr['ppy'], intr['fx'], intr['fy'], synth.DEPTH_SCALE]], np.float32)
+    out = ops.backproject_choose(_u16(depth[None]), _dev(np.array([bbox], np.int32)), _dev(choose[None].astype(np.int64)), _dev(cam))
+    got = out.cpu().numpy()[0]
+    assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+def test_backproject_choose_batch_and_border_bbox():
+    from autoposeestimation_b200 import ops
+    rng = np.random.RandomState(3)
+    F, H, W, N = 3, 480, 640, 300
+    depth = rng.randint(0, 4000, size=(F, H, W)).astype(np.uint16)
+    bboxes, chooses, frames, refs = [], [], [], []
+    for b in range(5):
+        m = np.zeros((H, W), bool)
+        r0, c0 = [(0, 0), (440, 600), (200, 300), (0, 620), (470, 0)][b]
+        m[r0:r0 + 10 + 7 * b, c0:c0 + 15 + 3 * b] = True           # touches the image borders -> clamped bbox
+        bbox = og.get_bbox(m)
+        f = b % F
+        cand = og.choose_candidates(m, depth[f], bbox)
+        ch = og.choose_fixed(cand, N, og.make_keep(len(cand), N, rng) if len(cand) > N else None)
+        bboxes.append(bbox); chooses.append(ch); frames.append(f)
+        refs.append(og.backproject_choose(depth[f], bbox, ch, 321.5, 238.25, 614.7, 615.3, 0.001))
+    cam = np.tile(np.array([[321.5, 238.25, 614.7, 615.3, 0.001]], np.float32), (5, 1))
+    out = ops.backproject_choose(_u16(depth), _dev(np.array(bboxes, np.int32)), _dev(np.array(chooses, np.int64)), _dev(cam),
+                                 frame_of=_dev(np.array(frames, np.int32))).cpu().numpy()
+    for b in range(5):
+        assert np.array_equal(out[b].view(np.uint32), refs[b].view(np.uint32))
+
+
+def test_get_bbox_oracle_rules():
+    # dataset.py:342-380 rules (host logic of the drop-in is the same function; see test_host_logic)
+    m = np.zeros((480, 640), bool); m[100:139, 50:131] = True      # 39 rows -> 40, 81 cols -> 120
+    assert og.get_bbox(m) == (99, 139, 30, 150)
+    m = np.zeros((480, 640), bool); m[0:5, 0:5] = True
+    assert og.get_bbox(m) == (0, 40, 0, 40)
+    m = np.zeros((480, 640), bool); m[470:480, 630:640] = True
+    assert og.get_bbox(m) == (440, 480, 600, 640)
+
+
+@pytest.mark.parametrize('seed', [0, 5])
+def test_surface_backproject_vs_oracle(seed):
+    from autoposeestimation_b200 import ops
+    fr = synth.render_ellipsoid_frame(seed)
+    ref_pts, ref_pix = og.surface_backproject(fr['label'], fr['depth'].astype(np.float64), fr['intr'], fr['robot2cam'])
+    intr = fr['intr']
+    cam = np.array([[intr['ppx'], intr['ppy'], intr['fx'], intr['fy']]], np.float64)
+    pts, pix, cnt = ops.surface_backproject(_dev(fr['label'][None]), _u16(fr['depth'][None]), _dev(cam), _dev(fr['robot2cam'][None]),
+                                            capacity=len(ref_pix) + 100)
+    n = int(cnt.cpu()[0])
+    assert n == len(ref_pix)
+    assert np.array_equal(pix.cpu().numpy()[0, :n], ref_pix.astype(np.int32))          # indices bit-exact, row-major order
+    assert np.allclose(pts.cpu().numpy()[0, :n], ref_pts, rtol=0, atol=1e-9)
+
+
+def test_surface_backproject_literal_loop_small():
+    """The reference's literal per-pixel loop (open3d_utils.py:175-192) on a small mask."""
+    from autoposeestimation_b200 import ops
+    rng = np.random.RandomState(9)
+    H, W = 480, 640
+    label = np.zeros((H, W), np.uint8); label[200:215, 310:330] = 255
+    depth = rng.randint(0, 3, size=(H, W)).astype(np.uint16) * rng.randint(400, 900, size=(H, W)).astype(np.uint16)
+    T = synth.hand_eye()
+    ref_pts, ref_pix = og.surface_backproject_literal(label, depth.astype(np.float64), synth.INTR, T)
+    cam = np.array([[synth.INTR['ppx'], synth.INTR['ppy'], synth.INTR['fx'], synth.INTR['fy']]], np.float64)
+    pts, pix, cnt = ops.surface_backproject(_dev(label[None]), _u16(depth[None]), _dev(cam), _dev(T[None]), capacity=400)
+    n = int(cnt.cpu()[0])
+    assert n == len(ref_pix) and np.array_equal(pix.cpu().numpy()[0, :n], ref_pix.astype(np.int32))
+    assert np.allclose(pts.cpu().numpy()[0, :n], ref_pts, rtol=0, atol=1e-9)
+
+
+def test_surface_backproject_views_labels_capacity_empty():
+    from autoposeestimation_b200 import ops
+    rng = np.random.RandomState(11)
+    F, H, W = 2, 480, 640
+    label = np.zeros((F, H, W), np.uint8)
+    label[0, 10:60, 20:90] = 1; label[0, 300:330, 500:640] = 2; label[1, 470:480, 0:640] = 3   # last rows / full width
+    depth = rng.randint(0, 2000, size=(F, H, W)).astype(np.uint16)
+    depth[rng.rand(F, H, W) < 0.1] = 0
+    T = np.stack([synth.hand_eye(), np.identity(4)])
+    views = [(0, 1), (0, 2), (1, 3), (1, 0), (0, 7)]           # (frame, label value); 0 = any non-zero; 7 = empty
+    cam = np.tile(np.array([[320.0, 240.0, 615.0, 615.0]]), (len(views), 1))
+    r2c = np.stack([T[f] for f, _ in views])
+    cap = 3000
+    pts, pix, cnt = ops.surface_backproject(_dev(label), _u16(depth), _dev(cam), _dev(r2c), capacity=cap,
+                                            frame_of=_dev(np.array([f for f, _ in views], np.int32)),
+                                            label_value=_dev(np.array([v for _, v in views], np.uint8)))
+    cnt = cnt.cpu().numpy(); pix = pix.cpu().numpy(); pts = pts.cpu().numpy()
+    for v, (f, val) in enumerate(views):
+        lab = (label[f] == val) if val else (label[f] != 0)
+        ref_pts, ref_pix = og.surface_backproject(lab.astype(np.uint8), depth[f].astype(np.float64),
+                                                  dict(ppx=320.0, ppy=240.0, fx=615.0, fy=615.0), T[f])
+        assert cnt[v] == len(ref_pix)                           # full count even when it exceeds capacity
+        n = min(cap, len(ref_pix))
+        assert np.array_equal(pix[v, :n], ref_pix[:n].astype(np.int32))
+        assert np.allclose(pts[v, :n], ref_pts[:n], rtol=0, atol=1e-9)
+    assert cnt[4] == 0 and cnt[1] > cap                         # empty view; overflowing view
+
+
+def test_surface_backproject_full_batch_property():
+    """BASELINE-size batch (64 frames): counts equal a torch reduction of the same predicate."""
+    from autoposeestimation_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(0)
+    F, H, W = 64, 480, 640
+    label = (torch.rand((F, H, W), device='cuda', generator=g) < 0.04).to(torch.uint8) * 255
+    depth = torch.randint(0, 1500, (F, H, W), device='cuda', generator=g, dtype=torch.int32)
+    depth[depth < 30] = 0
+    depth16 = depth.to(torch.int16)
+    cam = torch.tensor([[320.0, 240.0, 615.0, 615.0]], dtype=torch.float64, device='cuda').repeat(F, 1)
+    r2c = torch.eye(4, dtype=torch.float64, device='cuda').repeat(F, 1, 1)
+    pts, pix, cnt = ops.surface_backproject(label, depth16, cam, r2c, capacity=16384)
+    want = ((label != 0) & (depth != 0)).flatten(1).sum(1).to(torch.int32)
+    assert torch.equal(cnt, want)
+    n0 = int(cnt[0])
+    p0 = pix[0, :n0].long()
+    assert bool((p0[1:] > p0[:-1]).all())                       # strictly increasing = row-major order
+    z = pts[0, :n0, 2]
+    assert torch.equal(z, depth[0].flatten()[p0].double())      # identity extrinsic: z is the raw depth

@@ -1,0 +1,126 @@
+"""GPU parity: persistent ICP kernel and voxel grid vs the open3d-0.9-semantics oracle (transforms within 1e-5)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import geometry as og, icp as oicp, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _ragged(clouds):
+    off = np.zeros(len(clouds) + 1, np.int32)
+    off[1:] = np.cumsum([len(c) for c in clouds])
+    return np.concatenate(clouds, axis=0) if clouds else np.zeros((0, 3)), off
+
+
+def _surface(seed):
+    fr = synth.render_ellipsoid_frame(seed)
+    pts, _ = og.surface_backproject(fr['label'], fr['depth'].astype(np.float64), fr['intr'], fr['robot2cam'])
+    return oicp.voxel_down_sample(pts, 2.0), fr['model']
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_icp_c1_vs_oracle(seed):
+    """BASELINE config 1: one 640x480 frame back-projected + masked, registered to a 2000-pt model cloud."""
+    from autoposeestimation_b200 import ops
+    src, tgt = _surface(seed)
+    T_ref, info_ref = oicp.registration_icp_p2p(src, tgt, 10.0, return_info=True)
+    so, to = np.array([0, len(src)], np.int32), np.array([0, len(tgt)], np.int32)
+    T, info = ops.icp_p2p(_dev(src), _dev(so), _dev(tgt), _dev(to), 10.0)
+    T = T.cpu().numpy()[0]; info = info.cpu().numpy()[0]
+    assert int(info[2]) == info_ref['iterations'] and int(info[3]) == info_ref['n_corr']
+    assert abs(info[0] - info_ref['fitness']) < 1e-12 and abs(info[1] - info_ref['inlier_rmse']) < 1e-9
+    assert np.abs(T - T_ref).max() < 1e-5, np.abs(T - T_ref).max()                 # the parity gate
+    assert np.allclose(T[3], [0, 0, 0, 1])
+
+
+def test_icp_ragged_batch_init_and_edge_cases():
+    from autoposeestimation_b200 import ops
+    rng = np.random.RandomState(21)
+    srcs, tgts, inits = [], [], []
+    for r in range(6):
+        tgt = synth.ellipsoid_cloud(rng, 300 + 450 * r, (40.0 + 5 * r, 30.0, 20.0))
+        R = synth.random_rotation(rng, math.radians(8)); t = rng.uniform(-3, 3, size=3)
+        src = (tgt[rng.choice(len(tgt), 200 + 100 * r, replace=False)] - t) @ R + rng.standard_normal((200 + 100 * r, 3)) * 0.2
+        srcs.append(src); tgts.append(tgt)
+        I = np.identity(4)
+        if r % 2:
+            I[:3, :3] = synth.random_rotation(rng, math.radians(2)); I[:3, 3] = rng.uniform(-1, 1, size=3)
+        inits.append(I)
+    srcs.append(srcs[0] + 500.0); tgts.append(tgts[0]); inits.append(np.identity(4))      # no correspondences at all
+    srcs.append(srcs[1][:1]); tgts.append(tgts[1]); inits.append(np.identity(4))            # single source point
+    S, so = _ragged(srcs); Tg, to = _ragged(tgts)
+    T, info = ops.icp_p2p(_dev(S), _dev(so), _dev(Tg), _dev(to), 10.0, init=_dev(np.stack(inits)))
+    T = T.cpu().numpy(); info = info.cpu().numpy()
+    for r in range(len(srcs)):
+        T_ref, ir = oicp.registration_icp_p2p(srcs[r], tgts[r], 10.0, init=inits[r], return_info=True)
+        assert int(info[r, 2]) == ir['iterations'], (r, info[r], ir)
+        assert np.abs(T[r] - T_ref).max() < 1e-5, (r, np.abs(T[r] - T_ref).max())
+    assert info[6, 0] == 0.0 and np.allclose(T[6], np.identity(4))
+
+
+def test_icp_criteria_and_max_iteration():
+    from autoposeestimation_b200 import ops
+    src, tgt = _surface(3)
+    so, to = np.array([0, len(src)], np.int32), np.array([0, len(tgt)], np.int32)
+    for kw in (dict(max_iter=1), dict(max_iter=3), dict(rel_fitness=1e-6, rel_rmse=1e-6, max_iter=30), dict(max_iter=0)):
+        T_ref, ir = oicp.registration_icp_p2p(src, tgt, 10.0, relative_fitness=kw.get('rel_fitness', 1e-2),
+                                              relative_rmse=kw.get('rel_rmse', 1e-2), max_iteration=kw['max_iter'], return_info=True)
+        T, info = ops.icp_p2p(_dev(src), _dev(so), _dev(tgt), _dev(to), 10.0, **kw)
+        assert int(info.cpu()[0, 2]) == ir['iterations']
+        assert np.abs(T.cpu().numpy()[0] - T_ref).max() < 1e-5
+
+
+def test_icp_large_grid_and_small_threshold():
+    """Cloud much larger than the threshold: the cell size grows until the grid fits (<= 4096 cells)."""
+    from autoposeestimation_b200 import ops
+    rng = np.random.RandomState(5)
+    tgt = rng.uniform(-300, 300, size=(6000, 3))
+    R = synth.random_rotation(rng, math.radians(0.3)); t = np.array([0.4, -0.3, 0.2])
+    src = (tgt[:2500] - t) @ R
+    T_ref, ir = oicp.registration_icp_p2p(src, tgt, 2.0, return_info=True)
+    T, info = ops.icp_p2p(_dev(src), _dev(np.array([0, 2500], np.int32)), _dev(tgt), _dev(np.array([0, 6000], np.int32)), 2.0)
+    assert int(info.cpu()[0, 2]) == ir['iterations']
+    assert np.abs(T.cpu().numpy()[0] - T_ref).max() < 1e-5
+
+
+def test_icp_batch_property_identical_registrations():
+    """592 copies of one registration in a single launch (4 CTAs per SM) give bit-identical transforms."""
+    from autoposeestimation_b200 import ops
+    src, tgt = _surface(4)
+    R = 592
+    S = np.tile(src, (R, 1)); Tg = np.tile(tgt, (R, 1))
+    so = (np.arange(R + 1) * len(src)).astype(np.int32); to = (np.arange(R + 1) * len(tgt)).astype(np.int32)
+    T, info = ops.icp_p2p(_dev(S), _dev(so), _dev(Tg), _dev(to), 10.0)
+    assert bool((T == T[0:1]).all()) and bool((info == info[0:1]).all())
+    T_ref = oicp.registration_icp_p2p(src, tgt, 10.0)
+    assert np.abs(T[0].cpu().numpy() - T_ref).max() < 1e-5
+
+
+@pytest.mark.parametrize('voxel', [2.0, 5.0])
+def test_voxel_down_sample_exact(voxel):
+    from autoposeestimation_b200 import ops
+    rng = np.random.RandomState(int(voxel))
+    clouds = [synth.ellipsoid_cloud(rng, 5000) + rng.standard_normal((5000, 3)), rng.uniform(-50, 50, size=(16384, 3)),
+              rng.uniform(0, 1, size=(3, 3)), np.zeros((0, 3)), np.array([[1.0, 2.0, 3.0]])]
+    P, off = _ragged(clouds)
+    out, cnt = ops.voxel_down_sample(_dev(P), _dev(off), voxel)
+    out = out.cpu().numpy(); cnt = cnt.cpu().numpy()
+    for c, cl in enumerate(clouds):
+        want = oicp.voxel_down_sample(cl, voxel)
+        assert cnt[c] == len(want)
+        assert np.array_equal(out[off[c]:off[c] + cnt[c]], want)               # same order, same bits as the oracle
+
+
+def test_voxel_down_sample_too_large_is_reported():
+    from autoposeestimation_b200 import ops
+    P = torch.rand((16385, 3), dtype=torch.float64, device='cuda')
+    out, cnt = ops.voxel_down_sample(P, torch.tensor([0, 16385], dtype=torch.int32, device='cuda'), 0.01)
+    assert int(cnt[0]) == -1

@@ -1,0 +1,136 @@
+"""GPU parity: kNN indices (bit-exact vs the oracle and vs the reference's own binaries) and ADD / ADD-S."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import clib, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize('arith', [0, 1])
+@pytest.mark.parametrize('B,N,M', [(1, 2600, 500), (3, 257, 1), (2, 1, 33), (2, 4100, 513)])
+def test_knn3_top1_vs_oracle(arith, B, N, M):
+    from autoposeestimation_b200 import ops
+    rng = np.random.RandomState(B * 1000 + N + M)
+    ref = rng.uniform(-0.1, 0.1, size=(B, 3, N)).astype(np.float32)
+    qry = rng.uniform(-0.1, 0.1, size=(B, 3, M)).astype(np.float32)
+    if N > 20:
+        ref[:, :, 17] = ref[:, :, 5]; qry[:, :, 0] = ref[:, :, 5]        # exact tie -> lowest index
+    want = clib.knn(ref, qry, 1, arith)
+    got = ops.knn(_dev(ref), _dev(qry), 1, arith).cpu().numpy()
+    assert got.dtype == np.int64 and got.shape == (B, 1, M)
+    assert np.array_equal(got, want)
+
+
+def test_knn_golden_reference_cpu(golden_dir):
+    """Golden indices produced by the reference's own knn_cpu.cpp (oracle/gen_golden.py)."""
+    from autoposeestimation_b200 import ops
+    g = np.load(os.path.join(golden_dir, 'knn.npz'))
+    assert np.array_equal(ops.knn(_dev(g['ref']), _dev(g['qry']), 1).cpu().numpy(), g['idx_k1'])
+    assert np.array_equal(ops.knn(_dev(g['ref']), _dev(g['qry']), 4).cpu().numpy(), g['idx_k4'])
+    assert np.array_equal(ops.knn(_dev(g['refd']), _dev(g['qryd']), 2).cpu().numpy(), g['idxd_k2'])
+
+
+@pytest.mark.parametrize('D,k', [(128, 2), (3, 5), (7, 1), (16, 64)])
+def test_knn_generic_shapes(D, k):
+    from autoposeestimation_b200 import ops
+    rng = np.random.RandomState(D + k)
+    ref = rng.rand(2, D, 100).astype(np.float32); qry = rng.rand(2, D, 70).astype(np.float32)
+    for arith in (0, 1):
+        assert np.array_equal(ops.knn(_dev(ref), _dev(qry), k, arith).cpu().numpy(), clib.knn(ref, qry, k, arith))
+
+
+def test_knn_error_paths():
+    from autoposeestimation_b200 import ops, _lib
+    ref = torch.zeros((1, 3, 10), device='cuda'); qry = torch.zeros((1, 3, 4), device='cuda')
+    with pytest.raises(_lib.ApeError):
+        ops.knn(ref, qry, 11)                       # k > N
+    with pytest.raises(_lib.ApeError):
+        ops.knn(torch.zeros((1, 5, 100), device='cuda'), torch.zeros((1, 5, 4), device='cuda'), 65)   # k > 64 generic
+    with pytest.raises(_lib.ApeError):
+        ops.knn(ref.cpu(), qry.cpu(), 1)            # no CPU fallback
+    assert ops.knn(ref, torch.zeros((1, 3, 0), device='cuda'), 1).shape == (1, 1, 0)      # empty query set
+
+
+def test_knn_vs_reference_cuda_kernel():
+    """Bit-exact against the reference's own knn.cu (compiled unmodified, oracle/_ref) in FMA mode."""
+    from autoposeestimation_b200 import ops
+    lib = clib.ref_knn_cuda_lib()
+    if lib is None:
+        pytest.skip('oracle/_ref/libknn_cuda_ref.so not built')
+    rng = np.random.RandomState(77)
+    B, N, M = 4, 2600, 500
+    ref = _dev(rng.uniform(-0.1, 0.1, size=(B, 3, N)).astype(np.float32))
+    qry = _dev(rng.uniform(-0.1, 0.1, size=(B, 3, M)).astype(np.float32))
+    idx_ref = torch.zeros((B, 1, M), dtype=torch.int64, device='cuda')
+    scratch = torch.empty((N * M,), dtype=torch.float32, device='cuda')
+    torch.cuda.synchronize()
+    rc = lib.ref_knn_cuda(ref.data_ptr(), qry.data_ptr(), idx_ref.data_ptr(), scratch.data_ptr(), B, 3, N, M, 1, None)
+    torch.cuda.synchronize()
+    assert rc == 0
+    assert torch.equal(ops.knn(ref, qry, 1, ops.KNN_ARITH_FMA), idx_ref)
+
+
+def test_knn_full_size_property():
+    """C3 shape at scale (4096 instances of 500 x 2600): every returned index attains the row minimum."""
+    from autoposeestimation_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(1)
+    B, N, M = 4096, 2600, 500
+    ref = torch.rand((B, 3, N), device='cuda', generator=g)
+    qry = torch.rand((B, 3, M), device='cuda', generator=g)
+    idx = ops.knn(ref, qry, 1)
+    assert int(idx.min()) >= 1 and int(idx.max()) <= N
+    for b in (0, 777, 4095):
+        d = ((ref[b, :, :, None] - qry[b, :, None, :]) ** 2).sum(0)          # [N, M]
+        got = d.gather(0, (idx[b] - 1))[0]
+        assert torch.allclose(got, d.min(0).values, rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize('n_model,n_target', [(500, 2600), (120, 120), (1000, 1000), (700, 3000)])
+def test_add_metric_vs_oracle(n_model, n_target):
+    from autoposeestimation_b200 import ops
+    rng = np.random.RandomState(n_model)
+    B = 6
+    model = rng.uniform(-0.1, 0.1, size=(B, n_model, 3)).astype(np.float32)
+    target = rng.uniform(-0.1, 0.1, size=(B, n_target, 3)).astype(np.float32) + np.float32(0.5)
+    quat = rng.standard_normal((B, 4)).astype(np.float32); trans = rng.uniform(0.4, 0.6, size=(B, 3)).astype(np.float32)
+    sym = np.array([1, 0, 1, 1, 0, 1], np.uint8) if n_model == n_target else np.ones(B, np.uint8)
+    dis, nn = ops.add_metric(_dev(quat), _dev(trans), _dev(model), _dev(target), _dev(sym), want_index=True)
+    dis = dis.cpu().numpy()
+    for b in range(B):
+        want = clib.add_metric(quat[b], trans[b], model[b], target[b], bool(sym[b]))
+        assert abs(float(dis[b]) - want) < 1e-6, (b, dis[b], want)            # gate: ADD-S within 1e-5 m
+
+
+def test_add_metric_golden_reference_loss(golden_dir):
+    """dis of the reference's own Loss_refine (ADD-S and ADD) from tests/golden/losses.npz."""
+    from autoposeestimation_b200 import ops
+    g = np.load(os.path.join(golden_dir, 'losses.npz'))
+    for tag, sym in (('sym', 1), ('nosym', 0)):
+        dis = ops.add_metric(_dev(g['pr1']), _dev(g['pt1']), _dev(g['model']), _dev(g['target']), _dev(np.array([sym], np.uint8)))
+        assert abs(float(dis.cpu()[0]) - float(g['lr_dis_' + tag][0])) < 1e-6
+
+
+def test_add_metric_shared_models_c3():
+    """C3 layout: shared target cloud (stride 0) + per-instance poses; spot-check against the oracle."""
+    from autoposeestimation_b200 import ops
+    d = synth.adds_instances(2, 512)
+    cls0 = int(d['cls'][0])
+    sel = np.flatnonzero(d['cls'] == cls0)
+    model = d['models'][cls0]
+    from oracle import pose_math as pm
+    R = pm.quaternion_matrix(d['q_gt'][sel[0]])[:3, :3].astype(np.float32)
+    target = (model @ R.T + d['t_gt'][sel[0]]).astype(np.float32)          # one GT pose shared by the group
+    sub = model[d['subsample']]
+    q = d['q_pred'][sel]; t = d['t_pred'][sel]
+    dis = ops.add_metric(_dev(q), _dev(t), _dev(sub), _dev(target), _dev(np.ones(len(sel), np.uint8))).cpu().numpy()
+    for i in range(min(len(sel), 5)):
+        assert abs(float(dis[i]) - clib.add_metric(q[i], t[i], sub, target, True)) < 1e-6
