@@ -16,6 +16,8 @@ SIGNATURES = {
     'ape_version': (c_int, []),
     'ape_last_error': (ctypes.c_char_p, []),
     'ape_launch_count': (ctypes.c_uint64, []),
+    'ape_profile_enable': (c_int, [c_int]),
+    'ape_profile_report': (c_int, [ctypes.c_char_p, c_int]),
     'ape_backproject_choose': (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
     'ape_surface_backproject': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int,
                                         c_vp, c_vp, c_vp, c_vp]),

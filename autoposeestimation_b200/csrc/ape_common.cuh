@@ -14,6 +14,22 @@ void count_launch(int n = 1);
 int  check_launch(const char* what);     // cudaGetLastError -> APE_OK / APE_ERR_CUDA
 int  sm_count();
 
+// Optional per-launch device timing (bench.py roofline leg): CUDA events on the launching stream around
+// every kernel, aggregated by label in ape_profile_report().  Disabled by default (one branch per launch).
+bool prof_enabled();
+void prof_push(const char* label, cudaEvent_t e0, cudaEvent_t e1);
+struct ProfScope {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStream_t s;
+    const char* label;
+    ProfScope(const char* l, cudaStream_t st) : s(st), label(l) {
+        if (prof_enabled()) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
+    }
+    ~ProfScope() {
+        if (e0) { cudaEventRecord(e1, s); prof_push(label, e0, e1); }
+    }
+};
+
 #define APE_REQUIRE(cond, ...)                                   \
     do {                                                         \
         if (!(cond)) {                                           \

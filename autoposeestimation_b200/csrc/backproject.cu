@@ -182,6 +182,7 @@ extern "C" __attribute__((visibility("default"))) int ape_backproject_choose(con
     if (n_obj == 0 || n_points == 0) return APE_OK;
     APE_REQUIRE(n_obj <= 65535, "ape_backproject_choose: n_obj > 65535 (split the batch)");
     dim3 grid((n_points + 255) / 256, n_obj);
+    ape::ProfScope prof_("backproject_choose", (cudaStream_t)stream);
     ape::backproject_choose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(depth, n_frames, height, width, frame_of,
                                                                           bbox, choose, cam, n_points, cloud);
     ape::count_launch();
@@ -200,6 +201,7 @@ extern "C" __attribute__((visibility("default"))) int ape_surface_backproject(co
     APE_REQUIRE((((uintptr_t)label) & 15) == 0 && (((uintptr_t)depth) & 15) == 0,
                 "ape_surface_backproject: label/depth must be 16-byte aligned");
     if (n_views == 0) return APE_OK;
+    ape::ProfScope prof_("surface_backproject", (cudaStream_t)stream);
     ape::surface_backproject_kernel<<<n_views, ape::kSurfThreads, 0, (cudaStream_t)stream>>>(
         label, depth, height, width, frame_of, label_value, cam, robot2cam, capacity, points, pixel_index, counts);
     ape::count_launch();

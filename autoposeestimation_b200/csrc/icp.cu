@@ -400,6 +400,7 @@ extern "C" __attribute__((visibility("default"))) int ape_icp_p2p(const double* 
         attr_set = true;
     }
     const int grid = n_reg < ape::sm_count() * 4 ? n_reg : ape::sm_count() * 4;
+    ape::ProfScope prof_("icp_p2p", (cudaStream_t)stream);
     ape::icp_p2p_kernel<<<grid, ape::kIcpThreads, smem, (cudaStream_t)stream>>>(
         source, src_offset, target, tgt_offset, n_reg, threshold, rel_fitness, rel_rmse, max_iter, init, transform, info,
         wsrc, wtgt, worig, wcorr);

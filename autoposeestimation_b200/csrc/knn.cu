@@ -203,13 +203,15 @@ add_metric_kernel(const float* __restrict__ quat, const float* __restrict__ tran
 extern "C" __attribute__((visibility("default"))) int ape_knn(const float* ref, const float* query, int64_t* idx, int B, int D, int N, int M, int k,
                        int arith, void* stream)
 {
-    APE_REQUIRE(ref && query && idx, "ape_knn: null pointer");
     APE_REQUIRE(B >= 0 && D > 0 && N > 0 && M >= 0 && k > 0, "ape_knn: bad sizes");
+    if (B == 0 || M == 0) return APE_OK;                       // empty query set: nothing to write
+    APE_REQUIRE(ref && query && idx, "ape_knn: null pointer");
     APE_REQUIRE(k <= N, "ape_knn: k (%d) > number of reference points (%d)", k, N);
     APE_REQUIRE(arith == APE_KNN_ARITH_CPU || arith == APE_KNN_ARITH_FMA, "ape_knn: unknown arithmetic mode");
     if (B == 0 || M == 0) return APE_OK;
     APE_REQUIRE(B <= 65535, "ape_knn: batch > 65535 (split the batch)");
     cudaStream_t s = (cudaStream_t)stream;
+    ape::ProfScope prof_("knn", s);
     if (D == 3 && k == 1) {
         dim3 grid((M + ape::kKnnThreads * ape::kKnnQ - 1) / (ape::kKnnThreads * ape::kKnnQ), B);
         if (arith == APE_KNN_ARITH_FMA) ape::knn3_top1_kernel<true><<<grid, ape::kKnnThreads, 0, s>>>(ref, query, idx, N, M);
@@ -235,6 +237,7 @@ extern "C" __attribute__((visibility("default"))) int ape_add_metric(const float
     APE_REQUIRE(B >= 0 && n_model > 0 && n_target > 0, "ape_add_metric: bad sizes");
     APE_REQUIRE(symmetric || n_model == n_target, "ape_add_metric: ADD needs n_model == n_target");
     if (B == 0) return APE_OK;
+    ape::ProfScope prof_("add_metric", (cudaStream_t)stream);
     ape::add_metric_kernel<<<B, ape::kAddThreads, 0, (cudaStream_t)stream>>>(
         quat, trans, model_points, model_stride, n_model, target, target_stride, n_target, symmetric, dis, nn_index);
     ape::count_launch();

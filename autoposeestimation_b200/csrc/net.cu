@@ -515,8 +515,9 @@ int ape_net_set_gemm(ape_net* net, int gemm_impl)
 }
 
 // One GEMM layer: out = relu(A[:, a_k0 + g*a_kg : +K] * W_g^T + bias)
-static int run_gemm(ape_net* net, const SplitMat& A, const SplitMat& W, const ape::tc::Params& p, cudaStream_t s)
+static int run_gemm(ape_net* net, const SplitMat& A, const SplitMat& W, const ape::tc::Params& p, cudaStream_t s, const char* label)
 {
+    ape::ProfScope prof_(label, s);
     if (net->gemm_impl == APE_GEMM_TCGEN05) {
         dim3 grid(p.N / ape::tc::BN, p.M / ape::tc::BM, p.groups);
         ape::tc::gemm_split_bf16_kernel<<<grid, ape::tc::kThreads, ape::tc::kSmemBytes, s>>>(A.map_hi, A.map_lo, W.map_hi,
@@ -548,28 +549,32 @@ static int run_trunk(ape_net* net, const float* feat_src, int hw, const float* c
     const int Np = (N + 127) / 128 * 128;
     const int M = B * Np;
     dim3 gf((Np + 63) / 64, B);
+    {
+    ape::ProfScope prof_("frontend", s);
     if (net->kind == APE_NET_POSENET)
         ape::frontend_kernel<true><<<gf, 256, 0, s>>>(feat_src, hw, cloud, choose, net->w1.p, net->b1.p, net->we1.p, net->be1.p,
                                                      N, Np, net->PF.hi, net->PF.lo, 384, emb_out);
     else
         ape::frontend_kernel<false><<<gf, 256, 0, s>>>(feat_src, hw, cloud, nullptr, net->w1.p, net->b1.p, net->we1.p,
                                                       net->be1.p, N, Np, net->PF.hi, net->PF.lo, 384, nullptr);
+    }
     ape::count_launch();
     int rc = ape::check_launch("frontend");
     if (rc) return rc;
+    const bool pn = net->kind == APE_NET_POSENET, pn_ = pn;
     // conv2 (PF[:,0:64] -> PF[:,128:256]) and e_conv2 (PF[:,64:128] -> PF[:,256:384]) as two groups
     ape::tc::Params p = split_layer(M, 128, 64, 2, 0, 64, net->b_c2e2.p, net->PF, 128);
-    if ((rc = run_gemm(net, net->PF, net->W_c2e2, p, s))) return rc;
+    if ((rc = run_gemm(net, net->PF, net->W_c2e2, p, s, pn_ ? "gemm.pn.conv2" : "gemm.rf.conv2"))) return rc;
     // conv5: PoseNet reads pointfeat_2 = PF[:,128:384] (network.py:62); refiner reads pointfeat_3 = PF[:,0:384] (:162)
-    const bool pn = net->kind == APE_NET_POSENET;
     p = split_layer(M, 512, pn ? 256 : 384, 1, pn ? 128 : 0, 0, net->b_c5.p, net->H5, 0);
-    if ((rc = run_gemm(net, net->PF, net->W_c5, p, s))) return rc;
+    if ((rc = run_gemm(net, net->PF, net->W_c5, p, s, pn ? "gemm.pn.conv5" : "gemm.rf.conv5"))) return rc;
     // conv6 + ReLU + AvgPool1d: masked per-tile column sums, never materialising [1024, N]
     memset(&p, 0, sizeof(p));
     p.M = M; p.N = 1024; p.K = 512; p.groups = 1; p.bias = net->b_c6.p; p.mode = ape::tc::EPI_RELU_COLSUM;
     p.colsum = net->CS.p; p.rows_per_obj = Np; p.valid_rows = N;
-    if ((rc = run_gemm(net, net->H5, net->W_c6, p, s))) return rc;
+    if ((rc = run_gemm(net, net->H5, net->W_c6, p, s, pn ? "gemm.pn.conv6" : "gemm.rf.conv6"))) return rc;
     dim3 gp(1024 / 256, B);
+    ape::ProfScope prof_("pool_finish", s);
     ape::pool_finish_kernel<<<gp, 256, 0, s>>>(net->CS.p, Np / 128, 1024, (float)N, net->AP.p);
     ape::count_launch();
     return ape::check_launch("pool_finish");
@@ -580,6 +585,7 @@ static int dense(const float* in, int in_ld, int in_gs, const DevF32& W, const D
 {
     dim3 grid((npg * groups + 7) / 8, (B + ape::kDenseObj - 1) / ape::kDenseObj);
     if (grid.y > 64) grid.y = 64;
+    ape::ProfScope prof_("dense_small", s);
     ape::dense_small_kernel<<<grid, 256, 0, s>>>(in, in_ld, in_gs, W.p, bias.p, out, out_ld, B, K, npg, groups, relu);
     ape::count_launch();
     return ape::check_launch("dense_small");
@@ -604,12 +610,13 @@ int ape_posenet_forward(ape_net* net, const float* out_img, int hw, const float*
     // conv1_{r,t,c} on [pointfeat_1 | pointfeat_2] (K=384), N = 3*640, per-object bias
     ape::tc::Params p = split_layer(M, 1920, 384, 1, 0, 0, net->GB.p, net->H1, 0);
     p.bias_obj_rows = Np;
-    if ((rc = run_gemm(net, net->PF, net->W_h1, p, s))) return rc;
+    if ((rc = run_gemm(net, net->PF, net->W_h1, p, s, "gemm.pn.heads1"))) return rc;
     p = split_layer(M, 256, 640, 3, 0, 640, net->b_h2.p, net->H2, 0);          // conv2_{r,t,c}
-    if ((rc = run_gemm(net, net->H1, net->W_h2, p, s))) return rc;
+    if ((rc = run_gemm(net, net->H1, net->W_h2, p, s, "gemm.pn.heads2"))) return rc;
     p = split_layer(M, 128, 256, 3, 0, 256, net->b_h3.p, net->H3, 0);          // conv3_{r,t,c}
-    if ((rc = run_gemm(net, net->H2, net->W_h3, p, s))) return rc;
+    if ((rc = run_gemm(net, net->H2, net->W_h3, p, s, "gemm.pn.heads3"))) return rc;
     dim3 go((N + 7) / 8 < 64 ? (N + 7) / 8 : 64, B);
+    ape::ProfScope prof_("posenet_out", s);
     ape::posenet_out_kernel<<<go, 256, 0, s>>>(net->H3.hi, net->H3.lo, 384, N, Np, net->w4r.p, net->b4r.p, net->w4t.p,
                                               net->b4t.p, net->w4c.p, net->b4c.p, obj, net->num_obj, pred_r, pred_t, pred_c);
     ape::count_launch();
@@ -630,6 +637,7 @@ int ape_refiner_forward(ape_net* net, const float* new_points, const float* emb,
     if (rc) return rc;
     if ((rc = dense(net->AP.p, 1024, 0, net->Wr1, net->br1, net->G1.p, 1024, B, 1024, 1024, 1, 1, s))) return rc;   // conv1_{r,t}
     if ((rc = dense(net->G1.p, 1024, 512, net->Wr2, net->br2, net->G2.p, 256, B, 512, 128, 2, 1, s))) return rc;    // conv2_{r,t}
+    ape::ProfScope prof_("refiner_out", s);
     ape::refiner_out_kernel<<<B, 256, 0, s>>>(net->G2.p, net->w3r.p, net->b3r.p, net->w3t.p, net->b3t.p, obj, net->num_obj, r2, t2);
     ape::count_launch();
     return ape::check_launch("refiner_out");

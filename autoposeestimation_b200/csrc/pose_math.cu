@@ -177,6 +177,7 @@ extern "C" __attribute__((visibility("default"))) int ape_pose_select(const floa
     APE_REQUIRE(pred_r && pred_t && pred_c && cloud && which_max && my_r && my_t, "ape_pose_select: null pointer");
     APE_REQUIRE(B >= 0 && N > 0, "ape_pose_select: bad sizes");
     if (B == 0) return APE_OK;
+    ape::ProfScope prof_("pose_select", (cudaStream_t)stream);
     ape::pose_select_kernel<<<B, ape::kSelThreads, 0, (cudaStream_t)stream>>>(pred_r, pred_t, pred_c, cloud, N, which_max,
                                                                              my_r, my_t, new_points, pose);
     ape::count_launch();
@@ -190,6 +191,7 @@ extern "C" __attribute__((visibility("default"))) int ape_pose_compose(const dou
     APE_REQUIRE(B >= 0, "ape_pose_compose: bad sizes");
     APE_REQUIRE(!next_points || (cloud && N > 0), "ape_pose_compose: next_points needs cloud and N");
     if (B == 0) return APE_OK;
+    ape::ProfScope prof_("pose_compose", (cudaStream_t)stream);
     ape::pose_compose_kernel<<<B, ape::kSelThreads, 0, (cudaStream_t)stream>>>(pose_in, r2, t2, pose_out, cloud, N,
                                                                               next_points);
     ape::count_launch();

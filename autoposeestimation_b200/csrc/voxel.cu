@@ -139,6 +139,7 @@ int ape_voxel_down_sample(const double* points, const int32_t* offset, int n_clo
         APE_CUDA(cudaFuncSetAttribute(ape::voxel_down_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
+    ape::ProfScope prof_("voxel_down_sample", (cudaStream_t)stream);
     ape::voxel_down_sample_kernel<<<n_clouds, ape::kVoxThreads, smem, (cudaStream_t)stream>>>(points, offset, voxel_size,
                                                                                             out_points, out_counts);
     ape::count_launch();

@@ -46,6 +46,11 @@ int         ape_version(void);
 const char* ape_last_error(void);
 /* Number of kernel launches issued through this library by the calling process so far. */
 uint64_t    ape_launch_count(void);
+/* Optional per-launch device timing (used by bench.py for the roofline): when enabled, every kernel
+ * launch is bracketed by CUDA events on its stream.  ape_profile_report writes one line per kernel
+ * label, "label launches total_ms", into buf and returns the number of bytes needed.           */
+int         ape_profile_enable(int on);
+int         ape_profile_report(char* buf, int buflen);
 
 /* ---------------------------------------------------------------------------------------------
  * a3. DenseFusion back-projection at fixed sampling indices.
