@@ -1,0 +1,224 @@
+"""Drop-in `PoseNet` / `PoseRefineNet` (reference: DenseFusion/lib/network.py:70-132, :170-206).
+
+Same constructor arguments, same parameter names and shapes (reference checkpoints load with
+`load_state_dict`, including the `cnn.model.module.*` keys of the DataParallel-wrapped encoder), same
+forward signatures and return shapes.  Everything after the colour encoder runs on the hand-written
+sm_100a kernels (ops.NetHandle); the PSPNet/ResNet-18 encoder stays on PyTorch/cuDNN (outside the graft,
+BASELINE.json).  Extension over the reference: a batch of B objects is processed at once (the
+reference silently returns element 0 only, network.py:123).
+
+Training: kernels are forward-only in this round.  When autograd is recording and a parameter requires
+grad, the modules run the same layer stack with torch ops (cuDNN/cuBLAS on the GPU) so `dis.backward()`
+keeps working (train.py:215-223); that training path is NOT yet grafted.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+
+
+# ----------------------------------------------------------------------------------------------------
+# Colour encoder (outside the graft): ResNet-18 (dilated, no BatchNorm) + pyramid pooling + 3 upsampling
+# stages -> 32 channels per pixel.  Key names follow DenseFusion/lib/pspnet.py and lib/extractors.py.
+class _Block(nn.Module):
+    def __init__(self, cin, cout, stride=1, dilation=1, project=False):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride=stride, padding=dilation, dilation=dilation, bias=False)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=dilation, dilation=dilation, bias=False)
+        self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride=stride, bias=False)) if project else None
+
+    def forward(self, x):
+        y = self.conv2(F.relu(self.conv1(x)))
+        return F.relu(y + (x if self.downsample is None else self.downsample(x)))
+
+
+class _ResNet18(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
+        self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
+        # (cin, cout, stride of the first block, dilation of the following block)
+        spec = [(64, 64, 1, 1), (64, 128, 2, 1), (128, 256, 1, 2), (256, 512, 1, 4)]
+        for i, (ci, co, st, dil) in enumerate(spec, 1):
+            first = _Block(ci, co, stride=st, dilation=1, project=(st != 1 or ci != co))
+            setattr(self, 'layer%d' % i, nn.Sequential(first, _Block(co, co, dilation=dil)))
+
+    def forward(self, x):
+        x = self.maxpool(F.relu(self.conv1(x)))
+        return self.layer4(self.layer3(self.layer2(self.layer1(x))))
+
+
+class _Pyramid(nn.Module):
+    def __init__(self, feats=512, out=1024, sizes=(1, 2, 3, 6)):
+        super().__init__()
+        self.stages = nn.ModuleList(nn.Sequential(nn.AdaptiveAvgPool2d((s, s)), nn.Conv2d(feats, feats, 1, bias=False)) for s in sizes)
+        self.bottleneck = nn.Conv2d(feats * (len(sizes) + 1), out, 1)
+
+    def forward(self, f):
+        hw = f.shape[2:]
+        pri = [F.interpolate(st(f), size=hw, mode='bilinear', align_corners=False) for st in self.stages] + [f]
+        return F.relu(self.bottleneck(torch.cat(pri, 1)))
+
+
+class _Up(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv = nn.Sequential(nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True),
+                                  nn.Conv2d(cin, cout, 3, padding=1), nn.PReLU())
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class _PSPNet(nn.Module):
+    def __init__(self, n_classes=21):
+        super().__init__()
+        self.feats = _ResNet18()
+        self.psp = _Pyramid(512, 1024)
+        self.drop_1 = nn.Dropout2d(p=0.3)
+        self.up_1, self.up_2, self.up_3 = _Up(1024, 256), _Up(256, 64), _Up(64, 64)
+        self.drop_2 = nn.Dropout2d(p=0.15)
+        self.final = nn.Sequential(nn.Conv2d(64, 32, 1), nn.LogSoftmax(dim=1))
+        self.classifier = nn.Sequential(nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, n_classes))   # unused by forward (as upstream)
+
+    def forward(self, x):
+        p = self.drop_1(self.psp(self.feats(x)))
+        p = self.drop_2(self.up_1(p))
+        p = self.drop_2(self.up_2(p))
+        return self.final(self.up_3(p))
+
+
+class _Holder(nn.Module):
+    """Gives the encoder the `model.module.` key prefix of the reference's nn.DataParallel wrapper."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+    def forward(self, x):
+        return self.module(x)
+
+
+class ModifiedResnet(nn.Module):
+    def __init__(self, usegpu=True):
+        super().__init__()
+        self.model = _Holder(_PSPNet())
+
+    def forward(self, x):
+        return self.model(x)
+
+
+# ----------------------------------------------------------------------------------------------------
+class PoseNetFeat(nn.Module):
+    """Parameter holder with the reference's names (network.py:39-51); computed by the fused trunk."""
+
+    def __init__(self, num_points, refine=False):
+        super().__init__()
+        self.conv1 = nn.Conv1d(3, 64, 1); self.conv2 = nn.Conv1d(64, 128, 1)
+        self.e_conv1 = nn.Conv1d(32, 64, 1); self.e_conv2 = nn.Conv1d(64, 128, 1)
+        self.conv5 = nn.Conv1d(384 if refine else 256, 512, 1); self.conv6 = nn.Conv1d(512, 1024, 1)
+        self.num_points, self.refine = num_points, refine
+
+    def forward(self, x, emb):                     # torch path (autograd / training only)
+        x1 = F.relu(self.conv1(x)); e1 = F.relu(self.e_conv1(emb))
+        x2 = F.relu(self.conv2(x1)); e2 = F.relu(self.e_conv2(e1))
+        pf1, pf2 = torch.cat((x1, e1), 1), torch.cat((x2, e2), 1)
+        y = F.relu(self.conv6(F.relu(self.conv5(torch.cat((pf1, pf2), 1) if self.refine else pf2))))
+        ap = y.mean(dim=2, keepdim=True)
+        return ap.view(-1, 1024) if self.refine else torch.cat([pf1, pf2, ap.expand(-1, -1, x.shape[2])], 1)
+
+
+PoseRefineNetFeat = lambda num_points: PoseNetFeat(num_points, refine=True)   # noqa: E731  (network.py:136)
+
+
+class _Grafted(nn.Module):
+    """Builds / refreshes the C-side handle (split-bf16 weights + workspace) from the current parameters."""
+    _kind = None
+
+    def _handle(self, batch, n_points):
+        ps = [p for n, p in self.named_parameters() if not n.startswith('cnn.')]
+        key = (tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps), str(ps[0].device))
+        h = getattr(self, '_ape', None)
+        if h is None or self._ape_key != key or h.max_batch < batch or h.max_points < n_points:
+            if h is not None:
+                h.close()
+            sd = {k: v for k, v in self.state_dict().items() if not k.startswith('cnn.')}
+            self._ape = ops.NetHandle(self._kind, sd, self.num_obj, max(batch, getattr(h, 'max_batch', 1)),
+                                      max(n_points, getattr(h, 'max_points', 1)))
+            self._ape_key = key
+        return self._ape
+
+    def _needs_autograd(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for n, p in self.named_parameters() if not n.startswith('cnn.')) \
+            and self.training
+
+
+class PoseNet(_Grafted):
+    _kind = ops.NET_POSENET
+
+    def __init__(self, num_points, num_obj):
+        super().__init__()
+        self.num_points, self.num_obj = num_points, num_obj
+        self.cnn = ModifiedResnet()
+        self.feat = PoseNetFeat(num_points)
+        for h, w in (('r', 4), ('t', 3), ('c', 1)):
+            setattr(self, 'conv1_' + h, nn.Conv1d(1408, 640, 1)); setattr(self, 'conv2_' + h, nn.Conv1d(640, 256, 1))
+            setattr(self, 'conv3_' + h, nn.Conv1d(256, 128, 1)); setattr(self, 'conv4_' + h, nn.Conv1d(128, num_obj * w, 1))
+
+    def forward(self, img, x, choose, obj):
+        """img [B,3,h,w], x [B,N,3], choose [B,1,N] int64 (flat indices into h*w), obj [B,1] int64
+        -> pred_r [B,N,4], pred_t [B,N,3], pred_c [B,N,1], emb [B,32,N] (detached), as network.py:95-132."""
+        out_img = self.cnn(img)                                        # PyTorch/cuDNN, outside the graft
+        return self.forward_geometry(out_img, x, choose, obj)
+
+    def forward_geometry(self, out_img, x, choose, obj):
+        """Everything after the encoder (network.py:98-132) on the sm_100a kernels."""
+        B, N = x.shape[0], x.shape[1]
+        if self._needs_autograd():
+            return self._torch_geometry(out_img, x, choose, obj)
+        if not out_img.is_cuda:
+            raise ops._lib.ApeError('PoseNet: tensors must be on a CUDA device (no CPU fallback)')
+        return self._handle(B, N).posenet_forward(out_img.detach(), x, choose, obj)
+
+    def _torch_geometry(self, out_img, x, choose, obj):               # training only; not grafted yet
+        B, di = out_img.shape[:2]
+        N = x.shape[1]
+        emb = torch.gather(out_img.reshape(B, di, -1), 2, choose.reshape(B, 1, N).expand(B, di, N)).contiguous()
+        ap = self.feat(x.transpose(2, 1).contiguous(), emb)
+        outs = []
+        for h, w in (('r', 4), ('t', 3), ('c', 1)):
+            y = ap
+            for i in (1, 2, 3):
+                y = F.relu(getattr(self, 'conv%d_%s' % (i, h))(y))
+            y = getattr(self, 'conv4_' + h)(y)
+            y = (torch.sigmoid(y) if h == 'c' else y).view(B, self.num_obj, w, N)
+            sel = y[torch.arange(B, device=y.device), obj.reshape(B)]               # [B,w,N]
+            outs.append(sel.transpose(2, 1).contiguous())
+        return outs[0], outs[1], outs[2], emb.detach()
+
+
+class PoseRefineNet(_Grafted):
+    _kind = ops.NET_REFINER
+
+    def __init__(self, num_points, num_obj):
+        super().__init__()
+        self.num_points, self.num_obj = num_points, num_obj
+        self.feat = PoseNetFeat(num_points, refine=True)
+        self.conv1_r, self.conv1_t = nn.Linear(1024, 512), nn.Linear(1024, 512)
+        self.conv2_r, self.conv2_t = nn.Linear(512, 128), nn.Linear(512, 128)
+        self.conv3_r, self.conv3_t = nn.Linear(128, num_obj * 4), nn.Linear(128, num_obj * 3)
+
+    def forward(self, x, emb, obj):
+        """x = new_points [B,N,3], emb [B,32,N], obj [B,1] -> pred_r [B,4], pred_t [B,3] (network.py:187-206)."""
+        B, N = x.shape[0], x.shape[1]
+        if self._needs_autograd():
+            ap = self.feat(x.transpose(2, 1).contiguous(), emb)
+            idx = obj.reshape(B)
+            ar = torch.arange(B, device=x.device)
+            r = self.conv3_r(F.relu(self.conv2_r(F.relu(self.conv1_r(ap))))).view(B, self.num_obj, 4)[ar, idx]
+            t = self.conv3_t(F.relu(self.conv2_t(F.relu(self.conv1_t(ap))))).view(B, self.num_obj, 3)[ar, idx]
+            return r, t
+        if not x.is_cuda:
+            raise ops._lib.ApeError('PoseRefineNet: tensors must be on a CUDA device (no CPU fallback)')
+        return self._handle(B, N).refiner_forward(x, emb, obj)

@@ -1,0 +1,124 @@
+"""Drop-in for the hot functions of pc_reconstruction/open3d_utils.py (option 4, "Create Pose labels").
+
+  get_surface     :171-213  masked depth -> robot-frame cloud (+ voxel grid)       -> csrc/backproject.cu, voxel.cu
+  icp_regression  :63-122   voxel grid on both clouds + point-to-point ICP          -> csrc/voxel.cu, icp.cu
+  icp_regression_batch      the same for many (target, source) pairs in one launch (BASELINE config 4)
+
+open3d is not a dependency: clouds are carried by `PointCloud`, a minimal stand-in for
+o3d.geometry.PointCloud (points, transform, voxel_down_sample, get_center, translate) backed by an [n,3] fp64
+CUDA tensor.  Units are millimetres as in the reference.  There is no CPU fallback.
+
+Not yet grafted: remove_radius_outlier / remove_statistical_outlier /
+compute_mahalanobis_distance (:198-211).  get_surface therefore takes `outlier_filters=False`; asking for
+them raises NotImplementedError instead of silently returning an unfiltered cloud.
+"""
+import numpy as np
+import torch
+
+from .. import ops
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise ops._lib.ApeError('no CUDA device: the B200 path has no CPU fallback')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+class PointCloud:
+    """Minimal o3d.geometry.PointCloud stand-in: `.points` is an [n,3] fp64 CUDA tensor."""
+
+    def __init__(self, points=None):
+        if points is None:
+            points = torch.zeros((0, 3), dtype=torch.float64, device=_dev())
+        elif not isinstance(points, torch.Tensor):
+            points = torch.from_numpy(np.ascontiguousarray(points, dtype=np.float64)).to(_dev())
+        self.points = points.to(torch.float64).reshape(-1, 3).contiguous()
+
+    def __len__(self):
+        return self.points.shape[0]
+
+    def numpy(self):
+        return self.points.cpu().numpy()
+
+    def get_center(self):
+        return self.points.mean(dim=0).cpu().numpy()
+
+    def translate(self, translation):
+        self.points = self.points + torch.as_tensor(np.asarray(translation, np.float64), device=self.points.device)
+        return self
+
+    def transform(self, T):
+        T = torch.as_tensor(np.asarray(T, np.float64), device=self.points.device)
+        self.points = (self.points @ T[:3, :3].T + T[:3, 3]).contiguous()
+        return self
+
+    def voxel_down_sample(self, voxel_size):
+        n = len(self)
+        if n == 0:
+            return PointCloud(self.points.clone())
+        off = torch.tensor([0, n], dtype=torch.int32, device=self.points.device)
+        out, cnt = ops.voxel_down_sample(self.points, off, voxel_size)
+        c = int(cnt.cpu()[0])
+        if c < 0:
+            raise ops._lib.ApeError('voxel_down_sample: cloud too large for the kernel (%d points, status %d)' % (n, c))
+        return PointCloud(out[:c].clone())
+
+
+def get_surface(label, depth_frame, intr, robot2Cam_ft, min_friends=None, min_dist=None, nb_neighbors=None, voxel_size=None,
+                outlier_filters=False):
+    """open3d_utils.py:171-213.  label uint8 [H,W] (non-zero = object), depth_frame [H,W] raw depth (mm; integral
+    values, as read from the 16-bit PNG), intr dict(ppx,ppy,fx,fy), robot2Cam_ft 4x4.  Returns a PointCloud."""
+    if outlier_filters:
+        raise NotImplementedError('radius / statistical outlier filters are not grafted yet (SURVEY 8f rank 1)')
+    dev = _dev()
+    depth = np.asarray(depth_frame)
+    d16 = depth.astype(np.uint16)
+    if not np.array_equal(d16, depth):
+        raise ValueError('get_surface: depth_frame must hold integral 16-bit sensor values')
+    lab = torch.from_numpy(np.ascontiguousarray(label, dtype=np.uint8)[None]).to(dev)
+    dep = torch.from_numpy(d16.view(np.int16)[None].copy()).to(dev)
+    cam = torch.tensor([[intr['ppx'], intr['ppy'], intr['fx'], intr['fy']]], dtype=torch.float64, device=dev)
+    r2c = torch.from_numpy(np.asarray(robot2Cam_ft, np.float64)[None].copy()).to(dev)
+    cap = int(lab.shape[1] * lab.shape[2])
+    n_hint = int((lab != 0).sum())                         # capacity = number of labelled pixels (upper bound)
+    pts, _, cnt = ops.surface_backproject(lab, dep, cam, r2c, capacity=max(16, min(cap, n_hint)), want_pixels=False)
+    surface = PointCloud(pts[0, :int(cnt.cpu()[0])].clone())
+    if voxel_size:
+        surface = surface.voxel_down_sample(voxel_size)
+    return surface
+
+
+def icp_regression_batch(targets, sources, voxel_size=5, threshold=100, max_iteration=100, relative_fitness=1e-2,
+                         relative_rmse=1e-2):
+    """Many independent registrations in one ICP launch.  targets/sources: lists of PointCloud.
+    Returns (targets_down, sources_down, transforms [R,4,4] numpy fp64, info [R,4] numpy)."""
+    dev = _dev()
+    def pack(clouds):
+        off = np.zeros(len(clouds) + 1, np.int32)
+        off[1:] = np.cumsum([len(c) for c in clouds])
+        flat = torch.cat([c.points for c in clouds]) if clouds else torch.zeros((0, 3), dtype=torch.float64, device=dev)
+        return flat, off
+    def down(clouds):
+        flat, off = pack(clouds)
+        out, cnt = ops.voxel_down_sample(flat, torch.from_numpy(off).to(dev), voxel_size)
+        cnt = cnt.cpu().numpy()
+        if (cnt < 0).any():
+            raise ops._lib.ApeError('voxel_down_sample failed for a cloud (status %s)' % cnt.min())
+        return [PointCloud(out[off[i]:off[i] + cnt[i]].clone()) for i in range(len(clouds))]
+    td, sd = down(targets), down(sources)
+    tf, to = pack(td); sf, so = pack(sd)
+    T, info = ops.icp_p2p(sf, torch.from_numpy(so).to(dev), tf, torch.from_numpy(to).to(dev), threshold, relative_fitness,
+                          relative_rmse, max_iteration)
+    return td, sd, T.cpu().numpy(), info.cpu().numpy()
+
+
+def icp_regression(target, source, voxel_size=5, threshold=100, global_regression=False, icp_point2point=True,
+                   icp_point2plane=True, plot=False):
+    """open3d_utils.py:63-122 with the reference's signature.  Only the configuration the reference runs is
+    grafted (point-to-point; main.py:177-179 disables the FPFH/RANSAC and point-to-plane branches).
+    Returns (target_down, source_down, T 4x4 numpy fp64)."""
+    if global_regression or (icp_point2plane and not icp_point2point):
+        raise NotImplementedError('global (FPFH/RANSAC) and point-to-plane registration are disabled by the '
+                                  'reference configuration and are not grafted')
+    td, sd, T, _ = icp_regression_batch([target], [source], voxel_size, threshold)
+    return td[0], sd[0], (T[0] if icp_point2point else np.identity(4))

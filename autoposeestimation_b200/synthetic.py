@@ -162,3 +162,20 @@ def adds_instances(seed, n_inst, n_models=21, n_model_pts=2600, n_pred_pts=500, 
     sym = np.zeros(n_models, np.uint8); sym[:n_sym] = 1
     return dict(models=models, cls=cls, q_gt=q_gt.astype(np.float32), t_gt=t_gt.astype(np.float32),
                 q_pred=q_pr.astype(np.float32), t_pred=t_pr.astype(np.float32), subsample=sub, sym=sym)
+
+
+def encoder_state_dict(seed, shapes):
+    """Seeded weights for the colour encoder (keys/shapes as given, e.g. from tests/golden/state_dict_shapes.json).
+    Scaled like He-init so activations stay O(1) through the 17 conv layers."""
+    rng = np.random.RandomState(seed)
+    sd = {}
+    for k in sorted(shapes):
+        shp = tuple(shapes[k])
+        if k.endswith('.bias'):
+            sd[k] = (rng.standard_normal(shp) * 0.01).astype(np.float32)
+        elif len(shp) == 1:                      # PReLU slope
+            sd[k] = np.full(shp, 0.25, np.float32)
+        else:
+            fan_in = int(np.prod(shp[1:]))
+            sd[k] = (rng.standard_normal(shp) * math.sqrt(2.0 / fan_in)).astype(np.float32)
+    return sd

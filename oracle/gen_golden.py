@@ -107,6 +107,22 @@ def main():
                             r=r.numpy(), t=t.numpy(), c=c.numpy(), emb_sum=emb.numpy().sum(axis=1), new_points=newp.numpy(),
                             my_r=my_r, my_t=my_t, r2=r2.numpy(), t2=t2.numpy(), final_q=fq, final_t=ft)
 
+    # ------------------------------------------------------------------ state_dict contract + colour encoder
+    import json
+    est = network.PoseNet(500, 5); refn = network.PoseRefineNet(500, 5)
+    shapes = dict(posenet={k: list(v.shape) for k, v in est.state_dict().items()},
+                  refiner={k: list(v.shape) for k, v in refn.state_dict().items()})
+    with open(os.path.join(OUT, 'state_dict_shapes.json'), 'w') as f:
+        json.dump(shapes, f, indent=0, sort_keys=True)
+    enc_sd = synth.encoder_state_dict(77, {k[len('cnn.'):]: v for k, v in shapes['posenet'].items() if k.startswith('cnn.')})
+    est.cnn.load_state_dict(synth.to_torch(enc_sd), strict=True)
+    est.cnn.eval()
+    rng = np.random.RandomState(78)
+    img = rng.standard_normal((1, 3, 40, 56)).astype(np.float32)
+    with torch.no_grad():
+        enc_out = est.cnn(torch.from_numpy(img)).numpy()
+    np.savez_compressed(os.path.join(OUT, 'encoder.npz'), img=img, out_sub4=enc_out[:, :, ::4, ::4])   # small fixture
+
     # ------------------------------------------------------------------ losses (ADD / ADD-S)
     rng = np.random.RandomState(300)
     m = 120; npt = 60

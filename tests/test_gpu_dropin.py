@@ -1,0 +1,131 @@
+"""GPU: the reference-facing drop-in modules (same names / signatures as the reference) against golden vectors of
+the reference's own modules and against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import densefusion as odf, geometry as og, icp as oicp, pose_math as pm, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _modules(seed, npts, nobj):
+    from autoposeestimation_b200.densefusion import network
+    est = network.PoseNet(npts, nobj); ref = network.PoseRefineNet(npts, nobj)
+    est.load_state_dict(synth.to_torch(synth.posenet_state_dict(seed, nobj)), strict=False)
+    ref.load_state_dict(synth.to_torch(synth.refiner_state_dict(seed + 1000, nobj)), strict=True)
+    return est.cuda().eval(), ref.cuda().eval()
+
+
+@pytest.mark.parametrize('case', [0, 1])
+def test_modules_reproduce_reference_flow(golden_dir, case):
+    """estimator -> get_new_points -> my_estimator_prediction -> refiner -> my_refined_prediction, exactly as
+    pipeline/utils.py:564-571 calls them, against the reference's own outputs (tests/golden)."""
+    from autoposeestimation_b200.densefusion.tools_utils import get_new_points, my_estimator_prediction, my_refined_prediction
+    g = np.load(os.path.join(golden_dir, 'densefusion_case%d.npz' % case))
+    seed, npts, nobj = int(g['seed']), int(g['npts']), int(g['nobj'])
+    hw = tuple(int(v) for v in g['hw'])
+    est, ref = _modules(seed, npts, nobj)
+    est.cnn = torch.nn.Identity()                      # `img` is the encoder output, as in oracle/gen_golden.py
+    out_img, cloud, choose, idx = (torch.from_numpy(a).cuda() for a in synth.posenet_inputs(seed, npts, hw, nobj))
+    with torch.no_grad():
+        pred_r, pred_t, pred_c, emb = est(out_img, cloud, choose, idx)
+        assert pred_r.shape == (1, npts, 4) and pred_t.shape == (1, npts, 3) and pred_c.shape == (1, npts, 1) and emb.shape == (1, 32, npts)
+        new_points = get_new_points(pred_r, pred_t, pred_c, cloud)
+        _, my_r, my_t = my_estimator_prediction(pred_r, pred_t, pred_c, npts, 1, cloud)
+        for _ in range(2):
+            r2, t2 = ref(new_points, emb, idx)
+        my_pred, fq, ft = my_refined_prediction(r2, t2, my_r, my_t)
+    assert np.allclose(new_points.cpu().numpy(), g['new_points'], atol=2e-5)
+    assert np.allclose(my_r, g['my_r'], atol=2e-5) and np.allclose(my_t, g['my_t'], atol=2e-5)
+    assert pm.rotation_angle_between(fq, g['final_q']) < 1e-3 and np.abs(ft - g['final_t']).max() < 1e-4
+    assert my_pred.shape == (7,)
+
+
+def test_module_handle_refreshes_after_weight_update():
+    est, ref = _modules(3, 128, 2)
+    x = torch.randn(1, 128, 3, device='cuda'); emb = torch.randn(1, 32, 128, device='cuda'); idx = torch.zeros(1, 1, dtype=torch.long, device='cuda')
+    with torch.no_grad():
+        a = ref(x, emb, idx)[1].clone()
+        ref.conv3_t.bias.add_(1.0)                     # in-place parameter update (optimizer step) -> version bump
+        b = ref(x, emb, idx)[1]
+    assert torch.allclose(b - a, torch.ones_like(a), atol=1e-5)
+
+
+def test_knearestneighbor_and_loss_refine_symmetric(golden_dir):
+    from autoposeestimation_b200.densefusion.knn import KNearestNeighbor
+    from autoposeestimation_b200.densefusion.loss import Loss
+    from autoposeestimation_b200.densefusion.loss_refiner import Loss_refine
+    g = np.load(os.path.join(golden_dir, 'knn.npz'))
+    knn = KNearestNeighbor(1)
+    inds = knn(torch.from_numpy(g['ref']), torch.from_numpy(g['qry']))         # CPU tensors are moved, as the reference does
+    assert inds.is_cuda and inds.dtype == torch.int64 and np.array_equal(inds.cpu().numpy(), g['idx_k1'])
+    gl = np.load(os.path.join(golden_dir, 'losses.npz'))
+    T = lambda k: torch.from_numpy(gl[k]).cuda()
+    idx = torch.zeros((1, 1), dtype=torch.long, device='cuda')
+    pr = T('pr1').requires_grad_(True)
+    dis, npn, ntg, pred = Loss_refine(120, [0])(pr, T('pt1'), T('target'), T('model'), idx, T('points'))
+    assert abs(float(dis) - float(gl['lr_dis_sym'][0])) < 1e-6                   # ADD-S gate 1e-5 m
+    assert np.allclose(npn.cpu().numpy(), gl['lr_newp_sym'], atol=1e-6) and np.allclose(pred.detach().cpu().numpy(), gl['lr_pred_sym'], atol=1e-6)
+    dis.backward()
+    assert pr.grad is not None and float(pr.grad.abs().sum()) > 0                # differentiable (train.py:222)
+    lo, d, npn, ntg, _ = Loss(120, [0])(T('pr_n'), T('pt_n'), T('pc_n'), T('target'), T('model'), idx, T('points'), 0.015, False)
+    assert abs(float(lo) - float(gl['l_loss_sym'])) < 1e-5 and abs(float(d) - float(gl['l_dis_sym'])) < 1e-6
+
+
+def test_get_surface_and_icp_regression():
+    from autoposeestimation_b200.pc_reconstruction.open3d_utils import PointCloud, get_surface, icp_regression, icp_regression_batch
+    fr = synth.render_ellipsoid_frame(6)
+    surf = get_surface(fr['label'], fr['depth'].astype(np.float64), fr['intr'], fr['robot2cam'], 20, 5, 20, voxel_size=2)
+    pts, _ = og.surface_backproject(fr['label'], fr['depth'].astype(np.float64), fr['intr'], fr['robot2cam'])
+    want = oicp.voxel_down_sample(pts, 2.0)
+    assert len(surf) == len(want) and np.allclose(surf.numpy(), want, atol=1e-9)
+    tgt_d, src_d, T = icp_regression(PointCloud(fr['model']), surf, voxel_size=2, threshold=10, icp_point2plane=False)
+    t_ref, s_ref, T_ref = oicp.icp_regression(fr['model'], surf.numpy(), voxel_size=2, threshold=10)
+    assert len(tgt_d) == len(t_ref) and len(src_d) == len(s_ref)
+    assert np.abs(T - T_ref).max() < 1e-5
+    with pytest.raises(NotImplementedError):
+        icp_regression(PointCloud(fr['model']), surf, global_regression=True)
+    with pytest.raises(ValueError):
+        get_surface(fr['label'], fr['depth'] + 0.5, fr['intr'], fr['robot2cam'])
+    # merge step of create_pointcloud.py:307-312
+    merged = PointCloud(torch.cat([src_d.transform(T).points, tgt_d.points])).voxel_down_sample(2)
+    assert 0 < len(merged) <= len(src_d) + len(tgt_d)
+    td, sd, Ts, info = icp_regression_batch([PointCloud(fr['model'])] * 3, [surf] * 3, voxel_size=2, threshold=10)
+    assert np.abs(Ts - T_ref).max() < 1e-5 and info.shape == (3, 4)
+
+
+def test_predict_poses_frame_block():
+    """Option-6 geometry block for two objects of one frame vs the per-object reference flow (oracle)."""
+    from autoposeestimation_b200.pipeline.utils import predict_poses, get_bbox, choose_points
+    rng = np.random.RandomState(12)
+    H, W, N, nobj = 480, 640, 1000, 3
+    est, ref = _modules(9, N, nobj)
+    enc_w = torch.randn(32, 3, device='cuda') * 0.5                      # stand-in encoder: per-pixel linear map 3 -> 32
+    est.cnn = lambda crops: torch.einsum('oc,bchw->bohw', enc_w, crops)
+    image = torch.randn(3, H, W, device='cuda')
+    depth = rng.randint(400, 900, size=(H, W)).astype(np.uint16); depth[rng.rand(H, W) < 0.05] = 0
+    masks = []
+    for (r0, c0, h, w) in ((100, 150, 70, 90), (300, 400, 50, 130)):
+        m = np.zeros((H, W), np.uint8); m[r0:r0 + h, c0:c0 + w] = 255; masks.append(m)
+    masks.append(np.zeros((H, W), np.uint8))                              # empty mask -> skipped
+    meta = {'intr': dict(ppx=320.0, ppy=240.0, fx=615.0, fy=615.0), 'depth_scale': 0.001}
+    seed_state = np.random.RandomState(77)
+    out = predict_poses(image, depth, meta, masks, [0, 2, 1], est, ref, num_points=N, refine_mode='live', rng=seed_state)
+    assert sorted(out) == [0, 1]
+    sd_e = synth.to_torch(synth.posenet_state_dict(9, nobj)); sd_r = synth.to_torch(synth.refiner_state_dict(1009, nobj))
+    seed_state = np.random.RandomState(77)
+    for i, cls in ((0, 0), (1, 2)):
+        ml = masks[i] == 255
+        bbox = get_bbox(ml)
+        ch = choose_points(ml & (depth != 0), bbox, N, seed_state)
+        cloud = og.backproject_choose(depth, bbox, ch, 320.0, 240.0, 615.0, 615.0, 0.001)
+        crop = image[:, bbox[0]:bbox[1], bbox[2]:bbox[3]][None]
+        out_img = est.cnn(crop).cpu()
+        with torch.no_grad():
+            res = odf.live_prediction(sd_e, sd_r, out_img, torch.from_numpy(cloud)[None], torch.from_numpy(ch.astype(np.int64))[None, None],
+                                      torch.tensor([[cls]]), nobj, refine_calls=2)
+        assert pm.rotation_angle_between(out[i]['rotation'], res['q']) < 1e-3
+        assert np.abs(out[i]['position'] - res['t']).max() < 1e-4
