@@ -1,0 +1,259 @@
+// Persistent tcgen05 / TMEM / TMA GEMM for the DenseFusion 1x1-conv stacks (sm_100a only), second generation.
+//
+//   D[128 x bn] (fp32, TMEM) = sum over 3 split-bf16 passes of  A_p[128 x K] * W_p[bn x K]^T ,  bn in {128, 256}
+//
+// What changed against gemm_tc.cuh (kept as APE_GEMM_TCGEN05_V1 for A/B runs):
+//   * 128 x 256 tiles: one tcgen05.mma (M=128, N=256, K=16) reads 4 KB of A + 8 KB of B from shared memory per
+//     128 tensor-pipe cycles (96 B/clk); the 128 x 128 tile needs 8 KB per 64 cycles = 128 B/clk, which is the
+//     whole shared-memory bandwidth of an SM and is why v1 topped out near 1000 TFLOP/s.
+//   * persistent CTAs (one per SM, static round-robin over tiles, n fastest so the A row-block stays L2-hot),
+//     4-stage x 48 KB TMA ring that runs across tile boundaries;
+//   * two TMEM accumulators (2 x 256 columns): the epilogue of tile i overlaps the MMAs of tile i+1;
+//   * epilogue stores through shared memory + TMA (cp.async.bulk.tensor store, 64-byte-swizzled 32 x 32 boxes
+//     per warp, double-buffered) instead of 16-byte-per-row scattered global stores.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
+// (TMEM lane quadrant = warp % 4).
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace ape {
+namespace tc2 {
+
+using namespace ape::tc;   // PTX wrappers, Params, descriptors
+
+constexpr int kStages2 = 4;
+constexpr int kStageA = BM * BK * 2;                  // 16 KB
+constexpr int kStageB = 256 * BK * 2;                 // 32 KB (bn = 128 tiles use the first half)
+constexpr int kStage = kStageA + kStageB;             // 48 KB
+constexpr int kStgBuf = 32 * 32 * 2;                  // one 32-row x 32-col bf16 box = 2 KB
+constexpr int kStgWarp = 2 /*double buffer*/ * 2 /*hi, lo*/ * kStgBuf;   // 8 KB per epilogue warp
+constexpr int kStaging = 4 * kStgWarp;                // 32 KB (also the 4 KB column-sum scratch)
+constexpr int kSmemBytes2 = kStages2 * kStage + kStaging + 256 /*barriers*/ + 1024 /*align slack*/;
+constexpr uint32_t kTmemCols2 = 512;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+struct Tile { int g, m_tile, n0, bn; };
+
+// Static tile order: n fastest, then m, then group.  `wide` tiles are 256 columns (last one 128 when N % 256 != 0).
+__device__ __forceinline__ Tile decode_tile(int t, const Params& p, int m_tiles, int n_tiles, int bn_full) {
+    Tile r;
+    const int n_idx = t % n_tiles;
+    const int rest = t / n_tiles;
+    r.m_tile = rest % m_tiles;
+    r.g = rest / m_tiles;
+    r.n0 = n_idx * bn_full;
+    r.bn = min(bn_full, p.N - r.n0);
+    return r;
+}
+
+// grid = min(#tiles, #SMs).  Load maps: box {64 (K), 128 (rows)}, SWIZZLE_128B.  Store maps (EPI_RELU_SPLIT):
+// box {32 (cols), 32 (rows)}, SWIZZLE_64B.
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                                  const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
+                                  const Params p, const int bn_full)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char* staging = smem + kStages2 * kStage;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStaging);
+    uint64_t* empty_bar = full_bar + kStages2;
+    uint64_t* tfull_bar = empty_bar + kStages2;       // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;             // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = p.M / BM;
+    const int n_tiles = (p.N + bn_full - 1) / bn_full;
+    const int total_tiles = p.groups * m_tiles * n_tiles;
+    const int kb_per_pass = p.K / BK;
+    const int iters_per_tile = 3 * kb_per_pass;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
+        tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo);
+        if (p.mode == EPI_RELU_SPLIT) { tma_prefetch_desc(&map_o_hi); tma_prefetch_desc(&map_o_lo); }
+#pragma unroll
+        for (int s = 0; s < kStages2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols2);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const Tile tl = decode_tile(t, p, m_tiles, n_tiles, bn_full);
+                const int a_k = p.a_k0 + tl.g * p.a_kg;
+                const int a_row = tl.m_tile * BM;
+                const int w_row = tl.g * p.N + tl.n0;
+                const uint32_t bytes = (uint32_t)(kStageA + tl.bn * BK * 2);
+                for (int i = 0; i < iters_per_tile; ++i, ++it) {
+                    const int s = it % kStages2;
+                    const uint32_t ph = (uint32_t)(it / kStages2) & 1u;
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    const int pass = i / kb_per_pass, kb = i - pass * kb_per_pass;
+                    // pass 0: A_lo*W_hi, pass 1: A_hi*W_lo, pass 2: A_hi*W_hi (small terms first)
+                    const CUtensorMap* ma = (pass == 0) ? &map_a_lo : &map_a_hi;
+                    const CUtensorMap* mw = (pass == 1) ? &map_w_lo : &map_w_hi;
+                    unsigned char* sa = smem + s * kStage;
+                    unsigned char* sb = sa + kStageA;
+                    mbar_expect_tx(&full_bar[s], bytes);
+                    tma_load_2d(sa, ma, &full_bar[s], a_k + kb * BK, a_row);
+                    tma_load_2d(sb, mw, &full_bar[s], kb * BK, w_row);
+                    if (tl.bn > 128) tma_load_2d(sb + 128 * BK * 2, mw, &full_bar[s], kb * BK, w_row + 128);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int it = 0, lt = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+                const Tile tl = decode_tile(t, p, m_tiles, n_tiles, bn_full);
+                const int acc = lt & 1;
+                const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
+                mbar_wait(&tempty_bar[acc], aph ^ 1u);            // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t idesc = make_idesc_bf16(BM, tl.bn);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+                for (int i = 0; i < iters_per_tile; ++i, ++it) {
+                    const int s = it % kStages2;
+                    const uint32_t ph = (uint32_t)(it / kStages2) & 1u;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem + s * kStage));
+                    const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem + s * kStage + kStageA));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty_bar[s]);                   // frees the smem stage once these MMAs retire
+                }
+                umma_commit(&tfull_bar[acc]);                     // accumulator complete
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
+        const int quad = warp & 3;
+        unsigned char* stg = staging + quad * kStgWarp;           // [buf][hi|lo][32 rows x 64 B], SWIZZLE_64B
+        float* s_colsum = reinterpret_cast<float*>(staging);      // EPI_RELU_COLSUM: [4][256]
+        const int GN = p.groups * p.N;
+        int lt = 0;
+        uint32_t chunk_ctr = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+            const Tile tl = decode_tile(t, p, m_tiles, n_tiles, bn_full);
+            const int acc = lt & 1;
+            const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
+            mbar_wait(&tfull_bar[acc], aph);
+            tc_fence_after();
+            const int row0 = tl.m_tile * BM + quad * 32;
+            const int row = row0 + lane;
+            const int col_g = tl.g * p.N + tl.n0;                 // first column within [groups*N]
+            const float* bias = p.bias + (p.bias_obj_rows > 0 ? (size_t)(row0 / p.bias_obj_rows) * (size_t)GN : 0) + col_g;
+            const bool valid = (p.mode != EPI_RELU_COLSUM) || ((row % p.rows_per_obj) < p.valid_rows);
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256);
+#pragma unroll 1
+            for (int c0 = 0; c0 < tl.bn; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_addr + (uint32_t)c0, v);
+                if (c0 + 32 >= tl.bn) {                           // last read of this accumulator: hand it back early
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                }
+                const float bl = __ldg(bias + c0 + lane);         // coalesced; broadcast by shuffle below
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(__uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bl, j), 0.0f);
+                if (p.mode == EPI_RELU_SPLIT) {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                        const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h);
+                        const float r0 = f[2 * j] - __uint_as_float(hu << 16);
+                        const float r1 = f[2 * j + 1] - __uint_as_float(hu & 0xffff0000u);
+                        const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+                        hi[j] = hu; lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+                    }
+                    const uint32_t buf = chunk_ctr & 1u;
+                    unsigned char* sh = stg + buf * (2 * kStgBuf);
+                    unsigned char* sl = sh + kStgBuf;
+                    if (lane == 0) bulk_wait_read<1>();           // the store issued two chunks ago has read its buffer
+                    __syncwarp();
+                    const uint32_t sw = (uint32_t)(lane >> 1) & 3u;   // 64-byte swizzle: 16 B chunk ^= (row / 2) % 4
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t off = (uint32_t)lane * 64u + ((uint32_t)j ^ sw) * 16u;
+                        *reinterpret_cast<uint4*>(sh + off) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                        *reinterpret_cast<uint4*>(sl + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int oc = p.o_c0 + col_g + c0;
+                        tma_store_2d(&map_o_hi, sh, oc, row0);
+                        tma_store_2d(&map_o_lo, sl, oc, row0);
+                        bulk_commit();
+                    }
+                    ++chunk_ctr;
+                } else {
+                    // masked column sum over this warp's 32 rows: butterfly transpose-reduce, lane j ends
+                    // with the sum of column c0 + j
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = valid ? f[j] : 0.0f;
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool upper = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const float send = upper ? f[i] : f[i + off];
+                            const float keep = upper ? f[i + off] : f[i];
+                            f[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    s_colsum[quad * 256 + c0 + lane] = f[0];
+                }
+            }
+            if (p.mode == EPI_RELU_COLSUM) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");        // the four epilogue warps only
+                const int tt = threadIdx.x - 64;                       // 0..127
+                for (int c = tt; c < tl.bn; c += 128) {
+                    // fixed order over the quadrants -> deterministic
+                    const float sum = (s_colsum[c] + s_colsum[256 + c]) + (s_colsum[512 + c] + s_colsum[768 + c]);
+                    p.colsum[(size_t)tl.m_tile * (size_t)GN + col_g + c] = sum;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");        // scratch is free for the next tile
+            }
+        }
+        if (p.mode == EPI_RELU_SPLIT && lane == 0) bulk_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols2);
+    }
+}
+
+}  // namespace tc2
+}  // namespace ape

@@ -104,7 +104,11 @@ def test_predict_poses_frame_block():
     H, W, N, nobj = 480, 640, 1000, 3
     est, ref = _modules(9, N, nobj)
     enc_w = torch.randn(32, 3, device='cuda') * 0.5                      # stand-in encoder: per-pixel linear map 3 -> 32
-    est.cnn = lambda crops: torch.einsum('oc,bchw->bohw', enc_w, crops)
+
+    class _Enc(torch.nn.Module):
+        def forward(self, crops):
+            return torch.einsum('oc,bchw->bohw', enc_w, crops)
+    est.cnn = _Enc()
     image = torch.randn(3, H, W, device='cuda')
     depth = rng.randint(400, 900, size=(H, W)).astype(np.uint16); depth[rng.rand(H, W) < 0.05] = 0
     masks = []
