@@ -11,7 +11,8 @@
 //                      into a per-object bias (it is identical for every point of an object)
 // Kernels: front-end (gather + K=3 / K=32 convs, SIMT), tcgen05 split-bf16 GEMM (gemm_tc.cuh) for every
 // K>=64 layer, small dense layers / heads (SIMT fp32), final conv4 + sigmoid + class select.
-#include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -284,25 +285,34 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] tensor, box {64 cols, 128 rows}, 128-byte swizzle
-static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems) {
+// 2-D bf16 row-major [rows, cols] tensor.  Load maps: box {64 cols, 128 rows}, 128-byte swizzle (UMMA operand
+// layout); store maps: box {32 cols, 32 rows}, 64-byte swizzle (one epilogue warp's chunk, gemm_tc2.cuh).
+static int make_map_box(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                        uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swz) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { ape::set_error("cuTensorMapEncodeTiled entry point not available"); return APE_ERR_CUDA; }
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {ld_elems * 2};
-    cuuint32_t box[2] = {64, 128};
+    cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { ape::set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return APE_ERR_CUDA; }
     return APE_OK;
+}
+static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems) {
+    return make_map_box(map, base, rows, cols, ld_elems, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+static int make_store_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems) {
+    return make_map_box(map, base, rows, cols, ld_elems, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 struct SplitMat {            // split-bf16 matrix with its TMA maps
     bf16 *hi = nullptr, *lo = nullptr;
     int rows = 0, cols = 0;
-    CUtensorMap map_hi, map_lo;
+    CUtensorMap map_hi, map_lo;          // TMA loads (GEMM operands)
+    CUtensorMap st_hi, st_lo;            // TMA stores (activation buffers only)
 };
 
 struct DevF32 { float* p = nullptr; size_t n = 0; };
@@ -378,7 +388,9 @@ static int alloc_split(ape_net* net, SplitMat& m, size_t rows, int cols) {
     APE_CUDA(cudaMemset(m.lo, 0, bytes));
     m.rows = (int)rows; m.cols = cols;
     if ((rc = make_map(&m.map_hi, m.hi, rows, cols, cols))) return rc;
-    return make_map(&m.map_lo, m.lo, rows, cols, cols);
+    if ((rc = make_map(&m.map_lo, m.lo, rows, cols, cols))) return rc;
+    if ((rc = make_store_map(&m.st_hi, m.hi, rows, cols, cols))) return rc;
+    return make_store_map(&m.st_lo, m.lo, rows, cols, cols);
 }
 
 // vertical concatenation of [rows_i, cols] fp32 host matrices, keeping columns [c0, c0+ncols) of each
@@ -489,6 +501,9 @@ int ape_net_create(int kind, const float* const* w, int n_tensors, int num_obj, 
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(ape::tc::gemm_split_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              ape::tc::kSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(ape::tc2::gemm_split_bf16_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     ape::tc2::kSmemBytes2);
         if (e != cudaSuccess) { ape::set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); ape_net_destroy(net); return APE_ERR_CUDA; }
         attr_set = true;
     }
@@ -509,16 +524,37 @@ extern "C" __attribute__((visibility("default")))
 int ape_net_set_gemm(ape_net* net, int gemm_impl)
 {
     APE_REQUIRE(net, "ape_net_set_gemm: null handle");
-    APE_REQUIRE(gemm_impl == APE_GEMM_TCGEN05 || gemm_impl == APE_GEMM_SIMT, "ape_net_set_gemm: unknown implementation");
+    APE_REQUIRE(gemm_impl == APE_GEMM_TCGEN05 || gemm_impl == APE_GEMM_SIMT || gemm_impl == APE_GEMM_TCGEN05_V1,
+                "ape_net_set_gemm: unknown implementation");
     net->gemm_impl = gemm_impl;
     return APE_OK;
 }
 
 // One GEMM layer: out = relu(A[:, a_k0 + g*a_kg : +K] * W_g^T + bias)
-static int run_gemm(ape_net* net, const SplitMat& A, const SplitMat& W, const ape::tc::Params& p, cudaStream_t s, const char* label)
+// Tile-width choice per layer (bit i of APE_GEMM_WIDE_MASK; layers: conv2, conv5, conv6, heads1, heads2, heads3).
+// Tuning knob only: both widths give bit-identical results (same K order, same accumulator arithmetic).
+static bool wide_layer(int layer) {
+    static int mask = -1;
+    if (mask < 0) {
+        const char* e = getenv("APE_GEMM_WIDE_MASK");
+        mask = e ? (int)strtol(e, nullptr, 0) & 0x3f : 0x3f;
+    }
+    return (mask >> layer) & 1;
+}
+
+// `out` is the activation buffer EPI_RELU_SPLIT writes (its TMA store maps); `wide` selects 128 x 256 tiles.
+static int run_gemm(ape_net* net, const SplitMat& A, const SplitMat& W, const SplitMat* out, const ape::tc::Params& p, bool wide,
+                    cudaStream_t s, const char* label)
 {
     ape::ProfScope prof_(label, s);
     if (net->gemm_impl == APE_GEMM_TCGEN05) {
+        const int bn_full = (wide && p.N >= 256) ? 256 : 128;
+        const int tiles = p.groups * (p.M / ape::tc::BM) * ((p.N + bn_full - 1) / bn_full);
+        const int grid = tiles < ape::sm_count() ? tiles : ape::sm_count();
+        const SplitMat& O = out ? *out : A;          // EPI_RELU_COLSUM never touches the store maps
+        ape::tc2::gemm_split_bf16_persistent_kernel<<<grid, ape::tc::kThreads, ape::tc2::kSmemBytes2, s>>>(
+            A.map_hi, A.map_lo, W.map_hi, W.map_lo, O.st_hi, O.st_lo, p, bn_full);
+    } else if (net->gemm_impl == APE_GEMM_TCGEN05_V1) {
         dim3 grid(p.N / ape::tc::BN, p.M / ape::tc::BM, p.groups);
         ape::tc::gemm_split_bf16_kernel<<<grid, ape::tc::kThreads, ape::tc::kSmemBytes, s>>>(A.map_hi, A.map_lo, W.map_hi,
                                                                                            W.map_lo, p);
@@ -564,15 +600,15 @@ static int run_trunk(ape_net* net, const float* feat_src, int hw, const float* c
     const bool pn = net->kind == APE_NET_POSENET, pn_ = pn;
     // conv2 (PF[:,0:64] -> PF[:,128:256]) and e_conv2 (PF[:,64:128] -> PF[:,256:384]) as two groups
     ape::tc::Params p = split_layer(M, 128, 64, 2, 0, 64, net->b_c2e2.p, net->PF, 128);
-    if ((rc = run_gemm(net, net->PF, net->W_c2e2, p, s, pn_ ? "gemm.pn.conv2" : "gemm.rf.conv2"))) return rc;
+    if ((rc = run_gemm(net, net->PF, net->W_c2e2, &net->PF, p, wide_layer(0), s, pn_ ? "gemm.pn.conv2" : "gemm.rf.conv2"))) return rc;
     // conv5: PoseNet reads pointfeat_2 = PF[:,128:384] (network.py:62); refiner reads pointfeat_3 = PF[:,0:384] (:162)
     p = split_layer(M, 512, pn ? 256 : 384, 1, pn ? 128 : 0, 0, net->b_c5.p, net->H5, 0);
-    if ((rc = run_gemm(net, net->PF, net->W_c5, p, s, pn ? "gemm.pn.conv5" : "gemm.rf.conv5"))) return rc;
+    if ((rc = run_gemm(net, net->PF, net->W_c5, &net->H5, p, wide_layer(1), s, pn ? "gemm.pn.conv5" : "gemm.rf.conv5"))) return rc;
     // conv6 + ReLU + AvgPool1d: masked per-tile column sums, never materialising [1024, N]
     memset(&p, 0, sizeof(p));
     p.M = M; p.N = 1024; p.K = 512; p.groups = 1; p.bias = net->b_c6.p; p.mode = ape::tc::EPI_RELU_COLSUM;
     p.colsum = net->CS.p; p.rows_per_obj = Np; p.valid_rows = N;
-    if ((rc = run_gemm(net, net->H5, net->W_c6, p, s, pn ? "gemm.pn.conv6" : "gemm.rf.conv6"))) return rc;
+    if ((rc = run_gemm(net, net->H5, net->W_c6, nullptr, p, wide_layer(2), s, pn ? "gemm.pn.conv6" : "gemm.rf.conv6"))) return rc;
     dim3 gp(1024 / 256, B);
     ape::ProfScope prof_("pool_finish", s);
     ape::pool_finish_kernel<<<gp, 256, 0, s>>>(net->CS.p, Np / 128, 1024, (float)N, net->AP.p);
@@ -610,11 +646,11 @@ int ape_posenet_forward(ape_net* net, const float* out_img, int hw, const float*
     // conv1_{r,t,c} on [pointfeat_1 | pointfeat_2] (K=384), N = 3*640, per-object bias
     ape::tc::Params p = split_layer(M, 1920, 384, 1, 0, 0, net->GB.p, net->H1, 0);
     p.bias_obj_rows = Np;
-    if ((rc = run_gemm(net, net->PF, net->W_h1, p, s, "gemm.pn.heads1"))) return rc;
+    if ((rc = run_gemm(net, net->PF, net->W_h1, &net->H1, p, wide_layer(3), s, "gemm.pn.heads1"))) return rc;
     p = split_layer(M, 256, 640, 3, 0, 640, net->b_h2.p, net->H2, 0);          // conv2_{r,t,c}
-    if ((rc = run_gemm(net, net->H1, net->W_h2, p, s, "gemm.pn.heads2"))) return rc;
+    if ((rc = run_gemm(net, net->H1, net->W_h2, &net->H2, p, wide_layer(4), s, "gemm.pn.heads2"))) return rc;
     p = split_layer(M, 128, 256, 3, 0, 256, net->b_h3.p, net->H3, 0);          // conv3_{r,t,c}
-    if ((rc = run_gemm(net, net->H2, net->W_h3, p, s, "gemm.pn.heads3"))) return rc;
+    if ((rc = run_gemm(net, net->H2, net->W_h3, &net->H3, p, wide_layer(5), s, "gemm.pn.heads3"))) return rc;
     dim3 go((N + 7) / 8 < 64 ? (N + 7) / 8 : 64, B);
     ape::ProfScope prof_("posenet_out", s);
     ape::posenet_out_kernel<<<go, 256, 0, s>>>(net->H3.hi, net->H3.lo, 384, N, Np, net->w4r.p, net->b4r.p, net->w4t.p,
