@@ -9,8 +9,9 @@
 //   * persistent CTAs (one per SM, static round-robin over tiles, n fastest so the A row-block stays L2-hot),
 //     4-stage x 48 KB TMA ring that runs across tile boundaries;
 //   * two TMEM accumulators (2 x 256 columns): the epilogue of tile i overlaps the MMAs of tile i+1;
-//   * epilogue stores through shared memory + TMA (cp.async.bulk.tensor store, 64-byte-swizzled 32 x 32 boxes
-//     per warp, double-buffered) instead of 16-byte-per-row scattered global stores.
+//   * epilogue stores through shared memory + TMA (cp.async.bulk.tensor store, one 128-byte-swizzled 32-row x
+//     64-column box of hi and of lo per warp and chunk; the TMA engine drains the staging buffer while the warp
+//     converts the next chunk) instead of 16-byte-per-row scattered global stores.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
 // (TMEM lane quadrant = warp % 4).
 #pragma once
@@ -25,8 +26,8 @@ constexpr int kStages2 = 4;
 constexpr int kStageA = BM * BK * 2;                  // 16 KB
 constexpr int kStageB = 256 * BK * 2;                 // 32 KB (bn = 128 tiles use the first half)
 constexpr int kStage = kStageA + kStageB;             // 48 KB
-constexpr int kStgBuf = 32 * 32 * 2;                  // one 32-row x 32-col bf16 box = 2 KB
-constexpr int kStgWarp = 2 /*double buffer*/ * 2 /*hi, lo*/ * kStgBuf;   // 8 KB per epilogue warp
+constexpr int kStgBuf = 32 * 64 * 2;                  // one 32-row x 64-col bf16 box = 4 KB
+constexpr int kStgWarp = 2 /*hi, lo*/ * kStgBuf;      // 8 KB per epilogue warp
 constexpr int kStaging = 4 * kStgWarp;                // 32 KB (also the 4 KB column-sum scratch)
 constexpr int kSmemBytes2 = kStages2 * kStage + kStaging + 256 /*barriers*/ + 1024 /*align slack*/;
 constexpr uint32_t kTmemCols2 = 512;
@@ -58,7 +59,7 @@ __device__ __forceinline__ Tile decode_tile(int t, const Params& p, int m_tiles,
 }
 
 // grid = min(#tiles, #SMs).  Load maps: box {64 (K), 128 (rows)}, SWIZZLE_128B.  Store maps (EPI_RELU_SPLIT):
-// box {32 (cols), 32 (rows)}, SWIZZLE_64B.
+// box {64 (cols), 32 (rows)}, SWIZZLE_128B.
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                                   const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -154,11 +155,10 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
     } else {
         // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
         const int quad = warp & 3;
-        unsigned char* stg = staging + quad * kStgWarp;           // [buf][hi|lo][32 rows x 64 B], SWIZZLE_64B
+        unsigned char* stg = staging + quad * kStgWarp;           // [hi|lo][32 rows x 128 B], SWIZZLE_128B
         float* s_colsum = reinterpret_cast<float*>(staging);      // EPI_RELU_COLSUM: [4][256]
         const int GN = p.groups * p.N;
         int lt = 0;
-        uint32_t chunk_ctr = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
             const Tile tl = decode_tile(t, p, m_tiles, n_tiles, bn_full);
             const int acc = lt & 1;
@@ -171,39 +171,40 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
             const float* bias = p.bias + (p.bias_obj_rows > 0 ? (size_t)(row0 / p.bias_obj_rows) * (size_t)GN : 0) + col_g;
             const bool valid = (p.mode != EPI_RELU_COLSUM) || ((row % p.rows_per_obj) < p.valid_rows);
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256);
+            if (p.mode == EPI_RELU_SPLIT) {
 #pragma unroll 1
-            for (int c0 = 0; c0 < tl.bn; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(t_addr + (uint32_t)c0, v);
-                if (c0 + 32 >= tl.bn) {                           // last read of this accumulator: hand it back early
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                }
-                const float bl = __ldg(bias + c0 + lane);         // coalesced; broadcast by shuffle below
-                float f[32];
+                for (int c0 = 0; c0 < tl.bn; c0 += 64) {
+                    uint32_t hi[32], lo[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = fmaxf(__uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bl, j), 0.0f);
-                if (p.mode == EPI_RELU_SPLIT) {
-                    uint32_t hi[16], lo[16];
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(t_addr + (uint32_t)(c0 + 32 * h), v);
+                        if (h == 1 && c0 + 64 >= tl.bn) {             // last read of this accumulator: hand it back early
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                        }
+                        const float bl = __ldg(bias + c0 + 32 * h + lane);   // coalesced; broadcast by shuffle below
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                        const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h);
-                        const float r0 = f[2 * j] - __uint_as_float(hu << 16);
-                        const float r1 = f[2 * j + 1] - __uint_as_float(hu & 0xffff0000u);
-                        const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
-                        hi[j] = hu; lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+                        for (int j = 0; j < 16; ++j) {
+                            const float f0 = fmaxf(__uint_as_float(v[2 * j]) + __shfl_sync(0xffffffffu, bl, 2 * j), 0.0f);
+                            const float f1 = fmaxf(__uint_as_float(v[2 * j + 1]) + __shfl_sync(0xffffffffu, bl, 2 * j + 1), 0.0f);
+                            const __nv_bfloat162 hb = __floats2bfloat162_rn(f0, f1);
+                            const uint32_t hu = *reinterpret_cast<const uint32_t*>(&hb);
+                            const __nv_bfloat162 lb = __floats2bfloat162_rn(f0 - __uint_as_float(hu << 16),
+                                                                            f1 - __uint_as_float(hu & 0xffff0000u));
+                            hi[16 * h + j] = hu; lo[16 * h + j] = *reinterpret_cast<const uint32_t*>(&lb);
+                        }
                     }
-                    const uint32_t buf = chunk_ctr & 1u;
-                    unsigned char* sh = stg + buf * (2 * kStgBuf);
-                    unsigned char* sl = sh + kStgBuf;
-                    if (lane == 0) bulk_wait_read<1>();           // the store issued two chunks ago has read its buffer
+                    // single staging buffer: the previous chunk's TMA store read it while this chunk was converted
+                    if (lane == 0) bulk_wait_read<0>();
                     __syncwarp();
-                    const uint32_t sw = (uint32_t)(lane >> 1) & 3u;   // 64-byte swizzle: 16 B chunk ^= (row / 2) % 4
+                    unsigned char* sh = stg;
+                    unsigned char* sl = stg + kStgBuf;
+                    const uint32_t sw = (uint32_t)lane & 7u;          // 128-byte swizzle: 16 B chunk ^= row % 8
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t off = (uint32_t)lane * 64u + ((uint32_t)j ^ sw) * 16u;
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t off = (uint32_t)lane * 128u + ((uint32_t)j ^ sw) * 16u;
                         *reinterpret_cast<uint4*>(sh + off) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
                         *reinterpret_cast<uint4*>(sl + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
                     }
@@ -215,8 +216,21 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
                         tma_store_2d(&map_o_lo, sl, oc, row0);
                         bulk_commit();
                     }
-                    ++chunk_ctr;
-                } else {
+                }
+            } else {
+#pragma unroll 1
+                for (int c0 = 0; c0 < tl.bn; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_addr + (uint32_t)c0, v);
+                    if (c0 + 32 >= tl.bn) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    }
+                    const float bl = __ldg(bias + c0 + lane);
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(__uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bl, j), 0.0f);
                     // masked column sum over this warp's 32 rows: butterfly transpose-reduce, lane j ends
                     // with the sum of column c0 + j
 #pragma unroll

@@ -11,7 +11,7 @@
 //                      into a per-object bias (it is identical for every point of an object)
 // Kernels: front-end (gather + K=3 / K=32 convs, SIMT), tcgen05 split-bf16 GEMM (gemm_tc.cuh) for every
 // K>=64 layer, small dense layers / heads (SIMT fp32), final conv4 + sigmoid + class select.
-#include "gemm_tc2.cuh"
+#include "gemm_tc3.cuh"
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -286,7 +286,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D bf16 row-major [rows, cols] tensor.  Load maps: box {64 cols, 128 rows}, 128-byte swizzle (UMMA operand
-// layout); store maps: box {32 cols, 32 rows}, 64-byte swizzle (one epilogue warp's chunk, gemm_tc2.cuh).
+// layout); store maps: box {64 cols, 32 rows}, 128-byte swizzle (one epilogue warp's chunk, gemm_tc2.cuh).
 static int make_map_box(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                         uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swz) {
     EncodeTiledFn fn = get_encode_fn();
@@ -305,13 +305,14 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t 
     return make_map_box(map, base, rows, cols, ld_elems, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 static int make_store_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems) {
-    return make_map_box(map, base, rows, cols, ld_elems, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    return make_map_box(map, base, rows, cols, ld_elems, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 struct SplitMat {            // split-bf16 matrix with its TMA maps
     bf16 *hi = nullptr, *lo = nullptr;
     int rows = 0, cols = 0;
-    CUtensorMap map_hi, map_lo;          // TMA loads (GEMM operands)
+    CUtensorMap map_hi, map_lo;          // TMA loads (GEMM operands), box {64, 128 rows}
+    CUtensorMap w64_hi, w64_lo;          // weights only: box {64, 64 rows} (each CTA of a pair stages half of the B rows)
     CUtensorMap st_hi, st_lo;            // TMA stores (activation buffers only)
 };
 
@@ -377,7 +378,9 @@ static int upload_split(ape_net* net, SplitMat& m, const std::vector<float>& hos
     APE_CUDA(cudaMemcpy(m.lo, lo.data(), host.size() * 2, cudaMemcpyHostToDevice));
     m.rows = rows; m.cols = cols;
     if ((rc = make_map(&m.map_hi, m.hi, rows, cols, cols))) return rc;
-    return make_map(&m.map_lo, m.lo, rows, cols, cols);
+    if ((rc = make_map(&m.map_lo, m.lo, rows, cols, cols))) return rc;
+    if ((rc = make_map_box(&m.w64_hi, m.hi, rows, cols, cols, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    return make_map_box(&m.w64_lo, m.lo, rows, cols, cols, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 static int alloc_split(ape_net* net, SplitMat& m, size_t rows, int cols) {
     int rc;
@@ -427,8 +430,12 @@ int ape_net_create(int kind, const float* const* w, int n_tensors, int num_obj, 
     ape_net* net = new ape_net();
     net->kind = kind; net->num_obj = num_obj; net->max_batch = max_batch; net->max_points = max_points;
     net->np_max = (max_points + 127) / 128 * 128;
-    const size_t R = (size_t)max_batch * net->np_max;
+    const size_t R = ((size_t)max_batch * net->np_max + 255) / 256 * 256;    // CTA pairs take 256 rows at a time
     int rc = APE_OK;
+    {
+        const char* e = getenv("APE_GEMM_IMPL");          // bring-up / A-B knob; the default is the product path
+        if (e) net->gemm_impl = (int)strtol(e, nullptr, 0);
+    }
 #define TRY(x) do { if ((rc = (x)) != APE_OK) { ape_net_destroy(net); return rc; } } while (0)
     TRY(upload_f32(net, net->w1, w[0], 64 * 3));   TRY(upload_f32(net, net->b1, w[1], 64));
     TRY(upload_f32(net, net->we1, w[2], 64 * 32)); TRY(upload_f32(net, net->be1, w[3], 64));
@@ -471,7 +478,7 @@ int ape_net_create(int kind, const float* const* w, int n_tensors, int num_obj, 
         TRY(alloc_split(net, net->H1, R, 1920));
         TRY(alloc_split(net, net->H2, R, 768));
         TRY(alloc_split(net, net->H3, R, 384));
-        TRY(alloc_f32(net, net->GB, (size_t)max_batch * 1920));
+        TRY(alloc_f32(net, net->GB, (size_t)(max_batch + 1) * 1920));   // +1: the bias row the padding tile of an odd batch reads
         const size_t BN_ = (size_t)max_batch * max_points;
         TRY(alloc_f32(net, net->s_r, BN_ * 4)); TRY(alloc_f32(net, net->s_t, BN_ * 3)); TRY(alloc_f32(net, net->s_c, BN_));
         TRY(alloc_f32(net, net->s_emb, BN_ * 32)); TRY(alloc_f32(net, net->s_newp, BN_ * 3));
@@ -504,6 +511,9 @@ int ape_net_create(int kind, const float* const* w, int n_tensors, int num_obj, 
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(ape::tc2::gemm_split_bf16_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      ape::tc2::kSmemBytes2);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(ape::tc3::gemm_split_bf16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     ape::tc3::kSmemBytes3);
         if (e != cudaSuccess) { ape::set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); ape_net_destroy(net); return APE_ERR_CUDA; }
         attr_set = true;
     }
@@ -524,8 +534,7 @@ extern "C" __attribute__((visibility("default")))
 int ape_net_set_gemm(ape_net* net, int gemm_impl)
 {
     APE_REQUIRE(net, "ape_net_set_gemm: null handle");
-    APE_REQUIRE(gemm_impl == APE_GEMM_TCGEN05 || gemm_impl == APE_GEMM_SIMT || gemm_impl == APE_GEMM_TCGEN05_V1,
-                "ape_net_set_gemm: unknown implementation");
+    APE_REQUIRE(gemm_impl >= APE_GEMM_TCGEN05 && gemm_impl <= APE_GEMM_TCGEN05_PAIR, "ape_net_set_gemm: unknown implementation");
     net->gemm_impl = gemm_impl;
     return APE_OK;
 }
@@ -547,7 +556,15 @@ static int run_gemm(ape_net* net, const SplitMat& A, const SplitMat& W, const Sp
                     cudaStream_t s, const char* label)
 {
     ape::ProfScope prof_(label, s);
-    if (net->gemm_impl == APE_GEMM_TCGEN05) {
+    if (net->gemm_impl == APE_GEMM_TCGEN05_PAIR) {
+        const int bn_full = (wide && p.N >= 256) ? 256 : 128;
+        const int n_wide = bn_full == 256 ? p.N / 256 : 0;
+        const int tiles = p.groups * (p.M / 256) * (n_wide + (p.N - n_wide * 256) / 128);
+        const int pairs = tiles < ape::sm_count() / 2 ? tiles : ape::sm_count() / 2;
+        const SplitMat& O = out ? *out : A;          // EPI_RELU_COLSUM never touches the store maps
+        ape::tc3::gemm_split_bf16_pair_kernel<<<2 * pairs, ape::tc3::kThreads3, ape::tc3::kSmemBytes3, s>>>(
+            A.map_hi, A.map_lo, W.w64_hi, W.w64_lo, O.st_hi, O.st_lo, p, bn_full);
+    } else if (net->gemm_impl == APE_GEMM_TCGEN05) {
         const int bn_full = (wide && p.N >= 256) ? 256 : 128;
         const int tiles = p.groups * (p.M / ape::tc::BM) * ((p.N + bn_full - 1) / bn_full);
         const int grid = tiles < ape::sm_count() ? tiles : ape::sm_count();
@@ -583,7 +600,7 @@ static int run_trunk(ape_net* net, const float* feat_src, int hw, const float* c
                      float* emb_out, cudaStream_t s)
 {
     const int Np = (N + 127) / 128 * 128;
-    const int M = B * Np;
+    const int M = (B * Np + 255) / 256 * 256;       // GEMM rows: whole CTA-pair tiles (rows past B*Np are never read back)
     dim3 gf((Np + 63) / 64, B);
     {
     ape::ProfScope prof_("frontend", s);
@@ -638,7 +655,7 @@ int ape_posenet_forward(ape_net* net, const float* out_img, int hw, const float*
     APE_REQUIRE(B <= net->max_batch && N <= net->max_points, "ape_posenet_forward: B=%d N=%d exceed the handle's workspace (%d, %d)",
                 B, N, net->max_batch, net->max_points);
     cudaStream_t s = (cudaStream_t)stream;
-    const int Np = (N + 127) / 128 * 128, M = B * Np;
+    const int Np = (N + 127) / 128 * 128, M = (B * Np + 255) / 256 * 256;
     int rc = run_trunk(net, out_img, hw, cloud, choose, B, N, emb, s);
     if (rc) return rc;
     // global-feature half of conv1_{r,t,c} folded into a per-object bias: GB = b + Wg * AP

@@ -24,7 +24,7 @@ def _handles(seed, nobj, max_batch, max_points):
     return est, ref, synth.to_torch(sd_e), synth.to_torch(sd_r)
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tcgen05', 'tcgen05_v1'])
+@pytest.mark.parametrize('impl', ['simt', 'tcgen05', 'tcgen05_v1', 'tcgen05_pair'])
 @pytest.mark.parametrize('case', [0, 1, 2])
 def test_posenet_refiner_golden(golden_dir, case, impl):
     """Raw network outputs vs the reference's own PoseNet / PoseRefineNet (tests/golden)."""
@@ -33,7 +33,7 @@ def test_posenet_refiner_golden(golden_dir, case, impl):
     seed, npts, nobj = int(g['seed']), int(g['npts']), int(g['nobj'])
     hw = tuple(int(v) for v in g['hw'])
     est, ref, _, _ = _handles(seed, nobj, 2, npts)
-    gi = {'simt': ops.GEMM_SIMT, 'tcgen05': ops.GEMM_TCGEN05, 'tcgen05_v1': ops.GEMM_TCGEN05_V1}[impl]
+    gi = {'simt': ops.GEMM_SIMT, 'tcgen05': ops.GEMM_TCGEN05, 'tcgen05_v1': ops.GEMM_TCGEN05_V1, 'tcgen05_pair': ops.GEMM_TCGEN05_PAIR}[impl]
     est.set_gemm(gi); ref.set_gemm(gi)
     out_img, cloud, choose, idx = synth.posenet_inputs(seed, npts, hw, nobj)
     r, t, c, emb = est.posenet_forward(_dev(out_img), _dev(cloud), _dev(choose), _dev(idx))
