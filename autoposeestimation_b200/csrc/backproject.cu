@@ -41,13 +41,15 @@ backproject_choose_kernel(const uint16_t* __restrict__ depth, int n_frames, int 
 }
 
 // ---------------------------------------------------------------------------------- a4
-// One CTA per view.  The CTA walks the frame in chunks of kThreads*32 pixels; each thread owns
-// 32 consecutive pixels (2 x 16 B of label, 4 x 16 B of depth, all in flight together, next
-// chunk prefetched before the scan of the current one), builds a 32-bit validity mask, and a
-// block-wide exclusive scan of the pop-counts gives every thread its ordered output slot.
-constexpr int kSurfThreads = 512;
-constexpr int kSurfPix = 32;                       // pixels per thread per chunk
-constexpr int kSurfChunk = kSurfThreads * kSurfPix;
+// One CTA per 8192-pixel chunk of one view, many CTAs in flight per SM (the first version walked a whole frame with
+// one CTA: 1.35 TB/s, latency-bound).  Each thread owns 32 consecutive pixels (2 x 16 B of label, 4 x 16 B of depth,
+// streaming loads), builds a 32-bit validity mask; a block scan of the pop-counts gives the chunk-local slots; the
+// chunk's base offset is the sum of the totals published by the chunks before it in the same view (decoupled
+// look-back without a serial chain; tiles are taken from an atomic ticket so every predecessor is already running).  The valid pixels are first compacted into shared memory (16-bit in-chunk offsets, row-major order) and
+// then processed by ALL threads, so the fp64 work is balanced and the 24-byte point stores are contiguous.
+constexpr int kSurfThreads = 256;
+constexpr int kSurfPix = 32;                       // pixels per thread
+constexpr int kSurfChunk = kSurfThreads * kSurfPix;   // 8192 pixels = 24 KB of input per CTA
 
 struct SurfRegs { uint4 l0, l1, d0, d1, d2, d3; };
 
@@ -72,102 +74,128 @@ __device__ __forceinline__ void surf_load(SurfRegs& r, const uint8_t* lab, const
     }
 }
 
-__device__ __forceinline__ uint32_t label_bits(uint32_t w, uint32_t want) {
-    // 4 label bytes -> 4 bits (bit i set when byte i matches: !=0 if want==0 else ==want)
-    uint32_t m = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint32_t b = (w >> (8 * i)) & 0xffu;
-        m |= (uint32_t)(want ? (b == want) : (b != 0u)) << i;
-    }
-    return m;
+// 4 label bytes -> 4 bits (bit i set when byte i matches: != 0 if want == 0 else == want), SIMD-in-register
+__device__ __forceinline__ uint32_t label_bits(uint32_t w, uint32_t want4) {
+    // __vcmpeq4 gives 0xff per equal byte; want4 = want replicated (0 -> "byte == 0", inverted below)
+    const uint32_t eq = __vcmpeq4(w, want4);
+    const uint32_t hit = want4 ? eq : ~eq;                 // want == 0: label != 0
+    // gather the top bit of each byte into bits 0..3
+    return ((hit & 0x80808080u) * 0x00204081u) >> 28;
 }
 __device__ __forceinline__ uint32_t depth_bits(uint32_t w) {
-    return (uint32_t)((w & 0xffffu) != 0u) | ((uint32_t)((w >> 16) != 0u) << 1);
+    const uint32_t nz = ~__vcmpeq2(w, 0u);                 // 0xffff per non-zero half
+    return ((nz >> 15) & 1u) | ((nz >> 30) & 2u);
 }
 
-__global__ void __launch_bounds__(kSurfThreads)
+// work layout (zeroed by the launcher): [0] ticket counter, [1 + v*n_chunks + c] = 0x80000000 | valid pixels of the chunk
+__global__ void __launch_bounds__(kSurfThreads, 3)
 surface_backproject_kernel(const uint8_t* __restrict__ label, const uint16_t* __restrict__ depth, int H, int W,
                            const int32_t* __restrict__ frame_of, const uint8_t* __restrict__ label_value,
                            const double* __restrict__ cam, const double* __restrict__ robot2cam, int capacity,
                            double* __restrict__ points, int32_t* __restrict__ pixel_index,
-                           int32_t* __restrict__ counts)
+                           int32_t* __restrict__ counts, uint32_t* __restrict__ work, int n_chunks)
 {
-    __shared__ int warp_tot[2][kSurfThreads / 32];
-    const int v = blockIdx.x;
+    __shared__ uint16_t s_list[kSurfChunk];                // compacted in-chunk offsets of the valid pixels
+    __shared__ int s_warp_tot[kSurfThreads / 32];
+    __shared__ int s_tile, s_base;
+    __shared__ double s_par[16];                           // robot2cam rows 0..2 (12) + ppx, ppy, fx, fy
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(&work[0], 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    const int v = tile / n_chunks, c = tile - v * n_chunks;
     const int f = frame_of ? frame_of[v] : v;
     const uint32_t want = label_value ? label_value[v] : 0u;
+    const uint32_t want4 = want * 0x01010101u;
     const int npix = H * W;
     const uint8_t* lab = label + (size_t)f * npix;
     const uint16_t* dep = depth + (size_t)f * npix;
-    const double ppx = cam[4 * v + 0], ppy = cam[4 * v + 1], fx = cam[4 * v + 2], fy = cam[4 * v + 3];
-    double T[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) T[i] = robot2cam[16 * v + i];
-    double* out = points + (size_t)v * capacity * 3;
-    int32_t* opix = pixel_index ? pixel_index + (size_t)v * capacity : nullptr;
-
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int base = 0;                                          // valid pixels emitted before this chunk
-    SurfRegs cur, nxt = {};
-    surf_load(cur, lab, dep, threadIdx.x * kSurfPix, npix);
-    int it = 0;
-    for (int c0 = 0; c0 < npix; c0 += kSurfChunk, ++it) {
-        const int p = c0 + threadIdx.x * kSurfPix;
-        if (c0 + kSurfChunk < npix) surf_load(nxt, lab, dep, p + kSurfChunk, npix);
+    const int p0 = c * kSurfChunk;
+    const int p = p0 + threadIdx.x * kSurfPix;
 
-        const uint32_t lw[8] = {cur.l0.x, cur.l0.y, cur.l0.z, cur.l0.w, cur.l1.x, cur.l1.y, cur.l1.z, cur.l1.w};
-        const uint32_t dw[16] = {cur.d0.x, cur.d0.y, cur.d0.z, cur.d0.w, cur.d1.x, cur.d1.y, cur.d1.z, cur.d1.w,
-                                 cur.d2.x, cur.d2.y, cur.d2.z, cur.d2.w, cur.d3.x, cur.d3.y, cur.d3.z, cur.d3.w};
-        uint32_t mask = 0;
+    SurfRegs cur;
+    surf_load(cur, lab, dep, p, npix);
+    const uint32_t lw[8] = {cur.l0.x, cur.l0.y, cur.l0.z, cur.l0.w, cur.l1.x, cur.l1.y, cur.l1.z, cur.l1.w};
+    const uint32_t dw[16] = {cur.d0.x, cur.d0.y, cur.d0.z, cur.d0.w, cur.d1.x, cur.d1.y, cur.d1.z, cur.d1.w,
+                             cur.d2.x, cur.d2.y, cur.d2.z, cur.d2.w, cur.d3.x, cur.d3.y, cur.d3.z, cur.d3.w};
+    uint32_t mask = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mask |= label_bits(lw[i], want) << (4 * i);
-        uint32_t dmask = 0;
+    for (int i = 0; i < 8; ++i) mask |= label_bits(lw[i], want4) << (4 * i);
+    uint32_t dmask = 0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) dmask |= depth_bits(dw[i]) << (2 * i);
-        mask &= dmask;
+    for (int i = 0; i < 16; ++i) dmask |= depth_bits(dw[i]) << (2 * i);
+    mask &= dmask;
 
-        const int cnt = __popc(mask);
-        int incl = cnt;                                    // warp inclusive scan
+    const int cnt = __popc(mask);
+    int incl = cnt;                                        // warp inclusive scan
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) warp_tot[it & 1][warp] = incl;
-        __syncthreads();                                   // one barrier per chunk (ping-pong buffer)
-        int before = 0, total = 0;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    int before = 0, total = 0;
 #pragma unroll
-        for (int w = 0; w < kSurfThreads / 32; ++w) {
-            const int t = warp_tot[it & 1][w];
-            before += (w < warp) ? t : 0;
-            total += t;
+    for (int w = 0; w < kSurfThreads / 32; ++w) {
+        const int t = s_warp_tot[w];
+        before += (w < warp) ? t : 0;
+        total += t;
+    }
+    // Every chunk publishes its own total at once; the base offset is the sum of the totals of the chunks before it
+    // (no serial chain: predecessors hold smaller tickets, so they are running and publish without waiting on anyone).
+    if (warp == 0) {
+        volatile uint32_t* st = work + 1 + (size_t)v * n_chunks;
+        if (lane == 0) st[c] = 0x80000000u | (uint32_t)total;
+        uint32_t sum = 0;
+        for (int j = lane; j < c; j += 32) {
+            uint32_t x;
+            unsigned spin = 0;
+            while (((x = st[j]) & 0x80000000u) == 0u) { if (++spin > (1u << 26)) __trap(); }
+            sum += x & 0x7fffffffu;
         }
-        int slot = base + before + incl - cnt;
+        sum = (uint32_t)warp_sum((int)sum);
+        if (lane == 0) {
+            s_base = (int)sum;
+            if (c == n_chunks - 1) counts[v] = (int)sum + total;
+        }
+    }
+    // compaction of the in-chunk offsets (independent of the base)
+    {
+        int slot = before + incl - cnt;
         uint32_t m = mask;
         while (m) {
             const int i = __ffs(m) - 1;
             m &= m - 1;
-            if (slot < capacity) {
-                const int pix = p + i;
-                const int r = pix / W, col = pix - r * W;
-                const double z = (double)dep[pix];   // rare (valid pixels only): L2 hit, keeps dw[] in registers
-                // open3d_utils.py:185-189: p0 = ((px-ppx)*z)/fx, p1 = ((py-ppy)*z)/fy (fp64, rounded per op)
-                const double x = __ddiv_rn(__dmul_rn(__dsub_rn((double)col, ppx), z), fx);
-                const double y = __ddiv_rn(__dmul_rn(__dsub_rn((double)r, ppy), z), fy);
-                // robot2cam * [x y z 1]^T (:190-192)
-                double* o = out + (size_t)slot * 3;
-                o[0] = fma(T[0], x, fma(T[1], y, fma(T[2], z, T[3])));
-                o[1] = fma(T[4], x, fma(T[5], y, fma(T[6], z, T[7])));
-                o[2] = fma(T[8], x, fma(T[9], y, fma(T[10], z, T[11])));
-                if (opix) opix[slot] = pix;
-            }
-            ++slot;
+            s_list[slot++] = (uint16_t)(threadIdx.x * kSurfPix + i);
         }
-        base += total;
-        cur = nxt;
     }
-    if (threadIdx.x == 0) counts[v] = base;
+    if (threadIdx.x >= 32 && threadIdx.x < 48) {
+        const int i = threadIdx.x - 32;
+        s_par[i] = i < 12 ? robot2cam[16 * v + i] : cam[4 * v + (i - 12)];
+    }
+    __syncthreads();
+    const int base = s_base;
+    const double* T = s_par;
+    const double ppx = s_par[12], ppy = s_par[13], fx = s_par[14], fy = s_par[15];
+    double* out = points + (size_t)v * capacity * 3;
+    int32_t* opix = pixel_index ? pixel_index + (size_t)v * capacity : nullptr;
+    for (int i = threadIdx.x; i < total; i += kSurfThreads) {
+        const int slot = base + i;
+        if (slot >= capacity) break;
+        const int pix = p0 + (int)s_list[i];
+        const int r = pix / W, col = pix - r * W;
+        const double z = (double)dep[pix];                 // L2 hit (this CTA just streamed the chunk)
+        // open3d_utils.py:185-189: p0 = ((px-ppx)*z)/fx, p1 = ((py-ppy)*z)/fy (fp64, rounded per op)
+        const double x = __ddiv_rn(__dmul_rn(__dsub_rn((double)col, ppx), z), fx);
+        const double y = __ddiv_rn(__dmul_rn(__dsub_rn((double)r, ppy), z), fy);
+        // robot2cam * [x y z 1]^T (:190-192)
+        double* o = out + (size_t)slot * 3;
+        o[0] = fma(T[0], x, fma(T[1], y, fma(T[2], z, T[3])));
+        o[1] = fma(T[4], x, fma(T[5], y, fma(T[6], z, T[7])));
+        o[2] = fma(T[8], x, fma(T[9], y, fma(T[10], z, T[11])));
+        if (opix) opix[slot] = pix;
+    }
 }
 
 }  // namespace ape
@@ -189,21 +217,34 @@ extern "C" __attribute__((visibility("default"))) int ape_backproject_choose(con
     return ape::check_launch("ape_backproject_choose");
 }
 
+extern "C" __attribute__((visibility("default"))) size_t ape_surface_work_bytes(int n_views, int height, int width)
+{
+    const size_t chunks = ((size_t)(height > 0 ? height : 0) * (size_t)(width > 0 ? width : 0) + ape::kSurfChunk - 1) / ape::kSurfChunk;
+    return 4 * (1 + (size_t)(n_views > 0 ? n_views : 0) * chunks);
+}
+
 extern "C" __attribute__((visibility("default"))) int ape_surface_backproject(const uint8_t* label, const uint16_t* depth, int n_frames, int height,
                                        int width, const int32_t* frame_of, const uint8_t* label_value,
                                        const double* cam, const double* robot2cam, int n_views, int capacity,
-                                       double* points, int32_t* pixel_index, int32_t* counts, void* stream)
+                                       double* points, int32_t* pixel_index, int32_t* counts, void* work, void* stream)
 {
-    APE_REQUIRE(label && depth && cam && robot2cam && points && counts, "ape_surface_backproject: null pointer");
+    APE_REQUIRE(label && depth && cam && robot2cam && points && counts && work, "ape_surface_backproject: null pointer");
     APE_REQUIRE(n_frames > 0 && height > 0 && width > 0 && n_views >= 0 && capacity > 0,
                 "ape_surface_backproject: bad sizes");
     APE_REQUIRE(((size_t)height * width) % 16 == 0, "ape_surface_backproject: height*width must be a multiple of 16");
+    APE_REQUIRE((size_t)height * width < (1u << 30), "ape_surface_backproject: frame too large");
     APE_REQUIRE((((uintptr_t)label) & 15) == 0 && (((uintptr_t)depth) & 15) == 0,
                 "ape_surface_backproject: label/depth must be 16-byte aligned");
+    APE_REQUIRE((((uintptr_t)work) & 3) == 0, "ape_surface_backproject: work must be 4-byte aligned");
     if (n_views == 0) return APE_OK;
-    ape::ProfScope prof_("surface_backproject", (cudaStream_t)stream);
-    ape::surface_backproject_kernel<<<n_views, ape::kSurfThreads, 0, (cudaStream_t)stream>>>(
-        label, depth, height, width, frame_of, label_value, cam, robot2cam, capacity, points, pixel_index, counts);
+    const int n_chunks = (int)(((size_t)height * width + ape::kSurfChunk - 1) / ape::kSurfChunk);
+    APE_REQUIRE((size_t)n_views * n_chunks < (1u << 31), "ape_surface_backproject: too many views (split the batch)");
+    cudaStream_t s = (cudaStream_t)stream;
+    APE_CUDA(cudaMemsetAsync(work, 0, ape_surface_work_bytes(n_views, height, width), s));
+    ape::ProfScope prof_("surface_backproject", s);
+    ape::surface_backproject_kernel<<<n_views * n_chunks, ape::kSurfThreads, 0, s>>>(
+        label, depth, height, width, frame_of, label_value, cam, robot2cam, capacity, points, pixel_index, counts,
+        reinterpret_cast<uint32_t*>(work), n_chunks);
     ape::count_launch();
     return ape::check_launch("ape_surface_backproject");
 }

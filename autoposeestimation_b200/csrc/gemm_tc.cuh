@@ -28,7 +28,7 @@ constexpr int kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
 constexpr int kSmemBytes = kStages * (kStageBytesA + kStageBytesB) + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr uint32_t kTmemCols = 128;
 
-enum { EPI_RELU_SPLIT = 0, EPI_RELU_COLSUM = 1 };
+enum { EPI_RELU_SPLIT = 0, EPI_RELU_COLSUM = 1, EPI_HEAD_OUT = 2 };
 
 struct Params {
     int M, N, K, groups;          // rows (multiple of 128), outputs per group (multiple of 128), K (multiple of 64)
@@ -40,6 +40,13 @@ struct Params {
     int o_ld, o_c0;
     float* colsum;                // EPI_RELU_COLSUM: [M/128, groups*N] per-tile column sums of valid rows
     int rows_per_obj, valid_rows; // rows (r % rows_per_obj) >= valid_rows are padding
+    // EPI_HEAD_OUT (gemm_tc2.cuh only; PoseNet conv3_{r,t,c} with conv4_{r,t,c} of the object's class folded into the
+    // epilogue, network.py:115-130): groups = (r, t, c), N == 128;  pred = relu(D + bias) . w4[class]^T + b4[class]
+    const float* w4[3];           // [num_obj*4,128], [num_obj*3,128], [num_obj,128]
+    const float* b4[3];
+    const int64_t* obj;           // [batch] class ids
+    int num_obj, batch;
+    float* pred[3];               // pred_r [batch,valid_rows,4], pred_t [batch,valid_rows,3], pred_c [batch,valid_rows] (sigmoid)
 };
 
 // ---------------------------------------------------------------------------------- PTX wrappers

@@ -163,14 +163,30 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
             const Tile tl = decode_tile(t, p, m_tiles, n_tiles, bn_full);
             const int acc = lt & 1;
             const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
-            mbar_wait(&tfull_bar[acc], aph);
-            tc_fence_after();
             const int row0 = tl.m_tile * BM + quad * 32;
             const int row = row0 + lane;
             const int col_g = tl.g * p.N + tl.n0;                 // first column within [groups*N]
             const float* bias = p.bias + (p.bias_obj_rows > 0 ? (size_t)(row0 / p.bias_obj_rows) * (size_t)GN : 0) + col_g;
+            float bl = __ldg(bias + lane);                        // bias is prefetched one 32-column chunk ahead
             const bool valid = (p.mode != EPI_RELU_COLSUM) || ((row % p.rows_per_obj) < p.valid_rows);
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256);
+            // EPI_HEAD_OUT: stage the last-layer weights of this tile's object class before waiting for the accumulator
+            float* s_w4 = reinterpret_cast<float*>(stg);          // [4][128], rows >= n_out zero-filled
+            const int hb_obj = row0 / p.rows_per_obj;
+            const int n_out = tl.g == 0 ? 4 : (tl.g == 1 ? 3 : 1);
+            int cls = 0;
+            if (p.mode == EPI_HEAD_OUT) {
+                if (hb_obj < p.batch) {
+                    cls = (int)p.obj[hb_obj];
+                    cls = cls < 0 ? 0 : (cls >= p.num_obj ? p.num_obj - 1 : cls);
+                }
+                const float* wsrc = p.w4[tl.g] + (size_t)cls * n_out * 128;
+                __syncwarp();
+                for (int i = lane; i < 4 * 128; i += 32) s_w4[i] = i < n_out * 128 ? __ldg(wsrc + i) : 0.0f;
+                __syncwarp();
+            }
+            mbar_wait(&tfull_bar[acc], aph);
+            tc_fence_after();
             if (p.mode == EPI_RELU_SPLIT) {
 #pragma unroll 1
                 for (int c0 = 0; c0 < tl.bn; c0 += 64) {
@@ -179,16 +195,18 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
                     for (int h = 0; h < 2; ++h) {
                         uint32_t v[32];
                         tmem_ld_32x32(t_addr + (uint32_t)(c0 + 32 * h), v);
-                        if (h == 1 && c0 + 64 >= tl.bn) {             // last read of this accumulator: hand it back early
+                        const bool last = (h == 1) && (c0 + 64 >= tl.bn);
+                        if (last) {                                   // last read of this accumulator: hand it back early
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                         }
-                        const float bl = __ldg(bias + c0 + 32 * h + lane);   // coalesced; broadcast by shuffle below
+                        const float bcur = bl;
+                        if (!last) bl = __ldg(bias + c0 + 32 * h + 32 + lane);
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const float f0 = fmaxf(__uint_as_float(v[2 * j]) + __shfl_sync(0xffffffffu, bl, 2 * j), 0.0f);
-                            const float f1 = fmaxf(__uint_as_float(v[2 * j + 1]) + __shfl_sync(0xffffffffu, bl, 2 * j + 1), 0.0f);
+                            const float f0 = fmaxf(__uint_as_float(v[2 * j]) + __shfl_sync(0xffffffffu, bcur, 2 * j), 0.0f);
+                            const float f1 = fmaxf(__uint_as_float(v[2 * j + 1]) + __shfl_sync(0xffffffffu, bcur, 2 * j + 1), 0.0f);
                             const __nv_bfloat162 hb = __floats2bfloat162_rn(f0, f1);
                             const uint32_t hu = *reinterpret_cast<const uint32_t*>(&hb);
                             const __nv_bfloat162 lb = __floats2bfloat162_rn(f0 - __uint_as_float(hu << 16),
@@ -217,24 +235,69 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
                         bulk_commit();
                     }
                 }
+            } else if (p.mode == EPI_HEAD_OUT) {
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < tl.bn; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_addr + (uint32_t)c0, v);
+                    const bool last = c0 + 32 >= tl.bn;
+                    if (last) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    }
+                    const float bcur = bl;
+                    if (!last) bl = __ldg(bias + c0 + 32 + lane);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float f[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) f[q] = fmaxf(__uint_as_float(v[j + q]) + __shfl_sync(0xffffffffu, bcur, j + q), 0.0f);
+                        const float4 w0 = *reinterpret_cast<const float4*>(s_w4 + c0 + j);
+                        const float4 w1 = *reinterpret_cast<const float4*>(s_w4 + 128 + c0 + j);
+                        const float4 w2 = *reinterpret_cast<const float4*>(s_w4 + 256 + c0 + j);
+                        const float4 w3 = *reinterpret_cast<const float4*>(s_w4 + 384 + c0 + j);
+                        a0 = fmaf(f[3], w0.w, fmaf(f[2], w0.z, fmaf(f[1], w0.y, fmaf(f[0], w0.x, a0))));
+                        a1 = fmaf(f[3], w1.w, fmaf(f[2], w1.z, fmaf(f[1], w1.y, fmaf(f[0], w1.x, a1))));
+                        a2 = fmaf(f[3], w2.w, fmaf(f[2], w2.z, fmaf(f[1], w2.y, fmaf(f[0], w2.x, a2))));
+                        a3 = fmaf(f[3], w3.w, fmaf(f[2], w3.z, fmaf(f[1], w3.y, fmaf(f[0], w3.x, a3))));
+                    }
+                }
+                const int n = row % p.rows_per_obj;
+                if (hb_obj < p.batch && n < p.valid_rows) {
+                    const float* b4 = p.b4[tl.g] + cls * n_out;
+                    const size_t pt = (size_t)hb_obj * p.valid_rows + n;
+                    if (tl.g == 0) {
+                        *reinterpret_cast<float4*>(p.pred[0] + pt * 4) = make_float4(a0 + __ldg(b4), a1 + __ldg(b4 + 1), a2 + __ldg(b4 + 2), a3 + __ldg(b4 + 3));
+                    } else if (tl.g == 1) {
+                        float* o = p.pred[1] + pt * 3;
+                        o[0] = a0 + __ldg(b4); o[1] = a1 + __ldg(b4 + 1); o[2] = a2 + __ldg(b4 + 2);
+                    } else {
+                        p.pred[2][pt] = 1.0f / (1.0f + expf(-(a0 + __ldg(b4))));
+                    }
+                }
             } else {
 #pragma unroll 1
                 for (int c0 = 0; c0 < tl.bn; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld_32x32(t_addr + (uint32_t)c0, v);
-                    if (c0 + 32 >= tl.bn) {
+                    const bool last = c0 + 32 >= tl.bn;
+                    if (last) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                     }
-                    const float bl = __ldg(bias + c0 + lane);
+                    const float bcur = bl;
+                    if (!last) bl = __ldg(bias + c0 + 32 + lane);
                     float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(__uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bl, j), 0.0f);
+                    for (int j = 0; j < 32; ++j) {
+                        const float x = fmaxf(__uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bcur, j), 0.0f);
+                        f[j] = valid ? x : 0.0f;
+                    }
                     // masked column sum over this warp's 32 rows: butterfly transpose-reduce, lane j ends
                     // with the sum of column c0 + j
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = valid ? f[j] : 0.0f;
 #pragma unroll
                     for (int off = 16; off >= 1; off >>= 1) {
                         const bool upper = (lane & off) != 0;

@@ -16,7 +16,11 @@
 
 namespace ape {
 
-constexpr int kIcpThreads = 512;
+// (dy, dz) of the nine x-runs around a cell, centre first, then faces, then edges
+__constant__ signed char c_run_dy[9] = {0, -1, 1, 0, 0, -1, 1, -1, 1};
+__constant__ signed char c_run_dz[9] = {0, 0, 0, -1, 1, -1, -1, 1, 1};
+
+constexpr int kIcpThreads = 128;      // small CTAs, several registrations per SM: one CTA's serial Kabsch/SVD step overlaps the others' searches
 constexpr int kIcpWarps = kIcpThreads / 32;
 constexpr int kIcpMaxCells = 4096;
 
@@ -140,7 +144,7 @@ __device__ __forceinline__ int cell_coord(double v, double lo, double inv_h) {
     return (int)floor((v - lo) * inv_h);
 }
 
-__global__ void __launch_bounds__(kIcpThreads)
+__global__ void __launch_bounds__(kIcpThreads, 4)
 icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ src_offset,
                const double* __restrict__ target, const int32_t* __restrict__ tgt_offset, int n_reg,
                double threshold, double rel_fitness, double rel_rmse, int max_iter,
@@ -280,25 +284,39 @@ icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ sr
                 const double pz = fma(U[8], x0, fma(U[9], y0, fma(U[10], z0, U[11])));
                 wsrc[3 * i] = px; wsrc[3 * i + 1] = py; wsrc[3 * i + 2] = pz;
                 const int cx = cell_coord(px, g0, inv_h), cy = cell_coord(py, g1, inv_h), cz = cell_coord(pz, g2, inv_h);
-                double best = DBL_MAX; int bpos = -1, borig = 0x7fffffff;
+                // best starts at r^2: only candidates with d2 < r^2 can be accepted (open3d's strict radius test), and a
+                // run of cells whose bounding box is farther than the current best is skipped.  The centre run is
+                // scanned first, so in the common case (nearest neighbour a few mm away, 10 mm cells) the other eight
+                // runs are rejected by the box test.  Skipping needs boxdist^2 > best strictly (an exact tie in a skipped
+                // run could otherwise win on original index); delta widens the boxes against binning round-off.
+                double best = r2; int bpos = -1, borig = 0x7fffffff;
                 if (Nt > 0 && cx >= -1 && cx <= dim[0] && cy >= -1 && cy <= dim[1] && cz >= -1 && cz <= dim[2]) {
                     const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, dim[0] - 1);
-                    for (int zz = max(cz - 1, 0); zz <= min(cz + 1, dim[2] - 1); ++zz)
-                        for (int yy = max(cy - 1, 0); yy <= min(cy + 1, dim[1] - 1); ++yy) {
-                            if (x_lo > x_hi) continue;
+                    if (x_lo <= x_hi) {
+                        const double delta = 1e-6 * h;
+                        const double gx = fmax(fmax((g0 + x_lo * h - delta) - px, px - (g0 + (x_hi + 1) * h + delta)), 0.0);
+                        const double gx2 = gx * gx;
+#pragma unroll 1
+                        for (int k = 0; k < 9; ++k) {
+                            const int yy = cy + c_run_dy[k], zz = cz + c_run_dz[k];
+                            if (yy < 0 || yy >= dim[1] || zz < 0 || zz >= dim[2]) continue;
+                            const double gy = fmax(fmax((g1 + yy * h - delta) - py, py - (g1 + (yy + 1) * h + delta)), 0.0);
+                            const double gz = fmax(fmax((g2 + zz * h - delta) - pz, pz - (g2 + (zz + 1) * h + delta)), 0.0);
+                            if (gx2 + gy * gy + gz * gz > best) continue;
                             const int row = (zz * dim[1] + yy) * dim[0];
                             const int jb = s.cell_start[row + x_lo], je = s.cell_start[row + x_hi + 1];   // x-run is contiguous
                             for (int j = jb; j < je; ++j) {
                                 const double dx = px - wtgt[3 * j], dy = py - wtgt[3 * j + 1], dz = pz - wtgt[3 * j + 2];
                                 const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                                 if (d < best) { best = d; bpos = j; borig = 0x7fffffff; }
-                                else if (d == best) {             // exact tie: lowest ORIGINAL index wins
+                                else if (d == best && bpos >= 0) {    // exact tie: lowest ORIGINAL index wins
                                     if (borig == 0x7fffffff) borig = worig[bpos];
                                     const int o = worig[j];
                                     if (o < borig) { bpos = j; borig = o; }
                                 }
                             }
                         }
+                    }
                 }
                 if (bpos >= 0 && best < r2) {
                     corr[i] = bpos;
@@ -399,7 +417,7 @@ extern "C" __attribute__((visibility("default"))) int ape_icp_p2p(const double* 
         APE_CUDA(cudaFuncSetAttribute(ape::icp_p2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    const int grid = n_reg < ape::sm_count() * 4 ? n_reg : ape::sm_count() * 4;
+    const int grid = n_reg < ape::sm_count() * 4 ? n_reg : ape::sm_count() * 4;   // 4 resident CTAs per SM (registers)
     ape::ProfScope prof_("icp_p2p", (cudaStream_t)stream);
     ape::icp_p2p_kernel<<<grid, ape::kIcpThreads, smem, (cudaStream_t)stream>>>(
         source, src_offset, target, tgt_offset, n_reg, threshold, rel_fitness, rel_rmse, max_iter, init, transform, info,

@@ -21,63 +21,107 @@ namespace ape {
 typedef __nv_bfloat16 bf16;
 
 // ------------------------------------------------------------------------------------------------
-// Front end: one warp per point.  emb gather (network.py:100-102), conv1 (3->64), e_conv1 (32->64),
-// ReLU, written as split-bf16 into PF[:,0:128]; also emits emb [B,32,N] fp32 (PoseNet only).
+// Front end: one warp per 8 consecutive points of an object.  emb gather (network.py:100-102), conv1 (3->64),
+// e_conv1 (32->64), ReLU, written as split-bf16 into PF[:,0:128]; also emits emb [B,32,N] fp32 (PoseNet only).
+// All global loads of the 8 points are issued before the first use (the gather is a dependent, uncoalesced load:
+// latency, not bandwidth, is what this kernel has to hide); lane = emb channel on the load side, lane = output
+// channel pair (2*lane, 2*lane+1) on the compute side, so every PF store is 128 contiguous bytes per warp.
+constexpr int kFrontPts = 8;
 template <bool GATHER>
 __global__ void __launch_bounds__(256)
 frontend_kernel(const float* __restrict__ feat_src /*GATHER: out_img [B,32,hw]; else emb [B,32,N]*/, int hw,
                 const float* __restrict__ cloud, const int64_t* __restrict__ choose,
-                const float* __restrict__ w1, const float* __restrict__ b1,      // [64,3], [64]
-                const float* __restrict__ we1, const float* __restrict__ be1,    // [64,32], [64]
+                const float* __restrict__ fw,                                    // packed front-end weights (see below)
                 int N, int Np, bf16* __restrict__ pf_hi, bf16* __restrict__ pf_lo, int pf_ld,
                 float* __restrict__ emb_out)
 {
-    __shared__ float s_we1[32][65];          // [k][c], padded
-    __shared__ float s_w1[3][64];
-    __shared__ float s_b[128];
-    for (int i = threadIdx.x; i < 64 * 32; i += 256) s_we1[i & 31][i >> 5] = we1[i];       // we1[c][k]
-    for (int i = threadIdx.x; i < 64 * 3; i += 256) s_w1[i % 3][i / 3] = w1[i];
-    if (threadIdx.x < 64) s_b[threadIdx.x] = b1[threadIdx.x];
-    else if (threadIdx.x < 128) s_b[threadIdx.x] = be1[threadIdx.x - 64];
+    // fw = [e_conv1^T 32x64 | conv1^T 3x64 | b1 64 | be1 64] packed once at ape_net_create: straight float4 copy
+    __shared__ __align__(16) float s_fw[32 * 64 + 3 * 64 + 128];
+    float (*s_we1)[64] = reinterpret_cast<float (*)[64]>(s_fw);
+    float (*s_w1)[64] = reinterpret_cast<float (*)[64]>(s_fw + 32 * 64);
+    float* s_b = s_fw + 32 * 64 + 3 * 64;
+    for (int i = threadIdx.x; i < (32 * 64 + 3 * 64 + 128) / 4; i += 256)
+        reinterpret_cast<float4*>(s_fw)[i] = __ldg(reinterpret_cast<const float4*>(fw) + i);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
-    for (int n = blockIdx.x * 8 + warp; n < Np; n += gridDim.x * 8) {
-        const size_t row = (size_t)b * Np + n;
-        bf16* oh = pf_hi + row * pf_ld;
-        bf16* ol = pf_lo + row * pf_ld;
-        if (n >= N) {                                   // padding row: zeros
-            for (int c = lane; c < 128; c += 32) { oh[c] = __float2bfloat16_rn(0.f); ol[c] = __float2bfloat16_rn(0.f); }
-            continue;
-        }
-        float e;                                        // lane k holds emb channel k of this point
-        if (GATHER) {
-            const int64_t ci = choose[(size_t)b * N + n];
-            e = feat_src[((size_t)b * 32 + lane) * hw + ci];
-            emb_out[((size_t)b * 32 + lane) * N + n] = e;
-        } else {
-            e = feat_src[((size_t)b * 32 + lane) * N + n];
-        }
-        const float px = cloud[((size_t)b * N + n) * 3], py = cloud[((size_t)b * N + n) * 3 + 1],
-                    pz = cloud[((size_t)b * N + n) * 3 + 2];
-        // each lane produces channels lane and lane+32 of both 64-wide outputs
-        float x0 = s_b[lane], x1 = s_b[lane + 32], e0 = s_b[64 + lane], e1 = s_b[96 + lane];
-        x0 = fmaf(s_w1[0][lane], px, x0); x0 = fmaf(s_w1[1][lane], py, x0); x0 = fmaf(s_w1[2][lane], pz, x0);
-        x1 = fmaf(s_w1[0][lane + 32], px, x1); x1 = fmaf(s_w1[1][lane + 32], py, x1); x1 = fmaf(s_w1[2][lane + 32], pz, x1);
+    const int n0 = (blockIdx.x * 8 + warp) * kFrontPts;
+    if (n0 >= Np) return;
+    uint32_t* oh32 = reinterpret_cast<uint32_t*>(pf_hi);
+    uint32_t* ol32 = reinterpret_cast<uint32_t*>(pf_lo);
+    const int ld32 = pf_ld >> 1;
+    if (n0 >= N) {                                      // whole group is padding: zero rows
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            const float ek = __shfl_sync(0xffffffffu, e, k);
-            e0 = fmaf(s_we1[k][lane], ek, e0);
-            e1 = fmaf(s_we1[k][lane + 32], ek, e1);
+        for (int j = 0; j < kFrontPts; ++j) {
+            const size_t r32 = ((size_t)b * Np + n0 + j) * ld32;
+            oh32[r32 + lane] = 0u; oh32[r32 + 32 + lane] = 0u; ol32[r32 + lane] = 0u; ol32[r32 + 32 + lane] = 0u;
         }
-        const float vals[4] = {fmaxf(x0, 0.f), fmaxf(x1, 0.f), fmaxf(e0, 0.f), fmaxf(e1, 0.f)};
-        const int cols[4] = {lane, lane + 32, 64 + lane, 96 + lane};
+        return;
+    }
+    const int npts = min(kFrontPts, N - n0);
+    // ---- loads (all in flight together)
+    float e[kFrontPts];                                 // lane = channel
+    if (GATHER) {
+        int64_t ci = 0;
+        if (lane < npts) ci = choose[(size_t)b * N + n0 + lane];
+        const float* src = feat_src + ((size_t)b * 32 + lane) * hw;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const bf16 h = __float2bfloat16_rn(vals[j]);
-            oh[cols[j]] = h;
-            ol[cols[j]] = __float2bfloat16_rn(vals[j] - __bfloat162float(h));
+        for (int j = 0; j < kFrontPts; ++j) {
+            const int64_t c = __shfl_sync(0xffffffffu, ci, j);
+            e[j] = j < npts ? __ldg(src + c) : 0.f;
         }
+    } else {
+        const float* src = feat_src + ((size_t)b * 32 + lane) * N + n0;
+#pragma unroll
+        for (int j = 0; j < kFrontPts; ++j) e[j] = j < npts ? __ldg(src + j) : 0.f;
+    }
+    float cv = 0.f;                                     // lanes 0..23: the 8 points' xyz
+    if (lane < 3 * npts) cv = cloud[((size_t)b * N + n0) * 3 + lane];
+    if (GATHER) {                                       // emb [B,32,N]: lane = channel writes its 8 consecutive points
+        float* dst = emb_out + ((size_t)b * 32 + lane) * N + n0;
+#pragma unroll
+        for (int j = 0; j < kFrontPts; ++j) if (j < npts) dst[j] = e[j];
+    }
+    // ---- conv1 / e_conv1 for output channels 2*lane, 2*lane+1
+    float x0[kFrontPts], x1[kFrontPts], a0[kFrontPts], a1[kFrontPts];
+    {
+        const float2 bx = *reinterpret_cast<const float2*>(&s_b[2 * lane]);
+        const float2 be = *reinterpret_cast<const float2*>(&s_b[64 + 2 * lane]);
+        const float2 wx = *reinterpret_cast<const float2*>(&s_w1[0][2 * lane]);
+        const float2 wy = *reinterpret_cast<const float2*>(&s_w1[1][2 * lane]);
+        const float2 wz = *reinterpret_cast<const float2*>(&s_w1[2][2 * lane]);
+#pragma unroll
+        for (int j = 0; j < kFrontPts; ++j) {
+            const float px = __shfl_sync(0xffffffffu, cv, 3 * j), py = __shfl_sync(0xffffffffu, cv, 3 * j + 1),
+                        pz = __shfl_sync(0xffffffffu, cv, 3 * j + 2);
+            x0[j] = fmaf(wz.x, pz, fmaf(wy.x, py, fmaf(wx.x, px, bx.x)));
+            x1[j] = fmaf(wz.y, pz, fmaf(wy.y, py, fmaf(wx.y, px, bx.y)));
+            a0[j] = be.x; a1[j] = be.y;
+        }
+    }
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+        const float2 w = *reinterpret_cast<const float2*>(&s_we1[k][2 * lane]);
+#pragma unroll
+        for (int j = 0; j < kFrontPts; ++j) {
+            const float ek = __shfl_sync(0xffffffffu, e[j], k);
+            a0[j] = fmaf(w.x, ek, a0[j]);
+            a1[j] = fmaf(w.y, ek, a1[j]);
+        }
+    }
+    // ---- ReLU + split-bf16 stores; rows n >= N (padding inside the group) are zero
+#pragma unroll
+    for (int j = 0; j < kFrontPts; ++j) {
+        const bool live = j < npts;
+        const float v0 = live ? fmaxf(x0[j], 0.f) : 0.f, v1 = live ? fmaxf(x1[j], 0.f) : 0.f;
+        const float u0 = live ? fmaxf(a0[j], 0.f) : 0.f, u1 = live ? fmaxf(a1[j], 0.f) : 0.f;
+        const __nv_bfloat162 hx = __floats2bfloat162_rn(v0, v1), he = __floats2bfloat162_rn(u0, u1);
+        const uint32_t hxu = *reinterpret_cast<const uint32_t*>(&hx), heu = *reinterpret_cast<const uint32_t*>(&he);
+        const __nv_bfloat162 lx = __floats2bfloat162_rn(v0 - __uint_as_float(hxu << 16), v1 - __uint_as_float(hxu & 0xffff0000u));
+        const __nv_bfloat162 le = __floats2bfloat162_rn(u0 - __uint_as_float(heu << 16), u1 - __uint_as_float(heu & 0xffff0000u));
+        const size_t r32 = ((size_t)b * Np + n0 + j) * ld32;
+        oh32[r32 + lane] = hxu; oh32[r32 + 32 + lane] = heu;
+        ol32[r32 + lane] = *reinterpret_cast<const uint32_t*>(&lx); ol32[r32 + 32 + lane] = *reinterpret_cast<const uint32_t*>(&le);
     }
 }
 
@@ -149,37 +193,82 @@ __global__ void pool_finish_kernel(const float* __restrict__ cs, int tiles_per_o
     ap[(size_t)b * C + c] = s / inv_n;   // inv_n carries N: AvgPool1d divides
 }
 
-// Small dense layer over per-object vectors (fp32 SIMT): one warp per output, 8 objects per pass.
-//   out[b, g*npg + j] = act(bias[g*npg + j] + sum_k W[g*npg + j, k] * in[b, g*in_gs + k])
-constexpr int kDenseObj = 8;
-__global__ void __launch_bounds__(256)
-dense_small_kernel(const float* __restrict__ in, int in_ld, int in_gs, const float* __restrict__ W,
-                   const float* __restrict__ bias, float* __restrict__ out, int out_ld, int B, int K, int npg, int groups,
+// Small dense layer over per-object vectors (fp32 SIMT), the per-object GEMVs of both networks batched into one
+// [B x K] x [K x n_out] product:
+//   out[b, o] = act(bias[o] + sum_k W[o, k] * in[b, g*in_gs + k]),   g = o / npg
+// CTA = 8 outputs x 64 objects; thread = (object, K-quarter) with 8 accumulators, so every x value read from shared
+// memory feeds 8 FMAs and the W reads are warp-uniform broadcasts.  The four K-quarters are summed in a fixed
+// order (deterministic).  K must be a multiple of 128 and <= 1024, npg a multiple of 8.
+constexpr int kDenseOut = 8, kDenseObj = 64, kDenseKc = 32;
+constexpr int kDenseXld = 4 * kDenseKc + 4;
+__global__ void __launch_bounds__(256, 2)
+dense_batch_kernel(const float* __restrict__ in, int in_ld, int in_gs, const float* __restrict__ W,
+                   const float* __restrict__ bias, float* __restrict__ out, int out_ld, int B, int K, int npg, int n_out,
                    int relu)
 {
-    const int lane = threadIdx.x & 31;
-    const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (o >= npg * groups) return;
-    const int g = o / npg;
-    const float* w = W + (size_t)o * K;
-    for (int b0 = blockIdx.y * kDenseObj; b0 < B; b0 += gridDim.y * kDenseObj) {
-        float acc[kDenseObj] = {};
-        for (int k = lane * 4; k < K; k += 128) {
-            const float4 wv = *reinterpret_cast<const float4*>(w + k);
+    extern __shared__ __align__(16) float s_dense[];
+    float* s_w = s_dense;                                   // [8][K]
+    float* s_x = s_w + kDenseOut * K;                       // [2][64][4*32 + 4]   (cp.async double buffer)
+    float* s_red = s_x + 2 * kDenseObj * kDenseXld;         // [4][64][8]
+    const int o0 = blockIdx.x * kDenseOut;
+    const int g = o0 / npg;
+    const int tid = threadIdx.x, bl = tid & 63, q = tid >> 6;
+    const int kq = K >> 2;                                  // K per quarter
+    for (int i = tid * 4; i < kDenseOut * K; i += 256 * 4) {
+        const int o = i / K;
+        const float4 v = (o0 + o < n_out) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)(o0 + o) * K + (i - o * K))) : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(s_w + i) = v;
+    }
+    for (int b0 = 0; b0 < B; b0 += kDenseObj) {
+        // x chunk [b][quarter][32] = 64 objects x 4 quarters x 8 float4 = 8 x 16 B per thread, cp.async into the
+        // buffer that is not being read (rows past B are clamped to the last object and never written back)
+        auto fetch = [&](int kc, int buf) {
 #pragma unroll
-            for (int j = 0; j < kDenseObj; ++j) {
-                if (b0 + j < B) {
-                    const float4 x = *reinterpret_cast<const float4*>(in + (size_t)(b0 + j) * in_ld + g * in_gs + k);
-                    acc[j] = fmaf(wv.x, x.x, fmaf(wv.y, x.y, fmaf(wv.z, x.z, fmaf(wv.w, x.w, acc[j]))));
+            for (int r = 0; r < 8; ++r) {
+                const int i = tid + r * 256;
+                const int j4 = i & 7, qq = (i >> 3) & 3, bb = i >> 5;
+                const int bsrc = min(b0 + bb, B - 1);
+                const float* src = in + (size_t)bsrc * in_ld + g * in_gs + qq * kq + kc + j4 * 4;
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_x + (buf * kDenseObj + bb) * kDenseXld + qq * kDenseKc + j4 * 4);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        float acc[kDenseOut] = {};
+        __syncthreads();                                    // previous pass done with s_x / s_red; s_w visible
+        fetch(0, 0);
+        int buf = 0;
+        for (int kc = 0; kc < kq; kc += kDenseKc, buf ^= 1) {
+            if (kc + kDenseKc < kq) {
+                fetch(kc + kDenseKc, buf ^ 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncthreads();
+            const float* xr = s_x + (buf * kDenseObj + bl) * kDenseXld + q * kDenseKc;
+            const float* wr = s_w + q * kq + kc;
+#pragma unroll
+            for (int j = 0; j < kDenseKc; j += 4) {
+                const float4 x = *reinterpret_cast<const float4*>(xr + j);
+#pragma unroll
+                for (int o = 0; o < kDenseOut; ++o) {
+                    const float4 w = *reinterpret_cast<const float4*>(wr + o * K + j);
+                    acc[o] = fmaf(w.w, x.w, fmaf(w.z, x.z, fmaf(w.y, x.y, fmaf(w.x, x.x, acc[o]))));
                 }
             }
+            __syncthreads();                                // buffer `buf` may be refilled by the next iteration's fetch
         }
 #pragma unroll
-        for (int j = 0; j < kDenseObj; ++j) {
-            const float s = warp_sum(acc[j]);
-            if (lane == 0 && b0 + j < B) {
-                const float v = s + bias[o];
-                out[(size_t)(b0 + j) * out_ld + o] = relu ? fmaxf(v, 0.f) : v;
+        for (int o = 0; o < kDenseOut; ++o) s_red[(q * kDenseObj + bl) * kDenseOut + o] = acc[o];
+        __syncthreads();
+        // 64 objects x 8 outputs = 512 results, two per thread
+        for (int i = tid; i < kDenseObj * kDenseOut; i += 256) {
+            const int bb = i >> 3, o = i & 7;
+            if (b0 + bb < B && o0 + o < n_out) {
+                const float v = ((s_red[(0 * kDenseObj + bb) * kDenseOut + o] + s_red[(1 * kDenseObj + bb) * kDenseOut + o]) +
+                                 (s_red[(2 * kDenseObj + bb) * kDenseOut + o] + s_red[(3 * kDenseObj + bb) * kDenseOut + o])) + bias[o0 + o];
+                out[(size_t)(b0 + bb) * out_ld + o0 + o] = relu ? fmaxf(v, 0.f) : v;
             }
         }
     }
@@ -323,7 +412,7 @@ struct ape_net {
     int gemm_impl = APE_GEMM_TCGEN05;
     std::vector<void*> allocs;
     // fp32 parameters
-    DevF32 w1, b1, we1, be1;                 // front end
+    DevF32 fw;                               // front end: [e_conv1^T 32x64 | conv1^T 3x64 | b1 | be1]
     DevF32 b_c2e2, b_c5, b_c6;               // GEMM biases
     SplitMat W_c2e2, W_c5, W_c6;             // [256,64] (conv2 | e_conv2), [512,256|384], [1024,512]
     // PoseNet heads
@@ -437,8 +526,16 @@ int ape_net_create(int kind, const float* const* w, int n_tensors, int num_obj, 
         if (e) net->gemm_impl = (int)strtol(e, nullptr, 0);
     }
 #define TRY(x) do { if ((rc = (x)) != APE_OK) { ape_net_destroy(net); return rc; } } while (0)
-    TRY(upload_f32(net, net->w1, w[0], 64 * 3));   TRY(upload_f32(net, net->b1, w[1], 64));
-    TRY(upload_f32(net, net->we1, w[2], 64 * 32)); TRY(upload_f32(net, net->be1, w[3], 64));
+    {   // front-end weights transposed to [k][c] so the kernel's shared-memory fill is a straight copy
+        std::vector<float> fw(32 * 64 + 3 * 64 + 128);
+        for (int c = 0; c < 64; ++c) {
+            for (int k = 0; k < 32; ++k) fw[k * 64 + c] = w[2][c * 32 + k];
+            for (int k = 0; k < 3; ++k) fw[32 * 64 + k * 64 + c] = w[0][c * 3 + k];
+            fw[32 * 64 + 3 * 64 + c] = w[1][c];
+            fw[32 * 64 + 3 * 64 + 64 + c] = w[3][c];
+        }
+        TRY(upload_f32(net, net->fw, fw.data(), fw.size()));
+    }
     {   // conv2 | e_conv2 as two groups of a [256,64] matrix
         std::vector<float> W = vcat({w[4], w[6]}, {128, 128}, 64, 0, 64);
         TRY(upload_split(net, net->W_c2e2, W, 256, 64));
@@ -605,11 +702,9 @@ static int run_trunk(ape_net* net, const float* feat_src, int hw, const float* c
     {
     ape::ProfScope prof_("frontend", s);
     if (net->kind == APE_NET_POSENET)
-        ape::frontend_kernel<true><<<gf, 256, 0, s>>>(feat_src, hw, cloud, choose, net->w1.p, net->b1.p, net->we1.p, net->be1.p,
-                                                     N, Np, net->PF.hi, net->PF.lo, 384, emb_out);
+        ape::frontend_kernel<true><<<gf, 256, 0, s>>>(feat_src, hw, cloud, choose, net->fw.p, N, Np, net->PF.hi, net->PF.lo, 384, emb_out);
     else
-        ape::frontend_kernel<false><<<gf, 256, 0, s>>>(feat_src, hw, cloud, nullptr, net->w1.p, net->b1.p, net->we1.p,
-                                                      net->be1.p, N, Np, net->PF.hi, net->PF.lo, 384, nullptr);
+        ape::frontend_kernel<false><<<gf, 256, 0, s>>>(feat_src, hw, cloud, nullptr, net->fw.p, N, Np, net->PF.hi, net->PF.lo, 384, nullptr);
     }
     ape::count_launch();
     int rc = ape::check_launch("frontend");
@@ -636,12 +731,19 @@ static int run_trunk(ape_net* net, const float* feat_src, int hw, const float* c
 static int dense(const float* in, int in_ld, int in_gs, const DevF32& W, const DevF32& bias, float* out, int out_ld, int B, int K,
                  int npg, int groups, int relu, cudaStream_t s)
 {
-    dim3 grid((npg * groups + 7) / 8, (B + ape::kDenseObj - 1) / ape::kDenseObj);
-    if (grid.y > 64) grid.y = 64;
-    ape::ProfScope prof_("dense_small", s);
-    ape::dense_small_kernel<<<grid, 256, 0, s>>>(in, in_ld, in_gs, W.p, bias.p, out, out_ld, B, K, npg, groups, relu);
+    if (K % 128 != 0 || K > 1024 || npg % ape::kDenseOut != 0) { ape::set_error("dense: unsupported shape K=%d npg=%d", K, npg); return APE_ERR_UNSUPPORTED; }
+    const int n_out = npg * groups;
+    const size_t smem = sizeof(float) * ((size_t)ape::kDenseOut * K + 2 * ape::kDenseObj * ape::kDenseXld + 4 * ape::kDenseObj * ape::kDenseOut);
+    static bool attr_set = false;
+    if (!attr_set) {
+        APE_CUDA(cudaFuncSetAttribute(ape::dense_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        attr_set = true;
+    }
+    ape::ProfScope prof_("dense_batch", s);
+    ape::dense_batch_kernel<<<(n_out + ape::kDenseOut - 1) / ape::kDenseOut, 256, smem, s>>>(in, in_ld, in_gs, W.p, bias.p, out, out_ld, B, K,
+                                                                                            npg, n_out, relu);
     ape::count_launch();
-    return ape::check_launch("dense_small");
+    return ape::check_launch("dense_batch");
 }
 
 extern "C" __attribute__((visibility("default")))
@@ -667,6 +769,14 @@ int ape_posenet_forward(ape_net* net, const float* out_img, int hw, const float*
     p = split_layer(M, 256, 640, 3, 0, 640, net->b_h2.p, net->H2, 0);          // conv2_{r,t,c}
     if ((rc = run_gemm(net, net->H1, net->W_h2, &net->H2, p, wide_layer(4), s, "gemm.pn.heads2"))) return rc;
     p = split_layer(M, 128, 256, 3, 0, 256, net->b_h3.p, net->H3, 0);          // conv3_{r,t,c}
+    if (net->gemm_impl == APE_GEMM_TCGEN05) {
+        // conv4_{r,t,c} of the object's class + sigmoid folded into the conv3 epilogue: H3 is never written
+        p.mode = ape::tc::EPI_HEAD_OUT; p.rows_per_obj = Np; p.valid_rows = N; p.obj = obj; p.num_obj = net->num_obj; p.batch = B;
+        p.w4[0] = net->w4r.p; p.w4[1] = net->w4t.p; p.w4[2] = net->w4c.p;
+        p.b4[0] = net->b4r.p; p.b4[1] = net->b4t.p; p.b4[2] = net->b4c.p;
+        p.pred[0] = pred_r; p.pred[1] = pred_t; p.pred[2] = pred_c;
+        return run_gemm(net, net->H2, net->W_h3, nullptr, p, false, s, "gemm.pn.heads3");
+    }
     if ((rc = run_gemm(net, net->H2, net->W_h3, &net->H3, p, wide_layer(5), s, "gemm.pn.heads3"))) return rc;
     dim3 go((N + 7) / 8 < 64 ? (N + 7) / 8 : 64, B);
     ape::ProfScope prof_("posenet_out", s);

@@ -51,9 +51,11 @@ def surface_backproject(label, depth, cam, robot2cam, capacity, frame_of=None, l
     points = torch.empty((V, capacity, 3), dtype=torch.float64, device=dev)
     pix = torch.empty((V, capacity), dtype=torch.int32, device=dev) if want_pixels else None
     counts = torch.empty((V,), dtype=torch.int32, device=dev)
-    check(_lib.load().ape_surface_backproject(ptr(label), ptr(depth), F, H, W, ptr(frame_of), ptr(label_value), ptr(cam),
-                                              ptr(robot2cam), V, capacity, ptr(points), ptr(pix), ptr(counts),
-                                              stream_ptr()), 'ape_surface_backproject')
+    lib = _lib.load()
+    work = torch.empty(((int(lib.ape_surface_work_bytes(V, H, W)) + 3) // 4,), dtype=torch.int32, device=dev)
+    check(lib.ape_surface_backproject(ptr(label), ptr(depth), F, H, W, ptr(frame_of), ptr(label_value), ptr(cam),
+                                      ptr(robot2cam), V, capacity, ptr(points), ptr(pix), ptr(counts), ptr(work),
+                                      stream_ptr()), 'ape_surface_backproject')
     return points, pix, counts
 
 

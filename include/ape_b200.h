@@ -78,11 +78,14 @@ int ape_backproject_choose(const uint16_t* depth, int n_frames, int height, int 
  *   capacity     max points per view;  points [n_views,capacity,3] fp64 out
  *   pixel_index  [n_views,capacity] int32 flat pixel index of every emitted point, or NULL
  *   counts       [n_views] int32 out: number of valid pixels (may exceed capacity: the excess is dropped,
- *                the caller checks)                                                              */
+ *                the caller checks)
+ *   work         scratch of ape_surface_work_bytes(n_views, height, width) bytes (4-byte aligned; the call
+ *                zeroes it on `stream`): tile ticket + one look-back word per 8192-pixel chunk           */
+size_t ape_surface_work_bytes(int n_views, int height, int width);
 int ape_surface_backproject(const uint8_t* label, const uint16_t* depth, int n_frames, int height, int width,
                             const int32_t* frame_of, const uint8_t* label_value,
                             const double* cam, const double* robot2cam, int n_views, int capacity,
-                            double* points, int32_t* pixel_index, int32_t* counts, void* stream);
+                            double* points, int32_t* pixel_index, int32_t* counts, void* work, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a14. Brute-force k nearest neighbours.
