@@ -41,36 +41,44 @@ backproject_choose_kernel(const uint16_t* __restrict__ depth, int n_frames, int 
 }
 
 // ---------------------------------------------------------------------------------- a4
-// One CTA per 8192-pixel chunk of one view, many CTAs in flight per SM (the first version walked a whole frame with
-// one CTA: 1.35 TB/s, latency-bound).  Each thread owns 32 consecutive pixels (2 x 16 B of label, 4 x 16 B of depth,
-// streaming loads), builds a 32-bit validity mask; a block scan of the pop-counts gives the chunk-local slots; the
-// chunk's base offset is the sum of the totals published by the chunks before it in the same view (decoupled
-// look-back without a serial chain; tiles are taken from an atomic ticket so every predecessor is already running).  The valid pixels are first compacted into shared memory (16-bit in-chunk offsets, row-major order) and
-// then processed by ALL threads, so the fp64 work is balanced and the 24-byte point stores are contiguous.
+// Two embarrassingly parallel kernels, no inter-CTA waiting:
+//   surface_mask_kernel : pure stream over label + depth (the 921 600 B/frame of SURVEY 8d).  Each thread owns 32
+//                         consecutive pixels (2 x 16 B of label, 4 x 16 B of depth, streaming loads), builds a 32-bit
+//                         validity mask, writes it (4 B per 96 B read) and the CTA writes its chunk's pop-count.
+//   surface_emit_kernel : per 8192-pixel chunk with at least one valid pixel: base offset = sum of the counts of the
+//                         chunks before it in the same view (<= 37 words), block scan of the mask pop-counts, compaction
+//                         of the in-chunk offsets into shared memory (row-major = np.where order), then ALL threads
+//                         convert the compacted pixels (balanced fp64 work, contiguous 24-byte point stores).  Depth is
+//                         re-read only for valid pixels.
+// History (profiles/): one CTA per view walking the frame = 1.35 TB/s (latency-bound); single-pass chunked kernels
+// with a decoupled look-back = 1.5 TB/s, and 0.16 TB/s when made persistent (convoy on the look-back flags).
 constexpr int kSurfThreads = 256;
 constexpr int kSurfPix = 32;                       // pixels per thread
 constexpr int kSurfChunk = kSurfThreads * kSurfPix;   // 8192 pixels = 24 KB of input per CTA
 
 struct SurfRegs { uint4 l0, l1, d0, d1, d2, d3; };
 
+// ragged tail (a thread span that crosses the end of the frame): scalar, zero-filled; kept out of line so that its
+// byte arrays do not inflate the register budget of the streaming path
+__device__ __noinline__ void surf_load_tail(SurfRegs* r, const uint8_t* lab, const uint16_t* dep, int p, int npix) {
+    uint32_t lw[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dw[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 32 && p + i < npix; ++i) {
+        lw[i >> 2] |= (uint32_t)lab[p + i] << (8 * (i & 3));
+        dw[i >> 1] |= (uint32_t)dep[p + i] << (16 * (i & 1));
+    }
+    r->l0 = make_uint4(lw[0], lw[1], lw[2], lw[3]);   r->l1 = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+    r->d0 = make_uint4(dw[0], dw[1], dw[2], dw[3]);   r->d1 = make_uint4(dw[4], dw[5], dw[6], dw[7]);
+    r->d2 = make_uint4(dw[8], dw[9], dw[10], dw[11]); r->d3 = make_uint4(dw[12], dw[13], dw[14], dw[15]);
+}
 __device__ __forceinline__ void surf_load(SurfRegs& r, const uint8_t* lab, const uint16_t* dep, int p, int npix) {
     if (p + kSurfPix <= npix) {
         r.l0 = ld_stream16(lab + p);      r.l1 = ld_stream16(lab + p + 16);
         r.d0 = ld_stream16(dep + p);      r.d1 = ld_stream16(dep + p + 8);
         r.d2 = ld_stream16(dep + p + 16); r.d3 = ld_stream16(dep + p + 24);
-    } else {                              // ragged tail (or past the end): scalar, zero-filled
-        uint8_t lb[32]; uint16_t db[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const bool in = p + i < npix;
-            lb[i] = in ? lab[p + i] : (uint8_t)0;
-            db[i] = in ? dep[p + i] : (uint16_t)0;
-        }
-        const uint32_t* lw = reinterpret_cast<const uint32_t*>(lb);
-        const uint32_t* dw = reinterpret_cast<const uint32_t*>(db);
-        r.l0 = make_uint4(lw[0], lw[1], lw[2], lw[3]);   r.l1 = make_uint4(lw[4], lw[5], lw[6], lw[7]);
-        r.d0 = make_uint4(dw[0], dw[1], dw[2], dw[3]);   r.d1 = make_uint4(dw[4], dw[5], dw[6], dw[7]);
-        r.d2 = make_uint4(dw[8], dw[9], dw[10], dw[11]); r.d3 = make_uint4(dw[12], dw[13], dw[14], dw[15]);
+    } else if (p >= npix) {               // past the end of the frame (last chunk)
+        r.l0 = r.l1 = r.d0 = r.d1 = r.d2 = r.d3 = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+        surf_load_tail(&r, lab, dep, p, npix);
     }
 }
 
@@ -87,34 +95,19 @@ __device__ __forceinline__ uint32_t depth_bits(uint32_t w) {
     return ((nz >> 15) & 1u) | ((nz >> 30) & 2u);
 }
 
-// work layout (zeroed by the launcher): [0] ticket counter, [1 + v*n_chunks + c] = 0x80000000 | valid pixels of the chunk
-__global__ void __launch_bounds__(kSurfThreads, 3)
-surface_backproject_kernel(const uint8_t* __restrict__ label, const uint16_t* __restrict__ depth, int H, int W,
-                           const int32_t* __restrict__ frame_of, const uint8_t* __restrict__ label_value,
-                           const double* __restrict__ cam, const double* __restrict__ robot2cam, int capacity,
-                           double* __restrict__ points, int32_t* __restrict__ pixel_index,
-                           int32_t* __restrict__ counts, uint32_t* __restrict__ work, int n_chunks)
+// work layout: counts [n_views * n_chunks] int32, then masks [n_views * n_chunks * 256] u32 (one bit per pixel)
+__global__ void __launch_bounds__(kSurfThreads, 4)
+surface_mask_kernel(const uint8_t* __restrict__ label, const uint16_t* __restrict__ depth, int npix,
+                    const int32_t* __restrict__ frame_of, const uint8_t* __restrict__ label_value,
+                    int32_t* __restrict__ chunk_count, uint32_t* __restrict__ masks, int n_chunks)
 {
-    __shared__ uint16_t s_list[kSurfChunk];                // compacted in-chunk offsets of the valid pixels
     __shared__ int s_warp_tot[kSurfThreads / 32];
-    __shared__ int s_tile, s_base;
-    __shared__ double s_par[16];                           // robot2cam rows 0..2 (12) + ppx, ppy, fx, fy
-    if (threadIdx.x == 0) s_tile = (int)atomicAdd(&work[0], 1u);
-    __syncthreads();
-    const int tile = s_tile;
+    const int tile = blockIdx.x;
     const int v = tile / n_chunks, c = tile - v * n_chunks;
     const int f = frame_of ? frame_of[v] : v;
-    const uint32_t want = label_value ? label_value[v] : 0u;
-    const uint32_t want4 = want * 0x01010101u;
-    const int npix = H * W;
-    const uint8_t* lab = label + (size_t)f * npix;
-    const uint16_t* dep = depth + (size_t)f * npix;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int p0 = c * kSurfChunk;
-    const int p = p0 + threadIdx.x * kSurfPix;
-
+    const uint32_t want4 = (label_value ? (uint32_t)label_value[v] : 0u) * 0x01010101u;
     SurfRegs cur;
-    surf_load(cur, lab, dep, p, npix);
+    surf_load(cur, label + (size_t)f * npix, depth + (size_t)f * npix, c * kSurfChunk + threadIdx.x * kSurfPix, npix);
     const uint32_t lw[8] = {cur.l0.x, cur.l0.y, cur.l0.z, cur.l0.w, cur.l1.x, cur.l1.y, cur.l1.z, cur.l1.w};
     const uint32_t dw[16] = {cur.d0.x, cur.d0.y, cur.d0.z, cur.d0.w, cur.d1.x, cur.d1.y, cur.d1.z, cur.d1.w,
                              cur.d2.x, cur.d2.y, cur.d2.z, cur.d2.w, cur.d3.x, cur.d3.y, cur.d3.z, cur.d3.w};
@@ -125,7 +118,46 @@ surface_backproject_kernel(const uint8_t* __restrict__ label, const uint16_t* __
 #pragma unroll
     for (int i = 0; i < 16; ++i) dmask |= depth_bits(dw[i]) << (2 * i);
     mask &= dmask;
+    masks[(size_t)tile * kSurfThreads + threadIdx.x] = mask;
+    const int cnt = warp_sum(__popc(mask));
+    if ((threadIdx.x & 31) == 0) s_warp_tot[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < kSurfThreads / 32; ++w) t += s_warp_tot[w];
+        chunk_count[tile] = t;
+    }
+}
 
+__global__ void __launch_bounds__(kSurfThreads)
+surface_emit_kernel(const uint16_t* __restrict__ depth, int H, int W, const int32_t* __restrict__ frame_of,
+                    const double* __restrict__ cam, const double* __restrict__ robot2cam, int capacity,
+                    double* __restrict__ points, int32_t* __restrict__ pixel_index, int32_t* __restrict__ counts,
+                    const int32_t* __restrict__ chunk_count, const uint32_t* __restrict__ masks, int n_chunks)
+{
+    __shared__ uint16_t s_list[kSurfChunk];                // compacted in-chunk offsets of the valid pixels
+    __shared__ int s_warp_tot[kSurfThreads / 32];
+    __shared__ int s_base;
+    __shared__ double s_par[16];                           // robot2cam rows 0..2 (12) + ppx, ppy, fx, fy
+    const int tile = blockIdx.x;
+    const int v = tile / n_chunks, c = tile - v * n_chunks;
+    const int total = chunk_count[tile];
+    if (total == 0 && c != n_chunks - 1) return;           // nothing to emit (uniform across the CTA)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp == 0) {                                       // base = valid pixels of the chunks before this one
+        int sum = 0;
+        for (int j = lane; j < c; j += 32) sum += chunk_count[v * n_chunks + j];
+        sum = warp_sum(sum);
+        if (lane == 0) {
+            s_base = sum;
+            if (c == n_chunks - 1) counts[v] = sum + total;
+        }
+    } else if (warp == 1 && lane < 16) {
+        s_par[lane] = lane < 12 ? robot2cam[16 * v + lane] : cam[4 * v + (lane - 12)];
+    }
+    if (total == 0) return;
+    const uint32_t mask = masks[(size_t)tile * kSurfThreads + threadIdx.x];
     const int cnt = __popc(mask);
     int incl = cnt;                                        // warp inclusive scan
 #pragma unroll
@@ -135,32 +167,9 @@ surface_backproject_kernel(const uint8_t* __restrict__ label, const uint16_t* __
     }
     if (lane == 31) s_warp_tot[warp] = incl;
     __syncthreads();
-    int before = 0, total = 0;
+    int before = 0;
 #pragma unroll
-    for (int w = 0; w < kSurfThreads / 32; ++w) {
-        const int t = s_warp_tot[w];
-        before += (w < warp) ? t : 0;
-        total += t;
-    }
-    // Every chunk publishes its own total at once; the base offset is the sum of the totals of the chunks before it
-    // (no serial chain: predecessors hold smaller tickets, so they are running and publish without waiting on anyone).
-    if (warp == 0) {
-        volatile uint32_t* st = work + 1 + (size_t)v * n_chunks;
-        if (lane == 0) st[c] = 0x80000000u | (uint32_t)total;
-        uint32_t sum = 0;
-        for (int j = lane; j < c; j += 32) {
-            uint32_t x;
-            unsigned spin = 0;
-            while (((x = st[j]) & 0x80000000u) == 0u) { if (++spin > (1u << 26)) __trap(); }
-            sum += x & 0x7fffffffu;
-        }
-        sum = (uint32_t)warp_sum((int)sum);
-        if (lane == 0) {
-            s_base = (int)sum;
-            if (c == n_chunks - 1) counts[v] = (int)sum + total;
-        }
-    }
-    // compaction of the in-chunk offsets (independent of the base)
+    for (int w = 0; w < kSurfThreads / 32; ++w) before += (w < warp) ? s_warp_tot[w] : 0;
     {
         int slot = before + incl - cnt;
         uint32_t m = mask;
@@ -170,11 +179,10 @@ surface_backproject_kernel(const uint8_t* __restrict__ label, const uint16_t* __
             s_list[slot++] = (uint16_t)(threadIdx.x * kSurfPix + i);
         }
     }
-    if (threadIdx.x >= 32 && threadIdx.x < 48) {
-        const int i = threadIdx.x - 32;
-        s_par[i] = i < 12 ? robot2cam[16 * v + i] : cam[4 * v + (i - 12)];
-    }
     __syncthreads();
+    const int f = frame_of ? frame_of[v] : v;
+    const uint16_t* dep = depth + (size_t)f * H * W;
+    const int p0 = c * kSurfChunk;
     const int base = s_base;
     const double* T = s_par;
     const double ppx = s_par[12], ppy = s_par[13], fx = s_par[14], fy = s_par[15];
@@ -185,7 +193,7 @@ surface_backproject_kernel(const uint8_t* __restrict__ label, const uint16_t* __
         if (slot >= capacity) break;
         const int pix = p0 + (int)s_list[i];
         const int r = pix / W, col = pix - r * W;
-        const double z = (double)dep[pix];                 // L2 hit (this CTA just streamed the chunk)
+        const double z = (double)dep[pix];
         // open3d_utils.py:185-189: p0 = ((px-ppx)*z)/fx, p1 = ((py-ppy)*z)/fy (fp64, rounded per op)
         const double x = __ddiv_rn(__dmul_rn(__dsub_rn((double)col, ppx), z), fx);
         const double y = __ddiv_rn(__dmul_rn(__dsub_rn((double)r, ppy), z), fy);
@@ -220,7 +228,8 @@ extern "C" __attribute__((visibility("default"))) int ape_backproject_choose(con
 extern "C" __attribute__((visibility("default"))) size_t ape_surface_work_bytes(int n_views, int height, int width)
 {
     const size_t chunks = ((size_t)(height > 0 ? height : 0) * (size_t)(width > 0 ? width : 0) + ape::kSurfChunk - 1) / ape::kSurfChunk;
-    return 4 * (1 + (size_t)(n_views > 0 ? n_views : 0) * chunks);
+    const size_t tiles = (size_t)(n_views > 0 ? n_views : 0) * chunks;
+    return 4 * tiles + 4 * tiles * ape::kSurfThreads;        // chunk counts + one mask bit per pixel
 }
 
 extern "C" __attribute__((visibility("default"))) int ape_surface_backproject(const uint8_t* label, const uint16_t* depth, int n_frames, int height,
@@ -240,11 +249,20 @@ extern "C" __attribute__((visibility("default"))) int ape_surface_backproject(co
     const int n_chunks = (int)(((size_t)height * width + ape::kSurfChunk - 1) / ape::kSurfChunk);
     APE_REQUIRE((size_t)n_views * n_chunks < (1u << 31), "ape_surface_backproject: too many views (split the batch)");
     cudaStream_t s = (cudaStream_t)stream;
-    APE_CUDA(cudaMemsetAsync(work, 0, ape_surface_work_bytes(n_views, height, width), s));
-    ape::ProfScope prof_("surface_backproject", s);
-    ape::surface_backproject_kernel<<<n_views * n_chunks, ape::kSurfThreads, 0, s>>>(
-        label, depth, height, width, frame_of, label_value, cam, robot2cam, capacity, points, pixel_index, counts,
-        reinterpret_cast<uint32_t*>(work), n_chunks);
+    const int n_tiles = n_views * n_chunks;
+    int32_t* chunk_count = reinterpret_cast<int32_t*>(work);
+    uint32_t* masks = reinterpret_cast<uint32_t*>(work) + n_tiles;
+    {
+        ape::ProfScope prof_("surface_mask", s);
+        ape::surface_mask_kernel<<<n_tiles, ape::kSurfThreads, 0, s>>>(label, depth, height * width, frame_of, label_value,
+                                                                       chunk_count, masks, n_chunks);
+        ape::count_launch();
+    }
+    int rc = ape::check_launch("ape_surface_backproject (mask)");
+    if (rc) return rc;
+    ape::ProfScope prof_("surface_emit", s);
+    ape::surface_emit_kernel<<<n_tiles, ape::kSurfThreads, 0, s>>>(depth, height, width, frame_of, cam, robot2cam, capacity, points,
+                                                                   pixel_index, counts, chunk_count, masks, n_chunks);
     ape::count_launch();
-    return ape::check_launch("ape_surface_backproject");
+    return ape::check_launch("ape_surface_backproject (emit)");
 }

@@ -140,6 +140,17 @@ __device__ void kabsch_rotation(const double* sigma, double* R) {
             R[3 * i + j] = Um[3 * i] * V[3 * j] + Um[3 * i + 1] * V[3 * j + 1] + sgn * Um[3 * i + 2] * V[3 * j + 2];
 }
 
+// Candidate j at squared distance d against the running best: strict '<' replaces, an exact tie goes to the lowest
+// ORIGINAL target index (worig maps cell-sorted position -> original index; bpos < 0 while nothing is accepted).
+__device__ __forceinline__ void icp_consider(double d, int j, double& best, int& bpos, int& borig, const int32_t* __restrict__ worig) {
+    if (d < best) { best = d; bpos = j; borig = 0x7fffffff; }
+    else if (d == best && bpos >= 0) {
+        if (borig == 0x7fffffff) borig = worig[bpos];
+        const int o = worig[j];
+        if (o < borig) { bpos = j; borig = o; }
+    }
+}
+
 __device__ __forceinline__ int cell_coord(double v, double lo, double inv_h) {
     return (int)floor((v - lo) * inv_h);
 }
@@ -305,15 +316,24 @@ icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ sr
                             if (gx2 + gy * gy + gz * gz > best) continue;
                             const int row = (zz * dim[1] + yy) * dim[0];
                             const int jb = s.cell_start[row + x_lo], je = s.cell_start[row + x_hi + 1];   // x-run is contiguous
-                            for (int j = jb; j < je; ++j) {
-                                const double dx = px - wtgt[3 * j], dy = py - wtgt[3 * j + 1], dz = pz - wtgt[3 * j + 2];
-                                const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                                if (d < best) { best = d; bpos = j; borig = 0x7fffffff; }
-                                else if (d == best && bpos >= 0) {    // exact tie: lowest ORIGINAL index wins
-                                    if (borig == 0x7fffffff) borig = worig[bpos];
-                                    const int o = worig[j];
-                                    if (o < borig) { bpos = j; borig = o; }
+                            // groups of four candidates are reduced with min first (independent chains, no branch);
+                            // only a group that reaches the running best takes the slow path with the tie rule
+                            int j = jb;
+                            for (; j + 4 <= je; j += 4) {
+                                double d[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const double dx = px - wtgt[3 * (j + u)], dy = py - wtgt[3 * (j + u) + 1], dz = pz - wtgt[3 * (j + u) + 2];
+                                    d[u] = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                                 }
+                                if (fmin(fmin(d[0], d[1]), fmin(d[2], d[3])) <= best) {
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) icp_consider(d[u], j + u, best, bpos, borig, worig);
+                                }
+                            }
+                            for (; j < je; ++j) {
+                                const double dx = px - wtgt[3 * j], dy = py - wtgt[3 * j + 1], dz = pz - wtgt[3 * j + 2];
+                                icp_consider(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)), j, best, bpos, borig, worig);
                             }
                         }
                     }

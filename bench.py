@@ -196,10 +196,12 @@ def icp_leg(torch, ops, lib, peaks, steps):
         pts, _, cnt = ops.surface_backproject(label, depth, cam, r2c, capacity=cap, want_pixels=False)
     torch.cuda.synchronize()
     rep = profile_report(lib); lib.ape_profile_enable(0)
-    ms_bp = rep['surface_backproject'][1] / rep['surface_backproject'][0]
+    ms_bp = (rep['surface_mask'][1] + rep['surface_emit'][1]) / rep['surface_mask'][0]      # two kernels per call
+    ms_mask = rep['surface_mask'][1] / rep['surface_mask'][0]
     nvalid = int(cnt.sum())
     bytes_bp = F * H * W * 3 + nvalid * 24
-    bp = dict(frames_per_s=F / ms_bp * 1e3, ms_per_launch=ms_bp, frames_per_launch=F,
+    bp = dict(frames_per_s=F / ms_bp * 1e3, ms_per_launch=ms_bp, ms_mask_kernel=ms_mask, frames_per_launch=F,
+              kernels='surface_mask_kernel (stream label+depth -> validity bits) + surface_emit_kernel (ordered compaction, fp64 points)',
               roofline=dict(bound='hbm', achieved=bytes_bp / ms_bp / 1e6, peak=peaks['hbm'], unit='GB/s',
                             frac=bytes_bp / ms_bp / 1e6 / peaks['hbm'], traffic=None, peak_source=peaks['src'],
                             algorithmic_bytes_per_launch=bytes_bp))

@@ -80,7 +80,7 @@ int ape_backproject_choose(const uint16_t* depth, int n_frames, int height, int 
  *   counts       [n_views] int32 out: number of valid pixels (may exceed capacity: the excess is dropped,
  *                the caller checks)
  *   work         scratch of ape_surface_work_bytes(n_views, height, width) bytes (4-byte aligned; the call
- *                zeroes it on `stream`): tile ticket + one look-back word per 8192-pixel chunk           */
+ *                does not need it initialised): per-chunk valid-pixel counts + one validity bit per pixel           */
 size_t ape_surface_work_bytes(int n_views, int height, int width);
 int ape_surface_backproject(const uint8_t* label, const uint16_t* depth, int n_frames, int height, int width,
                             const int32_t* frame_of, const uint8_t* label_value,
