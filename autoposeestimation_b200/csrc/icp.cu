@@ -287,13 +287,21 @@ icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ sr
 #pragma unroll
             for (int k = 0; k < 12; ++k) U[k] = s.U[k];
             double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};            // n, sum d2, sum p(3), sum q(3)
-            for (int i = tid; i < Ns; i += kIcpThreads) {
-                const double* pin = first ? (src + 3 * i) : (wsrc + 3 * i);
-                const double x0 = pin[0], y0 = pin[1], z0 = pin[2];
-                const double px = fma(U[0], x0, fma(U[1], y0, fma(U[2], z0, U[3])));
-                const double py = fma(U[4], x0, fma(U[5], y0, fma(U[6], z0, U[7])));
-                const double pz = fma(U[8], x0, fma(U[9], y0, fma(U[10], z0, U[11])));
-                wsrc[3 * i] = px; wsrc[3 * i + 1] = py; wsrc[3 * i + 2] = pz;
+            // The point loop is warp-uniform (every lane runs every trip, lanes past Ns are masked) so that the lanes can
+            // be brought back together with a warp vote before each scan: without it each lane scanned its runs on its
+            // own and the inner loop ran with 7.5 of 32 lanes active (profiles/r01d).
+            for (int i0 = (tid & ~31); i0 < Ns; i0 += kIcpThreads) {
+                const int i = i0 + (tid & 31);
+                const bool live = i < Ns;
+                double px = 0.0, py = 0.0, pz = 0.0;
+                if (live) {
+                    const double* pin = first ? (src + 3 * i) : (wsrc + 3 * i);
+                    const double x0 = pin[0], y0 = pin[1], z0 = pin[2];
+                    px = fma(U[0], x0, fma(U[1], y0, fma(U[2], z0, U[3])));
+                    py = fma(U[4], x0, fma(U[5], y0, fma(U[6], z0, U[7])));
+                    pz = fma(U[8], x0, fma(U[9], y0, fma(U[10], z0, U[11])));
+                    wsrc[3 * i] = px; wsrc[3 * i + 1] = py; wsrc[3 * i + 2] = pz;
+                }
                 const int cx = cell_coord(px, g0, inv_h), cy = cell_coord(py, g1, inv_h), cz = cell_coord(pz, g2, inv_h);
                 // best starts at r^2: only candidates with d2 < r^2 can be accepted (open3d's strict radius test), and a
                 // run of cells whose bounding box is farther than the current best is skipped.  The centre run is
@@ -301,50 +309,64 @@ icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ sr
                 // runs are rejected by the box test.  Skipping needs boxdist^2 > best strictly (an exact tie in a skipped
                 // run could otherwise win on original index); delta widens the boxes against binning round-off.
                 double best = r2; int bpos = -1, borig = 0x7fffffff;
-                if (Nt > 0 && cx >= -1 && cx <= dim[0] && cy >= -1 && cy <= dim[1] && cz >= -1 && cz <= dim[2]) {
-                    const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, dim[0] - 1);
-                    if (x_lo <= x_hi) {
-                        const double delta = 1e-6 * h;
-                        const double gx = fmax(fmax((g0 + x_lo * h - delta) - px, px - (g0 + (x_hi + 1) * h + delta)), 0.0);
-                        const double gx2 = gx * gx;
-#pragma unroll 1
-                        for (int k = 0; k < 9; ++k) {
-                            const int yy = cy + c_run_dy[k], zz = cz + c_run_dz[k];
-                            if (yy < 0 || yy >= dim[1] || zz < 0 || zz >= dim[2]) continue;
-                            const double gy = fmax(fmax((g1 + yy * h - delta) - py, py - (g1 + (yy + 1) * h + delta)), 0.0);
-                            const double gz = fmax(fmax((g2 + zz * h - delta) - pz, pz - (g2 + (zz + 1) * h + delta)), 0.0);
-                            if (gx2 + gy * gy + gz * gz > best) continue;
-                            const int row = (zz * dim[1] + yy) * dim[0];
-                            const int jb = s.cell_start[row + x_lo], je = s.cell_start[row + x_hi + 1];   // x-run is contiguous
-                            // groups of four candidates are reduced with min first (independent chains, no branch);
-                            // only a group that reaches the running best takes the slow path with the tie rule
-                            int j = jb;
-                            for (; j + 4 <= je; j += 4) {
-                                double d[4];
+                const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, dim[0] - 1);
+                const double delta = 1e-6 * h;
+                const double gx = fmax(fmax((g0 + x_lo * h - delta) - px, px - (g0 + (x_hi + 1) * h + delta)), 0.0);
+                const double gx2 = gx * gx;
+                uint32_t need = 0;                                // the runs this lane may still have to scan
+                if (live && Nt > 0 && cx >= -1 && cx <= dim[0] && cy >= -1 && cy <= dim[1] && cz >= -1 && cz <= dim[2] && x_lo <= x_hi) {
 #pragma unroll
-                                for (int u = 0; u < 4; ++u) {
-                                    const double dx = px - wtgt[3 * (j + u)], dy = py - wtgt[3 * (j + u) + 1], dz = pz - wtgt[3 * (j + u) + 2];
-                                    d[u] = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                                }
-                                if (fmin(fmin(d[0], d[1]), fmin(d[2], d[3])) <= best) {
-#pragma unroll
-                                    for (int u = 0; u < 4; ++u) icp_consider(d[u], j + u, best, bpos, borig, worig);
-                                }
-                            }
-                            for (; j < je; ++j) {
-                                const double dx = px - wtgt[3 * j], dy = py - wtgt[3 * j + 1], dz = pz - wtgt[3 * j + 2];
-                                icp_consider(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)), j, best, bpos, borig, worig);
-                            }
-                        }
+                    for (int k = 0; k < 9; ++k) {
+                        const int yy = cy + c_run_dy[k], zz = cz + c_run_dz[k];
+                        need |= (uint32_t)(yy >= 0 && yy < dim[1] && zz >= 0 && zz < dim[2]) << k;
                     }
                 }
-                if (bpos >= 0 && best < r2) {
-                    corr[i] = bpos;
-                    acc[0] += 1.0; acc[1] += best;
-                    acc[2] += px; acc[3] += py; acc[4] += pz;
-                    acc[5] += wtgt[3 * bpos]; acc[6] += wtgt[3 * bpos + 1]; acc[7] += wtgt[3 * bpos + 2];
-                } else {
-                    corr[i] = -1;
+                for (;;) {
+                    // every lane advances to ITS next run that survives the box test (short loop) ...
+                    int jb = 0, je = 0;
+                    while (need) {
+                        const int k = __ffs(need) - 1;
+                        need &= need - 1;
+                        const int yy = cy + c_run_dy[k], zz = cz + c_run_dz[k];
+                        const double gy = fmax(fmax((g1 + yy * h - delta) - py, py - (g1 + (yy + 1) * h + delta)), 0.0);
+                        const double gz = fmax(fmax((g2 + zz * h - delta) - pz, pz - (g2 + (zz + 1) * h + delta)), 0.0);
+                        if (!(gx2 + gy * gy + gz * gz > best)) {
+                            const int row = (zz * dim[1] + yy) * dim[0];
+                            jb = s.cell_start[row + x_lo]; je = s.cell_start[row + x_hi + 1];   // x-run is contiguous
+                            break;
+                        }
+                    }
+                    // ... and the warp meets here, so the scans of the 32 lanes run side by side
+                    if (!__any_sync(0xffffffffu, je > jb || need != 0u)) break;
+                    // groups of four candidates are reduced with min first (independent chains, no branch);
+                    // only a group that reaches the running best takes the slow path with the tie rule
+                    int j = jb;
+                    for (; j + 4 <= je; j += 4) {
+                        double d[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const double dx = px - wtgt[3 * (j + u)], dy = py - wtgt[3 * (j + u) + 1], dz = pz - wtgt[3 * (j + u) + 2];
+                            d[u] = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                        }
+                        if (fmin(fmin(d[0], d[1]), fmin(d[2], d[3])) <= best) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) icp_consider(d[u], j + u, best, bpos, borig, worig);
+                        }
+                    }
+                    for (; j < je; ++j) {
+                        const double dx = px - wtgt[3 * j], dy = py - wtgt[3 * j + 1], dz = pz - wtgt[3 * j + 2];
+                        icp_consider(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)), j, best, bpos, borig, worig);
+                    }
+                }
+                if (live) {
+                    if (bpos >= 0 && best < r2) {
+                        corr[i] = bpos;
+                        acc[0] += 1.0; acc[1] += best;
+                        acc[2] += px; acc[3] += py; acc[4] += pz;
+                        acc[5] += wtgt[3 * bpos]; acc[6] += wtgt[3 * bpos + 1]; acc[7] += wtgt[3 * bpos + 2];
+                    } else {
+                        corr[i] = -1;
+                    }
                 }
             }
             block_sum<8>(acc, s);
@@ -437,7 +459,7 @@ extern "C" __attribute__((visibility("default"))) int ape_icp_p2p(const double* 
         APE_CUDA(cudaFuncSetAttribute(ape::icp_p2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    const int grid = n_reg < ape::sm_count() * 4 ? n_reg : ape::sm_count() * 4;   // 4 resident CTAs per SM (registers)
+    const int grid = n_reg < ape::sm_count() * 4 ? n_reg : ape::sm_count() * 4;   // 4 resident CTAs per SM (registers); 6 with spills measured slower
     ape::ProfScope prof_("icp_p2p", (cudaStream_t)stream);
     ape::icp_p2p_kernel<<<grid, ape::kIcpThreads, smem, (cudaStream_t)stream>>>(
         source, src_offset, target, tgt_offset, n_reg, threshold, rel_fitness, rel_rmse, max_iter, init, transform, info,
