@@ -37,6 +37,15 @@ SIGNATURES = {
     'ape_refiner_forward': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
     'ape_pose_pipeline': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
                                   c_vp, c_vp, c_vp]),
+    'ape_refiner_trainer_layout': (c_i64, [c_int, c_vp]),
+    'ape_refiner_trainer_create': (c_int, [c_vp, c_vp, c_int, c_int, c_int, ctypes.POINTER(c_vp)]),
+    'ape_refiner_trainer_destroy': (c_int, [c_vp]),
+    'ape_refiner_trainer_sync_weights': (c_int, [c_vp, c_vp]),
+    'ape_refiner_trainer_forward': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
+    'ape_refiner_trainer_backward': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
+    'ape_refine_loss': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'ape_adam_step': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                              c_int, ctypes.c_float, c_vp]),
 }
 
 _lib = None

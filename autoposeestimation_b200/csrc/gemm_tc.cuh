@@ -47,6 +47,11 @@ struct Params {
     const int64_t* obj;           // [batch] class ids
     int num_obj, batch;
     float* pred[3];               // pred_r [batch,valid_rows,4], pred_t [batch,valid_rows,3], pred_c [batch,valid_rows] (sigmoid)
+    // training forward (gemm_tc2.cuh only; csrc/train.cu): plain bf16 = the A_hi*W_hi pass alone, no lo stores, and the
+    // ReLU sign bits of the pooled layer kept for the backward pass
+    int passes;                   // 1: A_hi*W_hi only;  0 or 3: the three split-bf16 passes
+    int hi_only;                  // EPI_RELU_SPLIT: skip the lo store
+    uint32_t* relu_bits;          // EPI_RELU_COLSUM: [M, groups*N/32] bit j of word c/32 = (valid row && relu(x)[c] > 0)
 };
 
 // ---------------------------------------------------------------------------------- PTX wrappers

@@ -80,7 +80,8 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
     const int n_tiles = (p.N + bn_full - 1) / bn_full;
     const int total_tiles = p.groups * m_tiles * n_tiles;
     const int kb_per_pass = p.K / BK;
-    const int iters_per_tile = 3 * kb_per_pass;
+    const int n_pass = p.passes == 1 ? 1 : 3;
+    const int iters_per_tile = n_pass * kb_per_pass;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
@@ -112,8 +113,9 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
                     const int s = it % kStages2;
                     const uint32_t ph = (uint32_t)(it / kStages2) & 1u;
                     mbar_wait(&empty_bar[s], ph ^ 1u);
-                    const int pass = i / kb_per_pass, kb = i - pass * kb_per_pass;
-                    // pass 0: A_lo*W_hi, pass 1: A_hi*W_lo, pass 2: A_hi*W_hi (small terms first)
+                    const int pass_i = i / kb_per_pass, kb = i - pass_i * kb_per_pass;
+                    // pass 0: A_lo*W_hi, pass 1: A_hi*W_lo, pass 2: A_hi*W_hi (small terms first); plain bf16 = pass 2 alone
+                    const int pass = n_pass == 1 ? 2 : pass_i;
                     const CUtensorMap* ma = (pass == 0) ? &map_a_lo : &map_a_hi;
                     const CUtensorMap* mw = (pass == 1) ? &map_w_lo : &map_w_hi;
                     unsigned char* sa = smem + s * kStage;
@@ -224,14 +226,14 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
                     for (int j = 0; j < 8; ++j) {
                         const uint32_t off = (uint32_t)lane * 128u + ((uint32_t)j ^ sw) * 16u;
                         *reinterpret_cast<uint4*>(sh + off) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                        *reinterpret_cast<uint4*>(sl + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        if (!p.hi_only) *reinterpret_cast<uint4*>(sl + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
                     }
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
                         const int oc = p.o_c0 + col_g + c0;
                         tma_store_2d(&map_o_hi, sh, oc, row0);
-                        tma_store_2d(&map_o_lo, sl, oc, row0);
+                        if (!p.hi_only) tma_store_2d(&map_o_lo, sl, oc, row0);
                         bulk_commit();
                     }
                 }
@@ -295,6 +297,12 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
                     for (int j = 0; j < 32; ++j) {
                         const float x = fmaxf(__uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bcur, j), 0.0f);
                         f[j] = valid ? x : 0.0f;
+                    }
+                    if (p.relu_bits) {
+                        uint32_t bits = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) bits |= (f[j] > 0.0f ? 1u : 0u) << j;
+                        p.relu_bits[(size_t)row * (size_t)(GN >> 5) + (size_t)((col_g + c0) >> 5)] = bits;
                     }
                     // masked column sum over this warp's 32 rows: butterfly transpose-reduce, lane j ends
                     // with the sum of column c0 + j

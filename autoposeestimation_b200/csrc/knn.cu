@@ -198,6 +198,122 @@ add_metric_kernel(const float* __restrict__ quat, const float* __restrict__ tran
     }
 }
 
+
+// ------------------------------------------------------------------------------ refiner loss, forward + backward
+// Loss_refine (DenseFusion/lib/loss_refiner.py:12-64) for B objects with its gradient, one CTA per object:
+//   q = r / |r|, Rm = base(q), pred_j = Rm m_j + t (:39); symmetric: tgt_j = nearest target to pred_j (:41-47, the
+//   index is a constant of the backward pass exactly as the reference detaches it); dis = mean_j |pred_j - tgt_j| (:49)
+//   d dis / d pred_j = (pred_j - tgt_j) / (M |.|);  d_t = sum_j,  dRm = sum_j g_j m_j^T,  d_r through base() and
+//   the normalisation.  Also new_points = (points - t) Rm and new_target = (target - t) Rm (:51-60).
+constexpr int kLossThreads = 256;
+__global__ void __launch_bounds__(kLossThreads)
+refine_loss_kernel(const float* __restrict__ quat, const float* __restrict__ trans, const float* __restrict__ model,
+                   const float* __restrict__ target, int n_mesh, const float* __restrict__ points, int n_points,
+                   const uint8_t* __restrict__ symmetric, float* __restrict__ dis, float* __restrict__ d_r,
+                   float* __restrict__ d_t, float* __restrict__ new_points, float* __restrict__ new_target)
+{
+    __shared__ float4 s_ref[kKnnRefTile];
+    __shared__ float s_part[kLossThreads / 32][13];
+    const int b = blockIdx.x;
+    const float* Mp = model + (size_t)b * n_mesh * 3;
+    const float* Tg = target + (size_t)b * n_mesh * 3;
+    const float r0 = quat[4 * b], r1 = quat[4 * b + 1], r2 = quat[4 * b + 2], r3 = quat[4 * b + 3];
+    const float nrm = sqrtf(r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3);
+    const float w = r0 / nrm, x = r1 / nrm, y = r2 / nrm, z = r3 / nrm;
+    float R[9];
+    quat_to_base(w, x, y, z, R);
+    const float tx = trans[3 * b], ty = trans[3 * b + 1], tz = trans[3 * b + 2];
+    const bool sym = symmetric && symmetric[b];
+    float acc[13] = {};                                    // dis, d_t[3], dRm[9]
+    for (int p0 = 0; p0 < n_mesh; p0 += kLossThreads * kKnnQ) {
+        const int q0 = p0 + threadIdx.x * kKnnQ;
+        float qx[kKnnQ], qy[kKnnQ], qz[kKnnQ], best[kKnnQ], mx[kKnnQ], my[kKnnQ], mz[kKnnQ];
+        int bidx[kKnnQ];
+#pragma unroll
+        for (int q = 0; q < kKnnQ; ++q) {
+            const int i = min(q0 + q, n_mesh - 1);
+            mx[q] = Mp[3 * i]; my[q] = Mp[3 * i + 1]; mz[q] = Mp[3 * i + 2];
+            qx[q] = (mx[q] * R[0] + my[q] * R[1] + mz[q] * R[2]) + tx;
+            qy[q] = (mx[q] * R[3] + my[q] * R[4] + mz[q] * R[5]) + ty;
+            qz[q] = (mx[q] * R[6] + my[q] * R[7] + mz[q] * R[8]) + tz;
+            best[q] = FLT_MAX; bidx[q] = q0 + q < n_mesh ? q0 + q : 0;
+        }
+        if (sym) {
+            for (int t0 = 0; t0 < n_mesh; t0 += kKnnRefTile) {
+                const int n = min(kKnnRefTile, n_mesh - t0);
+                __syncthreads();
+                for (int i = threadIdx.x; i < n; i += kLossThreads)
+                    s_ref[i] = make_float4(Tg[3 * (t0 + i)], Tg[3 * (t0 + i) + 1], Tg[3 * (t0 + i) + 2], 0.f);
+                __syncthreads();
+                scan_tile<false>(s_ref, n, t0, qx, qy, qz, best, bidx);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kKnnQ; ++q) {
+            if (q0 + q < n_mesh) {
+                const int i = bidx[q];
+                const float dx = qx[q] - Tg[3 * i], dy = qy[q] - Tg[3 * i + 1], dz = qz[q] - Tg[3 * i + 2];
+                const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+                acc[0] += d;
+                const float inv = d > 0.f ? 1.0f / (d * (float)n_mesh) : 0.f;
+                const float gx = dx * inv, gy = dy * inv, gz = dz * inv;
+                acc[1] += gx; acc[2] += gy; acc[3] += gz;
+                acc[4] += gx * mx[q]; acc[5] += gx * my[q]; acc[6] += gx * mz[q];
+                acc[7] += gy * mx[q]; acc[8] += gy * my[q]; acc[9] += gy * mz[q];
+                acc[10] += gz * mx[q]; acc[11] += gz * my[q]; acc[12] += gz * mz[q];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 13; ++i) acc[i] = warp_sum(acc[i]);
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int i = 0; i < 13; ++i) s_part[threadIdx.x >> 5][i] = acc[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s[13];
+        for (int i = 0; i < 13; ++i) {
+            s[i] = 0.f;
+            for (int k = 0; k < kLossThreads / 32; ++k) s[i] += s_part[k][i];
+        }
+        dis[b] = s[0] / (float)n_mesh;
+        if (d_t) { d_t[3 * b] = s[1]; d_t[3 * b + 1] = s[2]; d_t[3 * b + 2] = s[3]; }
+        if (d_r) {
+            const float* D = s + 4;                         // dRm, row-major like R
+            const float gw = -2.f * z * D[1] + 2.f * y * D[2] + 2.f * z * D[3] - 2.f * x * D[5] - 2.f * y * D[6] + 2.f * x * D[7];
+            const float gx = 2.f * y * D[1] + 2.f * z * D[2] + 2.f * y * D[3] - 4.f * x * D[4] - 2.f * w * D[5] + 2.f * z * D[6] +
+                             2.f * w * D[7] - 4.f * x * D[8];
+            const float gy = -4.f * y * D[0] + 2.f * x * D[1] + 2.f * w * D[2] + 2.f * x * D[3] + 2.f * z * D[5] - 2.f * w * D[6] +
+                             2.f * z * D[7] - 4.f * y * D[8];
+            const float gz = -4.f * z * D[0] - 2.f * w * D[1] + 2.f * x * D[2] + 2.f * w * D[3] - 4.f * z * D[4] + 2.f * y * D[5] +
+                             2.f * x * D[6] + 2.f * y * D[7];
+            const float dot = gw * w + gx * x + gy * y + gz * z;
+            d_r[4 * b] = (gw - w * dot) / nrm; d_r[4 * b + 1] = (gx - x * dot) / nrm;
+            d_r[4 * b + 2] = (gy - y * dot) / nrm; d_r[4 * b + 3] = (gz - z * dot) / nrm;
+        }
+    }
+    // next-iteration cloud and target in the predicted frame: (p - t) . Rm  (row vector times ori_base)
+    if (new_points) {
+        const float* P = points + (size_t)b * n_points * 3;
+        float* O = new_points + (size_t)b * n_points * 3;
+        for (int i = threadIdx.x; i < n_points; i += kLossThreads) {
+            const float px = P[3 * i] - tx, py = P[3 * i + 1] - ty, pz = P[3 * i + 2] - tz;
+            O[3 * i] = px * R[0] + py * R[3] + pz * R[6];
+            O[3 * i + 1] = px * R[1] + py * R[4] + pz * R[7];
+            O[3 * i + 2] = px * R[2] + py * R[5] + pz * R[8];
+        }
+    }
+    if (new_target) {
+        float* O = new_target + (size_t)b * n_mesh * 3;
+        for (int i = threadIdx.x; i < n_mesh; i += kLossThreads) {
+            const float px = Tg[3 * i] - tx, py = Tg[3 * i + 1] - ty, pz = Tg[3 * i + 2] - tz;
+            O[3 * i] = px * R[0] + py * R[3] + pz * R[6];
+            O[3 * i + 1] = px * R[1] + py * R[4] + pz * R[7];
+            O[3 * i + 2] = px * R[2] + py * R[5] + pz * R[8];
+        }
+    }
+}
+
 }  // namespace ape
 
 extern "C" __attribute__((visibility("default"))) int ape_knn(const float* ref, const float* query, int64_t* idx, int B, int D, int N, int M, int k,
@@ -242,4 +358,20 @@ extern "C" __attribute__((visibility("default"))) int ape_add_metric(const float
         quat, trans, model_points, model_stride, n_model, target, target_stride, n_target, symmetric, dis, nn_index);
     ape::count_launch();
     return ape::check_launch("ape_add_metric");
+}
+
+extern "C" __attribute__((visibility("default"))) int ape_refine_loss(const float* quat, const float* trans, const float* model_points, const float* target,
+                               int n_mesh, const float* points, int n_points, const uint8_t* symmetric, int B, float* dis,
+                               float* d_r, float* d_t, float* new_points, float* new_target, void* stream)
+{
+    APE_REQUIRE(quat && trans && model_points && target && dis, "ape_refine_loss: null pointer");
+    APE_REQUIRE(B >= 0 && n_mesh > 0, "ape_refine_loss: bad sizes");
+    APE_REQUIRE(!new_points || (points && n_points > 0), "ape_refine_loss: new_points needs the input cloud");
+    APE_REQUIRE(new_points != points && new_target != target, "ape_refine_loss: outputs must not alias inputs");
+    if (B == 0) return APE_OK;
+    ape::ProfScope prof_("train.refine_loss", (cudaStream_t)stream);
+    ape::refine_loss_kernel<<<B, ape::kLossThreads, 0, (cudaStream_t)stream>>>(quat, trans, model_points, target, n_mesh, points,
+                                                                              n_points, symmetric, dis, d_r, d_t, new_points, new_target);
+    ape::count_launch();
+    return ape::check_launch("ape_refine_loss");
 }

@@ -428,6 +428,9 @@ struct ape_net {
     DevF32 s_r, s_t, s_c, s_emb, s_newp, s_r2, s_t2, s_myr, s_myt;
     double *s_pose_a = nullptr, *s_pose_b = nullptr;
     int32_t* s_which = nullptr;
+    // training forward (train.cuh): plain-bf16 GEMM passes, hi-only stores, ReLU sign bits of conv6 kept
+    int train = 0;
+    uint32_t* relu_bits = nullptr;
 };
 
 static int dev_alloc(ape_net* net, void** p, size_t bytes) {
@@ -712,14 +715,17 @@ static int run_trunk(ape_net* net, const float* feat_src, int hw, const float* c
     const bool pn = net->kind == APE_NET_POSENET, pn_ = pn;
     // conv2 (PF[:,0:64] -> PF[:,128:256]) and e_conv2 (PF[:,64:128] -> PF[:,256:384]) as two groups
     ape::tc::Params p = split_layer(M, 128, 64, 2, 0, 64, net->b_c2e2.p, net->PF, 128);
+    if (net->train) { p.passes = 1; p.hi_only = 1; }
     if ((rc = run_gemm(net, net->PF, net->W_c2e2, &net->PF, p, wide_layer(0), s, pn_ ? "gemm.pn.conv2" : "gemm.rf.conv2"))) return rc;
     // conv5: PoseNet reads pointfeat_2 = PF[:,128:384] (network.py:62); refiner reads pointfeat_3 = PF[:,0:384] (:162)
     p = split_layer(M, 512, pn ? 256 : 384, 1, pn ? 128 : 0, 0, net->b_c5.p, net->H5, 0);
+    if (net->train) { p.passes = 1; p.hi_only = 1; }
     if ((rc = run_gemm(net, net->PF, net->W_c5, &net->H5, p, wide_layer(1), s, pn ? "gemm.pn.conv5" : "gemm.rf.conv5"))) return rc;
     // conv6 + ReLU + AvgPool1d: masked per-tile column sums, never materialising [1024, N]
     memset(&p, 0, sizeof(p));
     p.M = M; p.N = 1024; p.K = 512; p.groups = 1; p.bias = net->b_c6.p; p.mode = ape::tc::EPI_RELU_COLSUM;
     p.colsum = net->CS.p; p.rows_per_obj = Np; p.valid_rows = N;
+    if (net->train) { p.passes = 1; p.relu_bits = net->relu_bits; }
     if ((rc = run_gemm(net, net->H5, net->W_c6, nullptr, p, wide_layer(2), s, pn ? "gemm.pn.conv6" : "gemm.rf.conv6"))) return rc;
     dim3 gp(1024 / 256, B);
     ape::ProfScope prof_("pool_finish", s);
@@ -838,3 +844,5 @@ int ape_pose_pipeline(ape_net* est, ape_net* ref, const float* out_img, int hw, 
     }
     return APE_OK;
 }
+
+#include "train.cuh"

@@ -1,0 +1,529 @@
+// PoseRefineNet training step (DenseFusion/tools/train.py:215-233) -- included at the end of net.cu.
+//
+//   forward   : the inference trunk in plain bf16 (one tcgen05 pass instead of the three split-bf16 passes; BASELINE
+//               config 5 is a bf16 training step), activations kept: PF [R,384], H5 [R,512], the ReLU sign bits of
+//               conv6 (the [R,1024] map itself is never written, as in inference), AP, G1, G2
+//   backward  : heads on SIMT fp32 (batch x 1024 matrices), trunk on gemm_train.cuh (dgrad / wgrad on tcgen05 straight
+//               from the row-major buffers), conv1 / e_conv1 weight gradients on SIMT
+//   optimizer : Adam (train.py:149, :410) over ONE flat fp32 parameter vector; its flat gradient is the buffer the
+//               caller all-reduces over NCCL (the only collective of the scope)
+//
+// Flat parameter layout (floats; O = num_obj).  Grouped layers are contiguous so the grouped GEMMs see one matrix:
+//   conv1.w [64,3] | e_conv1.w [64,32] | conv2.w, e_conv2.w [2x128,64] | conv5.w [512,384] | conv6.w [1024,512] |
+//   conv1_r.w, conv1_t.w [2x512,1024] | conv2_r.w, conv2_t.w [2x128,512] | conv3_r.w [4O,128] | conv3_t.w [3O,128] |
+//   biases in the same order.
+#include "gemm_train.cuh"
+
+namespace ape {
+
+struct TrainLayout {
+    size_t w1, we1, w2e2, w5, w6, wh1, wh2, w3r, w3t, b1, be1, b2e2, b5, b6, bh1, bh2, b3r, b3t, total;
+};
+static TrainLayout train_layout(int O) {
+    TrainLayout L; size_t o = 0;
+    L.w1 = o; o += 64 * 3;      L.we1 = o; o += 64 * 32;   L.w2e2 = o; o += 256 * 64;  L.w5 = o; o += 512 * 384;
+    L.w6 = o; o += 1024 * 512;  L.wh1 = o; o += 1024 * 1024; L.wh2 = o; o += 256 * 512;
+    L.w3r = o; o += (size_t)4 * O * 128; L.w3t = o; o += (size_t)3 * O * 128;
+    L.b1 = o; o += 64; L.be1 = o; o += 64; L.b2e2 = o; o += 256; L.b5 = o; o += 512; L.b6 = o; o += 1024;
+    L.bh1 = o; o += 1024; L.bh2 = o; o += 256; L.b3r = o; o += 4 * O; L.b3t = o; o += 3 * O;
+    L.total = o;
+    return L;
+}
+
+// ------------------------------------------------------------------------------------------------ small kernels
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n)
+{
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 4 <= n) {
+        const float4 v = *reinterpret_cast<const float4*>(src + i);
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        *reinterpret_cast<uint2*>(dst + i) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    } else {
+        for (size_t j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+    }
+}
+
+// packed front-end weights [e_conv1^T 32x64 | conv1^T 3x64 | b1 | be1] (frontend_kernel) from the flat vector
+__global__ void pack_frontend_kernel(const float* __restrict__ w1, const float* __restrict__ we1, const float* __restrict__ b1,
+                                     const float* __restrict__ be1, float* __restrict__ fw)
+{
+    for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) { const int k = i >> 6, c = i & 63; fw[i] = we1[c * 32 + k]; }
+    for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) { const int k = i >> 6, c = i & 63; fw[32 * 64 + i] = w1[c * 3 + k]; }
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) { fw[32 * 64 + 3 * 64 + i] = b1[i]; fw[32 * 64 + 3 * 64 + 64 + i] = be1[i]; }
+}
+
+// Generic small fp32 GEMM with arbitrary strides (the per-object head layers: every matrix is <= 4 MB):
+//   C[m, n] (op)= alpha * sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn],  groups on blockIdx.z
+enum { SG_STORE = 0, SG_ATOMIC = 1, SG_STORE_MASK = 2 };
+struct SgemmArgs {
+    const float* A; long long sam, sak, a_g;
+    const float* B; long long sbk, sbn, b_g;
+    float* C; long long ldc, c_g;
+    const float* mask; long long ldm, m_g;       // SG_STORE_MASK: C = mask > 0 ? v : 0
+    int M, N, K, epi;
+    float alpha;
+};
+__global__ void __launch_bounds__(256)
+sgemm_small_kernel(const SgemmArgs a)
+{
+    __shared__ float sA[16][65], sB[16][65];
+    const int g = blockIdx.z;
+    const float* A = a.A + g * a.a_g;
+    const float* B = a.B + g * a.b_g;
+    const int row0 = blockIdx.y * 64, col0 = blockIdx.x * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < a.K; k0 += 16) {
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            int m, k;
+            if (a.sak == 1) { k = i & 15; m = i >> 4; } else { m = i & 63; k = i >> 6; }
+            sA[k][m] = (row0 + m < a.M && k0 + k < a.K) ? A[(long long)(row0 + m) * a.sam + (long long)(k0 + k) * a.sak] : 0.f;
+            int n, kk;
+            if (a.sbn == 1) { n = i & 63; kk = i >> 6; } else { kk = i & 15; n = i >> 4; }
+            sB[kk][n] = (col0 + n < a.N && k0 + kk < a.K) ? B[(long long)(k0 + kk) * a.sbk + (long long)(col0 + n) * a.sbn] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float x[4], w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { x[i] = sA[k][ty * 4 + i]; w[i] = sB[k][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(x[i], w[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* C = a.C + g * a.c_g;
+    const float* Mk = a.mask ? a.mask + g * a.m_g : nullptr;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = row0 + ty * 4 + i;
+        if (m >= a.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = col0 + tx * 4 + j;
+            if (n >= a.N) continue;
+            float v = a.alpha * acc[i][j];
+            if (a.epi == SG_ATOMIC) atomicAdd(C + (long long)m * a.ldc + n, v);
+            else {
+                if (a.epi == SG_STORE_MASK && !(Mk[(long long)m * a.ldm + n] > 0.f)) v = 0.f;
+                C[(long long)m * a.ldc + n] = v;
+            }
+        }
+    }
+}
+
+// out[c] += sum_b x[b, c]   (bias gradients of the head layers)
+__global__ void colsum_add_kernel(const float* __restrict__ x, int B, int C, float* __restrict__ out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += x[(size_t)b * C + c];
+    out[c] += s;
+}
+
+// Backward of conv3_{r,t} restricted to the object's class (network.py:199-204) and of the ReLU in front of it:
+//   dz2[b, c] = G2[b, c] > 0 ? sum_j d[b, j] * w3[(o*nj + j), c % 128] : 0;   dW3, db3, db2 accumulate (atomics)
+__global__ void __launch_bounds__(256)
+head3_bwd_kernel(const float* __restrict__ d_r, const float* __restrict__ d_t, const int64_t* __restrict__ obj, int num_obj,
+                 const float* __restrict__ g2, const float* __restrict__ w3r, const float* __restrict__ w3t,
+                 float* __restrict__ dz2, float* __restrict__ gw3r, float* __restrict__ gw3t, float* __restrict__ gb3r,
+                 float* __restrict__ gb3t, float* __restrict__ gb2)
+{
+    const int b = blockIdx.x, c = threadIdx.x, h = c >> 7, k = c & 127;
+    int o = (int)obj[b];
+    o = o < 0 ? 0 : (o >= num_obj ? num_obj - 1 : o);
+    const int nj = h == 0 ? 4 : 3;
+    const float* d = h == 0 ? d_r + 4 * b : d_t + 3 * b;
+    const float* w = (h == 0 ? w3r : w3t) + (size_t)o * nj * 128;
+    float* gw = (h == 0 ? gw3r : gw3t) + (size_t)o * nj * 128;
+    const float x = g2[(size_t)b * 256 + c];
+    float s = 0.f;
+    for (int j = 0; j < nj; ++j) {
+        const float dj = d[j];
+        s = fmaf(dj, w[j * 128 + k], s);
+        atomicAdd(gw + j * 128 + k, dj * x);
+    }
+    const float dz = x > 0.f ? s : 0.f;
+    dz2[(size_t)b * 256 + c] = dz;
+    atomicAdd(gb2 + c, dz);
+    if (k < nj) atomicAdd((h == 0 ? gb3r : gb3t) + o * nj + k, d[k]);
+}
+
+// Backward of AvgPool1d + the ReLU of conv6 (network.py:163-167): dY6[r, c] = bit(r, c) ? g6[b, c] : 0 (bf16), where
+// g6 = dAP / N already, and db6[c] += sum_r dY6[r, c].  One CTA per 128-row tile, thread = 4 consecutive columns.
+__global__ void __launch_bounds__(256)
+dy6_kernel(const uint32_t* __restrict__ bits, const float* __restrict__ g6, int Np, int rows_live, bf16* __restrict__ dy6,
+           float* __restrict__ gb6)
+{
+    const int row0 = blockIdx.x * 128;
+    const int c = threadIdx.x * 4;
+    const int b = row0 / Np;                                  // Np is a multiple of 128: one object per tile
+    const bool live = row0 < rows_live;
+    const float4 g = live ? *reinterpret_cast<const float4*>(g6 + (size_t)b * 1024 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const __nv_bfloat162 g01 = __floats2bfloat162_rn(g.x, g.y), g23 = __floats2bfloat162_rn(g.z, g.w);
+    const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&g01), u23 = *reinterpret_cast<const uint32_t*>(&g23);
+    int cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0;
+    const int sh = c & 31;
+    for (int r = 0; r < 128; ++r) {
+        const size_t row = (size_t)row0 + r;
+        const uint32_t w = live ? (__ldg(bits + row * 32 + (c >> 5)) >> sh) : 0u;
+        const uint32_t lo = ((w & 1u) ? (u01 & 0xffffu) : 0u) | ((w & 2u) ? (u01 & 0xffff0000u) : 0u);
+        const uint32_t hi = ((w & 4u) ? (u23 & 0xffffu) : 0u) | ((w & 8u) ? (u23 & 0xffff0000u) : 0u);
+        *reinterpret_cast<uint2*>(dy6 + row * 1024 + c) = make_uint2(lo, hi);
+        cnt0 += w & 1u; cnt1 += (w >> 1) & 1u; cnt2 += (w >> 2) & 1u; cnt3 += (w >> 3) & 1u;
+    }
+    if (live) {
+        // the bias gradient sums the bf16-rounded values the GEMMs see
+        atomicAdd(gb6 + c, cnt0 * __uint_as_float(u01 << 16));
+        atomicAdd(gb6 + c + 1, cnt1 * __uint_as_float(u01 & 0xffff0000u));
+        atomicAdd(gb6 + c + 2, cnt2 * __uint_as_float(u23 << 16));
+        atomicAdd(gb6 + c + 3, cnt3 * __uint_as_float(u23 & 0xffff0000u));
+    }
+}
+
+// Weight gradients of the K=3 / K=32 first layers: dW1[c, k] += sum_r dz1[r, c] * cloud[r, k],
+// dWe1[c, k] += sum_r dze1[r, c] * emb[r, k];  dz = dPF[:, 0:128] (bf16).  Persistent CTAs over 64-row chunks.
+__global__ void __launch_bounds__(256)
+conv1_wgrad_kernel(const bf16* __restrict__ dpf, int ld, const float* __restrict__ cloud, const float* __restrict__ emb,
+                   int B, int N, int Np, float* __restrict__ gw1, float* __restrict__ gwe1)
+{
+    __shared__ float s_dz[64][129];
+    __shared__ float s_x[64][36];
+    const int tid = threadIdx.x, c = tid & 63, kq = tid >> 6;
+    float acc_e[8] = {}, acc_x[3] = {};
+    const int chunks = B * (Np / 64);
+    for (int ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        const int b = ch / (Np / 64), n0 = (ch % (Np / 64)) * 64;
+        if (n0 >= N) continue;                                  // whole chunk is padding (uniform per CTA)
+        __syncthreads();
+        for (int i = tid; i < 64 * 64; i += 256) {              // 64 rows x 64 bf16 pairs
+            const int r = i >> 6, p2 = i & 63;
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(dpf + ((size_t)b * Np + n0 + r) * ld + 2 * p2);
+            s_dz[r][2 * p2] = __uint_as_float(u << 16);
+            s_dz[r][2 * p2 + 1] = __uint_as_float(u & 0xffff0000u);
+        }
+        for (int i = tid; i < 32 * 64; i += 256) {              // emb [B,32,N]: n fastest
+            const int k = i >> 6, r = i & 63;
+            s_x[r][k] = (n0 + r < N) ? emb[((size_t)b * 32 + k) * N + n0 + r] : 0.f;
+        }
+        for (int i = tid; i < 64 * 3; i += 256) {
+            const int r = i / 3, k = i - 3 * r;
+            s_x[r][32 + k] = (n0 + r < N) ? cloud[((size_t)b * N + n0 + r) * 3 + k] : 0.f;
+        }
+        __syncthreads();
+        for (int r = 0; r < 64; ++r) {
+            const float de = s_dz[r][64 + c];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc_e[j] = fmaf(de, s_x[r][kq * 8 + j], acc_e[j]);
+            if (kq == 0) {
+                const float dx = s_dz[r][c];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) acc_x[j] = fmaf(dx, s_x[r][32 + j], acc_x[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(gwe1 + c * 32 + kq * 8 + j, acc_e[j]);
+    if (kq == 0) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) atomicAdd(gw1 + c * 3 + j, acc_x[j]);
+    }
+}
+
+// Adam as torch.optim.Adam (train.py:149): p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
+                            float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i] * grad_scale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+}
+
+}  // namespace ape
+
+// ================================================================================================ host side
+struct BfMat {                        // bf16 row-major matrix with its TMA maps
+    bf16* p = nullptr; int rows = 0, cols = 0;
+    CUtensorMap kmaj;                 // box {64 cols, 128 rows}: K-major operand (rows = M or N, cols = K)
+    CUtensorMap mn;                   // box {64 cols, 64 rows}:  MN-major operand (rows = K, cols = M or N)
+};
+
+struct ape_trainer {
+    ape_net net;                      // forward buffers and weights in the inference trunk's own structure (net.train = 1)
+    ape::TrainLayout L;
+    float *params = nullptr, *grads = nullptr;      // caller-owned flat vectors
+    int num_obj = 0, max_batch = 0, max_points = 0;
+    BfMat Wb2, Wb5, Wb6;              // bf16 copies of conv2|e_conv2, conv5, conv6 (one contiguous allocation)
+    BfMat PFm, H5m, dY6, dZ5, dPF;    // PFm / H5m alias net.PF.hi / net.H5.hi
+    float *dZ2h = nullptr, *dZ1h = nullptr, *g6 = nullptr;
+};
+
+static int make_bf_maps(BfMat& m) {
+    int rc = make_map_box(&m.kmaj, m.p, m.rows, m.cols, m.cols, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    return make_map_box(&m.mn, m.p, m.rows, m.cols, m.cols, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+extern "C" __attribute__((visibility("default")))
+int64_t ape_refiner_trainer_layout(int num_obj, int64_t* offsets24)
+{
+    if (num_obj <= 0) return -1;
+    const ape::TrainLayout L = ape::train_layout(num_obj);
+    if (offsets24) {
+        // reference state_dict order (weight, bias per layer): feat.conv1, feat.e_conv1, feat.conv2, feat.e_conv2, feat.conv5,
+        // feat.conv6, conv1_r, conv1_t, conv2_r, conv2_t, conv3_r, conv3_t
+        const size_t o[24] = {L.w1, L.b1, L.we1, L.be1, L.w2e2, L.b2e2, L.w2e2 + 128 * 64, L.b2e2 + 128, L.w5, L.b5, L.w6, L.b6,
+                              L.wh1, L.bh1, L.wh1 + 512 * 1024, L.bh1 + 512, L.wh2, L.bh2, L.wh2 + 128 * 512, L.bh2 + 128,
+                              L.w3r, L.b3r, L.w3t, L.b3t};
+        for (int i = 0; i < 24; ++i) offsets24[i] = (int64_t)o[i];
+    }
+    return (int64_t)L.total;
+}
+
+extern "C" __attribute__((visibility("default")))
+int ape_refiner_trainer_destroy(ape_trainer* tr)
+{
+    if (!tr) return APE_OK;
+    for (void* p : tr->net.allocs) cudaFree(p);
+    delete tr;
+    return APE_OK;
+}
+
+extern "C" __attribute__((visibility("default")))
+int ape_refiner_trainer_sync_weights(ape_trainer* tr, void* stream)
+{
+    APE_REQUIRE(tr, "ape_refiner_trainer_sync_weights: null handle");
+    cudaStream_t s = (cudaStream_t)stream;
+    const ape::TrainLayout& L = tr->L;
+    const size_t n = 256 * 64 + 512 * 384 + 1024 * 512;          // conv2|e_conv2, conv5, conv6 are contiguous
+    ape::f32_to_bf16_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(tr->params + L.w2e2, tr->Wb2.p, n);
+    ape::pack_frontend_kernel<<<1, 256, 0, s>>>(tr->params + L.w1, tr->params + L.we1, tr->params + L.b1, tr->params + L.be1, tr->net.fw.p);
+    ape::count_launch(2);
+    return ape::check_launch("trainer sync_weights");
+}
+
+extern "C" __attribute__((visibility("default")))
+int ape_refiner_trainer_create(float* params, float* grads, int num_obj, int max_batch, int max_points, ape_trainer** out)
+{
+    APE_REQUIRE(params && grads && out, "ape_refiner_trainer_create: null pointer");
+    APE_REQUIRE(num_obj > 0 && max_batch > 0 && max_points > 0, "ape_refiner_trainer_create: bad sizes");
+    int dev_count = 0;
+    if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) {
+        ape::set_error("ape_refiner_trainer_create: no CUDA device (there is no CPU fallback)");
+        return APE_ERR_CUDA;
+    }
+    ape_trainer* tr = new ape_trainer();
+    tr->L = ape::train_layout(num_obj);
+    tr->params = params; tr->grads = grads; tr->num_obj = num_obj; tr->max_batch = max_batch; tr->max_points = max_points;
+    const ape::TrainLayout& L = tr->L;
+    ape_net* net = &tr->net;
+    net->kind = APE_NET_REFINER; net->num_obj = num_obj; net->max_batch = max_batch; net->max_points = max_points;
+    net->np_max = (max_points + 127) / 128 * 128;
+    net->gemm_impl = APE_GEMM_TCGEN05; net->train = 1;
+    const size_t R = ((size_t)max_batch * net->np_max + 255) / 256 * 256;
+    int rc = APE_OK;
+#define TRY(x) do { if ((rc = (x)) != APE_OK) { ape_refiner_trainer_destroy(tr); return rc; } } while (0)
+    // weights: fp32 views into the flat vector (SIMT layers), bf16 copies for the tensor-core layers
+    net->b_c2e2.p = params + L.b2e2; net->b_c5.p = params + L.b5; net->b_c6.p = params + L.b6;
+    net->Wr1.p = params + L.wh1; net->br1.p = params + L.bh1; net->Wr2.p = params + L.wh2; net->br2.p = params + L.bh2;
+    net->w3r.p = params + L.w3r; net->b3r.p = params + L.b3r; net->w3t.p = params + L.w3t; net->b3t.p = params + L.b3t;
+    TRY(alloc_f32(net, net->fw, 32 * 64 + 3 * 64 + 128));
+    {
+        bf16* wb = nullptr;
+        TRY(dev_alloc(net, (void**)&wb, (size_t)(256 * 64 + 512 * 384 + 1024 * 512) * 2));
+        tr->Wb2.p = wb; tr->Wb2.rows = 256; tr->Wb2.cols = 64;
+        tr->Wb5.p = wb + 256 * 64; tr->Wb5.rows = 512; tr->Wb5.cols = 384;
+        tr->Wb6.p = tr->Wb5.p + 512 * 384; tr->Wb6.rows = 1024; tr->Wb6.cols = 512;
+        TRY(make_bf_maps(tr->Wb2)); TRY(make_bf_maps(tr->Wb5)); TRY(make_bf_maps(tr->Wb6));
+        SplitMat* W[3] = {&net->W_c2e2, &net->W_c5, &net->W_c6};
+        BfMat* Bm[3] = {&tr->Wb2, &tr->Wb5, &tr->Wb6};
+        for (int i = 0; i < 3; ++i) {            // the forward kernel only dereferences the hi maps when passes == 1
+            W[i]->hi = W[i]->lo = Bm[i]->p; W[i]->rows = Bm[i]->rows; W[i]->cols = Bm[i]->cols;
+            W[i]->map_hi = W[i]->map_lo = Bm[i]->kmaj;
+        }
+    }
+    TRY(alloc_split(net, net->PF, R, 384));      // the front end writes hi and lo; GEMM epilogues store hi only
+    {
+        SplitMat& H = net->H5;
+        TRY(dev_alloc(net, (void**)&H.hi, R * 512 * 2));
+        APE_CUDA(cudaMemset(H.hi, 0, R * 512 * 2));
+        H.lo = H.hi; H.rows = (int)R; H.cols = 512;
+        TRY(make_map(&H.map_hi, H.hi, R, 512, 512)); H.map_lo = H.map_hi;
+        TRY(make_store_map(&H.st_hi, H.hi, R, 512, 512)); H.st_lo = H.st_hi;
+    }
+    TRY(alloc_f32(net, net->CS, (R / 128) * 1024));
+    TRY(alloc_f32(net, net->AP, (size_t)max_batch * 1024));
+    TRY(alloc_f32(net, net->G1, (size_t)max_batch * 1024));
+    TRY(alloc_f32(net, net->G2, (size_t)max_batch * 256));
+    TRY(dev_alloc(net, (void**)&net->relu_bits, R * 32 * sizeof(uint32_t)));
+    APE_CUDA(cudaMemset(net->relu_bits, 0, R * 32 * sizeof(uint32_t)));
+    tr->PFm.p = net->PF.hi; tr->PFm.rows = (int)R; tr->PFm.cols = 384; TRY(make_bf_maps(tr->PFm));
+    tr->H5m.p = net->H5.hi; tr->H5m.rows = (int)R; tr->H5m.cols = 512; TRY(make_bf_maps(tr->H5m));
+    BfMat* G[3] = {&tr->dY6, &tr->dZ5, &tr->dPF};
+    const int gc[3] = {1024, 512, 384};
+    for (int i = 0; i < 3; ++i) {
+        TRY(dev_alloc(net, (void**)&G[i]->p, R * (size_t)gc[i] * 2));
+        APE_CUDA(cudaMemset(G[i]->p, 0, R * (size_t)gc[i] * 2));
+        G[i]->rows = (int)R; G[i]->cols = gc[i];
+        TRY(make_bf_maps(*G[i]));
+    }
+    TRY(dev_alloc(net, (void**)&tr->dZ2h, (size_t)max_batch * 256 * 4));
+    TRY(dev_alloc(net, (void**)&tr->dZ1h, (size_t)max_batch * 1024 * 4));
+    TRY(dev_alloc(net, (void**)&tr->g6, (size_t)max_batch * 1024 * 4));
+#undef TRY
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(ape::tc2::gemm_split_bf16_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             ape::tc2::kSmemBytes2);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(ape::tr::gemm_bf16_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ape::tr::kSmemBytesBwd);
+        if (e != cudaSuccess) { ape::set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); ape_refiner_trainer_destroy(tr); return APE_ERR_CUDA; }
+        attr_set = true;
+    }
+    rc = ape_refiner_trainer_sync_weights(tr, nullptr);
+    if (rc) { ape_refiner_trainer_destroy(tr); return rc; }
+    APE_CUDA(cudaStreamSynchronize(nullptr));
+    *out = tr;
+    return APE_OK;
+}
+
+// Training forward: identical call surface to ape_refiner_forward; keeps the activations for the backward pass.
+extern "C" __attribute__((visibility("default")))
+int ape_refiner_trainer_forward(ape_trainer* tr, const float* new_points, const float* emb, const int64_t* obj, int B, int N,
+                                float* r2, float* t2, void* stream)
+{
+    APE_REQUIRE(tr, "ape_refiner_trainer_forward: null handle");
+    return ape_refiner_forward(&tr->net, new_points, emb, obj, B, N, r2, t2, stream);
+}
+
+static int run_bwd_gemm(const BfMat& A, const BfMat& Bm, ape::tr::BwdParams p, cudaStream_t s, const char* label)
+{
+    ape::ProfScope prof_(label, s);
+    const bool wgrad = p.mode == ape::tr::BWD_WGRAD;
+    const int tiles = p.groups * (p.M / 128) * ((p.N + 255) / 256);
+    if (wgrad) {
+        const int kb = p.K / 64;
+        int ks = ape::sm_count() / tiles;
+        p.k_splits = ks < 1 ? 1 : (ks > kb ? kb : ks);
+    } else {
+        p.k_splits = 1;
+    }
+    const int total = tiles * p.k_splits;
+    const int grid = total < ape::sm_count() ? total : ape::sm_count();
+    ape::tr::gemm_bf16_bwd_kernel<<<grid, ape::tc::kThreads, ape::tr::kSmemBytesBwd, s>>>(wgrad ? A.mn : A.kmaj, Bm.mn, p);
+    ape::count_launch();
+    return ape::check_launch(label);
+}
+
+static int sgemm(const ape::SgemmArgs& a, int groups, cudaStream_t s, const char* label)
+{
+    ape::ProfScope prof_(label, s);
+    dim3 grid((a.N + 63) / 64, (a.M + 63) / 64, groups);
+    ape::sgemm_small_kernel<<<grid, 256, 0, s>>>(a);
+    ape::count_launch();
+    return ape::check_launch(label);
+}
+
+// Backward of the forward that ape_refiner_trainer_forward just ran (same new_points / emb / obj / B / N):
+// grads += d(sum_b <d_r[b], r2[b]> + <d_t[b], t2[b]>) / d params.
+extern "C" __attribute__((visibility("default")))
+int ape_refiner_trainer_backward(ape_trainer* tr, const float* new_points, const float* emb, const int64_t* obj, int B, int N,
+                                 const float* d_r, const float* d_t, void* stream)
+{
+    APE_REQUIRE(tr && new_points && emb && obj && d_r && d_t, "ape_refiner_trainer_backward: null pointer");
+    APE_REQUIRE(B > 0 && N > 0 && B <= tr->max_batch && N <= tr->max_points, "ape_refiner_trainer_backward: bad sizes");
+    cudaStream_t s = (cudaStream_t)stream;
+    ape_net* net = &tr->net;
+    const ape::TrainLayout& L = tr->L;
+    float* G = tr->grads;
+    const int Np = (N + 127) / 128 * 128, M = (B * Np + 255) / 256 * 256;
+    int rc;
+    {   // heads
+        ape::ProfScope prof_("train.head3_bwd", s);
+        ape::head3_bwd_kernel<<<B, 256, 0, s>>>(d_r, d_t, obj, tr->num_obj, net->G2.p, net->w3r.p, net->w3t.p, tr->dZ2h,
+                                               G + L.w3r, G + L.w3t, G + L.b3r, G + L.b3t, G + L.bh2);
+        ape::count_launch();
+        if ((rc = ape::check_launch("head3_bwd"))) return rc;
+    }
+    ape::SgemmArgs a;
+    // dW(conv2_{r,t}) [2 x 128, 512] += dZ2h[:, g]^T * G1[:, g]
+    a = {tr->dZ2h, 1, 256, 128, net->G1.p, 1024, 1, 512, G + L.wh2, 512, 128 * 512, nullptr, 0, 0, 128, 512, B, ape::SG_ATOMIC, 1.f};
+    if ((rc = sgemm(a, 2, s, "train.head2_wgrad"))) return rc;
+    // dZ1h [B, 2 x 512] = (dZ2h[:, g] * W2[g]) masked by G1 > 0
+    a = {tr->dZ2h, 256, 1, 128, net->Wr2.p, 512, 1, 128 * 512, tr->dZ1h, 1024, 512, net->G1.p, 1024, 512, B, 512, 128, ape::SG_STORE_MASK, 1.f};
+    if ((rc = sgemm(a, 2, s, "train.head2_dgrad"))) return rc;
+    {
+        ape::ProfScope prof_("train.head1_bias", s);
+        ape::colsum_add_kernel<<<4, 256, 0, s>>>(tr->dZ1h, B, 1024, G + L.bh1);
+        ape::count_launch();
+    }
+    // dW(conv1_{r,t}) [1024, 1024] += dZ1h^T * AP
+    a = {tr->dZ1h, 1, 1024, 0, net->AP.p, 1024, 1, 0, G + L.wh1, 1024, 0, nullptr, 0, 0, 1024, 1024, B, ape::SG_ATOMIC, 1.f};
+    if ((rc = sgemm(a, 1, s, "train.head1_wgrad"))) return rc;
+    // g6 [B, 1024] = (dZ1h * W1) / N   (AvgPool1d backward folded in)
+    a = {tr->dZ1h, 1024, 1, 0, net->Wr1.p, 1024, 1, 0, tr->g6, 1024, 0, nullptr, 0, 0, B, 1024, 1024, ape::SG_STORE, 1.0f / (float)N};
+    if ((rc = sgemm(a, 1, s, "train.head1_dgrad"))) return rc;
+    {
+        ape::ProfScope prof_("train.dy6", s);
+        ape::dy6_kernel<<<M / 128, 256, 0, s>>>(net->relu_bits, tr->g6, Np, B * Np, tr->dY6.p, G + L.b6);
+        ape::count_launch();
+        if ((rc = ape::check_launch("dy6"))) return rc;
+    }
+    ape::tr::BwdParams p;
+    // conv6: dW6 [1024, 512] += dY6^T * H5 ;  dZ5 = (dY6 * W6) masked by H5 > 0, db5
+    memset(&p, 0, sizeof(p));
+    p.mode = ape::tr::BWD_WGRAD; p.M = 1024; p.N = 512; p.K = M; p.groups = 1; p.dw = G + L.w6; p.dw_ld = 512;
+    if ((rc = run_bwd_gemm(tr->dY6, tr->H5m, p, s, "gemm.train.wgrad6"))) return rc;
+    memset(&p, 0, sizeof(p));
+    p.mode = ape::tr::BWD_DGRAD; p.M = M; p.N = 512; p.K = 1024; p.groups = 1; p.out = tr->dZ5.p; p.o_ld = 512;
+    p.mask = tr->H5m.p; p.m_ld = 512; p.bias_grad = G + L.b5;
+    if ((rc = run_bwd_gemm(tr->dY6, tr->Wb6, p, s, "gemm.train.dgrad6"))) return rc;
+    // conv5 (input = pointfeat_3 = PF[:, 0:384], network.py:160-162)
+    memset(&p, 0, sizeof(p));
+    p.mode = ape::tr::BWD_WGRAD; p.M = 512; p.N = 384; p.K = M; p.groups = 1; p.dw = G + L.w5; p.dw_ld = 384;
+    if ((rc = run_bwd_gemm(tr->dZ5, tr->PFm, p, s, "gemm.train.wgrad5"))) return rc;
+    memset(&p, 0, sizeof(p));
+    p.mode = ape::tr::BWD_DGRAD; p.M = M; p.N = 384; p.K = 512; p.groups = 1; p.out = tr->dPF.p; p.o_ld = 384;
+    p.mask = tr->PFm.p; p.m_ld = 384; p.mask_from = 128; p.bias_grad = G + L.b2e2 - 128;       // columns 128..383 = conv2 | e_conv2
+    if ((rc = run_bwd_gemm(tr->dZ5, tr->Wb5, p, s, "gemm.train.dgrad5"))) return rc;
+    // conv2 | e_conv2 (two groups): dW [2 x 128, 64] += dZ[:, 128 + g*128 ...]^T * PF[:, g*64 ...]; then
+    // dPF[:, g*64 ...] = (dZ * W_g + the conv5 share already there) masked by PF > 0, db1 | dbe1
+    memset(&p, 0, sizeof(p));
+    p.mode = ape::tr::BWD_WGRAD; p.M = 128; p.N = 64; p.K = M; p.groups = 2; p.a_c0 = 128; p.a_cg = 128; p.b_cg = 64;
+    p.dw = G + L.w2e2; p.dw_ld = 64; p.dw_rg = 128;
+    if ((rc = run_bwd_gemm(tr->dPF, tr->PFm, p, s, "gemm.train.wgrad2"))) return rc;
+    memset(&p, 0, sizeof(p));
+    p.mode = ape::tr::BWD_DGRAD; p.M = M; p.N = 64; p.K = 128; p.groups = 2; p.a_c0 = 128; p.a_cg = 128; p.b_rg = 128;
+    p.out = tr->dPF.p; p.o_ld = 384; p.o_cg = 64; p.add_out = 1; p.mask = tr->PFm.p; p.m_ld = 384; p.m_cg = 64;
+    p.bias_grad = G + L.b1;
+    if ((rc = run_bwd_gemm(tr->dPF, tr->Wb2, p, s, "gemm.train.dgrad2"))) return rc;
+    {
+        ape::ProfScope prof_("train.conv1_wgrad", s);
+        ape::conv1_wgrad_kernel<<<2 * ape::sm_count(), 256, 0, s>>>(tr->dPF.p, 384, new_points, emb, B, N, Np, G + L.w1, G + L.we1);
+        ape::count_launch();
+        if ((rc = ape::check_launch("conv1_wgrad"))) return rc;
+    }
+    return APE_OK;
+}
+
+extern "C" __attribute__((visibility("default")))
+int ape_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int step, float grad_scale, void* stream)
+{
+    APE_REQUIRE(params && grads && exp_avg && exp_avg_sq && n > 0 && step > 0, "ape_adam_step: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    const float bc1 = 1.f - powf(beta1, (float)step), bc2s = sqrtf(1.f - powf(beta2, (float)step));
+    ape::ProfScope prof_("train.adam", s);
+    ape::adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, (size_t)n, lr, beta1, beta2, eps,
+                                                                 bc1, bc2s, grad_scale);
+    ape::count_launch();
+    return ape::check_launch("adam");
+}

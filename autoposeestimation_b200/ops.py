@@ -249,3 +249,126 @@ def pose_pipeline(est, ref, out_img, cloud, choose, obj, iterations=2, canonical
                                         ptr(choose), ptr(obj), B, N, int(iterations), int(bool(canonical)), ptr(poses), ptr(wm),
                                         stream_ptr()), 'ape_pose_pipeline')
     return poses, wm
+
+
+# ------------------------------------------------------------------------------------------ refiner training (a16)
+def refine_loss(pred_r, pred_t, model_points, target, points=None, symmetric=None, want_grad=True, want_next=True):
+    """Loss_refine forward + backward (lib/loss_refiner.py:12-64) for B objects.  pred_r [B,4], pred_t [B,3],
+    model_points / target [B,M,3], points [B,N,3], symmetric [B] bool/uint8 ->
+    dict(dis [B], d_r [B,4], d_t [B,3], new_points [B,N,3], new_target [B,M,3])."""
+    require_cuda(pred_r, pred_t, model_points, target, points)
+    pred_r = _c(pred_r, torch.float32); pred_t = _c(pred_t, torch.float32)
+    model_points = _c(model_points, torch.float32); target = _c(target, torch.float32)
+    B, M = model_points.shape[0], model_points.shape[1]
+    dev = pred_r.device
+    sym = _c(symmetric.to(torch.uint8), torch.uint8) if symmetric is not None else None
+    dis = torch.empty((B,), dtype=torch.float32, device=dev)
+    d_r = torch.empty((B, 4), dtype=torch.float32, device=dev) if want_grad else None
+    d_t = torch.empty((B, 3), dtype=torch.float32, device=dev) if want_grad else None
+    newp = newt = None
+    N = 0
+    if want_next:
+        points = _c(points, torch.float32)
+        N = points.shape[1]
+        newp = torch.empty_like(points); newt = torch.empty_like(target)
+    check(_lib.load().ape_refine_loss(ptr(pred_r), ptr(pred_t), ptr(model_points), ptr(target), M, ptr(points), N, ptr(sym), B,
+                                      ptr(dis), ptr(d_r), ptr(d_t), ptr(newp), ptr(newt), stream_ptr()), 'ape_refine_loss')
+    return dict(dis=dis, d_r=d_r, d_t=d_t, new_points=newp, new_target=newt)
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+    """torch.optim.Adam update on flat fp32 device vectors (train.py:149)."""
+    require_cuda(params, grads, exp_avg, exp_avg_sq)
+    check(_lib.load().ape_adam_step(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), params.numel(), float(lr),
+                                    float(betas[0]), float(betas[1]), float(eps), int(step), float(grad_scale), stream_ptr()),
+          'ape_adam_step')
+
+
+def refiner_trainer_layout(num_obj):
+    """-> (flat parameter count, {reference state_dict key: (offset, shape)}) of the trainer's flat vector."""
+    import ctypes
+    off = (ctypes.c_int64 * 24)()
+    total = _lib.load().ape_refiner_trainer_layout(int(num_obj), off)
+    if total <= 0:
+        raise _lib.ApeError('ape_refiner_trainer_layout failed')
+    shapes = {'feat.conv1': (64, 3, 1), 'feat.e_conv1': (64, 32, 1), 'feat.conv2': (128, 64, 1), 'feat.e_conv2': (128, 64, 1),
+              'feat.conv5': (512, 384, 1), 'feat.conv6': (1024, 512, 1), 'conv1_r': (512, 1024), 'conv1_t': (512, 1024),
+              'conv2_r': (128, 512), 'conv2_t': (128, 512), 'conv3_r': (num_obj * 4, 128), 'conv3_t': (num_obj * 3, 128)}
+    table = {}
+    for i, name in enumerate(_REFINER_ORDER):
+        table[name + '.weight'] = (int(off[2 * i]), shapes[name])
+        table[name + '.bias'] = (int(off[2 * i + 1]), (shapes[name][0],))
+    return int(total), table
+
+
+class RefinerTrainerHandle:
+    """Owns an `ape_trainer`: flat fp32 parameter / gradient vectors (torch tensors, so NCCL can all-reduce the
+    gradient in place) plus the bf16 weight copies and the activation workspace of the training forward."""
+
+    def __init__(self, state_dict, num_obj, max_batch, max_points, device=None):
+        import ctypes
+        if not torch.cuda.is_available():
+            raise _lib.ApeError('no CUDA device: the B200 path has no CPU fallback')
+        self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        total, self.table = refiner_trainer_layout(num_obj)
+        self.params = torch.zeros((total,), dtype=torch.float32, device=self.device)
+        self.grads = torch.zeros_like(self.params)
+        self.num_obj, self.max_batch, self.max_points = num_obj, max_batch, max_points
+        self._h = None
+        self.load_state_dict(state_dict, sync=False)
+        out = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(_lib.load().ape_refiner_trainer_create(ptr(self.params), ptr(self.grads), int(num_obj), int(max_batch),
+                                                         int(max_points), ctypes.byref(out)), 'ape_refiner_trainer_create')
+        self._h = out
+
+    def view(self, key, flat=None):
+        off, shape = self.table[key]
+        n = 1
+        for s in shape:
+            n *= s
+        return (self.params if flat is None else flat)[off:off + n].view(shape)
+
+    def load_state_dict(self, state_dict, sync=True):
+        for key in self.table:
+            v = state_dict[key]
+            if not isinstance(v, torch.Tensor):
+                v = torch.as_tensor(v)
+            self.view(key).copy_(v.detach().to(self.device, torch.float32).reshape(self.table[key][1]))
+        if sync and self._h is not None:
+            self.sync_weights()
+
+    def state_dict(self):
+        return {key: self.view(key).detach().clone() for key in self.table}
+
+    def sync_weights(self):
+        check(_lib.load().ape_refiner_trainer_sync_weights(self._h, stream_ptr()), 'ape_refiner_trainer_sync_weights')
+
+    def forward(self, new_points, emb, obj):
+        require_cuda(new_points, emb, obj)
+        B, N = new_points.shape[0], new_points.shape[1]
+        new_points = _c(new_points, torch.float32); emb = _c(emb, torch.float32); obj = _c(obj, torch.int64).reshape(B)
+        r2 = torch.empty((B, 4), dtype=torch.float32, device=new_points.device)
+        t2 = torch.empty((B, 3), dtype=torch.float32, device=new_points.device)
+        check(_lib.load().ape_refiner_trainer_forward(self._h, ptr(new_points), ptr(emb), ptr(obj), B, N, ptr(r2), ptr(t2),
+                                                      stream_ptr()), 'ape_refiner_trainer_forward')
+        return r2, t2
+
+    def backward(self, new_points, emb, obj, d_r, d_t):
+        """Accumulates into self.grads; must follow the forward() of the same inputs."""
+        B, N = new_points.shape[0], new_points.shape[1]
+        new_points = _c(new_points, torch.float32); emb = _c(emb, torch.float32); obj = _c(obj, torch.int64).reshape(B)
+        d_r = _c(d_r, torch.float32); d_t = _c(d_t, torch.float32)
+        check(_lib.load().ape_refiner_trainer_backward(self._h, ptr(new_points), ptr(emb), ptr(obj), B, N, ptr(d_r), ptr(d_t),
+                                                       stream_ptr()), 'ape_refiner_trainer_backward')
+
+    def close(self):
+        if getattr(self, '_h', None):
+            _lib.load().ape_refiner_trainer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -203,6 +203,44 @@ int ape_pose_pipeline(ape_net* estimator, ape_net* refiner, const float* out_img
                       const int64_t* choose, const int64_t* obj, int B, int N, int iterations, int canonical,
                       double* poses, int32_t* which_max, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Refiner training step (a16): DenseFusion/tools/train.py:215-233 -- per sample `refiner(new_points, emb,
+ * idx)` -> `criterion_refine(...)` (lib/loss_refiner.py:12-64) -> `dis.backward()`, Adam step per batch
+ * (train.py:149, :231-233).  bf16 tensor-core forward / backward, fp32 master weights and gradients.
+ *
+ * All trainable parameters of PoseRefineNet live in ONE caller-owned flat fp32 device vector (and a flat
+ * gradient vector of the same size, which is what the caller all-reduces over NCCL between ranks).
+ * ape_refiner_trainer_layout returns the vector length and the offset of each of the 24 reference
+ * state_dict tensors (weight, bias of feat.conv1, feat.e_conv1, feat.conv2, feat.e_conv2, feat.conv5,
+ * feat.conv6, conv1_r, conv1_t, conv2_r, conv2_t, conv3_r, conv3_t) in it; shapes are the reference's.  */
+typedef struct ape_trainer ape_trainer;   /* opaque */
+int64_t ape_refiner_trainer_layout(int num_obj, int64_t* offsets24 /* out, may be NULL */);
+int ape_refiner_trainer_create(float* params, float* grads, int num_obj, int max_batch, int max_points,
+                               ape_trainer** out);
+int ape_refiner_trainer_destroy(ape_trainer* tr);
+/* Re-derive the bf16 weight copies from `params`; call after every change of the flat vector
+ * (optimizer step, checkpoint load).                                                               */
+int ape_refiner_trainer_sync_weights(ape_trainer* tr, void* stream);
+/* Forward as ape_refiner_forward (network.py:187-206) in plain bf16, keeping the activations.       */
+int ape_refiner_trainer_forward(ape_trainer* tr, const float* new_points, const float* emb,
+                                const int64_t* obj, int B, int N, float* r2, float* t2, void* stream);
+/* Backward of the forward just run (same inputs): grads += d(sum_b <d_r[b], r2[b]> + <d_t[b], t2[b]>)/dW.
+ * Gradients ACCUMULATE, as repeated dis.backward() calls do in train.py:222 (zero them per step).   */
+int ape_refiner_trainer_backward(ape_trainer* tr, const float* new_points, const float* emb,
+                                 const int64_t* obj, int B, int N, const float* d_r, const float* d_t,
+                                 void* stream);
+/* Loss_refine forward + backward for B objects (lib/loss_refiner.py:12-64):
+ *   quat [B,4], trans [B,3], model_points [B,M,3], target [B,M,3], points [B,N,3], symmetric [B] u8 or NULL
+ *   dis [B] out; d_r [B,4], d_t [B,3] = d dis[b] / d (quat, trans) out (NULL to skip);
+ *   new_points [B,N,3], new_target [B,M,3] out (NULL to skip): next iteration's cloud / target (:51-60). */
+int ape_refine_loss(const float* quat, const float* trans, const float* model_points, const float* target,
+                    int n_mesh, const float* points, int n_points, const uint8_t* symmetric, int B,
+                    float* dis, float* d_r, float* d_t, float* new_points, float* new_target, void* stream);
+/* torch.optim.Adam update (train.py:149) on flat vectors; grads are multiplied by grad_scale first
+ * (1/world_size after a sum all-reduce).  `step` counts from 1.                                     */
+int ape_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -215,3 +215,69 @@ def loss_estimator(pred_r, pred_t, pred_c, target, model_points, idx, points, w,
     new_pts = torch.bmm(points.view(1, n, 3) - tt, b).contiguous()
     new_tgt = torch.bmm(target.view(1, m, 3) - tt, b).contiguous()
     return loss, dis[i], new_pts.detach(), new_tgt.detach(), pred
+
+
+# ----------------------------------------------------------------------------- bf16 training emulation
+def _bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def refiner_train_bf16_emulation(sd, new_points, emb, obj, num_obj, d_r, d_t):
+    """Test infrastructure: PoseRefineNet forward + backward (network.py:151-206 and its autograd) for ONE object in
+    fp32 arithmetic with bf16 ROUNDING at exactly the points where the B200 training path stores bf16 (csrc/train.cuh):
+    trunk weights conv2/e_conv2/conv5/conv6, the activations x1|e1|x2|e2 and h5, the pooled-layer gradient g6, and the
+    activation gradients dZ5, dZ2|dZe2, the conv5 share of dX1|dE1, dZ1|dZe1.  Heads stay fp32.  Separates "the
+    kernels compute what they are meant to" (tight tolerance against this) from "bf16 differs from fp32" (loose
+    tolerance against plain autograd).  new_points [1,N,3], emb [1,32,N], d_r [4], d_t [3] ->
+    (r [4], t [3], {state_dict key: gradient})."""
+    W = {k: v.detach().to(torch.float32) for k, v in sd.items()}
+    w2d = lambda k: W[k].reshape(W[k].shape[0], -1)
+    n = new_points.shape[1]
+    p = new_points[0].to(torch.float32)                      # [N,3]
+    e = emb[0].t().contiguous().to(torch.float32)            # [N,32]
+    o = int(obj.reshape(-1)[0])
+    x1 = _bf(F.relu(p @ w2d('feat.conv1.weight').t() + W['feat.conv1.bias']))
+    e1 = _bf(F.relu(e @ w2d('feat.e_conv1.weight').t() + W['feat.e_conv1.bias']))
+    W2, We2, W5, W6 = (_bf(w2d('feat.%s.weight' % k)) for k in ('conv2', 'e_conv2', 'conv5', 'conv6'))
+    x2 = _bf(F.relu(x1 @ W2.t() + W['feat.conv2.bias']))
+    e2 = _bf(F.relu(e1 @ We2.t() + W['feat.e_conv2.bias']))
+    pf = torch.cat([x1, e1, x2, e2], 1)                      # [N,384]
+    h5 = _bf(F.relu(pf @ W5.t() + W['feat.conv5.bias']))
+    y6 = F.relu(h5 @ W6.t() + W['feat.conv6.bias'])          # never stored: only its sign bits and column mean
+    ap = y6.mean(0, keepdim=True)                            # [1,1024]
+    g = {}
+    r_t, dz1h = [], []
+    for h, width, d in (('r', 4, d_r), ('t', 3, d_t)):
+        g1 = F.relu(ap @ W['conv1_%s.weight' % h].t() + W['conv1_%s.bias' % h])
+        g2 = F.relu(g1 @ W['conv2_%s.weight' % h].t() + W['conv2_%s.bias' % h])
+        w3 = W['conv3_%s.weight' % h][o * width:(o + 1) * width]
+        r_t.append((g2 @ w3.t() + W['conv3_%s.bias' % h][o * width:(o + 1) * width])[0])
+        d = d.reshape(1, width).to(torch.float32)
+        gw3 = torch.zeros_like(W['conv3_%s.weight' % h]); gb3 = torch.zeros_like(W['conv3_%s.bias' % h])
+        gw3[o * width:(o + 1) * width] = d.t() @ g2; gb3[o * width:(o + 1) * width] = d[0]
+        dz2 = (d @ w3) * (g2 > 0)
+        dz1 = (dz2 @ W['conv2_%s.weight' % h]) * (g1 > 0)
+        g['conv3_%s.weight' % h], g['conv3_%s.bias' % h] = gw3, gb3
+        g['conv2_%s.weight' % h], g['conv2_%s.bias' % h] = dz2.t() @ g1, dz2[0]
+        g['conv1_%s.weight' % h], g['conv1_%s.bias' % h] = dz1.t() @ ap, dz1[0]
+        dz1h.append(dz1 @ W['conv1_%s.weight' % h])
+    g6 = _bf((dz1h[0] + dz1h[1]) / float(n))                 # [1,1024]
+    dy6 = (y6 > 0).to(torch.float32) * g6                    # [N,1024]
+    g['feat.conv6.weight'], g['feat.conv6.bias'] = dy6.t() @ h5, dy6.sum(0)
+    dz5_f = (dy6 @ W6) * (h5 > 0)
+    g['feat.conv5.bias'] = dz5_f.sum(0)
+    dz5 = _bf(dz5_f)
+    g['feat.conv5.weight'] = dz5.t() @ pf
+    dpf = dz5 @ W5                                           # [N,384]
+    dz22_f = dpf[:, 128:] * (pf[:, 128:] > 0)
+    g['feat.conv2.bias'], g['feat.e_conv2.bias'] = dz22_f[:, :128].sum(0), dz22_f[:, 128:].sum(0)
+    dz22 = _bf(dz22_f)
+    part = _bf(dpf[:, :128])
+    g['feat.conv2.weight'] = dz22[:, :128].t() @ x1
+    g['feat.e_conv2.weight'] = dz22[:, 128:].t() @ e1
+    dz1_f = (dz22[:, :128] @ W2 + part[:, :64]) * (x1 > 0)
+    dze1_f = (dz22[:, 128:] @ We2 + part[:, 64:]) * (e1 > 0)
+    g['feat.conv1.bias'], g['feat.e_conv1.bias'] = dz1_f.sum(0), dze1_f.sum(0)
+    g['feat.conv1.weight'] = _bf(dz1_f).t() @ p
+    g['feat.e_conv1.weight'] = _bf(dze1_f).t() @ e
+    return r_t[0], r_t[1], {k: v.reshape(sd[k].shape) for k, v in g.items()}
