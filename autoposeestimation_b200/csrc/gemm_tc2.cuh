@@ -60,7 +60,13 @@ __device__ __forceinline__ Tile decode_tile(int t, const Params& p, int m_tiles,
 
 // grid = min(#tiles, #SMs).  Load maps: box {64 (K), 128 (rows)}, SWIZZLE_128B.  Store maps (EPI_RELU_SPLIT):
 // box {64 (cols), 32 (rows)}, SWIZZLE_128B.
-__global__ void __launch_bounds__(kThreads, 1)
+// EPI8 (training forward, csrc/train.cuh: plain bf16, hi-only stores): warps 2..9 drain the accumulator, two per TMEM lane
+// quadrant, each taking half of the tile's columns -- with one bf16 pass over K <= 512 the epilogue, not the MMA, is the
+// critical path.  The second warp of a quadrant stages through the (unused) lo half of the quadrant's staging buffer.
+// EPI8 = false is the inference kernel, unchanged: 192 threads, warps 2..5.
+constexpr int kThreadsEpi8 = 320;
+template <bool EPI8>
+__global__ void __launch_bounds__(EPI8 ? kThreadsEpi8 : kThreads, 1)
 gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                                   const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                                   const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
@@ -90,7 +96,7 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
 #pragma unroll
         for (int s = 0; s < kStages2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
 #pragma unroll
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], EPI8 ? 8 : 4); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols2);
@@ -157,7 +163,8 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
     } else {
         // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
         const int quad = warp & 3;
-        unsigned char* stg = staging + quad * kStgWarp;           // [hi|lo][32 rows x 128 B], SWIZZLE_128B
+        const int half = EPI8 ? (warp - 2) >> 2 : 0;              // EPI8: which half of the tile's columns this warp drains
+        unsigned char* stg = staging + quad * kStgWarp + half * kStgBuf;   // [hi|lo][32 rows x 128 B], SWIZZLE_128B
         float* s_colsum = reinterpret_cast<float*>(staging);      // EPI_RELU_COLSUM: [4][256]
         const int GN = p.groups * p.N;
         int lt = 0;
@@ -169,7 +176,9 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
             const int row = row0 + lane;
             const int col_g = tl.g * p.N + tl.n0;                 // first column within [groups*N]
             const float* bias = p.bias + (p.bias_obj_rows > 0 ? (size_t)(row0 / p.bias_obj_rows) * (size_t)GN : 0) + col_g;
-            float bl = __ldg(bias + lane);                        // bias is prefetched one 32-column chunk ahead
+            const int c_beg = EPI8 ? half * (tl.bn >> 1) : 0;
+            const int c_end = EPI8 ? c_beg + (tl.bn >> 1) : tl.bn;
+            float bl = __ldg(bias + c_beg + lane);                // bias is prefetched one 32-column chunk ahead
             const bool valid = (p.mode != EPI_RELU_COLSUM) || ((row % p.rows_per_obj) < p.valid_rows);
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256);
             // EPI_HEAD_OUT: stage the last-layer weights of this tile's object class before waiting for the accumulator
@@ -191,13 +200,13 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
             tc_fence_after();
             if (p.mode == EPI_RELU_SPLIT) {
 #pragma unroll 1
-                for (int c0 = 0; c0 < tl.bn; c0 += 64) {
+                for (int c0 = c_beg; c0 < c_end; c0 += 64) {
                     uint32_t hi[32], lo[32];
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         uint32_t v[32];
                         tmem_ld_32x32(t_addr + (uint32_t)(c0 + 32 * h), v);
-                        const bool last = (h == 1) && (c0 + 64 >= tl.bn);
+                        const bool last = (h == 1) && (c0 + 64 >= c_end);
                         if (last) {                                   // last read of this accumulator: hand it back early
                             tc_fence_before();
                             __syncwarp();
@@ -281,10 +290,10 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
                 }
             } else {
 #pragma unroll 1
-                for (int c0 = 0; c0 < tl.bn; c0 += 32) {
+                for (int c0 = c_beg; c0 < c_end; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld_32x32(t_addr + (uint32_t)c0, v);
-                    const bool last = c0 + 32 >= tl.bn;
+                    const bool last = c0 + 32 >= c_end;
                     if (last) {
                         tc_fence_before();
                         __syncwarp();
@@ -320,13 +329,15 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
                 }
             }
             if (p.mode == EPI_RELU_COLSUM) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");        // the four epilogue warps only
-                const int tt = threadIdx.x - 64;                       // 0..127
-                for (int c = tt; c < tl.bn; c += 128) {
+                if (EPI8) asm volatile("bar.sync 1, 256;" ::: "memory"); else
+                asm volatile("bar.sync 1, 128;" ::: "memory");        // the epilogue warps only
+                const int tt = threadIdx.x - 64;                       // 0..127 (0..255 with EPI8)
+                for (int c = tt; c < tl.bn; c += (EPI8 ? 256 : 128)) {
                     // fixed order over the quadrants -> deterministic
                     const float sum = (s_colsum[c] + s_colsum[256 + c]) + (s_colsum[512 + c] + s_colsum[768 + c]);
                     p.colsum[(size_t)tl.m_tile * (size_t)GN + col_g + c] = sum;
                 }
+                if (EPI8) asm volatile("bar.sync 1, 256;" ::: "memory"); else
                 asm volatile("bar.sync 1, 128;" ::: "memory");        // scratch is free for the next tile
             }
         }

@@ -609,7 +609,7 @@ int ape_net_create(int kind, const float* const* w, int n_tensors, int num_obj, 
         cudaError_t e = cudaFuncSetAttribute(ape::tc::gemm_split_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              ape::tc::kSmemBytes);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(ape::tc2::gemm_split_bf16_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            e = cudaFuncSetAttribute(ape::tc2::gemm_split_bf16_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      ape::tc2::kSmemBytes2);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(ape::tc3::gemm_split_bf16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -669,8 +669,12 @@ static int run_gemm(ape_net* net, const SplitMat& A, const SplitMat& W, const Sp
         const int tiles = p.groups * (p.M / ape::tc::BM) * ((p.N + bn_full - 1) / bn_full);
         const int grid = tiles < ape::sm_count() ? tiles : ape::sm_count();
         const SplitMat& O = out ? *out : A;          // EPI_RELU_COLSUM never touches the store maps
-        ape::tc2::gemm_split_bf16_persistent_kernel<<<grid, ape::tc::kThreads, ape::tc2::kSmemBytes2, s>>>(
-            A.map_hi, A.map_lo, W.map_hi, W.map_lo, O.st_hi, O.st_lo, p, bn_full);
+        if (p.passes == 1 && (p.hi_only || p.mode == ape::tc::EPI_RELU_COLSUM))     // training forward: 8 epilogue warps
+            ape::tc2::gemm_split_bf16_persistent_kernel<true><<<grid, ape::tc2::kThreadsEpi8, ape::tc2::kSmemBytes2, s>>>(
+                A.map_hi, A.map_lo, W.map_hi, W.map_lo, O.st_hi, O.st_lo, p, bn_full);
+        else
+            ape::tc2::gemm_split_bf16_persistent_kernel<false><<<grid, ape::tc::kThreads, ape::tc2::kSmemBytes2, s>>>(
+                A.map_hi, A.map_lo, W.map_hi, W.map_lo, O.st_hi, O.st_lo, p, bn_full);
     } else if (net->gemm_impl == APE_GEMM_TCGEN05_V1) {
         dim3 grid(p.N / ape::tc::BN, p.M / ape::tc::BM, p.groups);
         ape::tc::gemm_split_bf16_kernel<<<grid, ape::tc::kThreads, ape::tc::kSmemBytes, s>>>(A.map_hi, A.map_lo, W.map_hi,

@@ -62,25 +62,28 @@ struct SgemmArgs {
     const float* mask; long long ldm, m_g;       // SG_STORE_MASK: C = mask > 0 ? v : 0
     int M, N, K, epi;
     float alpha;
+    int groups, ksplit;                          // blockIdx.z = g + groups * k_slice (ksplit > 1 needs SG_ATOMIC)
 };
 __global__ void __launch_bounds__(256)
 sgemm_small_kernel(const SgemmArgs a)
 {
     __shared__ float sA[16][65], sB[16][65];
-    const int g = blockIdx.z;
+    const int g = blockIdx.z % a.groups, ks = blockIdx.z / a.groups;
     const float* A = a.A + g * a.a_g;
     const float* B = a.B + g * a.b_g;
     const int row0 = blockIdx.y * 64, col0 = blockIdx.x * 64;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int kc = ((a.K + a.ksplit - 1) / a.ksplit + 15) / 16 * 16;
+    const int k_end = min(a.K, (ks + 1) * kc);
     float acc[4][4] = {};
-    for (int k0 = 0; k0 < a.K; k0 += 16) {
+    for (int k0 = ks * kc; k0 < k_end; k0 += 16) {
         for (int i = threadIdx.x; i < 64 * 16; i += 256) {
             int m, k;
             if (a.sak == 1) { k = i & 15; m = i >> 4; } else { m = i & 63; k = i >> 6; }
-            sA[k][m] = (row0 + m < a.M && k0 + k < a.K) ? A[(long long)(row0 + m) * a.sam + (long long)(k0 + k) * a.sak] : 0.f;
+            sA[k][m] = (row0 + m < a.M && k0 + k < k_end) ? A[(long long)(row0 + m) * a.sam + (long long)(k0 + k) * a.sak] : 0.f;
             int n, kk;
             if (a.sbn == 1) { n = i & 63; kk = i >> 6; } else { kk = i & 15; n = i >> 4; }
-            sB[kk][n] = (col0 + n < a.N && k0 + kk < a.K) ? B[(long long)(k0 + kk) * a.sbk + (long long)(col0 + n) * a.sbn] : 0.f;
+            sB[kk][n] = (col0 + n < a.N && k0 + kk < k_end) ? B[(long long)(k0 + kk) * a.sbk + (long long)(col0 + n) * a.sbn] : 0.f;
         }
         __syncthreads();
 #pragma unroll
@@ -154,34 +157,109 @@ head3_bwd_kernel(const float* __restrict__ d_r, const float* __restrict__ d_t, c
 }
 
 // Backward of AvgPool1d + the ReLU of conv6 (network.py:163-167): dY6[r, c] = bit(r, c) ? g6[b, c] : 0 (bf16), where
-// g6 = dAP / N already, and db6[c] += sum_r dY6[r, c].  One CTA per 128-row tile, thread = 4 consecutive columns.
+// g6 = dAP / N already, and db6[c] += sum_r dY6[r, c].  One CTA per 128-row tile; thread = 8 consecutive columns (one
+// byte of sign bits in, one 16-byte store out per row), two row phases per CTA, 4 rows in flight per thread.
 __global__ void __launch_bounds__(256)
 dy6_kernel(const uint32_t* __restrict__ bits, const float* __restrict__ g6, int Np, int rows_live, bf16* __restrict__ dy6,
-           float* __restrict__ gb6)
+           float* __restrict__ part6 /* [tiles][1024]: this tile's column sums (no atomics: see gemm_train.cuh) */)
 {
+    __shared__ uint32_t s_cnt[128][8];
     const int row0 = blockIdx.x * 128;
-    const int c = threadIdx.x * 4;
+    const int cg = threadIdx.x & 127, rh = threadIdx.x >> 7;
+    const int c = cg * 8;
     const int b = row0 / Np;                                  // Np is a multiple of 128: one object per tile
     const bool live = row0 < rows_live;
-    const float4 g = live ? *reinterpret_cast<const float4*>(g6 + (size_t)b * 1024 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const __nv_bfloat162 g01 = __floats2bfloat162_rn(g.x, g.y), g23 = __floats2bfloat162_rn(g.z, g.w);
-    const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&g01), u23 = *reinterpret_cast<const uint32_t*>(&g23);
-    int cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0;
-    const int sh = c & 31;
-    for (int r = 0; r < 128; ++r) {
-        const size_t row = (size_t)row0 + r;
-        const uint32_t w = live ? (__ldg(bits + row * 32 + (c >> 5)) >> sh) : 0u;
-        const uint32_t lo = ((w & 1u) ? (u01 & 0xffffu) : 0u) | ((w & 2u) ? (u01 & 0xffff0000u) : 0u);
-        const uint32_t hi = ((w & 4u) ? (u23 & 0xffffu) : 0u) | ((w & 8u) ? (u23 & 0xffff0000u) : 0u);
-        *reinterpret_cast<uint2*>(dy6 + row * 1024 + c) = make_uint2(lo, hi);
-        cnt0 += w & 1u; cnt1 += (w >> 1) & 1u; cnt2 += (w >> 2) & 1u; cnt3 += (w >> 3) & 1u;
-    }
+    uint32_t u[4] = {0u, 0u, 0u, 0u};
     if (live) {
-        // the bias gradient sums the bf16-rounded values the GEMMs see
-        atomicAdd(gb6 + c, cnt0 * __uint_as_float(u01 << 16));
-        atomicAdd(gb6 + c + 1, cnt1 * __uint_as_float(u01 & 0xffff0000u));
-        atomicAdd(gb6 + c + 2, cnt2 * __uint_as_float(u23 << 16));
-        atomicAdd(gb6 + c + 3, cnt3 * __uint_as_float(u23 & 0xffff0000u));
+        const float4 g0 = *reinterpret_cast<const float4*>(g6 + (size_t)b * 1024 + c);
+        const float4 g1 = *reinterpret_cast<const float4*>(g6 + (size_t)b * 1024 + c + 4);
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(g0.x, g0.y), h1 = __floats2bfloat162_rn(g0.z, g0.w);
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(g1.x, g1.y), h3 = __floats2bfloat162_rn(g1.z, g1.w);
+        u[0] = *reinterpret_cast<const uint32_t*>(&h0); u[1] = *reinterpret_cast<const uint32_t*>(&h1);
+        u[2] = *reinterpret_cast<const uint32_t*>(&h2); u[3] = *reinterpret_cast<const uint32_t*>(&h3);
+    }
+    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(bits);       // little-endian: byte j of a word = columns 8j..8j+7
+    uint32_t cnt[8] = {};
+    for (int r0 = rh; r0 < 128; r0 += 8) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = live ? (uint32_t)__ldg(bytes + ((size_t)row0 + r0 + 2 * i) * 128 + cg) : 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t b0 = (w[i] >> (2 * q)) & 1u, b1 = (w[i] >> (2 * q + 1)) & 1u;
+                o[q] = (b0 ? (u[q] & 0xffffu) : 0u) | (b1 ? (u[q] & 0xffff0000u) : 0u);
+                cnt[2 * q] += b0; cnt[2 * q + 1] += b1;
+            }
+            *reinterpret_cast<uint4*>(dy6 + ((size_t)row0 + r0 + 2 * i) * 1024 + c) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    // the bias gradient sums the bf16-rounded values the GEMMs see; the two row phases are combined through smem
+    if (rh == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_cnt[cg][j] = cnt[j];
+    }
+    __syncthreads();
+    if (rh == 0) {
+        float o[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            o[2 * q] = (float)(cnt[2 * q] + s_cnt[cg][2 * q]) * __uint_as_float(u[q] << 16);
+            o[2 * q + 1] = (float)(cnt[2 * q + 1] + s_cnt[cg][2 * q + 1]) * __uint_as_float(u[q] & 0xffff0000u);
+        }
+        float4* dst = reinterpret_cast<float4*>(part6 + (size_t)blockIdx.x * 1024 + c);
+        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+// Folds the partial sums of one backward pass into the flat gradient (one short launch instead of deep atomic chains):
+//   biases of conv5 | conv2,e_conv2 | conv1,e_conv1 from kBiasCopies copies, conv1 / e_conv1 weights from kW1Copies
+//   copies, conv6 bias from the per-tile sums of dy6_kernel.
+constexpr int kW1Copies = 16;
+constexpr int kBiasPart = 1024;                 // floats per bias copy: [b5 512 | b2e2 256 | b1,be1 128 | pad]
+constexpr int kW1Part = 64 * 3 + 64 * 32;       // conv1.w | e_conv1.w, contiguous in the flat layout
+__global__ void __launch_bounds__(1024)
+fold_partials_kernel(const float* __restrict__ part_b, const float* __restrict__ part_w1, const float* __restrict__ part6, int tiles,
+                     float* __restrict__ g_b5, float* __restrict__ g_b2e2, float* __restrict__ g_b1, float* __restrict__ g_w1,
+                     float* __restrict__ g_b6)
+{
+    __shared__ float s_red[32][33];
+    if (blockIdx.x < 32) {
+        // conv6 bias: block = 32 columns x 32 tile segments, 4 loads in flight per thread, fixed-order tree over the segments
+        const int cx = threadIdx.x & 31, sg = threadIdx.x >> 5, c = blockIdx.x * 32 + cx;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int t = sg;
+        for (; t + 96 < tiles; t += 128) {
+            s0 += part6[(size_t)t * 1024 + c]; s1 += part6[(size_t)(t + 32) * 1024 + c];
+            s2 += part6[(size_t)(t + 64) * 1024 + c]; s3 += part6[(size_t)(t + 96) * 1024 + c];
+        }
+        for (; t < tiles; t += 32) s0 += part6[(size_t)t * 1024 + c];
+        s_red[sg][cx] = (s0 + s1) + (s2 + s3);
+        __syncthreads();
+        if (sg == 0) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) s += s_red[k][cx];
+            g_b6[c] += s;
+        }
+        return;
+    }
+    const int i = (blockIdx.x - 32) * 1024 + threadIdx.x;
+    if (i < 896) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < tr::kBiasCopies; ++k) s += part_b[k * kBiasPart + i];
+        float* dst = i < 512 ? g_b5 + i : (i < 768 ? g_b2e2 + (i - 512) : g_b1 + (i - 768));
+        *dst += s;
+    } else if (i >= 1024 && i < 1024 + kW1Part) {
+        const int j = i - 1024;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < kW1Copies; ++k) s += part_w1[k * kW1Part + j];
+        g_w1[j] += s;
     }
 }
 
@@ -192,7 +270,7 @@ conv1_wgrad_kernel(const bf16* __restrict__ dpf, int ld, const float* __restrict
                    int B, int N, int Np, float* __restrict__ gw1, float* __restrict__ gwe1)
 {
     __shared__ float s_dz[64][129];
-    __shared__ float s_x[64][36];
+    __shared__ __align__(16) float s_x[64][36];
     const int tid = threadIdx.x, c = tid & 63, kq = tid >> 6;
     float acc_e[8] = {}, acc_x[3] = {};
     const int chunks = B * (Np / 64);
@@ -200,11 +278,15 @@ conv1_wgrad_kernel(const bf16* __restrict__ dpf, int ld, const float* __restrict
         const int b = ch / (Np / 64), n0 = (ch % (Np / 64)) * 64;
         if (n0 >= N) continue;                                  // whole chunk is padding (uniform per CTA)
         __syncthreads();
-        for (int i = tid; i < 64 * 64; i += 256) {              // 64 rows x 64 bf16 pairs
-            const int r = i >> 6, p2 = i & 63;
-            const uint32_t u = *reinterpret_cast<const uint32_t*>(dpf + ((size_t)b * Np + n0 + r) * ld + 2 * p2);
-            s_dz[r][2 * p2] = __uint_as_float(u << 16);
-            s_dz[r][2 * p2 + 1] = __uint_as_float(u & 0xffff0000u);
+        for (int i = tid; i < 64 * 16; i += 256) {              // 64 rows x 16 chunks of 8 bf16 (16-byte loads)
+            const int r = i >> 4, ch8 = i & 15;
+            const uint4 v = *reinterpret_cast<const uint4*>(dpf + ((size_t)b * Np + n0 + r) * ld + 8 * ch8);
+            const uint32_t u4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                s_dz[r][8 * ch8 + 2 * e] = __uint_as_float(u4[e] << 16);
+                s_dz[r][8 * ch8 + 2 * e + 1] = __uint_as_float(u4[e] & 0xffff0000u);
+            }
         }
         for (int i = tid; i < 32 * 64; i += 256) {              // emb [B,32,N]: n fastest
             const int k = i >> 6, r = i & 63;
@@ -217,8 +299,10 @@ conv1_wgrad_kernel(const bf16* __restrict__ dpf, int ld, const float* __restrict
         __syncthreads();
         for (int r = 0; r < 64; ++r) {
             const float de = s_dz[r][64 + c];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc_e[j] = fmaf(de, s_x[r][kq * 8 + j], acc_e[j]);
+            const float4 xa = *reinterpret_cast<const float4*>(&s_x[r][kq * 8]), xb = *reinterpret_cast<const float4*>(&s_x[r][kq * 8 + 4]);
+            acc_e[0] = fmaf(de, xa.x, acc_e[0]); acc_e[1] = fmaf(de, xa.y, acc_e[1]); acc_e[2] = fmaf(de, xa.z, acc_e[2]);
+            acc_e[3] = fmaf(de, xa.w, acc_e[3]); acc_e[4] = fmaf(de, xb.x, acc_e[4]); acc_e[5] = fmaf(de, xb.y, acc_e[5]);
+            acc_e[6] = fmaf(de, xb.z, acc_e[6]); acc_e[7] = fmaf(de, xb.w, acc_e[7]);
             if (kq == 0) {
                 const float dx = s_dz[r][c];
 #pragma unroll
@@ -226,11 +310,13 @@ conv1_wgrad_kernel(const bf16* __restrict__ dpf, int ld, const float* __restrict
             }
         }
     }
+    // gw1 / gwe1 point at kW1Copies partial copies [conv1.w 192 | e_conv1.w 2048]: short atomic chains
+    const size_t copy = (size_t)(blockIdx.x % 16) * (64 * 3 + 64 * 32);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(gwe1 + c * 32 + kq * 8 + j, acc_e[j]);
+    for (int j = 0; j < 8; ++j) atomicAdd(gwe1 + copy + c * 32 + kq * 8 + j, acc_e[j]);
     if (kq == 0) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) atomicAdd(gw1 + c * 3 + j, acc_x[j]);
+        for (int j = 0; j < 3; ++j) atomicAdd(gw1 + copy + c * 3 + j, acc_x[j]);
     }
 }
 
@@ -253,7 +339,10 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 struct BfMat {                        // bf16 row-major matrix with its TMA maps
     bf16* p = nullptr; int rows = 0, cols = 0;
     CUtensorMap kmaj;                 // box {64 cols, 128 rows}: K-major operand (rows = M or N, cols = K)
-    CUtensorMap mn;                   // box {64 cols, 64 rows}:  MN-major operand (rows = K, cols = M or N)
+    CUtensorMap mn2, mn4;             // 3-D view (64 cols, rows, cols/64 chunks), box {64, 64 rows, 2 | min(4, chunks)}: a whole
+                                      // MN-major operand stage (rows = K, chunks = M or N) in one TMA op
+    int mn4_chunks = 0;
+    CUtensorMap st;                   // box {64 cols, 32 rows}:  one epilogue chunk (DGRAD mask / addend loads, result stores)
 };
 
 struct ape_trainer {
@@ -264,12 +353,29 @@ struct ape_trainer {
     BfMat Wb2, Wb5, Wb6;              // bf16 copies of conv2|e_conv2, conv5, conv6 (one contiguous allocation)
     BfMat PFm, H5m, dY6, dZ5, dPF;    // PFm / H5m alias net.PF.hi / net.H5.hi
     float *dZ2h = nullptr, *dZ1h = nullptr, *g6 = nullptr;
+    float *part_b = nullptr, *part_w1 = nullptr, *part6 = nullptr;   // partial sums folded by fold_partials_kernel
 };
 
 static int make_bf_maps(BfMat& m) {
     int rc = make_map_box(&m.kmaj, m.p, m.rows, m.cols, m.cols, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    return make_map_box(&m.mn, m.p, m.rows, m.cols, m.cols, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+    if ((rc = make_map_box(&m.st, m.p, m.rows, m.cols, m.cols, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { ape::set_error("cuTensorMapEncodeTiled entry point not available"); return APE_ERR_CUDA; }
+    const int chunks = m.cols / 64;
+    m.mn4_chunks = chunks < 4 ? chunks : 4;
+    for (int which = 0; which < 2; ++which) {
+        const int bc = which == 0 ? (chunks < 2 ? chunks : 2) : m.mn4_chunks;
+        cuuint64_t dims[3] = {64, (cuuint64_t)m.rows, (cuuint64_t)chunks};
+        cuuint64_t strides[2] = {(cuuint64_t)m.cols * 2, 128};                 // bytes: next row, next 64-column chunk
+        cuuint32_t box[3] = {64, 64, (cuuint32_t)bc};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = fn(which == 0 ? &m.mn2 : &m.mn4, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, m.p, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { ape::set_error("cuTensorMapEncodeTiled (3-D) failed (%d)", (int)r); return APE_ERR_CUDA; }
+    }
+    return APE_OK;
 }
 
 extern "C" __attribute__((visibility("default")))
@@ -378,11 +484,17 @@ int ape_refiner_trainer_create(float* params, float* grads, int num_obj, int max
     TRY(dev_alloc(net, (void**)&tr->dZ2h, (size_t)max_batch * 256 * 4));
     TRY(dev_alloc(net, (void**)&tr->dZ1h, (size_t)max_batch * 1024 * 4));
     TRY(dev_alloc(net, (void**)&tr->g6, (size_t)max_batch * 1024 * 4));
+    TRY(dev_alloc(net, (void**)&tr->part_b, (size_t)ape::tr::kBiasCopies * ape::kBiasPart * 4));
+    TRY(dev_alloc(net, (void**)&tr->part_w1, (size_t)ape::kW1Copies * ape::kW1Part * 4));
+    TRY(dev_alloc(net, (void**)&tr->part6, (R / 128) * 1024 * 4));
 #undef TRY
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(ape::tc2::gemm_split_bf16_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(ape::tc2::gemm_split_bf16_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              ape::tc2::kSmemBytes2);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(ape::tc2::gemm_split_bf16_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     ape::tc2::kSmemBytes2);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(ape::tr::gemm_bf16_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ape::tr::kSmemBytesBwd);
         if (e != cudaSuccess) { ape::set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); ape_refiner_trainer_destroy(tr); return APE_ERR_CUDA; }
@@ -404,7 +516,9 @@ int ape_refiner_trainer_forward(ape_trainer* tr, const float* new_points, const 
     return ape_refiner_forward(&tr->net, new_points, emb, obj, B, N, r2, t2, stream);
 }
 
-static int run_bwd_gemm(const BfMat& A, const BfMat& Bm, ape::tr::BwdParams p, cudaStream_t s, const char* label)
+// `mask` / `out`: the matrices behind p.mask / p.out (DGRAD only; their chunk maps feed the TMA-staged epilogue)
+static int run_bwd_gemm(const BfMat& A, const BfMat& Bm, const BfMat* mask, const BfMat* out, ape::tr::BwdParams p, cudaStream_t s,
+                        const char* label)
 {
     ape::ProfScope prof_(label, s);
     const bool wgrad = p.mode == ape::tr::BWD_WGRAD;
@@ -418,15 +532,22 @@ static int run_bwd_gemm(const BfMat& A, const BfMat& Bm, ape::tr::BwdParams p, c
     }
     const int total = tiles * p.k_splits;
     const int grid = total < ape::sm_count() ? total : ape::sm_count();
-    ape::tr::gemm_bf16_bwd_kernel<<<grid, ape::tc::kThreads, ape::tr::kSmemBytesBwd, s>>>(wgrad ? A.mn : A.kmaj, Bm.mn, p);
+    if (!wgrad && (!out || (p.add_out && p.N != 64) || (p.mask_from % 64) != 0)) {
+        ape::set_error("run_bwd_gemm: unsupported DGRAD epilogue configuration");
+        return APE_ERR_UNSUPPORTED;
+    }
+    p.b_box_chunks = Bm.mn4_chunks;
+    ape::tr::gemm_bf16_bwd_kernel<<<grid, ape::tr::kThreadsBwd, ape::tr::kSmemBytesBwd, s>>>(
+        wgrad ? A.mn2 : A.kmaj, Bm.mn4, mask ? mask->st : A.kmaj, out ? out->st : A.kmaj, p);
     ape::count_launch();
     return ape::check_launch(label);
 }
 
-static int sgemm(const ape::SgemmArgs& a, int groups, cudaStream_t s, const char* label)
+static int sgemm(ape::SgemmArgs a, int groups, cudaStream_t s, const char* label, int ksplit = 1)
 {
     ape::ProfScope prof_(label, s);
-    dim3 grid((a.N + 63) / 64, (a.M + 63) / 64, groups);
+    a.groups = groups; a.ksplit = ksplit;
+    dim3 grid((a.N + 63) / 64, (a.M + 63) / 64, groups * ksplit);
     ape::sgemm_small_kernel<<<grid, 256, 0, s>>>(a);
     ape::count_launch();
     return ape::check_launch(label);
@@ -446,6 +567,8 @@ int ape_refiner_trainer_backward(ape_trainer* tr, const float* new_points, const
     float* G = tr->grads;
     const int Np = (N + 127) / 128 * 128, M = (B * Np + 255) / 256 * 256;
     int rc;
+    APE_CUDA(cudaMemsetAsync(tr->part_b, 0, (size_t)ape::tr::kBiasCopies * ape::kBiasPart * 4, s));
+    APE_CUDA(cudaMemsetAsync(tr->part_w1, 0, (size_t)ape::kW1Copies * ape::kW1Part * 4, s));
     {   // heads
         ape::ProfScope prof_("train.head3_bwd", s);
         ape::head3_bwd_kernel<<<B, 256, 0, s>>>(d_r, d_t, obj, tr->num_obj, net->G2.p, net->w3r.p, net->w3t.p, tr->dZ2h,
@@ -456,7 +579,7 @@ int ape_refiner_trainer_backward(ape_trainer* tr, const float* new_points, const
     ape::SgemmArgs a;
     // dW(conv2_{r,t}) [2 x 128, 512] += dZ2h[:, g]^T * G1[:, g]
     a = {tr->dZ2h, 1, 256, 128, net->G1.p, 1024, 1, 512, G + L.wh2, 512, 128 * 512, nullptr, 0, 0, 128, 512, B, ape::SG_ATOMIC, 1.f};
-    if ((rc = sgemm(a, 2, s, "train.head2_wgrad"))) return rc;
+    if ((rc = sgemm(a, 2, s, "train.head2_wgrad", 4))) return rc;
     // dZ1h [B, 2 x 512] = (dZ2h[:, g] * W2[g]) masked by G1 > 0
     a = {tr->dZ2h, 256, 1, 128, net->Wr2.p, 512, 1, 128 * 512, tr->dZ1h, 1024, 512, net->G1.p, 1024, 512, B, 512, 128, ape::SG_STORE_MASK, 1.f};
     if ((rc = sgemm(a, 2, s, "train.head2_dgrad"))) return rc;
@@ -469,11 +592,12 @@ int ape_refiner_trainer_backward(ape_trainer* tr, const float* new_points, const
     a = {tr->dZ1h, 1, 1024, 0, net->AP.p, 1024, 1, 0, G + L.wh1, 1024, 0, nullptr, 0, 0, 1024, 1024, B, ape::SG_ATOMIC, 1.f};
     if ((rc = sgemm(a, 1, s, "train.head1_wgrad"))) return rc;
     // g6 [B, 1024] = (dZ1h * W1) / N   (AvgPool1d backward folded in)
-    a = {tr->dZ1h, 1024, 1, 0, net->Wr1.p, 1024, 1, 0, tr->g6, 1024, 0, nullptr, 0, 0, B, 1024, 1024, ape::SG_STORE, 1.0f / (float)N};
-    if ((rc = sgemm(a, 1, s, "train.head1_dgrad"))) return rc;
+    APE_CUDA(cudaMemsetAsync(tr->g6, 0, (size_t)B * 1024 * sizeof(float), s));
+    a = {tr->dZ1h, 1024, 1, 0, net->Wr1.p, 1024, 1, 0, tr->g6, 1024, 0, nullptr, 0, 0, B, 1024, 1024, ape::SG_ATOMIC, 1.0f / (float)N};
+    if ((rc = sgemm(a, 1, s, "train.head1_dgrad", 8))) return rc;
     {
         ape::ProfScope prof_("train.dy6", s);
-        ape::dy6_kernel<<<M / 128, 256, 0, s>>>(net->relu_bits, tr->g6, Np, B * Np, tr->dY6.p, G + L.b6);
+        ape::dy6_kernel<<<M / 128, 256, 0, s>>>(net->relu_bits, tr->g6, Np, B * Np, tr->dY6.p, tr->part6);
         ape::count_launch();
         if ((rc = ape::check_launch("dy6"))) return rc;
     }
@@ -481,35 +605,44 @@ int ape_refiner_trainer_backward(ape_trainer* tr, const float* new_points, const
     // conv6: dW6 [1024, 512] += dY6^T * H5 ;  dZ5 = (dY6 * W6) masked by H5 > 0, db5
     memset(&p, 0, sizeof(p));
     p.mode = ape::tr::BWD_WGRAD; p.M = 1024; p.N = 512; p.K = M; p.groups = 1; p.dw = G + L.w6; p.dw_ld = 512;
-    if ((rc = run_bwd_gemm(tr->dY6, tr->H5m, p, s, "gemm.train.wgrad6"))) return rc;
+    if ((rc = run_bwd_gemm(tr->dY6, tr->H5m, nullptr, nullptr, p, s, "gemm.train.wgrad6"))) return rc;
     memset(&p, 0, sizeof(p));
     p.mode = ape::tr::BWD_DGRAD; p.M = M; p.N = 512; p.K = 1024; p.groups = 1; p.out = tr->dZ5.p; p.o_ld = 512;
-    p.mask = tr->H5m.p; p.m_ld = 512; p.bias_grad = G + L.b5;
-    if ((rc = run_bwd_gemm(tr->dY6, tr->Wb6, p, s, "gemm.train.dgrad6"))) return rc;
+    p.mask = tr->H5m.p; p.m_ld = 512; p.bias_grad = tr->part_b; p.bg_stride = ape::kBiasPart;
+    if ((rc = run_bwd_gemm(tr->dY6, tr->Wb6, &tr->H5m, &tr->dZ5, p, s, "gemm.train.dgrad6"))) return rc;
     // conv5 (input = pointfeat_3 = PF[:, 0:384], network.py:160-162)
     memset(&p, 0, sizeof(p));
     p.mode = ape::tr::BWD_WGRAD; p.M = 512; p.N = 384; p.K = M; p.groups = 1; p.dw = G + L.w5; p.dw_ld = 384;
-    if ((rc = run_bwd_gemm(tr->dZ5, tr->PFm, p, s, "gemm.train.wgrad5"))) return rc;
+    if ((rc = run_bwd_gemm(tr->dZ5, tr->PFm, nullptr, nullptr, p, s, "gemm.train.wgrad5"))) return rc;
     memset(&p, 0, sizeof(p));
     p.mode = ape::tr::BWD_DGRAD; p.M = M; p.N = 384; p.K = 512; p.groups = 1; p.out = tr->dPF.p; p.o_ld = 384;
-    p.mask = tr->PFm.p; p.m_ld = 384; p.mask_from = 128; p.bias_grad = G + L.b2e2 - 128;       // columns 128..383 = conv2 | e_conv2
-    if ((rc = run_bwd_gemm(tr->dZ5, tr->Wb5, p, s, "gemm.train.dgrad5"))) return rc;
+    p.mask = tr->PFm.p; p.m_ld = 384; p.mask_from = 128;
+    p.bias_grad = tr->part_b + 512 - 128; p.bg_stride = ape::kBiasPart;          // columns 128..383 = conv2 | e_conv2
+    if ((rc = run_bwd_gemm(tr->dZ5, tr->Wb5, &tr->PFm, &tr->dPF, p, s, "gemm.train.dgrad5"))) return rc;
     // conv2 | e_conv2 (two groups): dW [2 x 128, 64] += dZ[:, 128 + g*128 ...]^T * PF[:, g*64 ...]; then
     // dPF[:, g*64 ...] = (dZ * W_g + the conv5 share already there) masked by PF > 0, db1 | dbe1
     memset(&p, 0, sizeof(p));
     p.mode = ape::tr::BWD_WGRAD; p.M = 128; p.N = 64; p.K = M; p.groups = 2; p.a_c0 = 128; p.a_cg = 128; p.b_cg = 64;
     p.dw = G + L.w2e2; p.dw_ld = 64; p.dw_rg = 128;
-    if ((rc = run_bwd_gemm(tr->dPF, tr->PFm, p, s, "gemm.train.wgrad2"))) return rc;
+    if ((rc = run_bwd_gemm(tr->dPF, tr->PFm, nullptr, nullptr, p, s, "gemm.train.wgrad2"))) return rc;
     memset(&p, 0, sizeof(p));
     p.mode = ape::tr::BWD_DGRAD; p.M = M; p.N = 64; p.K = 128; p.groups = 2; p.a_c0 = 128; p.a_cg = 128; p.b_rg = 128;
     p.out = tr->dPF.p; p.o_ld = 384; p.o_cg = 64; p.add_out = 1; p.mask = tr->PFm.p; p.m_ld = 384; p.m_cg = 64;
-    p.bias_grad = G + L.b1;
-    if ((rc = run_bwd_gemm(tr->dPF, tr->Wb2, p, s, "gemm.train.dgrad2"))) return rc;
+    p.bias_grad = tr->part_b + 768; p.bg_stride = ape::kBiasPart;
+    if ((rc = run_bwd_gemm(tr->dPF, tr->Wb2, &tr->PFm, &tr->dPF, p, s, "gemm.train.dgrad2"))) return rc;
     {
         ape::ProfScope prof_("train.conv1_wgrad", s);
-        ape::conv1_wgrad_kernel<<<2 * ape::sm_count(), 256, 0, s>>>(tr->dPF.p, 384, new_points, emb, B, N, Np, G + L.w1, G + L.we1);
+        ape::conv1_wgrad_kernel<<<5 * ape::sm_count(), 256, 0, s>>>(tr->dPF.p, 384, new_points, emb, B, N, Np, tr->part_w1,
+                                                                   tr->part_w1 + 64 * 3);
         ape::count_launch();
         if ((rc = ape::check_launch("conv1_wgrad"))) return rc;
+    }
+    {
+        ape::ProfScope prof_("train.fold_partials", s);
+        ape::fold_partials_kernel<<<32 + 4, 1024, 0, s>>>(tr->part_b, tr->part_w1, tr->part6, M / 128, G + L.b5, G + L.b2e2,
+                                                                     G + L.b1, G + L.w1, G + L.b6);
+        ape::count_launch();
+        if ((rc = ape::check_launch("fold_partials"))) return rc;
     }
     return APE_OK;
 }

@@ -5,11 +5,14 @@ branch) runs on the sm_100a kernel; the rest is differentiable torch glue on the
 import torch
 from torch.nn.modules.loss import _Loss
 
+from .. import ops
 from .knn import KNearestNeighbor
 from .loss_refiner import quat_to_base
 
 
 def loss_calculation(pred_r, pred_t, pred_c, target, model_points, idx, points, w, refine, num_point_mesh, sym_list):
+    if not pred_r.is_cuda:
+        raise ops._lib.ApeError('Loss: tensors must be on a CUDA device (no CPU fallback)')
     knn = KNearestNeighbor(1)
     bs, num_p, _ = pred_c.size()
     m = num_point_mesh

@@ -7,9 +7,14 @@ sm_100a kernels (ops.NetHandle); the PSPNet/ResNet-18 encoder stays on PyTorch/c
 BASELINE.json).  Extension over the reference: a batch of B objects is processed at once (the
 reference silently returns element 0 only, network.py:123).
 
-Training: kernels are forward-only in this round.  When autograd is recording and a parameter requires
-grad, the modules run the same layer stack with torch ops (cuDNN/cuBLAS on the GPU) so `dis.backward()`
-keeps working (train.py:215-223); that training path is NOT yet grafted.
+Training (row a16, DenseFusion/tools/train.py:215-233): when autograd is recording, `PoseRefineNet.forward` runs the
+bf16 training forward of csrc/train.cuh and its backward accumulates into the parameters' `.grad` through the
+hand-written dgrad / wgrad kernels -- `dis.backward()` and `torch.optim.Adam(refiner.parameters())` work as in the
+reference.  The parameters are views of ONE flat fp32 vector (and the gradients of one flat gradient vector, which
+is what gets all-reduced over NCCL between ranks).  Training the ESTIMATOR (`PoseNet` with autograd) is outside the
+graft (SURVEY 8 row a16 covers the refiner step; the estimator is in eval mode there, train.py:191-193) and raises
+unless `PoseNet.allow_torch_training` is set, in which case the layer stack runs as torch ops on the GPU like the
+colour encoder does.  CPU tensors are always an error: there is no CPU path.
 """
 import torch
 import torch.nn as nn
@@ -172,16 +177,22 @@ class PoseNet(_Grafted):
         out_img = self.cnn(img)                                        # PyTorch/cuDNN, outside the graft
         return self.forward_geometry(out_img, x, choose, obj)
 
+    allow_torch_training = False      # opt-in: estimator training as torch ops on the GPU (outside the graft)
+
     def forward_geometry(self, out_img, x, choose, obj):
         """Everything after the encoder (network.py:98-132) on the sm_100a kernels."""
         B, N = x.shape[0], x.shape[1]
-        if self._needs_autograd():
-            return self._torch_geometry(out_img, x, choose, obj)
         if not out_img.is_cuda:
             raise ops._lib.ApeError('PoseNet: tensors must be on a CUDA device (no CPU fallback)')
+        if self._needs_autograd():
+            if not self.allow_torch_training:
+                raise NotImplementedError('PoseNet training is outside the graft (SURVEY 8: only the refiner training step, '
+                                          'train.py:215-233, is grafted); call .eval() / torch.no_grad() for inference or set '
+                                          'PoseNet.allow_torch_training = True to run the estimator as torch ops on the GPU')
+            return self._torch_geometry(out_img, x, choose, obj)
         return self._handle(B, N).posenet_forward(out_img.detach(), x, choose, obj)
 
-    def _torch_geometry(self, out_img, x, choose, obj):               # training only; not grafted yet
+    def _torch_geometry(self, out_img, x, choose, obj):               # estimator training only; outside the graft
         B, di = out_img.shape[:2]
         N = x.shape[1]
         emb = torch.gather(out_img.reshape(B, di, -1), 2, choose.reshape(B, 1, N).expand(B, di, N)).contiguous()
@@ -198,6 +209,27 @@ class PoseNet(_Grafted):
         return outs[0], outs[1], outs[2], emb.detach()
 
 
+class _RefinerTrainFn(torch.autograd.Function):
+    """Autograd node of the training forward: backward accumulates straight into the flat gradient vector that the
+    parameters' `.grad` tensors are views of (so nothing is returned for the parameter inputs)."""
+
+    @staticmethod
+    def forward(ctx, module, x, emb, obj, *params):
+        tr = module._trainer(x.shape[0], x.shape[1])
+        r, t = tr.forward(x, emb, obj)
+        ctx.module = module
+        ctx.save_for_backward(x, emb, obj)
+        return r, t
+
+    @staticmethod
+    def backward(ctx, d_r, d_t):
+        x, emb, obj = ctx.saved_tensors
+        m = ctx.module
+        m._attach_grads()
+        m._tr.backward(x, emb, obj, d_r.contiguous(), d_t.contiguous())
+        return (None,) * (4 + len(list(m.parameters())))
+
+
 class PoseRefineNet(_Grafted):
     _kind = ops.NET_REFINER
 
@@ -208,17 +240,62 @@ class PoseRefineNet(_Grafted):
         self.conv1_r, self.conv1_t = nn.Linear(1024, 512), nn.Linear(1024, 512)
         self.conv2_r, self.conv2_t = nn.Linear(512, 128), nn.Linear(512, 128)
         self.conv3_r, self.conv3_t = nn.Linear(128, num_obj * 4), nn.Linear(128, num_obj * 3)
+        self._tr = None
+
+    # -- training plumbing -------------------------------------------------------------------------
+    def _trainer(self, batch, n_points):
+        """Trainer handle whose flat parameter vector the module's parameters alias (re-created when the workspace
+        must grow); bf16 weight copies are re-derived whenever a parameter was updated in place (optimizer step)."""
+        tr = self._tr
+        dev = next(self.parameters()).device
+        first_name, first = next(iter(self.named_parameters()))
+        moved = tr is not None and first.data_ptr() != tr.view(first_name).data_ptr()      # .to() / .cuda() re-allocated them
+        if tr is None or moved or tr.max_batch < batch or tr.max_points < n_points or tr.device != dev:
+            grads = None if (tr is None or moved) else tr.grads.clone()
+            sd = {k: v.detach() for k, v in self.state_dict().items()}
+            with torch.cuda.device(dev):
+                new = ops.RefinerTrainerHandle(sd, self.num_obj, max(batch, getattr(tr, 'max_batch', 1)),
+                                               max(n_points, getattr(tr, 'max_points', 1)), device=dev)
+            if grads is not None:
+                new.grads.copy_(grads)
+                tr.close()
+            for name, p in self.named_parameters():
+                had_grad = p.grad is not None
+                p.data = new.view(name)
+                p.grad = new.view(name, new.grads) if had_grad else None
+            self._tr = tr = new
+            self._tr_key = None
+        key = tuple(p._version for p in self.parameters())
+        if key != self._tr_key:
+            tr.sync_weights()
+            self._tr_key = key
+        return tr
+
+    def _attach_grads(self):
+        """Make every parameter's .grad a view of the flat gradient vector (zeroed first when the optimizer dropped
+        the gradients with zero_grad(set_to_none=True))."""
+        tr = self._tr
+        params = list(self.named_parameters())
+        if all(p.grad is None for _, p in params):
+            tr.grads.zero_()
+        for name, p in params:
+            view = tr.view(name, tr.grads)
+            if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                if p.grad is not None:
+                    view.copy_(p.grad)
+                p.grad = view
+
+    def flat_gradient(self):
+        """The flat fp32 gradient vector (all-reduce this between ranks), or None before the first backward."""
+        return None if self._tr is None else self._tr.grads
 
     def forward(self, x, emb, obj):
         """x = new_points [B,N,3], emb [B,32,N], obj [B,1] -> pred_r [B,4], pred_t [B,3] (network.py:187-206)."""
         B, N = x.shape[0], x.shape[1]
-        if self._needs_autograd():
-            ap = self.feat(x.transpose(2, 1).contiguous(), emb)
-            idx = obj.reshape(B)
-            ar = torch.arange(B, device=x.device)
-            r = self.conv3_r(F.relu(self.conv2_r(F.relu(self.conv1_r(ap))))).view(B, self.num_obj, 4)[ar, idx]
-            t = self.conv3_t(F.relu(self.conv2_t(F.relu(self.conv1_t(ap))))).view(B, self.num_obj, 3)[ar, idx]
-            return r, t
         if not x.is_cuda:
             raise ops._lib.ApeError('PoseRefineNet: tensors must be on a CUDA device (no CPU fallback)')
+        if self._needs_autograd():
+            return _RefinerTrainFn.apply(self, x.detach(), emb.detach(), obj, *self.parameters())
+        if self._tr is not None:                      # parameters live in the trainer's flat vector: keep one source of truth
+            return self._trainer(B, N).forward(x, emb, obj)
         return self._handle(B, N).refiner_forward(x, emb, obj)

@@ -17,9 +17,8 @@ Multi-GPU is data parallel: every rank holds the full 1.93 M-parameter model, ta
 the flat gradient (one 7.7 MB fp32 buffer) is all-reduced once per step.  There is no CPU fallback.
 """
 import torch
-import torch.distributed as dist
 
-from .. import ops
+from .. import ops, sharding
 
 
 class RefinerTrainer:
@@ -61,8 +60,7 @@ class RefinerTrainer:
 
     def allreduce_gradient(self):
         """Sum the flat gradient over ranks (NCCL on the GPU box; identity for a single process)."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.h.grads, op=dist.ReduceOp.SUM)
+        sharding.allreduce_gradient(self.h.grads)
 
     def optimizer_step(self):
         self.step_count += 1

@@ -31,6 +31,18 @@ def allreduce_scalars(values, op='sum', device=None):
     return t.cpu().tolist()
 
 
+def allreduce_gradient(flat, average=False):
+    """The one data-path collective of the scope: sum the refiner's flat fp32 gradient vector over ranks,
+    in place (NCCL over NVLink on the GPU box, gloo in the CPU tests).  The reference accumulates the SUM of per-sample
+    gradients before optimizer.step() (train.py:222, :231-233), so the data-parallel equivalent is a sum, not a mean;
+    `average` divides by the world size for callers that want the mean."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        if average:
+            flat.div_(dist.get_world_size())
+    return flat
+
+
 def sharded_add_eval(n_instances, dis_fn, threshold=0.02):
     """BASELINE config 3 driver: `dis_fn(lo, hi)` returns the ADD/ADD-S distances (1-D tensor/array) of instances
     [lo, hi) computed on this rank's GPU.  Returns the global (mean distance, fraction below `threshold`,

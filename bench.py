@@ -52,6 +52,16 @@ GEMM_EXEC_PER_ROW = {
 }
 
 
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
+    (profiles/traffic.json, written by tools/summarize_profiles.py); None when there is no capture."""
+    p = os.path.join(ROOT, 'profiles', 'traffic.json')
+    try:
+        return json.load(open(p))[kernel]['dram_bytes_per_launch']
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -251,6 +261,69 @@ def icp_leg(torch, ops, lib, peaks, steps):
                 label_path_32_frames_ms=prep_ms)
 
 
+TRAIN_BATCH, TRAIN_ITERS = 256, 2
+# reference-formulation FLOPs of one refiner forward per object: 1 479 040 FLOP/pt + per-object heads
+REFINER_FWD_FLOPS = 1479040 * NPTS + 2359296 + 2 * 128 * 7 * NUM_OBJ
+
+
+def train_leg(torch, dist, lib, peaks, world, rank, dev, steps):
+    """Extra leg (BASELINE config 5): PoseRefineNet training step, bf16, GLOBAL batch 256 objects x 500 points split over
+    the ranks (strong scaling), 2 refinement iterations, NCCL all-reduce of the flat fp32 gradient, Adam.  Every rank runs
+    it (the all-reduce is a collective); returns the dict on rank 0."""
+    from autoposeestimation_b200 import synthetic as synth
+    from autoposeestimation_b200.densefusion.train_refiner import RefinerTrainer
+    B = TRAIN_BATCH // world
+    g = torch.Generator(device=dev).manual_seed(4 + rank)
+    pts = torch.randn((B, NPTS, 3), device=dev, generator=g) * 0.05
+    emb = torch.randn((B, 32, NPTS), device=dev, generator=g)
+    idx = torch.randint(0, NUM_OBJ, (B,), device=dev, generator=g)
+    model = (torch.rand((B, NPTS, 3), device=dev, generator=g) - 0.5) * 0.2
+    target = model + 0.01 * torch.randn((B, 1, 3), device=dev, generator=g)
+    sd = synth.refiner_state_dict(1007, NUM_OBJ)
+    sd['conv3_r.bias'] = sd['conv3_r.bias'].copy(); sd['conv3_r.bias'][0::4] += 1.0       # near-identity start, as a trained refiner
+    trainer = RefinerTrainer(sd, NUM_OBJ, B, NPTS, sym_list=[0], iterations=TRAIN_ITERS)
+    for _ in range(3):
+        trainer.train_step(pts, emb, idx, target, model)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n = max(3, min(steps, 20))
+    l0 = lib.ape_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        dis = trainer.train_step(pts, emb, idx, target, model)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = int(lib.ape_launch_count() - l0)
+    ms = torch.tensor([e0.elapsed_time(e1) / n], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    out = None
+    if rank == 0:
+        lib.ape_profile_enable(1)
+        for _ in range(3):
+            trainer.train_step(pts, emb, idx, target, model)
+        torch.cuda.synchronize()
+        rep = profile_report(lib); lib.ape_profile_enable(0)
+        kern = {k: v[1] / 3 for k, v in rep.items()}
+        flops = 3 * REFINER_FWD_FLOPS * TRAIN_ITERS * TRAIN_BATCH            # fwd + dgrad + wgrad, whole job
+        gemm_ms = sum(v for k, v in kern.items() if k.startswith('gemm.'))
+        out = dict(objects_per_s=TRAIN_BATCH / ms * 1e3, ms_per_step=ms, global_batch=TRAIN_BATCH, batch_per_gpu=B, points=NPTS,
+                   iterations=TRAIN_ITERS, dtype='bf16 operands, fp32 accumulate / master weights / gradients',
+                   allreduce_bytes=int(trainer.h.grads.numel() * 4) if world > 1 else 0, gpu_launches_per_step=launches / n,
+                   mean_dis=float(dis.mean()),
+                   roofline=dict(bound='tensor', achieved=flops / ms / 1e9, peak=peaks['bf16'] * world, unit='TFLOP/s',
+                                 frac=flops / ms / 1e9 / (peaks['bf16'] * world), algorithmic_flops_per_step=flops,
+                                 note='reference-formulation FLOPs x3 (forward, dgrad, wgrad) over the whole step time'),
+                   rank0_kernel_ms_per_step=kern, rank0_gemm_ms_per_step=gemm_ms)
+    trainer.h.close()
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -324,6 +397,12 @@ def run_b200(args):
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = world * BATCH * args.steps / float(ms2) * 1e3
     clocks = sampler.stop() if sampler else None
+    train = None
+    if not args.no_train:
+        try:
+            train = train_leg(torch, dist, lib, peaks, world, rank, dev, args.steps)
+        except Exception as ex:                               # an extra leg must never take the headline down
+            train = dict(error=repr(ex))
 
     line = None
     if rank == 0:
@@ -348,7 +427,8 @@ def run_b200(args):
         roofline = dict(bound='tensor', kernel='gemm_split_bf16_kernel (tcgen05, %d launches/step)' % sum(
             round(rep[k][0] / args.steps) for k in rep if k.startswith('gemm.')),
             achieved=alg / gemm_ms / 1e9, peak=peaks['bf16'], unit='TFLOP/s', frac=alg / gemm_ms / 1e9 / peaks['bf16'],
-            traffic=None, peak_source=peaks['src'] + ' bf16_tflops_sustained',
+            traffic=measured_traffic('gemm'), traffic_source='profiles/traffic.json (ncu --set full, bytes per GEMM launch)',
+            peak_source=peaks['src'] + ' bf16_tflops_sustained',
             algorithmic_flops_per_step=alg, executed_bf16_tflops=exe / gemm_ms / 1e9,
             executed_frac=exe / gemm_ms / 1e9 / peaks['bf16'], gemm_ms_per_step=gemm_ms, all_kernels_ms_per_step=all_ms,
             gemm_share_of_kernel_time=gemm_ms / all_ms, layers=layers,
@@ -363,6 +443,8 @@ def run_b200(args):
                 extra = icp_leg(torch, ops, lib, peaks, args.steps)
             except Exception as ex:                           # the extra leg must never take the headline down
                 extra = dict(error=repr(ex))
+        if train is not None:
+            extra = dict(extra or {}, refiner_training=train)
         line = dict(metric='pose_frames_per_sec', value=value, unit='frames/s', n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
                     ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16x3',
                     data='synthetic', impl='b200',
@@ -390,6 +472,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-icp', action='store_true', help='skip the extra ICP / back-projection leg')
+    ap.add_argument('--no-train', action='store_true', help='skip the extra refiner-training leg (BASELINE config 5)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -75,6 +75,70 @@ def test_knearestneighbor_and_loss_refine_symmetric(golden_dir):
     assert abs(float(lo) - float(gl['l_loss_sym'])) < 1e-5 and abs(float(d) - float(gl['l_dis_sym'])) < 1e-6
 
 
+def test_loss_dropins_nonsymmetric_match_reference(golden_dir):
+    """Loss / Loss_refine (non-symmetric branch) vs the outputs of the reference's own modules (tests/golden/losses.npz)."""
+    from autoposeestimation_b200.densefusion.loss import Loss
+    from autoposeestimation_b200.densefusion.loss_refiner import Loss_refine
+    g = np.load(os.path.join(golden_dir, 'losses.npz'))
+    T = lambda k: torch.from_numpy(g[k]).cuda()
+    idx = torch.zeros((1, 1), dtype=torch.long, device='cuda')
+    dis, npn, ntg, pred = Loss_refine(120, [])(T('pr1'), T('pt1'), T('target'), T('model'), idx, T('points'))
+    N = lambda x: x.detach().cpu().numpy()
+    assert np.allclose(N(dis), g['lr_dis_nosym'], atol=1e-6) and np.allclose(N(npn), g['lr_newp_nosym'], atol=1e-6)
+    assert np.allclose(N(ntg), g['lr_newt_nosym'], atol=1e-6) and np.allclose(N(pred), g['lr_pred_nosym'], atol=1e-6)
+    for tag, sym, refine in (('nosym', [], False), ('symrefine', [0], True)):
+        lo, d, npn, ntg, _ = Loss(120, sym)(T('pr_n'), T('pt_n'), T('pc_n'), T('target'), T('model'), idx, T('points'), 0.015, refine)
+        assert np.allclose(N(lo), g['l_loss_' + tag], atol=1e-6) and np.allclose(N(d), g['l_dis_' + tag], atol=1e-6)
+        assert np.allclose(N(npn), g['l_newp_' + tag], atol=1e-6) and np.allclose(N(ntg), g['l_newt_' + tag], atol=1e-6)
+
+
+def test_refiner_dropin_trains_like_reference_loop(golden_dir):
+    """train.py:215-233 written against the drop-ins: refiner.train(); per sample and iteration
+    `refiner(new_points, emb, idx)` -> `Loss_refine` -> `dis.backward()`; `optim.Adam(refiner.parameters()).step()`.
+    The gradients land in the parameters' .grad (views of one flat vector) and equal the batched trainer's."""
+    from autoposeestimation_b200 import synthetic as synth
+    from autoposeestimation_b200.densefusion import network
+    from autoposeestimation_b200.densefusion.loss_refiner import Loss_refine
+    from autoposeestimation_b200.densefusion.train_refiner import RefinerTrainer
+    nobj, N, M = 3, 200, 150
+    sd = synth.refiner_state_dict(77, nobj)
+    sd['conv3_r.bias'] = sd['conv3_r.bias'].copy(); sd['conv3_r.bias'][0::4] += 1.0
+    rng = np.random.RandomState(5)
+    B = 3
+    pts = torch.from_numpy((rng.randn(B, N, 3) * 0.05).astype(np.float32)).cuda()
+    emb = torch.from_numpy(rng.randn(B, 32, N).astype(np.float32)).cuda()
+    idx = torch.from_numpy(rng.randint(0, nobj, (B, 1)).astype(np.int64)).cuda()
+    model = torch.from_numpy(((rng.rand(B, M, 3) - 0.5) * 0.2).astype(np.float32)).cuda()
+    target = model + 0.01
+    refiner = network.PoseRefineNet(N, nobj).cuda()
+    refiner.load_state_dict(synth.to_torch(sd))
+    refiner.train()
+    optimizer = torch.optim.Adam(refiner.parameters(), lr=1e-4)
+    criterion_refine = Loss_refine(M, [1])
+    optimizer.zero_grad()
+    for b in range(B):                                               # the reference's batch-1 loop
+        p, tg = pts[b:b + 1], target[b:b + 1]
+        for ite in range(2):
+            pred_r, pred_t = refiner(p, emb[b:b + 1], idx[b:b + 1])
+            dis, p, tg, _ = criterion_refine(pred_r, pred_t, tg, model[b:b + 1], idx[b:b + 1], p)
+            dis.backward()
+    trainer = RefinerTrainer(sd, nobj, B, N, sym_list=[1])
+    trainer.zero_grad()
+    trainer.accumulate(pts, emb, idx.view(-1), target, model)
+    flat = refiner.flat_gradient()
+    assert refiner.conv1_r.weight.grad.data_ptr() == refiner._tr.view('conv1_r.weight', flat).data_ptr()
+    rel = float((flat - trainer.h.grads).norm() / trainer.h.grads.norm())
+    assert rel < 2e-3, rel                                            # same kernels; only fp32 atomic order / batching differ
+    before = refiner.conv1_r.weight.detach().clone()
+    r_before = refiner(pts, emb, idx)[0].detach().clone()
+    optimizer.step()
+    assert float((refiner.conv1_r.weight - before).abs().max()) > 0
+    refiner.eval()
+    with torch.no_grad():
+        r_after = refiner(pts, emb, idx)[0]
+    assert float((r_after - r_before).abs().max()) > 0               # the bf16 weight copies follow the in-place update
+
+
 def test_get_surface_and_icp_regression():
     from autoposeestimation_b200.pc_reconstruction.open3d_utils import PointCloud, get_surface, icp_regression, icp_regression_batch
     fr = synth.render_ellipsoid_frame(6)

@@ -76,3 +76,45 @@ def test_shard_bounds_cover_everything():
             b = [sharding.shard_bounds(n, r, w) for r in range(w)]
             assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def _grad_worker(rank, world, port, B, q):
+    """Data-parallel refiner step on CPU: this rank's shard of the batch -> per-sample fp32 gradient (oracle autograd,
+    the CPU stand-in for the per-rank GPU backward) -> flat vector -> sharding.allreduce_gradient."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    flat = _shard_gradient(B, *sharding.shard_bounds(B))
+    sharding.allreduce_gradient(flat)
+    q.put((rank, flat.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _shard_gradient(B, lo, hi, nobj=2, N=40, M=30):
+    from oracle import densefusion as odf
+    from autoposeestimation_b200 import synthetic as synth
+    sd = {k: torch.from_numpy(np.array(v)).requires_grad_(True) for k, v in synth.refiner_state_dict(3, nobj).items()}
+    rng = np.random.RandomState(0)
+    pts = torch.from_numpy((rng.randn(B, N, 3) * 0.05).astype(np.float32)); emb = torch.from_numpy(rng.randn(B, 32, N).astype(np.float32))
+    idx = torch.from_numpy(rng.randint(0, nobj, (B, 1))); model = torch.from_numpy(((rng.rand(B, M, 3) - 0.5) * 0.2).astype(np.float32))
+    for b in range(lo, hi):
+        r, t = odf.refiner_forward(sd, pts[b:b + 1], emb[b:b + 1], idx[b:b + 1], nobj)
+        d, _, _, _ = odf.loss_refine(r, t, model[b:b + 1] + 0.01, model[b:b + 1], idx[b], pts[b:b + 1], [])
+        d.sum().backward()
+    return torch.cat([(v.grad if v.grad is not None else torch.zeros_like(v)).reshape(-1) for _, v in sorted(sd.items())]).detach()
+
+
+def test_two_rank_gradient_allreduce_equals_whole_batch_gradient():
+    B = 5
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, B, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=180) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    whole = _shard_gradient(B, 0, B).numpy()
+    assert np.array_equal(res[0], res[1])                                        # every rank holds the same reduced vector
+    assert np.allclose(res[0], whole, rtol=1e-5, atol=1e-7) and np.abs(whole).max() > 0   # SUM over shards (train.py:222 semantics)
