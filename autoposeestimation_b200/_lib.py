@@ -37,6 +37,10 @@ SIGNATURES = {
     'ape_refiner_forward': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
     'ape_pose_pipeline': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
                                   c_vp, c_vp, c_vp]),
+    'ape_radius_outlier': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_dbl, c_vp, c_vp, c_vp]),
+    'ape_mahalanobis': (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
+    'ape_statistical_outlier': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_dbl, c_vp, c_vp, c_vp, c_vp]),
+    'ape_compact_points': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     'ape_refiner_trainer_layout': (c_i64, [c_int, c_vp]),
     'ape_refiner_trainer_create': (c_int, [c_vp, c_vp, c_int, c_int, c_int, ctypes.POINTER(c_vp)]),
     'ape_refiner_trainer_destroy': (c_int, [c_vp]),

@@ -123,6 +123,63 @@ def voxel_down_sample(points, offset, voxel_size):
     return out, counts
 
 
+def _max_cloud(offset_host):
+    import numpy as np
+    return int(np.diff(offset_host).max()) if len(offset_host) > 1 else 0
+
+
+def radius_outlier(points, offset, nb_points, radius, offset_host=None):
+    """f-1.  Ragged batch points [P,3] fp64 + offset [C+1] int32 -> keep [P] uint8 (pcd.remove_radius_outlier)."""
+    require_cuda(points, offset)
+    points = _c(points, torch.float64); offset = _c(offset, torch.int32)
+    oh = offset_host if offset_host is not None else offset.cpu().numpy()
+    keep = torch.zeros((points.shape[0],), dtype=torch.uint8, device=points.device)
+    check(_lib.load().ape_radius_outlier(ptr(points), ptr(offset), offset.numel() - 1, _max_cloud(oh), int(nb_points), float(radius),
+                                         ptr(keep), None, stream_ptr()), 'ape_radius_outlier')
+    return keep
+
+
+def mahalanobis(points, offset, want_dist=True):
+    """f-1.  -> (dist [P] fp64 or None, std [C] fp64 = np.std(|dist|) per cloud) (pcd.compute_mahalanobis_distance)."""
+    require_cuda(points, offset)
+    points = _c(points, torch.float64); offset = _c(offset, torch.int32)
+    C = offset.numel() - 1
+    dist = torch.zeros((points.shape[0],), dtype=torch.float64, device=points.device) if want_dist else None
+    std = torch.zeros((C,), dtype=torch.float64, device=points.device)
+    check(_lib.load().ape_mahalanobis(ptr(points), ptr(offset), C, ptr(dist), ptr(std), stream_ptr()), 'ape_mahalanobis')
+    return dist, std
+
+
+def statistical_outlier(points, offset, nb_neighbors, std_ratio, offset_host=None):
+    """f-1.  std_ratio: python float or a [C] fp64 device tensor (one ratio per cloud) ->
+    (keep [P] uint8, avg_dist [P] fp64, threshold [C] fp64) (pcd.remove_statistical_outlier)."""
+    require_cuda(points, offset)
+    points = _c(points, torch.float64); offset = _c(offset, torch.int32)
+    oh = offset_host if offset_host is not None else offset.cpu().numpy()
+    C = offset.numel() - 1
+    keep = torch.zeros((points.shape[0],), dtype=torch.uint8, device=points.device)
+    avg = torch.zeros((points.shape[0],), dtype=torch.float64, device=points.device)
+    thr = torch.zeros((C,), dtype=torch.float64, device=points.device)
+    dev_ratio = _c(std_ratio, torch.float64) if isinstance(std_ratio, torch.Tensor) else None
+    check(_lib.load().ape_statistical_outlier(ptr(points), ptr(offset), C, _max_cloud(oh), int(nb_neighbors), ptr(dev_ratio),
+                                              0.0 if dev_ratio is not None else float(std_ratio), ptr(keep), ptr(avg), ptr(thr),
+                                              stream_ptr()), 'ape_statistical_outlier')
+    return keep, avg, thr
+
+
+def compact_points(points, offset, keep, want_index=False):
+    """Ordered per-cloud compaction -> (out_points [P,3] (cloud c at offset[c] : offset[c]+counts[c]), counts [C][, index [P]])."""
+    require_cuda(points, offset, keep)
+    points = _c(points, torch.float64); offset = _c(offset, torch.int32); keep = _c(keep, torch.uint8)
+    C = offset.numel() - 1
+    out = torch.empty_like(points)
+    counts = torch.zeros((C,), dtype=torch.int32, device=points.device)
+    index = torch.empty((points.shape[0],), dtype=torch.int32, device=points.device) if want_index else None
+    check(_lib.load().ape_compact_points(ptr(points), ptr(offset), ptr(keep), C, ptr(out), ptr(counts), ptr(index), stream_ptr()),
+          'ape_compact_points')
+    return (out, counts, index) if want_index else (out, counts)
+
+
 def pose_select(pred_r, pred_t, pred_c, cloud, want_new_points=True):
     """a8/a9.  pred_r [B,N,4], pred_t [B,N,3], pred_c [B,N(,1)], cloud [B,N,3] fp32 ->
     dict(which_max [B] int32, my_r [B,4], my_t [B,3], new_points [B,N,3] or None, pose [B,7] fp64)."""

@@ -8,9 +8,8 @@ open3d is not a dependency: clouds are carried by `PointCloud`, a minimal stand-
 o3d.geometry.PointCloud (points, transform, voxel_down_sample, get_center, translate) backed by an [n,3] fp64
 CUDA tensor.  Units are millimetres as in the reference.  There is no CPU fallback.
 
-Not yet grafted: remove_radius_outlier / remove_statistical_outlier /
-compute_mahalanobis_distance (:198-211).  get_surface therefore takes `outlier_filters=False`; asking for
-them raises NotImplementedError instead of silently returning an unfiltered cloud.
+  get_surface's filter chain :198-211 and align_point_clouds :125-168 (voxel grid -> remove_radius_outlier ->
+  std of the Mahalanobis distances -> remove_statistical_outlier) run on csrc/filters.cu.
 """
 import numpy as np
 import torch
@@ -63,13 +62,54 @@ class PointCloud:
             raise ops._lib.ApeError('voxel_down_sample: cloud too large for the kernel (%d points, status %d)' % (n, c))
         return PointCloud(out[:c].clone())
 
+    def _offset(self):
+        return torch.tensor([0, len(self)], dtype=torch.int32, device=self.points.device), np.array([0, len(self)], np.int32)
+
+    def select_down_sample(self, keep):
+        """Points with keep != 0, original order.  Returns (PointCloud, kept indices int64 tensor)."""
+        idx = torch.nonzero(keep.to(torch.bool)).reshape(-1)
+        return PointCloud(self.points[idx].clone()), idx
+
+    def remove_radius_outlier(self, nb_points, radius):
+        """o3d PointCloud.remove_radius_outlier -> (filtered cloud, kept indices)."""
+        if len(self) == 0:
+            return PointCloud(self.points.clone()), torch.zeros((0,), dtype=torch.int64, device=self.points.device)
+        off, oh = self._offset()
+        return self.select_down_sample(ops.radius_outlier(self.points, off, nb_points, radius, oh))
+
+    def compute_mahalanobis_distance(self):
+        """o3d PointCloud.compute_mahalanobis_distance -> [n] fp64 numpy (the reference takes np.std of it on the host)."""
+        off, _ = self._offset()
+        return ops.mahalanobis(self.points, off)[0].cpu().numpy()
+
+    def remove_statistical_outlier(self, nb_neighbors, std_ratio):
+        """o3d PointCloud.remove_statistical_outlier -> (filtered cloud, kept indices)."""
+        if len(self) == 0:
+            return PointCloud(self.points.clone()), torch.zeros((0,), dtype=torch.int64, device=self.points.device)
+        off, oh = self._offset()
+        keep, _, _ = ops.statistical_outlier(self.points, off, nb_neighbors, std_ratio, oh)
+        return self.select_down_sample(keep)
+
+
+def _filter_chain(surface, min_friends, min_dist, nb_neighbors):
+    """open3d_utils.py:203-211 / :161-166: radius outliers, then statistical outliers whose ratio is the std of the
+    Mahalanobis distances of the radius-filtered cloud -- all on the device, no host round trip in between."""
+    surface, _ = surface.remove_radius_outlier(nb_points=min_friends, radius=min_dist)
+    if len(surface) < 2:
+        return surface
+    off, oh = surface._offset()
+    _, ratio = ops.mahalanobis(surface.points, off, want_dist=False)              # std_ratio = np.std(|dist|), stays on device
+    keep, _, _ = ops.statistical_outlier(surface.points, off, nb_neighbors, ratio, oh)
+    return surface.select_down_sample(keep)[0]
+
 
 def get_surface(label, depth_frame, intr, robot2Cam_ft, min_friends=None, min_dist=None, nb_neighbors=None, voxel_size=None,
-                outlier_filters=False):
+                outlier_filters=True):
     """open3d_utils.py:171-213.  label uint8 [H,W] (non-zero = object), depth_frame [H,W] raw depth (mm; integral
-    values, as read from the 16-bit PNG), intr dict(ppx,ppy,fx,fy), robot2Cam_ft 4x4.  Returns a PointCloud."""
-    if outlier_filters:
-        raise NotImplementedError('radius / statistical outlier filters are not grafted yet (SURVEY 8f rank 1)')
+    values, as read from the 16-bit PNG), intr dict(ppx,ppy,fx,fy), robot2Cam_ft 4x4.  Returns a PointCloud.
+    outlier_filters=False stops after the voxel grid (the back-projection + voxel part alone)."""
+    if outlier_filters and (min_friends is None or min_dist is None or nb_neighbors is None or not voxel_size):
+        raise ValueError('get_surface: min_friends, min_dist, nb_neighbors and voxel_size are required (open3d_utils.py:171)')
     dev = _dev()
     depth = np.asarray(depth_frame)
     d16 = depth.astype(np.uint16)
@@ -85,7 +125,26 @@ def get_surface(label, depth_frame, intr, robot2Cam_ft, min_friends=None, min_di
     surface = PointCloud(pts[0, :int(cnt.cpu()[0])].clone())
     if voxel_size:
         surface = surface.voxel_down_sample(voxel_size)
+    if outlier_filters:
+        surface = _filter_chain(surface, min_friends, min_dist, nb_neighbors)
     return surface
+
+
+def align_point_clouds(point_clouds, min_friends, min_dist, nb_neighbors, plot=False, global_regression=False, icp_point2point=True,
+                       icp_point2plane=False, voxel_size=5, threshold=50):
+    """open3d_utils.py:125-168: register every further rotation run onto the first, merge, voxel grid, outlier filters."""
+    target = point_clouds[0]
+    for source in point_clouds[1:]:
+        diff = np.array(source.get_center()) - np.array(target.get_center())
+        if diff[1] > -30:                                                         # :141-143
+            source.translate([0, -30 - diff[1], 0])
+        target, source, init_tf = icp_regression(target, source, voxel_size=voxel_size, threshold=threshold,
+                                                 global_regression=global_regression, icp_point2point=True, icp_point2plane=False)
+        source = source.transform(init_tf)
+        target = PointCloud(torch.cat((source.points, target.points)))            # :156-157 (source first)
+        target = target.voxel_down_sample(voxel_size)
+        target = _filter_chain(target, min_friends, min_dist, nb_neighbors)
+    return target
 
 
 def icp_regression_batch(targets, sources, voxel_size=5, threshold=100, max_iteration=100, relative_fitness=1e-2,

@@ -303,11 +303,13 @@ def train_leg(torch, dist, lib, peaks, world, rank, dev, steps):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms)
     out = None
+    # per-kernel split: EVERY rank runs these steps (train_step contains the all-reduce); only rank 0 records events
     if rank == 0:
         lib.ape_profile_enable(1)
-        for _ in range(3):
-            trainer.train_step(pts, emb, idx, target, model)
-        torch.cuda.synchronize()
+    for _ in range(3):
+        trainer.train_step(pts, emb, idx, target, model)
+    torch.cuda.synchronize()
+    if rank == 0:
         rep = profile_report(lib); lib.ape_profile_enable(0)
         kern = {k: v[1] / 3 for k, v in rep.items()}
         flops = 3 * REFINER_FWD_FLOPS * TRAIN_ITERS * TRAIN_BATCH            # fwd + dgrad + wgrad, whole job
@@ -332,6 +334,7 @@ def run_b200(args):
         raise SystemExit('bench.py: no CUDA device (the B200 path has no CPU fallback; use --impl reference for the CPU arm)')
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ['NCCL_DEBUG'] = os.environ.get('APE_NCCL_DEBUG', 'WARN')      # keep NCCL's banner off stdout (one JSON line)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from autoposeestimation_b200 import _lib, ops, synthetic as synth
     from autoposeestimation_b200.densefusion import estimate_poses          # public drop-in API (host buffers -> poses)

@@ -204,6 +204,29 @@ int ape_pose_pipeline(ape_net* estimator, ape_net* refiner, const float* out_img
                       double* poses, int32_t* which_max, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Point-cloud outlier filters, open3d 0.9.0 semantics, ragged batches
+ * (points [P,3] fp64 + int32 offsets [C+1], millimetres as the reference).  Replace
+ * pcd.remove_radius_outlier / compute_mahalanobis_distance / remove_statistical_outlier at
+ * pc_reconstruction/open3d_utils.py:158-166 and :198-211.  max_cloud_points = largest cloud of the batch.  */
+/* keep[i] = 1 iff more than nb_points points (itself included) lie strictly within `radius`.          */
+int ape_radius_outlier(const double* points, const int32_t* offset, int n_clouds, int max_cloud_points,
+                       int nb_points, double radius, uint8_t* keep /* [P] */,
+                       int32_t* n_neighbors /* [P] or NULL */, void* stream);
+/* dist[i] = Mahalanobis distance to the cloud's mean (population covariance); std_out[c] = np.std(|dist|). */
+int ape_mahalanobis(const double* points, const int32_t* offset, int n_clouds, double* dist /* [P] or NULL */,
+                    double* std_out /* [C] or NULL */, void* stream);
+/* avg_dist[i] = mean distance to the nb_neighbors nearest points (itself included); keep[i] = 1 iff
+ * 0 < avg_dist[i] < mean + ratio * std (Bessel-corrected) over the cloud.  ratio = std_ratio_dev[c] when
+ * the device array is given (e.g. ape_mahalanobis' std_out, as the reference feeds it), else std_ratio.   */
+int ape_statistical_outlier(const double* points, const int32_t* offset, int n_clouds, int max_cloud_points,
+                            int nb_neighbors, const double* std_ratio_dev, double std_ratio, uint8_t* keep,
+                            double* avg_dist /* [P] out */, double* threshold /* [C] or NULL */, void* stream);
+/* Ordered compaction (pcd.select_down_sample): cloud c of the result occupies
+ * out_points[offset[c] : offset[c] + out_counts[c]]; out_index = kept point's index within its cloud.     */
+int ape_compact_points(const double* points, const int32_t* offset, const uint8_t* keep, int n_clouds,
+                       double* out_points, int32_t* out_counts, int32_t* out_index /* or NULL */, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Refiner training step (a16): DenseFusion/tools/train.py:215-233 -- per sample `refiner(new_points, emb,
  * idx)` -> `criterion_refine(...)` (lib/loss_refiner.py:12-64) -> `dis.backward()`, Adam step per batch
  * (train.py:149, :231-233).  bf16 tensor-core forward / backward, fp32 master weights and gradients.

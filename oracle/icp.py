@@ -146,3 +146,86 @@ def icp_regression(target, source, voxel_size=5, threshold=100, use_kdtree=False
     src = voxel_down_sample(source, voxel_size)
     T = registration_icp_p2p(src, tgt, threshold, use_kdtree=use_kdtree)
     return tgt, src, T
+
+
+# ----------------------------------------------------------------------------- outlier filters (open3d 0.9.0)
+def _sq_dists(points, lo, hi):
+    """[hi-lo, n] squared distances, fp64, ((dx^2 + dy^2) + dz^2) -- FLANN's L2 functor order."""
+    q = points[lo:hi]
+    d = None
+    for a in range(3):
+        diff = points[None, :, a] - q[:, None, a]
+        sq = diff * diff
+        d = sq if d is None else d + sq
+    return d
+
+
+def remove_radius_outlier(points, nb_points, radius, chunk=512):
+    """pcd.remove_radius_outlier (open3d_utils.py:161, :205; Open3D v0.9.0 PointCloud::RemoveRadiusOutliers): keep point i
+    iff more than `nb_points` points (itself included) lie strictly within `radius` (KDTreeFlann::SearchRadius ->
+    FLANN radius search, d^2 < r^2).  Returns (kept points, kept indices)."""
+    points = np.asarray(points, np.float64)
+    keep = np.zeros(len(points), bool)
+    r2 = radius * radius
+    for s in range(0, len(points), chunk):
+        keep[s:s + chunk] = (_sq_dists(points, s, min(len(points), s + chunk)) < r2).sum(axis=1) > nb_points
+    idx = np.nonzero(keep)[0]
+    return points[idx], idx
+
+
+def compute_mahalanobis_distance(points):
+    """pcd.compute_mahalanobis_distance (open3d_utils.py:163, :200, :207): mean / POPULATION covariance from the
+    cumulants (PointCloud::ComputeMeanAndCovariance, sequential sums), then sqrt(p^T cov^-1 p)."""
+    points = np.asarray(points, np.float64)
+    cu = np.zeros(9)
+    for p in points:                                        # sequential accumulation, as the C++ loop
+        cu += (p[0], p[1], p[2], p[0] * p[0], p[0] * p[1], p[0] * p[2], p[1] * p[1], p[1] * p[2], p[2] * p[2])
+    cu /= float(len(points))
+    mean = cu[:3]
+    cov = np.array([[cu[3] - cu[0] * cu[0], cu[4] - cu[0] * cu[1], cu[5] - cu[0] * cu[2]],
+                    [cu[4] - cu[0] * cu[1], cu[6] - cu[1] * cu[1], cu[7] - cu[1] * cu[2]],
+                    [cu[5] - cu[0] * cu[2], cu[7] - cu[1] * cu[2], cu[8] - cu[2] * cu[2]]])
+    inv = np.linalg.inv(cov)
+    d = points - mean
+    return np.sqrt(np.einsum('ij,jk,ik->i', d, inv, d))
+
+
+def remove_statistical_outlier(points, nb_neighbors, std_ratio, chunk=512):
+    """pcd.remove_statistical_outlier (open3d_utils.py:165, :210; v0.9.0 PointCloud::RemoveStatisticalOutliers): per point
+    the mean of the distances to its nb_neighbors nearest points (SearchKNN: itself included, ascending), cloud mean and
+    Bessel-corrected std over the valid points accumulated SEQUENTIALLY (std::accumulate / inner_product), keep iff
+    0 < avg < mean + std_ratio * std.  Returns (kept points, kept indices, avg distances, threshold)."""
+    points = np.asarray(points, np.float64)
+    n = len(points)
+    avg = np.empty(n)
+    k = min(nb_neighbors, n)
+    for s in range(0, n, chunk):
+        d2 = np.sort(_sq_dists(points, s, min(n, s + chunk)), axis=1)[:, :k]
+        d = np.sqrt(d2)
+        acc = np.zeros(len(d))
+        for j in range(k):                                  # ascending order, as std::accumulate over the sorted result
+            acc = acc + d[:, j]
+        avg[s:s + chunk] = acc / float(k)
+    valid = 0
+    mean = 0.0
+    for a in avg:
+        if a > 0:
+            mean += a; valid += 1
+    mean /= valid
+    sq = 0.0
+    for a in avg:
+        if a > 0:
+            sq += (a - mean) * (a - mean)
+    thr = mean + std_ratio * np.sqrt(sq / (valid - 1))
+    idx = np.nonzero((avg > 0) & (avg < thr))[0]
+    return points[idx], idx, avg, thr
+
+
+def get_surface_filters(points, min_friends, min_dist, nb_neighbors, voxel_size):
+    """The filter chain of get_surface (open3d_utils.py:198-211) on an already back-projected cloud:
+    voxel grid -> radius outliers -> std of |Mahalanobis| -> statistical outliers with that std as ratio."""
+    s = voxel_down_sample(points, voxel_size)
+    s, _ = remove_radius_outlier(s, min_friends, min_dist)
+    ratio = float(np.std(np.abs(compute_mahalanobis_distance(s))))
+    s, _, _, _ = remove_statistical_outlier(s, nb_neighbors, ratio)
+    return s

@@ -142,10 +142,15 @@ def test_refiner_dropin_trains_like_reference_loop(golden_dir):
 def test_get_surface_and_icp_regression():
     from autoposeestimation_b200.pc_reconstruction.open3d_utils import PointCloud, get_surface, icp_regression, icp_regression_batch
     fr = synth.render_ellipsoid_frame(6)
-    surf = get_surface(fr['label'], fr['depth'].astype(np.float64), fr['intr'], fr['robot2cam'], 20, 5, 20, voxel_size=2)
+    surf = get_surface(fr['label'], fr['depth'].astype(np.float64), fr['intr'], fr['robot2cam'], 20, 5, 20, voxel_size=2,
+                       outlier_filters=False)
     pts, _ = og.surface_backproject(fr['label'], fr['depth'].astype(np.float64), fr['intr'], fr['robot2cam'])
     want = oicp.voxel_down_sample(pts, 2.0)
     assert len(surf) == len(want) and np.allclose(surf.numpy(), want, atol=1e-9)
+    # the reference's full chain (open3d_utils.py:198-211): voxel grid -> radius outliers -> statistical outliers
+    full = get_surface(fr['label'], fr['depth'].astype(np.float64), fr['intr'], fr['robot2cam'], 20, 5, 20, voxel_size=2)
+    want_full = oicp.get_surface_filters(pts, 20, 5, 20, 2.0)
+    assert len(full) == len(want_full) and np.allclose(full.numpy(), want_full, atol=1e-9)
     tgt_d, src_d, T = icp_regression(PointCloud(fr['model']), surf, voxel_size=2, threshold=10, icp_point2plane=False)
     t_ref, s_ref, T_ref = oicp.icp_regression(fr['model'], surf.numpy(), voxel_size=2, threshold=10)
     assert len(tgt_d) == len(t_ref) and len(src_d) == len(s_ref)
@@ -153,7 +158,9 @@ def test_get_surface_and_icp_regression():
     with pytest.raises(NotImplementedError):
         icp_regression(PointCloud(fr['model']), surf, global_regression=True)
     with pytest.raises(ValueError):
-        get_surface(fr['label'], fr['depth'] + 0.5, fr['intr'], fr['robot2cam'])
+        get_surface(fr['label'], fr['depth'] + 0.5, fr['intr'], fr['robot2cam'], 20, 5, 20, voxel_size=2)
+    with pytest.raises(ValueError):
+        get_surface(fr['label'], fr['depth'].astype(np.float64), fr['intr'], fr['robot2cam'])         # filter parameters are required
     # merge step of create_pointcloud.py:307-312
     merged = PointCloud(torch.cat([src_d.transform(T).points, tgt_d.points])).voxel_down_sample(2)
     assert 0 < len(merged) <= len(src_d) + len(tgt_d)
