@@ -60,10 +60,11 @@ __device__ __forceinline__ Tile decode_tile(int t, const Params& p, int m_tiles,
 
 // grid = min(#tiles, #SMs).  Load maps: box {64 (K), 128 (rows)}, SWIZZLE_128B.  Store maps (EPI_RELU_SPLIT):
 // box {64 (cols), 32 (rows)}, SWIZZLE_128B.
-// EPI8 (training forward, csrc/train.cuh: plain bf16, hi-only stores): warps 2..9 drain the accumulator, two per TMEM lane
-// quadrant, each taking half of the tile's columns -- with one bf16 pass over K <= 512 the epilogue, not the MMA, is the
-// critical path.  The second warp of a quadrant stages through the (unused) lo half of the quadrant's staging buffer.
-// EPI8 = false is the inference kernel, unchanged: 192 threads, warps 2..5.
+// EPI8: warps 2..9 drain the accumulator, two per TMEM lane quadrant, each taking half of the tile's columns.  For the
+// layers whose mainloop is short (conv2 / e_conv2 with K = 64, and every layer of the plain-bf16 training forward) the
+// epilogue, not the MMA, is the critical path; the deep layers keep EPI8 = false (192 threads, warps 2..5, 4 ring stages:
+// measured, K = 256 x 3 passes already loses more from the shorter ring than it gains).  Results are bit-identical: the
+// arithmetic per element is the same.
 constexpr int kThreadsEpi8 = 320;
 template <bool EPI8>
 __global__ void __launch_bounds__(EPI8 ? kThreadsEpi8 : kThreads, 1)
@@ -74,8 +75,11 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
 {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    unsigned char* staging = smem + kStages2 * kStage;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStaging);
+    // EPI8 trades one ring stage for a private hi+lo staging pair per epilogue warp (3 x 48 KB + 8 x 8 KB = 208 KB)
+    constexpr int NS = EPI8 ? 3 : kStages2;
+    constexpr int kStagingK = EPI8 ? 8 * kStgWarp : kStaging;
+    unsigned char* staging = smem + NS * kStage;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingK);
     uint64_t* empty_bar = full_bar + kStages2;
     uint64_t* tfull_bar = empty_bar + kStages2;       // [2]
     uint64_t* tempty_bar = tfull_bar + 2;             // [2]
@@ -94,7 +98,7 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
         tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo);
         if (p.mode == EPI_RELU_SPLIT) { tma_prefetch_desc(&map_o_hi); tma_prefetch_desc(&map_o_lo); }
 #pragma unroll
-        for (int s = 0; s < kStages2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
 #pragma unroll
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], EPI8 ? 8 : 4); }
         fence_barrier_init();
@@ -116,8 +120,8 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
                 const int w_row = tl.g * p.N + tl.n0;
                 const uint32_t bytes = (uint32_t)(kStageA + tl.bn * BK * 2);
                 for (int i = 0; i < iters_per_tile; ++i, ++it) {
-                    const int s = it % kStages2;
-                    const uint32_t ph = (uint32_t)(it / kStages2) & 1u;
+                    const int s = it % NS;
+                    const uint32_t ph = (uint32_t)(it / NS) & 1u;
                     mbar_wait(&empty_bar[s], ph ^ 1u);
                     const int pass_i = i / kb_per_pass, kb = i - pass_i * kb_per_pass;
                     // pass 0: A_lo*W_hi, pass 1: A_hi*W_lo, pass 2: A_hi*W_hi (small terms first); plain bf16 = pass 2 alone
@@ -146,8 +150,8 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
                 const uint32_t idesc = make_idesc_bf16(BM, tl.bn);
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
                 for (int i = 0; i < iters_per_tile; ++i, ++it) {
-                    const int s = it % kStages2;
-                    const uint32_t ph = (uint32_t)(it / kStages2) & 1u;
+                    const int s = it % NS;
+                    const uint32_t ph = (uint32_t)(it / NS) & 1u;
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem + s * kStage));
@@ -164,7 +168,7 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
         // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
         const int quad = warp & 3;
         const int half = EPI8 ? (warp - 2) >> 2 : 0;              // EPI8: which half of the tile's columns this warp drains
-        unsigned char* stg = staging + quad * kStgWarp + half * kStgBuf;   // [hi|lo][32 rows x 128 B], SWIZZLE_128B
+        unsigned char* stg = staging + (EPI8 ? warp - 2 : quad) * kStgWarp;   // [hi|lo][32 rows x 128 B], SWIZZLE_128B
         float* s_colsum = reinterpret_cast<float*>(staging);      // EPI_RELU_COLSUM: [4][256]
         const int GN = p.groups * p.N;
         int lt = 0;

@@ -612,6 +612,9 @@ int ape_net_create(int kind, const float* const* w, int n_tensors, int num_obj, 
             e = cudaFuncSetAttribute(ape::tc2::gemm_split_bf16_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      ape::tc2::kSmemBytes2);
         if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(ape::tc2::gemm_split_bf16_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     ape::tc2::kSmemBytes2);
+        if (e == cudaSuccess)
             e = cudaFuncSetAttribute(ape::tc3::gemm_split_bf16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      ape::tc3::kSmemBytes3);
         if (e != cudaSuccess) { ape::set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); ape_net_destroy(net); return APE_ERR_CUDA; }
@@ -669,7 +672,10 @@ static int run_gemm(ape_net* net, const SplitMat& A, const SplitMat& W, const Sp
         const int tiles = p.groups * (p.M / ape::tc::BM) * ((p.N + bn_full - 1) / bn_full);
         const int grid = tiles < ape::sm_count() ? tiles : ape::sm_count();
         const SplitMat& O = out ? *out : A;          // EPI_RELU_COLSUM never touches the store maps
-        if (p.passes == 1 && (p.hi_only || p.mode == ape::tc::EPI_RELU_COLSUM))     // training forward: 8 epilogue warps
+        const int kblocks = (p.passes == 1 ? 1 : 3) * (p.K / ape::tc::BK);
+        static int epi8_max = -1;
+        if (epi8_max < 0) { const char* e = getenv("APE_GEMM_EPI8_MAX_KB"); epi8_max = e ? (int)strtol(e, nullptr, 0) : 3; }
+        if (p.mode != ape::tc::EPI_HEAD_OUT && (p.passes == 1 || kblocks <= epi8_max))     // short mainloop: 8 epilogue warps
             ape::tc2::gemm_split_bf16_persistent_kernel<true><<<grid, ape::tc2::kThreadsEpi8, ape::tc2::kSmemBytes2, s>>>(
                 A.map_hi, A.map_lo, W.map_hi, W.map_lo, O.st_hi, O.st_lo, p, bn_full);
         else

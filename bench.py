@@ -334,7 +334,10 @@ def run_b200(args):
         raise SystemExit('bench.py: no CUDA device (the B200 path has no CPU fallback; use --impl reference for the CPU arm)')
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ['NCCL_DEBUG'] = os.environ.get('APE_NCCL_DEBUG', 'WARN')      # keep NCCL's banner off stdout (one JSON line)
+        if 'APE_NCCL_DEBUG' in os.environ:
+            os.environ['NCCL_DEBUG'] = os.environ['APE_NCCL_DEBUG']
+        else:
+            os.environ.pop('NCCL_DEBUG', None)               # NCCL prints its banner on STDOUT at any debug level: keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from autoposeestimation_b200 import _lib, ops, synthetic as synth
     from autoposeestimation_b200.densefusion import estimate_poses          # public drop-in API (host buffers -> poses)
