@@ -261,6 +261,52 @@ def icp_leg(torch, ops, lib, peaks, steps):
                 label_path_32_frames_ms=prep_ms)
 
 
+def live_leg(torch, ops, steps):
+    """Extra leg: ONE live frame as main.py option 6 sees it (pipeline/utils.py:517-574): 5 detected objects x 1000 sampled
+    points (the fork's num_points, :520), PoseNet + 2 canonical refine iterations, as launch-by-launch stream work and as
+    one CUDA-graph replay (the whole block is graph-capturable: no host sync, no allocation inside ape_pose_pipeline)."""
+    from autoposeestimation_b200 import synthetic as synth
+    B, N = 5, 1000
+    dev = torch.device('cuda', torch.cuda.current_device())
+    est = ops.NetHandle(ops.NET_POSENET, synth.posenet_state_dict(7, NUM_OBJ), NUM_OBJ, B, N)
+    ref = ops.NetHandle(ops.NET_REFINER, synth.refiner_state_dict(1007, NUM_OBJ), NUM_OBJ, B, N)
+    d = [torch.from_numpy(a).to(dev) for a in synth.posenet_inputs(77, N, CROP, NUM_OBJ, batch=B)]
+    d[0] = d[0].reshape(B, 32, -1).contiguous(); d[2] = d[2].reshape(B, N).contiguous(); d[3] = d[3].reshape(B).contiguous()
+    poses = torch.empty((B, 7), dtype=torch.float64, device=dev)
+
+    def run():
+        ops.pose_pipeline(est, ref, d[0], d[1], d[2], d[3], iterations=REFINE_ITERS, canonical=True, out=poses)
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n * 1e3                   # microseconds per frame
+
+    for _ in range(5):
+        run()
+    n = max(20, min(steps, 200))
+    us_stream = timed(run, n)
+    ref_pose = poses.clone()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        run()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        run()
+    graph.replay(); torch.cuda.synchronize()
+    same = bool(torch.equal(ref_pose, poses))
+    us_graph = timed(graph.replay, n)
+    est.close(); ref.close()
+    return dict(objects=B, points=N, refine_iters=REFINE_ITERS, us_per_frame_stream=us_stream, us_per_frame_cuda_graph=us_graph,
+                frames_per_s_cuda_graph=1e6 / us_graph, graph_matches_stream_bitwise=same,
+                note='device-resident inputs; one frame = 5 objects; latency mode of the same kernels as the headline')
+
+
 TRAIN_BATCH, TRAIN_ITERS = 256, 2
 # reference-formulation FLOPs of one refiner forward per object (SURVEY 8d): 1 479 040 FLOP/pt + per-object heads
 REFINER_FWD_FLOPS = 1479040 * NPTS + 2359296 + 2 * 128 * 7 * NUM_OBJ
@@ -442,7 +488,8 @@ def run_b200(args):
             note='achieved = reference-formulation FLOPs (SURVEY 8d: 7.94 MFLOP/pt PoseNet + 1.48 MFLOP/pt per refine iter, GEMM layers) / '
                  'summed GEMM kernel time; executed = 3 split-bf16 passes on padded rows with the global feature hoisted')
         # ---- CPU baseline beside it (bounded sample)
-        cpu_fps, cpu_s, cpu_threads = cpu_pose_frames_per_s(32)
+        # rank 0 at N=1 only (under torchrun OMP_NUM_THREADS=1 would make it a 1-thread number that looks like a regression)
+        cpu_fps, cpu_s, cpu_threads = cpu_pose_frames_per_s(32) if world == 1 else (None, 0.0, 0)
         extra = None
         if not args.no_icp:
             try:
@@ -451,6 +498,10 @@ def run_b200(args):
                 extra = dict(error=repr(ex))
         if train is not None:
             extra = dict(extra or {}, refiner_training=train)
+        try:
+            extra = dict(extra or {}, live_frame=live_leg(torch, ops, args.steps))
+        except Exception as ex:
+            extra = dict(extra or {}, live_frame=dict(error=repr(ex)))
         line = dict(metric='pose_frames_per_sec', value=value, unit='frames/s', n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
                     ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16x3',
                     data='synthetic', impl='b200',
@@ -461,8 +512,9 @@ def run_b200(args):
                              ms_per_step=float(ms2) / args.steps, wall_s=wall_e2e,
                              api='autoposeestimation_b200.densefusion.estimate_poses.Runner (pinned host buffers, copy/compute double-buffered)'),
                     gpu_launches=launches, clocks=clocks, roofline=roofline,
-                    cpu_baseline=dict(value=cpu_fps, unit='frames/s', cores=cpu_threads, kind='port',
-                                      sample='32 objects of the same workload, per-sample torch-CPU oracle port (%.1f s)' % cpu_s),
+                    cpu_baseline=(dict(value=cpu_fps, unit='frames/s', cores=cpu_threads, kind='port',
+                                       sample='32 objects of the same workload, per-sample torch-CPU oracle port (%.1f s)' % cpu_s)
+                                  if cpu_fps is not None else None),
                     extra=extra, checksum=float(out_host.sum()))
     if world > 1:
         dist.barrier()

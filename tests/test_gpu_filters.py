@@ -112,3 +112,38 @@ def test_pointcloud_methods_and_align_point_clouds():
     ratio = float(np.std(oicp.compute_mahalanobis_distance(want)))
     want, _, _, _ = oicp.remove_statistical_outlier(want, 20, ratio)
     assert len(merged) == len(want) and np.allclose(merged.numpy(), want, atol=1e-6)
+
+
+def test_get_surfaces_batch_and_reconstruct_run():
+    """create_pointcloud.py:232-317: all views through batched launches == per-view get_surface; the sequential
+    register-and-merge loop == the same flow built from the oracle pieces."""
+    from autoposeestimation_b200.pc_reconstruction.open3d_utils import get_surface
+    from autoposeestimation_b200.pc_reconstruction.create_pointcloud import get_surfaces_batch, reconstruct_run, rotate_about_center
+    seeds = [20, 21, 22]
+    frames = [synth.render_ellipsoid_frame(s, max_rot_deg=3.0, max_trans_mm=2.0) for s in seeds]
+    lab = _dev(np.stack([f['label'] for f in frames])); dep = _dev(np.stack([f['depth'] for f in frames]).view(np.int16))
+    intr = frames[0]['intr']
+    cam = _dev(np.tile(np.array([[intr['ppx'], intr['ppy'], intr['fx'], intr['fy']]]), (3, 1)))
+    r2c = _dev(np.stack([f['robot2cam'] for f in frames]))
+    # an empty view in the middle must come back as an empty cloud
+    lab[1].zero_()
+    surfs = get_surfaces_batch(lab, dep, cam, r2c, 5, 5.0, 20, 2.0)
+    assert len(surfs) == 3 and len(surfs[1]) == 0
+    for v in (0, 2):
+        single = get_surface(frames[v]['label'], frames[v]['depth'].astype(np.float64), intr, frames[v]['robot2cam'], 5, 5.0, 20, voxel_size=2.0)
+        assert len(single) == len(surfs[v]) and np.array_equal(single.numpy(), surfs[v].numpy())
+        pts, _ = og.surface_backproject(frames[v]['label'], frames[v]['depth'].astype(np.float64), intr, frames[v]['robot2cam'])
+        want = oicp.get_surface_filters(pts, 5, 5.0, 20, 2.0)
+        assert len(want) == len(surfs[v]) and np.allclose(surfs[v].numpy(), want, atol=1e-9)
+    # sequential loop: the same physical surface seen twice with a small rigid offset -> register, merge, voxel
+    a = surfs[0].numpy()
+    R = synth.random_rotation(np.random.RandomState(3), 0.03); t = np.array([1.5, -1.0, 0.8])
+    from autoposeestimation_b200.pc_reconstruction.open3d_utils import PointCloud
+    b = PointCloud((a - a.mean(0)) @ R.T + a.mean(0) + t)
+    cloud = reconstruct_run([surfs[0], surfs[1], b], voxel_size=2.0, threshold=10.0)
+    td, sd, T = oicp.icp_regression(a, b.numpy(), voxel_size=2.0, threshold=10.0)
+    want = oicp.voxel_down_sample(np.concatenate((sd @ T[:3, :3].T + T[:3, 3], td)), 2.0)
+    assert len(cloud) == len(want) and np.allclose(cloud.numpy(), want, atol=1e-6)
+    c0 = cloud.numpy().mean(0)
+    rot = rotate_about_center(cloud, R)
+    assert np.allclose(rot.numpy().mean(0), c0, atol=1e-9)
