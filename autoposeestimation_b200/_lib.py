@@ -19,11 +19,13 @@ SIGNATURES = {
     'ape_profile_enable': (c_int, [c_int]),
     'ape_profile_report': (c_int, [ctypes.c_char_p, c_int]),
     'ape_backproject_choose': (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
+    'ape_mask_bbox_choose': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'ape_surface_work_bytes': (c_sz, [c_int, c_int, c_int]),
     'ape_surface_backproject': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int,
                                         c_vp, c_vp, c_vp, c_vp, c_vp]),
     'ape_knn': (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     'ape_add_metric': (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),
+    'ape_add_metric_std': (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),
     'ape_icp_work_bytes': (c_sz, [c_int, c_int]),
     'ape_icp_p2p': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_dbl, c_dbl, c_dbl, c_int,
                             c_vp, c_vp, c_vp, c_vp, c_vp]),

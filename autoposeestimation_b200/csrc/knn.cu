@@ -130,10 +130,13 @@ __global__ void __launch_bounds__(kAddThreads)
 add_metric_kernel(const float* __restrict__ quat, const float* __restrict__ trans,
                   const float* __restrict__ model, int64_t model_stride, int n_model,
                   const float* __restrict__ target, int64_t target_stride, int n_target,
-                  const uint8_t* __restrict__ symmetric, float* __restrict__ dis, int32_t* __restrict__ nn_index)
+                  const uint8_t* __restrict__ symmetric, float* __restrict__ dis, int32_t* __restrict__ nn_index,
+                  float* __restrict__ std_out /* unbiased std of the per-point distances (loss.py:50), or NULL */)
 {
     __shared__ float4 s_ref[kKnnRefTile];
     __shared__ float s_part[kAddThreads / 32];
+    __shared__ float s_mean;
+    __shared__ float s_d[kKnnRefTile];                   // per-point distances (std_out only)
     const int b = blockIdx.x;
     const float* Mp = model + (size_t)b * model_stride;
     const float* Tg = target + (size_t)b * target_stride;
@@ -184,6 +187,7 @@ add_metric_kernel(const float* __restrict__ quat, const float* __restrict__ tran
                     if (nn_index) nn_index[(size_t)b * n_model + i] = i;
                 }
                 acc += d;
+                if (std_out) s_d[q0 + q] = d;                  // n_model <= kKnnRefTile (checked by the caller)
             }
         }
     }
@@ -194,7 +198,28 @@ add_metric_kernel(const float* __restrict__ quat, const float* __restrict__ tran
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < kAddThreads / 32; ++i) s += s_part[i];
-        dis[b] = s / (float)n_model;
+        s_mean = s / (float)n_model;
+        dis[b] = s_mean;
+    }
+    if (std_out) {
+        // torch.std: two passes, Bessel's correction
+        __syncthreads();
+        const float mean = s_mean;
+        float q = 0.f;
+        for (int i = threadIdx.x; i < n_model; i += kAddThreads) {
+            const float d = s_d[i] - mean;
+            q += d * d;
+        }
+        q = warp_sum(q);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = q;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < kAddThreads / 32; ++i) s += s_part[i];
+            std_out[b] = sqrtf(s / (float)(n_model - 1));
+        }
     }
 }
 
@@ -355,9 +380,28 @@ extern "C" __attribute__((visibility("default"))) int ape_add_metric(const float
     if (B == 0) return APE_OK;
     ape::ProfScope prof_("add_metric", (cudaStream_t)stream);
     ape::add_metric_kernel<<<B, ape::kAddThreads, 0, (cudaStream_t)stream>>>(
-        quat, trans, model_points, model_stride, n_model, target, target_stride, n_target, symmetric, dis, nn_index);
+        quat, trans, model_points, model_stride, n_model, target, target_stride, n_target, symmetric, dis, nn_index, nullptr);
     ape::count_launch();
     return ape::check_launch("ape_add_metric");
+}
+
+// Candidate-pose distances of the estimator loss (lib/loss.py:30-50): B = the N per-point candidate poses of one object,
+// model / target shared (stride 0).  dis[i] = mean_j |pred_ij - tgt_j| and its unbiased std, with the nearest-neighbour
+// target for symmetric objects -- without materialising pred [N,M,3] or the N*M-query kNN.
+extern "C" __attribute__((visibility("default"))) int ape_add_metric_std(const float* quat, const float* trans, const float* model_points, int64_t model_stride,
+                                  int n_model, const float* target, int64_t target_stride, int n_target,
+                                  const uint8_t* symmetric, int B, float* dis, float* std_out, void* stream)
+{
+    APE_REQUIRE(quat && trans && model_points && target && dis && std_out, "ape_add_metric_std: null pointer");
+    APE_REQUIRE(B >= 0 && n_model > 1 && n_target > 0, "ape_add_metric_std: bad sizes");
+    APE_REQUIRE(symmetric || n_model == n_target, "ape_add_metric_std: ADD needs n_model == n_target");
+    APE_REQUIRE(n_model <= ape::kKnnRefTile, "ape_add_metric_std: at most %d model points", ape::kKnnRefTile);
+    if (B == 0) return APE_OK;
+    ape::ProfScope prof_("add_metric_std", (cudaStream_t)stream);
+    ape::add_metric_kernel<<<B, ape::kAddThreads, 0, (cudaStream_t)stream>>>(
+        quat, trans, model_points, model_stride, n_model, target, target_stride, n_target, symmetric, dis, nullptr, std_out);
+    ape::count_launch();
+    return ape::check_launch("ape_add_metric_std");
 }
 
 extern "C" __attribute__((visibility("default"))) int ape_refine_loss(const float* quat, const float* trans, const float* model_points, const float* target,

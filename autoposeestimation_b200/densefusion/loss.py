@@ -13,9 +13,11 @@ from .loss_refiner import quat_to_base
 def loss_calculation(pred_r, pred_t, pred_c, target, model_points, idx, points, w, refine, num_point_mesh, sym_list):
     if not pred_r.is_cuda:
         raise ops._lib.ApeError('Loss: tensors must be on a CUDA device (no CPU fallback)')
-    knn = KNearestNeighbor(1)
     bs, num_p, _ = pred_c.size()
     m = num_point_mesh
+    if bs == 1 and m <= 2048 and not (torch.is_grad_enabled() and (pred_r.requires_grad or pred_t.requires_grad or pred_c.requires_grad)):
+        return _fused_forward(pred_r, pred_t, pred_c, target, model_points, idx, points, w, refine, m, sym_list)
+    knn = KNearestNeighbor(1)
     q = pred_r.reshape(bs * num_p, 4)
     q = q / torch.norm(q, dim=1, keepdim=True)
     ori_base = quat_to_base(q)
@@ -39,6 +41,30 @@ def loss_calculation(pred_r, pred_t, pred_c, target, model_points, idx, points, 
     new_points = torch.bmm(points.reshape(1, bs * num_p, 3) - t, b).contiguous()
     new_target = torch.bmm(tg[0].view(1, m, 3) - t, b).contiguous()
     return loss, dis.view(bs, num_p)[0][which], new_points.detach(), new_target.detach(), pred
+
+
+def _fused_forward(pred_r, pred_t, pred_c, target, model_points, idx, points, w, refine, m, sym_list):
+    """Forward-only path (evaluation, and the refine phase of train.py:205-216 where `loss` is not back-propagated): the
+    per-candidate mean / std distances come from ONE fused kernel (csrc/knn.cu: add_metric_kernel with B = num_p candidate
+    poses, shared model / target) -- no [N,M,3] gather, no N*M-query kNN, no N x M distance matrix."""
+    num_p = pred_c.shape[1]
+    with torch.no_grad():
+        q = pred_r.reshape(num_p, 4)
+        trans = (points.reshape(num_p, 3) + pred_t.reshape(num_p, 3)).contiguous()
+        sym = torch.full((num_p,), 1 if ((not refine) and int(idx.reshape(-1)[0]) in sym_list) else 0, dtype=torch.uint8, device=q.device)
+        dis, std = ops.add_metric_std(q, trans, model_points.reshape(m, 3), target.reshape(m, 3), sym)
+        c = pred_c.reshape(num_p)
+        loss = torch.mean((dis + 2 * std) * c - w * torch.log(c), dim=0)                        # :53
+        which = torch.argmax(c)
+        qn = q / torch.norm(q, dim=1, keepdim=True)
+        ori_base = quat_to_base(qn)
+        t = trans[which].view(1, 1, 3)
+        b = ori_base[which].view(1, 3, 3)
+        new_points = torch.bmm(points.reshape(1, num_p, 3) - t, b).contiguous()
+        new_target = torch.bmm(target.reshape(1, m, 3) - t, b).contiguous()
+        # `pred` (:38) is part of the returned tuple; it is cheap to form once the distances no longer depend on it
+        pred = torch.bmm(model_points.reshape(1, m, 3).expand(num_p, m, 3), ori_base.transpose(2, 1)) + trans.view(num_p, 1, 3)
+    return loss, dis[which], new_points, new_target, pred
 
 
 class Loss(_Loss):

@@ -34,6 +34,34 @@ def backproject_choose(depth, bbox, choose, cam, frame_of=None):
     return cloud
 
 
+def mask_bbox_choose(label, depth, cam, n_points, frame_of=None, label_value=None, seeds=None, want_cloud=True):
+    """f-2 (a1+a2+a3 on the device).  label [F,H,W] uint8, depth [F,H,W] uint16/int16 storage, cam [B,5] fp32 ->
+    dict(bbox [B,4] int32, n_candidates [B] int32, choose [B,N] int64, cloud [B,N,3] fp32 or None)."""
+    require_cuda(label, depth, cam, frame_of, label_value, seeds)
+    assert label.dtype == torch.uint8 and depth.dtype in (torch.uint16, torch.int16)
+    label = label.contiguous(); depth = depth.contiguous(); cam = _c(cam, torch.float32)
+    F, H, W = label.shape
+    B = cam.shape[0]
+    dev = label.device
+    if frame_of is not None:
+        frame_of = _c(frame_of, torch.int32)
+    if label_value is not None:
+        label_value = _c(label_value, torch.uint8)
+    if seeds is not None:
+        if seeds.dtype != torch.int32:                           # any integer dtype: keep the low 32 bits (same bit pattern)
+            v = seeds.to(torch.int64) & 0xffffffff
+            seeds = torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32)
+        seeds = seeds.contiguous()
+    bbox = torch.zeros((B, 4), dtype=torch.int32, device=dev)
+    ncand = torch.zeros((B,), dtype=torch.int32, device=dev)
+    choose = torch.zeros((B, n_points), dtype=torch.int64, device=dev)
+    cloud = torch.zeros((B, n_points, 3), dtype=torch.float32, device=dev) if want_cloud else None
+    check(_lib.load().ape_mask_bbox_choose(ptr(label), ptr(depth), F, H, W, ptr(frame_of), ptr(label_value), ptr(seeds), ptr(cam),
+                                           B, int(n_points), ptr(bbox), ptr(ncand), ptr(choose), ptr(cloud), stream_ptr()),
+          'ape_mask_bbox_choose')
+    return dict(bbox=bbox, n_candidates=ncand, choose=choose, cloud=cloud)
+
+
 def surface_backproject(label, depth, cam, robot2cam, capacity, frame_of=None, label_value=None, want_pixels=True):
     """a4.  label [F,H,W] uint8, depth [F,H,W] uint16, cam [V,4] fp64, robot2cam [V,4,4] fp64.
     Returns (points [V,capacity,3] fp64, pixel_index [V,capacity] int32 or None, counts [V] int32)."""
@@ -87,6 +115,24 @@ def add_metric(quat, trans, model_points, target, symmetric, want_index=False):
     check(_lib.load().ape_add_metric(ptr(quat), ptr(trans), ptr(model_points), ms, mq, ptr(target), ts, nt, ptr(sym), B,
                                      ptr(dis), ptr(nn), stream_ptr()), 'ape_add_metric')
     return (dis, nn) if want_index else dis
+
+
+def add_metric_std(quat, trans, model_points, target, symmetric):
+    """f-3.  As add_metric, plus the unbiased std of the per-point distances: -> (dis [B], std [B]).  With 2-D
+    model_points / target ([M,3]) they are shared by all B poses: the per-point candidate poses of `Loss` (loss.py:30-50)."""
+    require_cuda(quat, trans, model_points, target)
+    quat = _c(quat, torch.float32); trans = _c(trans, torch.float32)
+    model_points = _c(model_points, torch.float32); target = _c(target, torch.float32)
+    B = quat.shape[0]
+    mq, nt = model_points.shape[-2], target.shape[-2]
+    ms = 0 if model_points.dim() == 2 else mq * 3
+    ts = 0 if target.dim() == 2 else nt * 3
+    sym = _c(symmetric.to(torch.uint8), torch.uint8)
+    dis = torch.empty((B,), dtype=torch.float32, device=quat.device)
+    std = torch.empty((B,), dtype=torch.float32, device=quat.device)
+    check(_lib.load().ape_add_metric_std(ptr(quat), ptr(trans), ptr(model_points), ms, mq, ptr(target), ts, nt, ptr(sym), B,
+                                         ptr(dis), ptr(std), stream_ptr()), 'ape_add_metric_std')
+    return dis, std
 
 
 def icp_p2p(source, src_offset, target, tgt_offset, threshold, rel_fitness=1e-2, rel_rmse=1e-2, max_iter=100, init=None):

@@ -55,16 +55,22 @@ def choose_points(mask, bbox, num_points, rng=np.random):
 
 
 def predict_poses(image_chw, depth, meta, masks, class_ids, estimator, refiner, num_points=1000, refine_mode='live',
-                  iterations=2, rng=np.random):
+                  iterations=2, rng=np.random, device_sampling=False, seed=0):
     """Geometry block of full_prediction for the objects of one frame.
 
     image_chw : normalised colour image as a [3,480,640] float CUDA tensor (what `normalize(to_tensor)` gives)
     depth     : [480,640] uint16 numpy;  meta: {'intr': {ppx,ppy,fx,fy}, 'depth_scale': float}
     masks     : list of [480,640] uint8 numpy (255 = object) ; class_ids: list of int
     estimator / refiner : densefusion.network.PoseNet / PoseRefineNet (CUDA, eval mode)
+    device_sampling : mask -> bbox -> choose -> back-projection run in ONE kernel on the device (ops.mask_bbox_choose,
+                SURVEY 8f rank 2); the random subset then comes from a seeded hash instead of numpy's global RNG (same
+                distribution).  masks may then also be a [n,480,640] uint8 CUDA tensor (e.g. straight from the segmentor).
     Returns {i: {'position': np[3] (m), 'rotation': np[4] wxyz}} for every object with at least one valid pixel
     (objects without one are skipped, as :530-531)."""
     dev = image_chw.device
+    if device_sampling:
+        return _predict_poses_device(image_chw, depth, meta, masks, class_ids, estimator, refiner, num_points, refine_mode,
+                                     iterations, seed)
     depth = np.ascontiguousarray(depth)
     sel, bboxes, chooses = [], [], []
     for i, m in enumerate(masks):
@@ -105,3 +111,56 @@ def predict_poses(image_chw, depth, meta, masks, class_ids, estimator, refiner, 
             for k, j in enumerate(js):
                 out[sel[j]] = {'rotation': poses[k, :4].copy(), 'position': poses[k, 4:].copy()}
     return out
+
+
+def _run_groups(image_chw, bboxes, cloud, choose_t, idx, sel, estimator, refiner, num_points, refine_mode, iterations):
+    """Encoder per distinct crop size (PyTorch/cuDNN, outside the graft), geometry kernels once per group."""
+    dev = image_chw.device
+    out, groups = {}, {}
+    for j, bb in enumerate(bboxes):
+        groups.setdefault((bb[1] - bb[0], bb[3] - bb[2]), []).append(j)
+    with torch.no_grad():
+        for (h, w), js in groups.items():
+            crops = torch.stack([image_chw[:, bboxes[j][0]:bboxes[j][1], bboxes[j][2]:bboxes[j][3]] for j in js])
+            out_img = estimator.cnn(crops)
+            jt = torch.tensor(js, device=dev)
+            est_h = estimator._handle(len(js), num_points)
+            ref_h = refiner._handle(len(js), num_points) if refiner is not None and iterations > 0 else None
+            poses, _ = ops.pose_pipeline(est_h, ref_h, out_img, cloud[jt], choose_t[jt], idx[jt],
+                                         iterations=iterations if ref_h is not None else 0, canonical=(refine_mode == 'canonical'))
+            poses = poses.cpu().numpy()
+            for k, j in enumerate(js):
+                out[sel[j]] = {'rotation': poses[k, :4].copy(), 'position': poses[k, 4:].copy()}
+    return out
+
+
+def _predict_poses_device(image_chw, depth, meta, masks, class_ids, estimator, refiner, num_points, refine_mode, iterations, seed):
+    dev = image_chw.device
+    if isinstance(masks, torch.Tensor):
+        lab = masks.to(dev, torch.uint8).contiguous()
+    else:
+        if len(masks) == 0:
+            return {}
+        lab = torch.from_numpy(np.ascontiguousarray(np.stack([np.asarray(m, np.uint8) for m in masks]))).to(dev)
+    n = lab.shape[0]
+    if n == 0:
+        return {}
+    if isinstance(depth, torch.Tensor):
+        d16 = depth.to(dev).reshape(1, IMG_H, IMG_W).contiguous()
+    else:
+        d16 = torch.from_numpy(np.ascontiguousarray(depth).astype(np.uint16).view(np.int16)[None].copy()).to(dev)
+    intr = meta['intr']
+    cam = torch.tensor([[intr['ppx'], intr['ppy'], intr['fx'], intr['fy'], meta['depth_scale']]], dtype=torch.float32, device=dev).repeat(n, 1)
+    # object i = mask i (its own label plane) over the one depth frame
+    depth_n = d16.expand(n, IMG_H, IMG_W).contiguous() if n > 1 else d16
+    seeds = torch.arange(n, device=dev, dtype=torch.int64) * 0x9E3779B1 + int(seed)
+    r = ops.mask_bbox_choose(lab, depth_n, cam, num_points, seeds=seeds)
+    ncand = r['n_candidates'].cpu().numpy()                 # the one host sync: which objects exist + their crop boxes
+    bbox = r['bbox'].cpu().numpy()
+    sel = [i for i in range(n) if ncand[i] > 0]
+    if not sel:
+        return {}
+    st = torch.tensor(sel, device=dev)
+    idx = torch.tensor([class_ids[i] for i in sel], dtype=torch.int64, device=dev)
+    return _run_groups(image_chw, [tuple(int(v) for v in bbox[i]) for i in sel], r['cloud'][st], r['choose'][st], idx, sel,
+                       estimator, refiner, num_points, refine_mode, iterations)

@@ -67,6 +67,22 @@ int ape_backproject_choose(const uint16_t* depth, int n_frames, int height, int 
                            const float* cam, int n_obj, int n_points, float* cloud, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * a1 + a2 + a3 on the device: per detected object, label mask -> get_bbox
+ * (datasets/myDatasetAugmented/dataset.py:342-380) -> choose (pipeline/utils.py:524-539) -> fp32
+ * back-projection (:542-553), without the host round trip and without the xmap/ymap lists (:518-519).
+ *   label [n_frames,H,W] u8, depth [n_frames,H,W] u16; frame_of [n_obj] or NULL; label_value [n_obj] or NULL (= 255)
+ *   seeds [n_obj] u32 or NULL: more than n_points candidates -> the n_points with the smallest keys
+ *         mix32(seed ^ c * 0x9E3779B9) (murmur3 finaliser; ties: lower index) are kept, ascending -- the distribution of
+ *         the reference's np.random.shuffle subset, bit-exact against oracle/geometry.py; at most n_points -> 'wrap'
+ *   cam [n_obj,5] fp32 (ppx,ppy,fx,fy,depth_scale)
+ *   bbox [n_obj,4] out (rmin,rmax,cmin,cmax), n_candidates [n_obj] out (0 = object skipped, as :530-531),
+ *   choose [n_obj,n_points] int64 out, cloud [n_obj,n_points,3] fp32 out or NULL                          */
+int ape_mask_bbox_choose(const uint8_t* label, const uint16_t* depth, int n_frames, int height, int width,
+                         const int32_t* frame_of, const uint8_t* label_value, const uint32_t* seeds,
+                         const float* cam, int n_obj, int n_points, int32_t* bbox, int32_t* n_candidates,
+                         int64_t* choose, float* cloud, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * a4. Masked depth -> point cloud in the robot frame (ordered stream compaction).
  * Replaces the per-pixel loop of pc_reconstruction/open3d_utils.py:172-192 (get_surface).
  * A "view" is one (frame, label value) pair; pixels are emitted in row-major order
@@ -202,6 +218,14 @@ int ape_refiner_forward(ape_net* net, const float* new_points, const float* emb,
 int ape_pose_pipeline(ape_net* estimator, ape_net* refiner, const float* out_img, int hw, const float* cloud,
                       const int64_t* choose, const int64_t* obj, int B, int N, int iterations, int canonical,
                       double* poses, int32_t* which_max, void* stream);
+
+/* Candidate-pose distances of the estimator loss `Loss` (DenseFusion/lib/loss.py:30-50):
+ * as ape_add_metric for B = the N per-point candidate poses of an object (pass model / target with stride 0
+ * to share them), plus std_out[i] = unbiased std of the per-point distances (torch.std, loss.py:50).
+ * The reference materialises pred [N,M,3] and runs an N*M-query kNN for symmetric objects; this does neither. */
+int ape_add_metric_std(const float* quat, const float* trans, const float* model_points, int64_t model_stride,
+                       int n_model, const float* target, int64_t target_stride, int n_target,
+                       const uint8_t* symmetric, int B, float* dis, float* std_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Point-cloud outlier filters, open3d 0.9.0 semantics, ragged batches

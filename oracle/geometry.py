@@ -127,3 +127,28 @@ def surface_backproject(label, depth_frame, intr, robot2cam):
     for i in range(3):
         out[:, i] = T[i, 0] * x + T[i, 1] * y + T[i, 2] * z + T[i, 3]
     return out, (rr * label.shape[1] + cc).astype(np.int64)
+
+
+# ----------------------------------------------------------------------------- device-side sampling
+def mix32(x):
+    """murmur3 finaliser on uint32 arrays (csrc/choose.cu: mix32)."""
+    x = np.asarray(x, np.uint64) & 0xffffffff
+    x ^= x >> 16; x = (x * 0x85ebca6b) & 0xffffffff
+    x ^= x >> 13; x = (x * 0xc2b2ae35) & 0xffffffff
+    x ^= x >> 16
+    return x.astype(np.uint32)
+
+
+def choose_hashed(candidates, num_points, seed):
+    """The device's replacement for the np.random.shuffle subset of pipeline/utils.py:532-537: candidate c gets the key
+    mix32(seed ^ c * 0x9E3779B9); the num_points smallest keys are kept (ties: lower index first), in ascending index
+    order.  At most num_points candidates -> 'wrap' padding (:539); none -> None (:530-531)."""
+    n = len(candidates)
+    if n == 0:
+        return None
+    if n <= num_points:
+        return np.pad(candidates, (0, num_points - n), 'wrap')
+    c = np.asarray(candidates, np.uint64)
+    keys = mix32((np.uint64(seed & 0xffffffff) ^ ((c * np.uint64(0x9E3779B9)) & np.uint64(0xffffffff))))
+    order = np.lexsort((np.asarray(candidates), keys))            # by key, then by index
+    return np.sort(np.asarray(candidates)[order[:num_points]])

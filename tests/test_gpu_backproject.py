@@ -148,3 +148,49 @@ def test_surface_backproject_full_batch_property():
     assert bool((p0[1:] > p0[:-1]).all())                       # strictly increasing = row-major order
     z = pts[0, :n0, 2]
     assert torch.equal(z, depth[0].flatten()[p0].double())      # identity extrinsic: z is the raw depth
+
+
+@pytest.mark.parametrize('num_points', [500, 1000, 20000])
+def test_mask_bbox_choose_on_device_vs_oracle(num_points):
+    """label -> get_bbox -> choose -> back-projection in one kernel, bit-exact against the oracle with
+    the same hash keys (subset branch for 500 / 1000 points, 'wrap' branch for 20000), several objects of one frame,
+    a border-touching object, a label value other than 255, and an object without valid depth."""
+    from autoposeestimation_b200 import ops
+    rng = np.random.RandomState(7)
+    H, W = 480, 640
+    label = np.zeros((2, H, W), np.uint8)
+    yy, xx = np.mgrid[0:H, 0:W]
+    label[0][((yy - 200) / 50.0) ** 2 + ((xx - 300) / 70.0) ** 2 < 1] = 255         # ~11 k px
+    label[0][((yy - 30) / 45.0) ** 2 + ((xx - 600) / 60.0) ** 2 < 1] = 7            # touches the top / right border, value 7
+    label[1][100:140, 20:75] = 255                                                  # small box (wrap at 20000 and 1000? 2200 px)
+    label[1][400:420, 400:430] = 9                                                  # will have zero depth everywhere
+    depth = rng.randint(400, 900, size=(2, H, W)).astype(np.uint16)
+    depth[rng.rand(2, H, W) < 0.05] = 0
+    depth[1, 400:420, 400:430] = 0
+    frame_of = np.array([0, 0, 1, 1], np.int32); values = np.array([255, 7, 255, 9], np.uint8)
+    seeds = np.array([1, 123456789, 0xdeadbeef, 5], np.int64)
+    cam = np.tile(np.array([[synth.INTR['ppx'], synth.INTR['ppy'], synth.INTR['fx'], synth.INTR['fy'], synth.DEPTH_SCALE]], np.float32), (4, 1))
+    out = ops.mask_bbox_choose(_dev(label), _dev(depth.view(np.int16)), _dev(cam), num_points, frame_of=_dev(frame_of),
+                               label_value=_dev(values), seeds=_dev(seeds))
+    bbox = out['bbox'].cpu().numpy(); ncand = out['n_candidates'].cpu().numpy()
+    choose = out['choose'].cpu().numpy(); cloud = out['cloud'].cpu().numpy()
+    for b in range(4):
+        f = frame_of[b]
+        mask_label = label[f] == values[b]
+        want_bbox = og.get_bbox(mask_label)
+        cand = og.choose_candidates(mask_label, depth[f], want_bbox)
+        assert ncand[b] == len(cand)
+        if len(cand) == 0:
+            continue                                                                # skipped object (:530-531)
+        assert tuple(bbox[b]) == tuple(want_bbox)
+        want = og.choose_hashed(cand, num_points, int(seeds[b]))
+        assert np.array_equal(choose[b], want)                                      # bit-exact indices
+        ref_cloud = og.backproject_choose(depth[f], want_bbox, want, cam[b, 0], cam[b, 1], cam[b, 2], cam[b, 3], cam[b, 4])
+        assert np.array_equal(cloud[b].view(np.uint32), ref_cloud.view(np.uint32))  # bit-exact fp32 points
+    assert ncand[3] == 0 and ncand[0] > 1000
+    # the subset really is a subset without repeats, and different seeds give different subsets
+    if num_points < ncand[0]:
+        assert len(np.unique(choose[0])) == num_points
+        out2 = ops.mask_bbox_choose(_dev(label), _dev(depth.view(np.int16)), _dev(cam), num_points, frame_of=_dev(frame_of),
+                                    label_value=_dev(values), seeds=_dev(seeds + 1))
+        assert not np.array_equal(out2['choose'].cpu().numpy()[0], choose[0])

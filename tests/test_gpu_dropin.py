@@ -92,6 +92,23 @@ def test_loss_dropins_nonsymmetric_match_reference(golden_dir):
         assert np.allclose(N(npn), g['l_newp_' + tag], atol=1e-6) and np.allclose(N(ntg), g['l_newt_' + tag], atol=1e-6)
 
 
+def test_loss_fused_forward_equals_differentiable_path(golden_dir):
+    """`Loss` has two implementations of loss.py:12-73: the fused forward-only kernel path and the
+    differentiable torch glue around the kNN kernel; both must give the reference's numbers."""
+    from autoposeestimation_b200.densefusion.loss import Loss
+    g = np.load(os.path.join(golden_dir, 'losses.npz'))
+    T = lambda k: torch.from_numpy(g[k]).cuda()
+    idx = torch.zeros((1, 1), dtype=torch.long, device='cuda')
+    for sym, refine in (([0], False), ([], False), ([0], True)):
+        fused = Loss(120, sym)(T('pr_n'), T('pt_n'), T('pc_n'), T('target'), T('model'), idx, T('points'), 0.015, refine)
+        pr = T('pr_n').requires_grad_(True)
+        glue = Loss(120, sym)(pr, T('pt_n'), T('pc_n'), T('target'), T('model'), idx, T('points'), 0.015, refine)
+        for a, b in zip(fused, glue):
+            assert a.shape == b.shape and torch.allclose(a, b.detach(), atol=2e-6, rtol=1e-5)
+        glue[0].backward()
+        assert pr.grad is not None and float(pr.grad.abs().sum()) > 0
+
+
 def test_refiner_dropin_trains_like_reference_loop(golden_dir):
     """train.py:215-233 written against the drop-ins: refiner.train(); per sample and iteration
     `refiner(new_points, emb, idx)` -> `Loss_refine` -> `dis.backward()`; `optim.Adam(refiner.parameters()).step()`.
@@ -204,3 +221,17 @@ def test_predict_poses_frame_block():
                                       torch.tensor([[cls]]), nobj, refine_calls=2)
         assert pm.rotation_angle_between(out[i]['rotation'], res['q']) < 1e-3
         assert np.abs(out[i]['position'] - res['t']).max() < 1e-4
+    # device-side sampling: same flow, mask -> bbox -> choose -> cloud in one kernel, hashed subset
+    out_d = predict_poses(image, depth, meta, masks, [0, 2, 1], est, ref, num_points=N, refine_mode='live', device_sampling=True, seed=5)
+    assert sorted(out_d) == [0, 1]
+    for i, cls in ((0, 0), (1, 2)):
+        ml = masks[i] == 255
+        bbox = og.get_bbox(ml)
+        ch = og.choose_hashed(og.choose_candidates(ml, depth, bbox), N, (i * 0x9E3779B1 + 5) & 0xffffffff)
+        cloud = og.backproject_choose(depth, bbox, ch, 320.0, 240.0, 615.0, 615.0, 0.001)
+        out_img = est.cnn(image[:, bbox[0]:bbox[1], bbox[2]:bbox[3]][None]).cpu()
+        with torch.no_grad():
+            res = odf.live_prediction(sd_e, sd_r, out_img, torch.from_numpy(cloud)[None], torch.from_numpy(ch.astype(np.int64))[None, None],
+                                      torch.tensor([[cls]]), nobj, refine_calls=2)
+        assert pm.rotation_angle_between(out_d[i]['rotation'], res['q']) < 1e-3
+        assert np.abs(out_d[i]['position'] - res['t']).max() < 1e-4
