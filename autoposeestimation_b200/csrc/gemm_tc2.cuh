@@ -46,15 +46,32 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 
 struct Tile { int g, m_tile, n0, bn; };
 
+// Tail splitting: with T wide tiles on G persistent CTAs the last round is only partly filled (conv5: 512 tiles on 148
+// SMs = 3.46 rounds, heads2: 768 = 5.19).  When the leftover `rem = T mod G` wide tiles fit one round as 2*rem HALF-width
+// tiles, items >= `full` are those halves (two adjacent items share the A tile through L2): 3.46 rounds become ~3.55
+// instead of 4.  Returns the item count; `full` = first item index of the split region (== item count when unused).
+__device__ __forceinline__ int tail_split(int wide_tiles, int grid, int bn_full, int N, int* full) {
+    const int rem = wide_tiles % grid;
+    if (bn_full == 256 && (N % 256) == 0 && rem > 0 && 2 * rem <= grid && wide_tiles > grid) {
+        *full = wide_tiles - rem;
+        return wide_tiles + rem;
+    }
+    *full = wide_tiles;
+    return wide_tiles;
+}
+
 // Static tile order: n fastest, then m, then group.  `wide` tiles are 256 columns (last one 128 when N % 256 != 0).
-__device__ __forceinline__ Tile decode_tile(int t, const Params& p, int m_tiles, int n_tiles, int bn_full) {
+__device__ __forceinline__ Tile decode_tile(int t, const Params& p, int m_tiles, int n_tiles, int bn_full, int full) {
     Tile r;
+    int half = -1;
+    if (t >= full) { const int u = t - full; half = u & 1; t = full + (u >> 1); }
     const int n_idx = t % n_tiles;
     const int rest = t / n_tiles;
     r.m_tile = rest % m_tiles;
     r.g = rest / m_tiles;
     r.n0 = n_idx * bn_full;
     r.bn = min(bn_full, p.N - r.n0);
+    if (half >= 0) { r.n0 += half * 128; r.bn = 128; }
     return r;
 }
 
@@ -88,7 +105,8 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = p.M / BM;
     const int n_tiles = (p.N + bn_full - 1) / bn_full;
-    const int total_tiles = p.groups * m_tiles * n_tiles;
+    int full_tiles;
+    const int total_tiles = tail_split(p.groups * m_tiles * n_tiles, (int)gridDim.x, bn_full, p.N, &full_tiles);
     const int kb_per_pass = p.K / BK;
     const int n_pass = p.passes == 1 ? 1 : 3;
     const int iters_per_tile = n_pass * kb_per_pass;
@@ -114,7 +132,7 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
         if (lane == 0) {
             int it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const Tile tl = decode_tile(t, p, m_tiles, n_tiles, bn_full);
+                const Tile tl = decode_tile(t, p, m_tiles, n_tiles, bn_full, full_tiles);
                 const int a_k = p.a_k0 + tl.g * p.a_kg;
                 const int a_row = tl.m_tile * BM;
                 const int w_row = tl.g * p.N + tl.n0;
@@ -142,7 +160,7 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
         if (lane == 0) {
             int it = 0, lt = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
-                const Tile tl = decode_tile(t, p, m_tiles, n_tiles, bn_full);
+                const Tile tl = decode_tile(t, p, m_tiles, n_tiles, bn_full, full_tiles);
                 const int acc = lt & 1;
                 const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
                 mbar_wait(&tempty_bar[acc], aph ^ 1u);            // epilogue has drained this accumulator
@@ -173,7 +191,7 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
         const int GN = p.groups * p.N;
         int lt = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
-            const Tile tl = decode_tile(t, p, m_tiles, n_tiles, bn_full);
+            const Tile tl = decode_tile(t, p, m_tiles, n_tiles, bn_full, full_tiles);
             const int acc = lt & 1;
             const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
             const int row0 = tl.m_tile * BM + quad * 32;
