@@ -49,6 +49,9 @@ SIGNATURES = {
     'ape_refiner_trainer_sync_weights': (c_int, [c_vp, c_vp]),
     'ape_refiner_trainer_forward': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
     'ape_refiner_trainer_backward': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
+    'ape_refiner_trainer_step': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    'ape_refiner_trainer_adam': (c_int, [c_vp, c_vp, c_vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_int,
+                                         ctypes.c_float, c_vp]),
     'ape_refine_loss': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'ape_adam_step': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                               c_int, ctypes.c_float, c_vp]),

@@ -219,7 +219,7 @@ dense_batch_kernel(const float* __restrict__ in, int in_ld, int in_gs, const flo
         const float4 v = (o0 + o < n_out) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)(o0 + o) * K + (i - o * K))) : make_float4(0.f, 0.f, 0.f, 0.f);
         *reinterpret_cast<float4*>(s_w + i) = v;
     }
-    for (int b0 = 0; b0 < B; b0 += kDenseObj) {
+    for (int b0 = blockIdx.y * kDenseObj; b0 < B; b0 += gridDim.y * kDenseObj) {     // grid.y splits large batches (training)
         // x chunk [b][quarter][32] = 64 objects x 4 quarters x 8 float4 = 8 x 16 B per thread, cp.async into the
         // buffer that is not being read (rows past B are clamped to the last object and never written back)
         auto fetch = [&](int kc, int buf) {
@@ -756,8 +756,9 @@ static int dense(const float* in, int in_ld, int in_gs, const DevF32& W, const D
         attr_set = true;
     }
     ape::ProfScope prof_("dense_batch", s);
-    ape::dense_batch_kernel<<<(n_out + ape::kDenseOut - 1) / ape::kDenseOut, 256, smem, s>>>(in, in_ld, in_gs, W.p, bias.p, out, out_ld, B, K,
-                                                                                            npg, n_out, relu);
+    const int chunks = (B + ape::kDenseObj - 1) / ape::kDenseObj;
+    dim3 grid((n_out + ape::kDenseOut - 1) / ape::kDenseOut, chunks < 8 ? chunks : 8);
+    ape::dense_batch_kernel<<<grid, 256, smem, s>>>(in, in_ld, in_gs, W.p, bias.p, out, out_ld, B, K, npg, n_out, relu);
     ape::count_launch();
     return ape::check_launch("dense_batch");
 }

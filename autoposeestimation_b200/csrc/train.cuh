@@ -354,6 +354,9 @@ struct ape_trainer {
     BfMat PFm, H5m, dY6, dZ5, dPF;    // PFm / H5m alias net.PF.hi / net.H5.hi
     float *dZ2h = nullptr, *dZ1h = nullptr, *g6 = nullptr;
     float *part_b = nullptr, *part_w1 = nullptr, *part6 = nullptr;   // partial sums folded by fold_partials_kernel
+    // scratch of ape_refiner_trainer_step (allocated on first use, sized for max_batch x max(max_points, mesh points))
+    float *s_r = nullptr, *s_t = nullptr, *s_dr = nullptr, *s_dt = nullptr, *s_pts[2] = {nullptr, nullptr}, *s_tgt[2] = {nullptr, nullptr};
+    int s_mesh = 0;
 };
 
 static int make_bf_maps(BfMat& m) {
@@ -659,4 +662,66 @@ int ape_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                                                                  bc1, bc2s, grad_scale);
     ape::count_launch();
     return ape::check_launch("adam");
+}
+
+
+// Whole accumulation phase of one optimizer step for B objects (train.py:215-223 batched): zero the flat gradient, then
+// `iterations` x (training forward -> Loss_refine forward + backward -> backward), the cloud / target re-expressed in the
+// predicted frame between iterations.  One host call, no host synchronisation, graph-capturable after the first call
+// (the first call allocates scratch).  dis [iterations, B] out.
+extern "C" __attribute__((visibility("default")))
+int ape_refiner_trainer_step(ape_trainer* tr, const float* points, const float* emb, const int64_t* obj, const float* target,
+                             const float* model_points, const uint8_t* symmetric, int B, int N, int n_mesh, int iterations,
+                             int zero_grad, float* dis, void* stream)
+{
+    APE_REQUIRE(tr && points && emb && obj && target && model_points && dis, "ape_refiner_trainer_step: null pointer");
+    APE_REQUIRE(B > 0 && N > 0 && n_mesh > 0 && iterations > 0, "ape_refiner_trainer_step: bad sizes");
+    APE_REQUIRE(B <= tr->max_batch && N <= tr->max_points, "ape_refiner_trainer_step: B=%d N=%d exceed the trainer's workspace (%d, %d)",
+                B, N, tr->max_batch, tr->max_points);
+    cudaStream_t s = (cudaStream_t)stream;
+    ape_net* net = &tr->net;
+    if (!tr->s_r || tr->s_mesh < n_mesh) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(s, &cap);
+        APE_REQUIRE(cap == cudaStreamCaptureStatusNone, "ape_refiner_trainer_step: first call (scratch allocation) must not be captured");
+        int rc;
+        const size_t mb = (size_t)tr->max_batch;
+        if (!tr->s_r) {
+            if ((rc = dev_alloc(net, (void**)&tr->s_r, mb * 4 * 4)) || (rc = dev_alloc(net, (void**)&tr->s_t, mb * 3 * 4)) ||
+                (rc = dev_alloc(net, (void**)&tr->s_dr, mb * 4 * 4)) || (rc = dev_alloc(net, (void**)&tr->s_dt, mb * 3 * 4)) ||
+                (rc = dev_alloc(net, (void**)&tr->s_pts[0], mb * tr->max_points * 3 * 4)) ||
+                (rc = dev_alloc(net, (void**)&tr->s_pts[1], mb * tr->max_points * 3 * 4))) return rc;
+        }
+        if ((rc = dev_alloc(net, (void**)&tr->s_tgt[0], mb * n_mesh * 3 * 4)) || (rc = dev_alloc(net, (void**)&tr->s_tgt[1], mb * n_mesh * 3 * 4)))
+            return rc;                                        // (a smaller earlier pair stays owned by the handle until destroy)
+        tr->s_mesh = n_mesh;
+    }
+    if (zero_grad) APE_CUDA(cudaMemsetAsync(tr->grads, 0, tr->L.total * sizeof(float), s));
+    const float* p_cur = points;
+    const float* t_cur = target;
+    for (int it = 0; it < iterations; ++it) {
+        int rc = ape_refiner_trainer_forward(tr, p_cur, emb, obj, B, N, tr->s_r, tr->s_t, stream);
+        if (rc) return rc;
+        const bool last = it == iterations - 1;
+        float* p_nxt = last ? nullptr : tr->s_pts[it & 1];
+        float* t_nxt = last ? nullptr : tr->s_tgt[it & 1];
+        rc = ape_refine_loss(tr->s_r, tr->s_t, model_points, t_cur, n_mesh, p_cur, N, symmetric, B, dis + (size_t)it * B, tr->s_dr, tr->s_dt,
+                             p_nxt, t_nxt, stream);
+        if (rc) return rc;
+        rc = ape_refiner_trainer_backward(tr, p_cur, emb, obj, B, N, tr->s_dr, tr->s_dt, stream);
+        if (rc) return rc;
+        if (!last) { p_cur = p_nxt; t_cur = t_nxt; }
+    }
+    return APE_OK;
+}
+
+// Adam on the trainer's own flat vectors followed by the bf16 weight refresh: the tail of an optimizer step in one call.
+extern "C" __attribute__((visibility("default")))
+int ape_refiner_trainer_adam(ape_trainer* tr, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2, float eps, int step,
+                             float grad_scale, void* stream)
+{
+    APE_REQUIRE(tr, "ape_refiner_trainer_adam: null handle");
+    int rc = ape_adam_step(tr->params, tr->grads, exp_avg, exp_avg_sq, (int64_t)tr->L.total, lr, beta1, beta2, eps, step, grad_scale, stream);
+    if (rc) return rc;
+    return ape_refiner_trainer_sync_weights(tr, stream);
 }

@@ -64,13 +64,13 @@ class RefinerTrainer:
 
     def optimizer_step(self):
         self.step_count += 1
-        ops.adam_step(self.h.params, self.h.grads, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.betas, self.eps)
-        self.h.sync_weights()
+        self.h.adam(self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.betas, self.eps)
 
     def train_step(self, points, emb, idx, target, model_points):
-        """One optimizer step over this rank's shard of the batch (train.py:215-233).  Returns dis [iterations, B]."""
-        self.zero_grad()
-        dis = self.accumulate(points, emb, idx, target, model_points)
+        """One optimizer step over this rank's shard of the batch (train.py:215-233).  Returns dis [iterations, B].
+        Three host calls per step: the whole accumulation phase (ape_refiner_trainer_step), the NCCL all-reduce of the
+        flat gradient, Adam + weight refresh -- so the step stays GPU-bound when the per-rank batch gets small."""
+        dis = self.h.step(points, emb, idx, target, model_points, self.symmetric_flags(idx), self.iterations, zero_grad=True)
         self.allreduce_gradient()
         self.optimizer_step()
         return dis

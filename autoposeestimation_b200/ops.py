@@ -465,6 +465,24 @@ class RefinerTrainerHandle:
         check(_lib.load().ape_refiner_trainer_backward(self._h, ptr(new_points), ptr(emb), ptr(obj), B, N, ptr(d_r), ptr(d_t),
                                                        stream_ptr()), 'ape_refiner_trainer_backward')
 
+    def step(self, points, emb, obj, target, model_points, symmetric=None, iterations=2, zero_grad=True, out=None):
+        """Accumulation phase of one optimizer step in one C call (no Python between the launches): -> dis [iterations, B]."""
+        require_cuda(points, emb, obj, target, model_points)
+        B, N, M = points.shape[0], points.shape[1], model_points.shape[1]
+        points = _c(points, torch.float32); emb = _c(emb, torch.float32); obj = _c(obj, torch.int64).reshape(B)
+        target = _c(target, torch.float32); model_points = _c(model_points, torch.float32)
+        sym = _c(symmetric.to(torch.uint8), torch.uint8) if symmetric is not None else None
+        dis = out if out is not None else torch.empty((iterations, B), dtype=torch.float32, device=points.device)
+        check(_lib.load().ape_refiner_trainer_step(self._h, ptr(points), ptr(emb), ptr(obj), ptr(target), ptr(model_points), ptr(sym),
+                                                   B, N, M, int(iterations), int(bool(zero_grad)), ptr(dis), stream_ptr()),
+              'ape_refiner_trainer_step')
+        return dis
+
+    def adam(self, exp_avg, exp_avg_sq, step, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+        """Adam on the flat vectors + refresh of the bf16 weight copies (one C call)."""
+        check(_lib.load().ape_refiner_trainer_adam(self._h, ptr(exp_avg), ptr(exp_avg_sq), float(lr), float(betas[0]), float(betas[1]),
+                                                   float(eps), int(step), float(grad_scale), stream_ptr()), 'ape_refiner_trainer_adam')
+
     def close(self):
         if getattr(self, '_h', None):
             _lib.load().ape_refiner_trainer_destroy(self._h)

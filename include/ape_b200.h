@@ -276,6 +276,16 @@ int ape_refiner_trainer_forward(ape_trainer* tr, const float* new_points, const 
 int ape_refiner_trainer_backward(ape_trainer* tr, const float* new_points, const float* emb,
                                  const int64_t* obj, int B, int N, const float* d_r, const float* d_t,
                                  void* stream);
+/* The accumulation phase of one optimizer step in ONE call (train.py:215-223 for a batch): optional zeroing of the flat
+ * gradient, then `iterations` x (forward -> Loss_refine fwd + bwd -> backward), cloud and target re-expressed in the
+ * predicted frame in between.  points [B,N,3], emb [B,32,N], obj [B], target / model_points [B,n_mesh,3], symmetric [B]
+ * u8 or NULL; dis [iterations,B] out.  No host synchronisation; graph-capturable after the first call.
+ * ape_refiner_trainer_adam = ape_adam_step on the trainer's vectors + ape_refiner_trainer_sync_weights.          */
+int ape_refiner_trainer_step(ape_trainer* tr, const float* points, const float* emb, const int64_t* obj,
+                             const float* target, const float* model_points, const uint8_t* symmetric, int B, int N,
+                             int n_mesh, int iterations, int zero_grad, float* dis, void* stream);
+int ape_refiner_trainer_adam(ape_trainer* tr, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2,
+                             float eps, int step, float grad_scale, void* stream);
 /* Loss_refine forward + backward for B objects (lib/loss_refiner.py:12-64):
  *   quat [B,4], trans [B,3], model_points [B,M,3], target [B,M,3], points [B,N,3], symmetric [B] u8 or NULL
  *   dis [B] out; d_r [B,4], d_t [B,3] = d dis[b] / d (quat, trans) out (NULL to skip);

@@ -177,6 +177,12 @@ def test_train_step_matches_reference_loop_and_learns():
         g = trainer.h.view(key, trainer.h.grads).cpu()
         rel, cos = _rel_cos(g, sd[key].grad.reshape(g.shape))
         assert rel < 1.5e-1 and cos > 0.99, (key, rel, cos)            # bf16 vs fp32 over two chained iterations
+    # the single-call accumulation phase gives the same gradient as the three-call loop
+    g_loop = trainer.h.grads.clone()
+    dis2 = trainer.h.step(_dev(points), _dev(emb), _dev(idx), _dev(target), _dev(model), trainer.symmetric_flags(_dev(idx)), 2).cpu().numpy()
+    assert np.allclose(dis2, dis, atol=1e-7)
+    rel, _ = _rel_cos(trainer.h.grads, g_loop)
+    assert rel < 1e-3                                               # same kernels; fp32 atomic order only
     first = float(dis.mean())
     for _ in range(30):
         d = trainer.train_step(_dev(points), _dev(emb), _dev(idx), _dev(target), _dev(model))
