@@ -37,7 +37,7 @@ using ape::tc2::bulk_wait_all;
 enum { BWD_DGRAD = 0, BWD_WGRAD = 1 };
 
 constexpr int kBoxBytes = 64 * 64 * 2;                 // one MN-major box: 64 k-rows x 128 B
-constexpr int kScratch = 4 * 256 * 4 + 512 * 4;        // per-quadrant column sums + per-CTA bias-gradient accumulators
+constexpr int kScratch = 4 * 256 * 4 + 1024 * 4;       // per-quadrant column sums + per-CTA bias-gradient accumulators
 constexpr int kThreadsBwd = 320;                       // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
 constexpr int kBiasCopies = 8;                         // bias partial sums are spread over this many copies (short atomic chains)
 constexpr int kStgChunk = 32 * 64 * 2;                  // one epilogue chunk: 32 rows x 64 bf16, 128-byte swizzled (TMA box)
@@ -113,7 +113,7 @@ gemm_bf16_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* staging = smem + 3 * kStage;                                        // DGRAD epilogue chunks (over ring stage 3)
     float* s_colsum = reinterpret_cast<float*>(smem + kRingBwd);                       // [4][256]
-    float* s_bias = s_colsum + 4 * 256;                                                // [groups * N <= 512]
+    float* s_bias = s_colsum + 4 * 256;                                                // [groups * N <= 1024]
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kRingBwd + kScratch);
     uint64_t* empty_bar = full_bar + kStages2;
     uint64_t* tfull_bar = empty_bar + kStages2;
@@ -140,7 +140,7 @@ gemm_bf16_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols2);
-    for (int i = threadIdx.x; i < 512; i += kThreadsBwd) s_bias[i] = 0.f;
+    for (int i = threadIdx.x; i < 1024; i += kThreadsBwd) s_bias[i] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();

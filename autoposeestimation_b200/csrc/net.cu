@@ -183,14 +183,17 @@ gemm_simt_kernel(const bf16* __restrict__ a_hi, const bf16* __restrict__ a_lo, i
 
 // ------------------------------------------------------------------------------------------------
 // AvgPool1d over the points of each object from the per-tile column sums: ap[b,c] = sum_t cs[b*tpo+t,c] / N
-__global__ void pool_finish_kernel(const float* __restrict__ cs, int tiles_per_obj, int C, float inv_n, float* __restrict__ ap)
+__global__ void pool_finish_kernel(const float* __restrict__ cs, int tiles_per_obj, int C, float inv_n, float* __restrict__ ap,
+                                   bf16* __restrict__ ap_b16 /* training: bf16 copy for the tensor-core heads, or NULL */)
 {
     const int b = blockIdx.y;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float s = 0.f;
     for (int t = 0; t < tiles_per_obj; ++t) s += cs[((size_t)b * tiles_per_obj + t) * C + c];
-    ap[(size_t)b * C + c] = s / inv_n;   // inv_n carries N: AvgPool1d divides
+    const float v = s / inv_n;           // inv_n carries N: AvgPool1d divides
+    ap[(size_t)b * C + c] = v;
+    if (ap_b16) ap_b16[(size_t)b * C + c] = __float2bfloat16_rn(v);
 }
 
 // Small dense layer over per-object vectors (fp32 SIMT), the per-object GEMVs of both networks batched into one
@@ -331,7 +334,8 @@ posenet_out_kernel(const bf16* __restrict__ h_hi, const bf16* __restrict__ h_lo,
 
 // PoseRefineNet last layer: conv3_{r,t} rows of the object's class (network.py:199-204); in = [r128 | t128] fp32
 __global__ void __launch_bounds__(256)
-refiner_out_kernel(const float* __restrict__ g2, const float* __restrict__ w3r, const float* __restrict__ b3r,
+refiner_out_kernel(const float* __restrict__ g2, const bf16* __restrict__ g2_b16 /* training: bf16 activations instead */,
+                   const float* __restrict__ w3r, const float* __restrict__ b3r,
                    const float* __restrict__ w3t, const float* __restrict__ b3t, const int64_t* __restrict__ obj,
                    int num_obj, float* __restrict__ r2, float* __restrict__ t2)
 {
@@ -340,10 +344,10 @@ refiner_out_kernel(const float* __restrict__ g2, const float* __restrict__ w3r, 
     int o = (int)obj[b];
     o = o < 0 ? 0 : (o >= num_obj ? num_obj - 1 : o);
     const float* w = j < 4 ? w3r + (size_t)(o * 4 + j) * 128 : w3t + (size_t)(o * 3 + j - 4) * 128;
-    const float* x = g2 + (size_t)b * 256 + (j < 4 ? 0 : 128);
+    const size_t xo = (size_t)b * 256 + (j < 4 ? 0 : 128);
     float acc = 0.f;
 #pragma unroll
-    for (int k = lane; k < 128; k += 32) acc = fmaf(w[k], x[k], acc);
+    for (int k = lane; k < 128; k += 32) acc = fmaf(w[k], g2_b16 ? __bfloat162float(g2_b16[xo + k]) : g2[xo + k], acc);
     acc = warp_sum(acc);
     if (lane == 0) {
         if (j < 4) r2[b * 4 + j] = acc + b3r[o * 4 + j];
@@ -428,9 +432,11 @@ struct ape_net {
     DevF32 s_r, s_t, s_c, s_emb, s_newp, s_r2, s_t2, s_myr, s_myt;
     double *s_pose_a = nullptr, *s_pose_b = nullptr;
     int32_t* s_which = nullptr;
-    // training forward (train.cuh): plain-bf16 GEMM passes, hi-only stores, ReLU sign bits of conv6 kept
+    // training forward (train.cuh): plain-bf16 GEMM passes, hi-only stores, ReLU sign bits of conv6 kept; the heads
+    // (batch x 1024 matrices) also run on the tensor cores from bf16 copies: APb -> G1b -> G2b with weights Wh1b, Wh2b
     int train = 0;
     uint32_t* relu_bits = nullptr;
+    SplitMat APb, G1b, G2b, Wh1b, Wh2b;
 };
 
 static int dev_alloc(ape_net* net, void** p, size_t bytes) {
@@ -739,7 +745,7 @@ static int run_trunk(ape_net* net, const float* feat_src, int hw, const float* c
     if ((rc = run_gemm(net, net->H5, net->W_c6, nullptr, p, wide_layer(2), s, pn ? "gemm.pn.conv6" : "gemm.rf.conv6"))) return rc;
     dim3 gp(1024 / 256, B);
     ape::ProfScope prof_("pool_finish", s);
-    ape::pool_finish_kernel<<<gp, 256, 0, s>>>(net->CS.p, Np / 128, 1024, (float)N, net->AP.p);
+    ape::pool_finish_kernel<<<gp, 256, 0, s>>>(net->CS.p, Np / 128, 1024, (float)N, net->AP.p, net->train ? net->APb.hi : nullptr);
     ape::count_launch();
     return ape::check_launch("pool_finish");
 }
@@ -815,10 +821,22 @@ int ape_refiner_forward(ape_net* net, const float* new_points, const float* emb,
     cudaStream_t s = (cudaStream_t)stream;
     int rc = run_trunk(net, emb, 0, new_points, nullptr, B, N, nullptr, s);
     if (rc) return rc;
-    if ((rc = dense(net->AP.p, 1024, 0, net->Wr1, net->br1, net->G1.p, 1024, B, 1024, 1024, 1, 1, s))) return rc;   // conv1_{r,t}
-    if ((rc = dense(net->G1.p, 1024, 512, net->Wr2, net->br2, net->G2.p, 256, B, 512, 128, 2, 1, s))) return rc;    // conv2_{r,t}
+    if (net->train) {
+        // heads on the tensor cores (bf16 operands): conv1_{r,t} [Bp,1024] x [1024,1024]^T, conv2_{r,t} as two groups
+        const int Bp = (B + 127) / 128 * 128;
+        ape::tc::Params p = split_layer(Bp, 1024, 1024, 1, 0, 0, net->br1.p, net->G1b, 0);
+        p.passes = 1; p.hi_only = 1;
+        if ((rc = run_gemm(net, net->APb, net->Wh1b, &net->G1b, p, true, s, "gemm.rf.head1"))) return rc;
+        p = split_layer(Bp, 128, 512, 2, 0, 512, net->br2.p, net->G2b, 0);
+        p.passes = 1; p.hi_only = 1;
+        if ((rc = run_gemm(net, net->G1b, net->Wh2b, &net->G2b, p, false, s, "gemm.rf.head2"))) return rc;
+    } else {
+        if ((rc = dense(net->AP.p, 1024, 0, net->Wr1, net->br1, net->G1.p, 1024, B, 1024, 1024, 1, 1, s))) return rc;   // conv1_{r,t}
+        if ((rc = dense(net->G1.p, 1024, 512, net->Wr2, net->br2, net->G2.p, 256, B, 512, 128, 2, 1, s))) return rc;    // conv2_{r,t}
+    }
     ape::ProfScope prof_("refiner_out", s);
-    ape::refiner_out_kernel<<<B, 256, 0, s>>>(net->G2.p, net->w3r.p, net->b3r.p, net->w3t.p, net->b3t.p, obj, net->num_obj, r2, t2);
+    ape::refiner_out_kernel<<<B, 256, 0, s>>>(net->G2.p, net->train ? net->G2b.hi : nullptr, net->w3r.p, net->b3r.p, net->w3t.p,
+                                              net->b3t.p, obj, net->num_obj, r2, t2);
     ape::count_launch();
     return ape::check_launch("refiner_out");
 }

@@ -52,88 +52,12 @@ __global__ void pack_frontend_kernel(const float* __restrict__ w1, const float* 
     for (int i = threadIdx.x; i < 64; i += blockDim.x) { fw[32 * 64 + 3 * 64 + i] = b1[i]; fw[32 * 64 + 3 * 64 + 64 + i] = be1[i]; }
 }
 
-// Generic small fp32 GEMM with arbitrary strides (the per-object head layers: every matrix is <= 4 MB):
-//   C[m, n] (op)= alpha * sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn],  groups on blockIdx.z
-enum { SG_STORE = 0, SG_ATOMIC = 1, SG_STORE_MASK = 2 };
-struct SgemmArgs {
-    const float* A; long long sam, sak, a_g;
-    const float* B; long long sbk, sbn, b_g;
-    float* C; long long ldc, c_g;
-    const float* mask; long long ldm, m_g;       // SG_STORE_MASK: C = mask > 0 ? v : 0
-    int M, N, K, epi;
-    float alpha;
-    int groups, ksplit;                          // blockIdx.z = g + groups * k_slice (ksplit > 1 needs SG_ATOMIC)
-};
-__global__ void __launch_bounds__(256)
-sgemm_small_kernel(const SgemmArgs a)
-{
-    __shared__ float sA[16][65], sB[16][65];
-    const int g = blockIdx.z % a.groups, ks = blockIdx.z / a.groups;
-    const float* A = a.A + g * a.a_g;
-    const float* B = a.B + g * a.b_g;
-    const int row0 = blockIdx.y * 64, col0 = blockIdx.x * 64;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int kc = ((a.K + a.ksplit - 1) / a.ksplit + 15) / 16 * 16;
-    const int k_end = min(a.K, (ks + 1) * kc);
-    float acc[4][4] = {};
-    for (int k0 = ks * kc; k0 < k_end; k0 += 16) {
-        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
-            int m, k;
-            if (a.sak == 1) { k = i & 15; m = i >> 4; } else { m = i & 63; k = i >> 6; }
-            sA[k][m] = (row0 + m < a.M && k0 + k < k_end) ? A[(long long)(row0 + m) * a.sam + (long long)(k0 + k) * a.sak] : 0.f;
-            int n, kk;
-            if (a.sbn == 1) { n = i & 63; kk = i >> 6; } else { kk = i & 15; n = i >> 4; }
-            sB[kk][n] = (col0 + n < a.N && k0 + kk < k_end) ? B[(long long)(k0 + kk) * a.sbk + (long long)(col0 + n) * a.sbn] : 0.f;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            float x[4], w[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { x[i] = sA[k][ty * 4 + i]; w[i] = sB[k][tx * 4 + i]; }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(x[i], w[j], acc[i][j]);
-        }
-        __syncthreads();
-    }
-    float* C = a.C + g * a.c_g;
-    const float* Mk = a.mask ? a.mask + g * a.m_g : nullptr;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = row0 + ty * 4 + i;
-        if (m >= a.M) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = col0 + tx * 4 + j;
-            if (n >= a.N) continue;
-            float v = a.alpha * acc[i][j];
-            if (a.epi == SG_ATOMIC) atomicAdd(C + (long long)m * a.ldc + n, v);
-            else {
-                if (a.epi == SG_STORE_MASK && !(Mk[(long long)m * a.ldm + n] > 0.f)) v = 0.f;
-                C[(long long)m * a.ldc + n] = v;
-            }
-        }
-    }
-}
-
-// out[c] += sum_b x[b, c]   (bias gradients of the head layers)
-__global__ void colsum_add_kernel(const float* __restrict__ x, int B, int C, float* __restrict__ out)
-{
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    float s = 0.f;
-    for (int b = 0; b < B; ++b) s += x[(size_t)b * C + c];
-    out[c] += s;
-}
-
 // Backward of conv3_{r,t} restricted to the object's class (network.py:199-204) and of the ReLU in front of it:
 //   dz2[b, c] = G2[b, c] > 0 ? sum_j d[b, j] * w3[(o*nj + j), c % 128] : 0;   dW3, db3, db2 accumulate (atomics)
 __global__ void __launch_bounds__(256)
 head3_bwd_kernel(const float* __restrict__ d_r, const float* __restrict__ d_t, const int64_t* __restrict__ obj, int num_obj,
-                 const float* __restrict__ g2, const float* __restrict__ w3r, const float* __restrict__ w3t,
-                 float* __restrict__ dz2, float* __restrict__ gw3r, float* __restrict__ gw3t, float* __restrict__ gb3r,
+                 const bf16* __restrict__ g2, const float* __restrict__ w3r, const float* __restrict__ w3t,
+                 bf16* __restrict__ dz2, float* __restrict__ gw3r, float* __restrict__ gw3t, float* __restrict__ gb3r,
                  float* __restrict__ gb3t, float* __restrict__ gb2)
 {
     const int b = blockIdx.x, c = threadIdx.x, h = c >> 7, k = c & 127;
@@ -143,7 +67,7 @@ head3_bwd_kernel(const float* __restrict__ d_r, const float* __restrict__ d_t, c
     const float* d = h == 0 ? d_r + 4 * b : d_t + 3 * b;
     const float* w = (h == 0 ? w3r : w3t) + (size_t)o * nj * 128;
     float* gw = (h == 0 ? gw3r : gw3t) + (size_t)o * nj * 128;
-    const float x = g2[(size_t)b * 256 + c];
+    const float x = __bfloat162float(g2[(size_t)b * 256 + c]);
     float s = 0.f;
     for (int j = 0; j < nj; ++j) {
         const float dj = d[j];
@@ -151,7 +75,7 @@ head3_bwd_kernel(const float* __restrict__ d_r, const float* __restrict__ d_t, c
         atomicAdd(gw + j * 128 + k, dj * x);
     }
     const float dz = x > 0.f ? s : 0.f;
-    dz2[(size_t)b * 256 + c] = dz;
+    dz2[(size_t)b * 256 + c] = __float2bfloat16_rn(dz);
     atomicAdd(gb2 + c, dz);
     if (k < nj) atomicAdd((h == 0 ? gb3r : gb3t) + o * nj + k, d[k]);
 }
@@ -160,8 +84,8 @@ head3_bwd_kernel(const float* __restrict__ d_r, const float* __restrict__ d_t, c
 // g6 = dAP / N already, and db6[c] += sum_r dY6[r, c].  One CTA per 128-row tile; thread = 8 consecutive columns (one
 // byte of sign bits in, one 16-byte store out per row), two row phases per CTA, 4 rows in flight per thread.
 __global__ void __launch_bounds__(256)
-dy6_kernel(const uint32_t* __restrict__ bits, const float* __restrict__ g6, int Np, int rows_live, bf16* __restrict__ dy6,
-           float* __restrict__ part6 /* [tiles][1024]: this tile's column sums (no atomics: see gemm_train.cuh) */)
+dy6_kernel(const uint32_t* __restrict__ bits, const bf16* __restrict__ g6 /* dAP [Bp,1024] */, float inv_n, int Np, int rows_live,
+           bf16* __restrict__ dy6, float* __restrict__ part6 /* [tiles][1024]: this tile's column sums (no atomics: see gemm_train.cuh) */)
 {
     __shared__ uint32_t s_cnt[128][8];
     const int row0 = blockIdx.x * 128;
@@ -171,10 +95,13 @@ dy6_kernel(const uint32_t* __restrict__ bits, const float* __restrict__ g6, int 
     const bool live = row0 < rows_live;
     uint32_t u[4] = {0u, 0u, 0u, 0u};
     if (live) {
-        const float4 g0 = *reinterpret_cast<const float4*>(g6 + (size_t)b * 1024 + c);
-        const float4 g1 = *reinterpret_cast<const float4*>(g6 + (size_t)b * 1024 + c + 4);
-        const __nv_bfloat162 h0 = __floats2bfloat162_rn(g0.x, g0.y), h1 = __floats2bfloat162_rn(g0.z, g0.w);
-        const __nv_bfloat162 h2 = __floats2bfloat162_rn(g1.x, g1.y), h3 = __floats2bfloat162_rn(g1.z, g1.w);
+        const uint4 gv = *reinterpret_cast<const uint4*>(g6 + (size_t)b * 1024 + c);          // 8 bf16 of dAP; AvgPool1d backward = / N
+        const uint32_t gu[4] = {gv.x, gv.y, gv.z, gv.w};
+        float ge[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { ge[2 * q] = __uint_as_float(gu[q] << 16) * inv_n; ge[2 * q + 1] = __uint_as_float(gu[q] & 0xffff0000u) * inv_n; }
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(ge[0], ge[1]), h1 = __floats2bfloat162_rn(ge[2], ge[3]);
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(ge[4], ge[5]), h3 = __floats2bfloat162_rn(ge[6], ge[7]);
         u[0] = *reinterpret_cast<const uint32_t*>(&h0); u[1] = *reinterpret_cast<const uint32_t*>(&h1);
         u[2] = *reinterpret_cast<const uint32_t*>(&h2); u[3] = *reinterpret_cast<const uint32_t*>(&h3);
     }
@@ -219,12 +146,12 @@ dy6_kernel(const uint32_t* __restrict__ bits, const float* __restrict__ g6, int 
 //   biases of conv5 | conv2,e_conv2 | conv1,e_conv1 from kBiasCopies copies, conv1 / e_conv1 weights from kW1Copies
 //   copies, conv6 bias from the per-tile sums of dy6_kernel.
 constexpr int kW1Copies = 16;
-constexpr int kBiasPart = 1024;                 // floats per bias copy: [b5 512 | b2e2 256 | b1,be1 128 | pad]
+constexpr int kBiasPart = 2048;                 // floats per bias copy: [b5 512 | b2e2 256 | b1,be1 128 | pad 128 | bh1 1024]
 constexpr int kW1Part = 64 * 3 + 64 * 32;       // conv1.w | e_conv1.w, contiguous in the flat layout
 __global__ void __launch_bounds__(1024)
 fold_partials_kernel(const float* __restrict__ part_b, const float* __restrict__ part_w1, const float* __restrict__ part6, int tiles,
                      float* __restrict__ g_b5, float* __restrict__ g_b2e2, float* __restrict__ g_b1, float* __restrict__ g_w1,
-                     float* __restrict__ g_b6)
+                     float* __restrict__ g_b6, float* __restrict__ g_bh1)
 {
     __shared__ float s_red[32][33];
     if (blockIdx.x < 32) {
@@ -260,6 +187,12 @@ fold_partials_kernel(const float* __restrict__ part_b, const float* __restrict__
 #pragma unroll
         for (int k = 0; k < kW1Copies; ++k) s += part_w1[k * kW1Part + j];
         g_w1[j] += s;
+    } else if (i >= 4096 && i < 4096 + 1024) {
+        const int j = i - 4096;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < tr::kBiasCopies; ++k) s += part_b[k * kBiasPart + 1024 + j];
+        g_bh1[j] += s;
     }
 }
 
@@ -350,9 +283,10 @@ struct ape_trainer {
     ape::TrainLayout L;
     float *params = nullptr, *grads = nullptr;      // caller-owned flat vectors
     int num_obj = 0, max_batch = 0, max_points = 0;
-    BfMat Wb2, Wb5, Wb6;              // bf16 copies of conv2|e_conv2, conv5, conv6 (one contiguous allocation)
+    BfMat Wb2, Wb5, Wb6, Wbh1, Wbh2;  // bf16 copies of conv2|e_conv2, conv5, conv6, conv1_{r,t}, conv2_{r,t} (one contiguous allocation)
     BfMat PFm, H5m, dY6, dZ5, dPF;    // PFm / H5m alias net.PF.hi / net.H5.hi
-    float *dZ2h = nullptr, *dZ1h = nullptr, *g6 = nullptr;
+    BfMat APm, G1m, G2m, dZ2h, dZ1h, g6; // heads: [Bp,1024], [Bp,1024], [Bp,256] activations and their gradients (bf16)
+    int bp_max = 0;
     float *part_b = nullptr, *part_w1 = nullptr, *part6 = nullptr;   // partial sums folded by fold_partials_kernel
     // scratch of ape_refiner_trainer_step (allocated on first use, sized for max_batch x max(max_points, mesh points))
     float *s_r = nullptr, *s_t = nullptr, *s_dr = nullptr, *s_dt = nullptr, *s_pts[2] = {nullptr, nullptr}, *s_tgt[2] = {nullptr, nullptr};
@@ -412,7 +346,7 @@ int ape_refiner_trainer_sync_weights(ape_trainer* tr, void* stream)
     APE_REQUIRE(tr, "ape_refiner_trainer_sync_weights: null handle");
     cudaStream_t s = (cudaStream_t)stream;
     const ape::TrainLayout& L = tr->L;
-    const size_t n = 256 * 64 + 512 * 384 + 1024 * 512;          // conv2|e_conv2, conv5, conv6 are contiguous
+    const size_t n = 256 * 64 + 512 * 384 + 1024 * 512 + 1024 * 1024 + 256 * 512;   // conv2|e_conv2 ... conv2_{r,t}: contiguous in the flat vector
     ape::f32_to_bf16_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(tr->params + L.w2e2, tr->Wb2.p, n);
     ape::pack_frontend_kernel<<<1, 256, 0, s>>>(tr->params + L.w1, tr->params + L.we1, tr->params + L.b1, tr->params + L.be1, tr->net.fw.p);
     ape::count_launch(2);
@@ -447,16 +381,35 @@ int ape_refiner_trainer_create(float* params, float* grads, int num_obj, int max
     TRY(alloc_f32(net, net->fw, 32 * 64 + 3 * 64 + 128));
     {
         bf16* wb = nullptr;
-        TRY(dev_alloc(net, (void**)&wb, (size_t)(256 * 64 + 512 * 384 + 1024 * 512) * 2));
+        TRY(dev_alloc(net, (void**)&wb, (size_t)(256 * 64 + 512 * 384 + 1024 * 512 + 1024 * 1024 + 256 * 512) * 2));
         tr->Wb2.p = wb; tr->Wb2.rows = 256; tr->Wb2.cols = 64;
         tr->Wb5.p = wb + 256 * 64; tr->Wb5.rows = 512; tr->Wb5.cols = 384;
         tr->Wb6.p = tr->Wb5.p + 512 * 384; tr->Wb6.rows = 1024; tr->Wb6.cols = 512;
-        TRY(make_bf_maps(tr->Wb2)); TRY(make_bf_maps(tr->Wb5)); TRY(make_bf_maps(tr->Wb6));
-        SplitMat* W[3] = {&net->W_c2e2, &net->W_c5, &net->W_c6};
-        BfMat* Bm[3] = {&tr->Wb2, &tr->Wb5, &tr->Wb6};
-        for (int i = 0; i < 3; ++i) {            // the forward kernel only dereferences the hi maps when passes == 1
+        tr->Wbh1.p = tr->Wb6.p + 1024 * 512; tr->Wbh1.rows = 1024; tr->Wbh1.cols = 1024;
+        tr->Wbh2.p = tr->Wbh1.p + 1024 * 1024; tr->Wbh2.rows = 256; tr->Wbh2.cols = 512;
+        SplitMat* W[5] = {&net->W_c2e2, &net->W_c5, &net->W_c6, &net->Wh1b, &net->Wh2b};
+        BfMat* Bm[5] = {&tr->Wb2, &tr->Wb5, &tr->Wb6, &tr->Wbh1, &tr->Wbh2};
+        for (int i = 0; i < 5; ++i) {            // the forward kernel only dereferences the hi maps when passes == 1
+            TRY(make_bf_maps(*Bm[i]));
             W[i]->hi = W[i]->lo = Bm[i]->p; W[i]->rows = Bm[i]->rows; W[i]->cols = Bm[i]->cols;
             W[i]->map_hi = W[i]->map_lo = Bm[i]->kmaj;
+        }
+    }
+    {   // head activations and their gradients, bf16, rows padded to whole 128-row tiles (padding rows stay zero in the
+        // gradient buffers, so they contribute nothing)
+        tr->bp_max = (max_batch + 127) / 128 * 128;
+        BfMat* Hm[6] = {&tr->APm, &tr->G1m, &tr->G2m, &tr->dZ2h, &tr->dZ1h, &tr->g6};
+        const int hc[6] = {1024, 1024, 256, 256, 1024, 1024};
+        for (int i = 0; i < 6; ++i) {
+            TRY(dev_alloc(net, (void**)&Hm[i]->p, (size_t)tr->bp_max * hc[i] * 2));
+            APE_CUDA(cudaMemset(Hm[i]->p, 0, (size_t)tr->bp_max * hc[i] * 2));
+            Hm[i]->rows = tr->bp_max; Hm[i]->cols = hc[i];
+            TRY(make_bf_maps(*Hm[i]));
+        }
+        SplitMat* S[3] = {&net->APb, &net->G1b, &net->G2b};
+        for (int i = 0; i < 3; ++i) {
+            S[i]->hi = S[i]->lo = Hm[i]->p; S[i]->rows = Hm[i]->rows; S[i]->cols = Hm[i]->cols;
+            S[i]->map_hi = S[i]->map_lo = Hm[i]->kmaj; S[i]->st_hi = S[i]->st_lo = Hm[i]->st;
         }
     }
     TRY(alloc_split(net, net->PF, R, 384));      // the front end writes hi and lo; GEMM epilogues store hi only
@@ -484,9 +437,6 @@ int ape_refiner_trainer_create(float* params, float* grads, int num_obj, int max
         G[i]->rows = (int)R; G[i]->cols = gc[i];
         TRY(make_bf_maps(*G[i]));
     }
-    TRY(dev_alloc(net, (void**)&tr->dZ2h, (size_t)max_batch * 256 * 4));
-    TRY(dev_alloc(net, (void**)&tr->dZ1h, (size_t)max_batch * 1024 * 4));
-    TRY(dev_alloc(net, (void**)&tr->g6, (size_t)max_batch * 1024 * 4));
     TRY(dev_alloc(net, (void**)&tr->part_b, (size_t)ape::tr::kBiasCopies * ape::kBiasPart * 4));
     TRY(dev_alloc(net, (void**)&tr->part_w1, (size_t)ape::kW1Copies * ape::kW1Part * 4));
     TRY(dev_alloc(net, (void**)&tr->part6, (R / 128) * 1024 * 4));
@@ -546,16 +496,6 @@ static int run_bwd_gemm(const BfMat& A, const BfMat& Bm, const BfMat* mask, cons
     return ape::check_launch(label);
 }
 
-static int sgemm(ape::SgemmArgs a, int groups, cudaStream_t s, const char* label, int ksplit = 1)
-{
-    ape::ProfScope prof_(label, s);
-    a.groups = groups; a.ksplit = ksplit;
-    dim3 grid((a.N + 63) / 64, (a.M + 63) / 64, groups * ksplit);
-    ape::sgemm_small_kernel<<<grid, 256, 0, s>>>(a);
-    ape::count_launch();
-    return ape::check_launch(label);
-}
-
 // Backward of the forward that ape_refiner_trainer_forward just ran (same new_points / emb / obj / B / N):
 // grads += d(sum_b <d_r[b], r2[b]> + <d_t[b], t2[b]>) / d params.
 extern "C" __attribute__((visibility("default")))
@@ -572,39 +512,40 @@ int ape_refiner_trainer_backward(ape_trainer* tr, const float* new_points, const
     int rc;
     APE_CUDA(cudaMemsetAsync(tr->part_b, 0, (size_t)ape::tr::kBiasCopies * ape::kBiasPart * 4, s));
     APE_CUDA(cudaMemsetAsync(tr->part_w1, 0, (size_t)ape::kW1Copies * ape::kW1Part * 4, s));
-    {   // heads
+    const int Bp = (B + 127) / 128 * 128;
+    ape::tr::BwdParams p;
+    {   // heads: conv3 (class rows, SIMT) then conv2_{r,t} / conv1_{r,t} on the tensor cores (bf16, K or M = padded batch)
         ape::ProfScope prof_("train.head3_bwd", s);
-        ape::head3_bwd_kernel<<<B, 256, 0, s>>>(d_r, d_t, obj, tr->num_obj, net->G2.p, net->w3r.p, net->w3t.p, tr->dZ2h,
+        ape::head3_bwd_kernel<<<B, 256, 0, s>>>(d_r, d_t, obj, tr->num_obj, tr->G2m.p, net->w3r.p, net->w3t.p, tr->dZ2h.p,
                                                G + L.w3r, G + L.w3t, G + L.b3r, G + L.b3t, G + L.bh2);
         ape::count_launch();
         if ((rc = ape::check_launch("head3_bwd"))) return rc;
     }
-    ape::SgemmArgs a;
     // dW(conv2_{r,t}) [2 x 128, 512] += dZ2h[:, g]^T * G1[:, g]
-    a = {tr->dZ2h, 1, 256, 128, net->G1.p, 1024, 1, 512, G + L.wh2, 512, 128 * 512, nullptr, 0, 0, 128, 512, B, ape::SG_ATOMIC, 1.f};
-    if ((rc = sgemm(a, 2, s, "train.head2_wgrad", 4))) return rc;
-    // dZ1h [B, 2 x 512] = (dZ2h[:, g] * W2[g]) masked by G1 > 0
-    a = {tr->dZ2h, 256, 1, 128, net->Wr2.p, 512, 1, 128 * 512, tr->dZ1h, 1024, 512, net->G1.p, 1024, 512, B, 512, 128, ape::SG_STORE_MASK, 1.f};
-    if ((rc = sgemm(a, 2, s, "train.head2_dgrad"))) return rc;
-    {
-        ape::ProfScope prof_("train.head1_bias", s);
-        ape::colsum_add_kernel<<<4, 256, 0, s>>>(tr->dZ1h, B, 1024, G + L.bh1);
-        ape::count_launch();
-    }
+    memset(&p, 0, sizeof(p));
+    p.mode = ape::tr::BWD_WGRAD; p.M = 128; p.N = 512; p.K = Bp; p.groups = 2; p.a_cg = 128; p.b_cg = 512;
+    p.dw = G + L.wh2; p.dw_ld = 512; p.dw_rg = 128;
+    if ((rc = run_bwd_gemm(tr->dZ2h, tr->G1m, nullptr, nullptr, p, s, "gemm.train.head2_wgrad"))) return rc;
+    // dZ1h [Bp, 2 x 512] = (dZ2h[:, g] * W2[g]) masked by G1 > 0, bias gradient of conv1_{r,t}
+    memset(&p, 0, sizeof(p));
+    p.mode = ape::tr::BWD_DGRAD; p.M = Bp; p.N = 512; p.K = 128; p.groups = 2; p.a_cg = 128; p.b_rg = 128;
+    p.out = tr->dZ1h.p; p.o_ld = 1024; p.o_cg = 512; p.mask = tr->G1m.p; p.m_ld = 1024; p.m_cg = 512;
+    p.bias_grad = tr->part_b + 1024; p.bg_stride = ape::kBiasPart;
+    if ((rc = run_bwd_gemm(tr->dZ2h, tr->Wbh2, &tr->G1m, &tr->dZ1h, p, s, "gemm.train.head2_dgrad"))) return rc;
     // dW(conv1_{r,t}) [1024, 1024] += dZ1h^T * AP
-    a = {tr->dZ1h, 1, 1024, 0, net->AP.p, 1024, 1, 0, G + L.wh1, 1024, 0, nullptr, 0, 0, 1024, 1024, B, ape::SG_ATOMIC, 1.f};
-    if ((rc = sgemm(a, 1, s, "train.head1_wgrad"))) return rc;
-    // g6 [B, 1024] = (dZ1h * W1) / N   (AvgPool1d backward folded in)
-    APE_CUDA(cudaMemsetAsync(tr->g6, 0, (size_t)B * 1024 * sizeof(float), s));
-    a = {tr->dZ1h, 1024, 1, 0, net->Wr1.p, 1024, 1, 0, tr->g6, 1024, 0, nullptr, 0, 0, B, 1024, 1024, ape::SG_ATOMIC, 1.0f / (float)N};
-    if ((rc = sgemm(a, 1, s, "train.head1_dgrad", 8))) return rc;
+    memset(&p, 0, sizeof(p));
+    p.mode = ape::tr::BWD_WGRAD; p.M = 1024; p.N = 1024; p.K = Bp; p.groups = 1; p.dw = G + L.wh1; p.dw_ld = 1024;
+    if ((rc = run_bwd_gemm(tr->dZ1h, tr->APm, nullptr, nullptr, p, s, "gemm.train.head1_wgrad"))) return rc;
+    // dAP [Bp, 1024] = dZ1h * W1   (AvgPool1d's 1/N is applied where dY6 is formed)
+    memset(&p, 0, sizeof(p));
+    p.mode = ape::tr::BWD_DGRAD; p.M = Bp; p.N = 1024; p.K = 1024; p.groups = 1; p.out = tr->g6.p; p.o_ld = 1024;
+    if ((rc = run_bwd_gemm(tr->dZ1h, tr->Wbh1, nullptr, &tr->g6, p, s, "gemm.train.head1_dgrad"))) return rc;
     {
         ape::ProfScope prof_("train.dy6", s);
-        ape::dy6_kernel<<<M / 128, 256, 0, s>>>(net->relu_bits, tr->g6, Np, B * Np, tr->dY6.p, tr->part6);
+        ape::dy6_kernel<<<M / 128, 256, 0, s>>>(net->relu_bits, tr->g6.p, 1.0f / (float)N, Np, B * Np, tr->dY6.p, tr->part6);
         ape::count_launch();
         if ((rc = ape::check_launch("dy6"))) return rc;
     }
-    ape::tr::BwdParams p;
     // conv6: dW6 [1024, 512] += dY6^T * H5 ;  dZ5 = (dY6 * W6) masked by H5 > 0, db5
     memset(&p, 0, sizeof(p));
     p.mode = ape::tr::BWD_WGRAD; p.M = 1024; p.N = 512; p.K = M; p.groups = 1; p.dw = G + L.w6; p.dw_ld = 512;
@@ -642,8 +583,8 @@ int ape_refiner_trainer_backward(ape_trainer* tr, const float* new_points, const
     }
     {
         ape::ProfScope prof_("train.fold_partials", s);
-        ape::fold_partials_kernel<<<32 + 4, 1024, 0, s>>>(tr->part_b, tr->part_w1, tr->part6, M / 128, G + L.b5, G + L.b2e2,
-                                                                     G + L.b1, G + L.w1, G + L.b6);
+        ape::fold_partials_kernel<<<32 + 5, 1024, 0, s>>>(tr->part_b, tr->part_w1, tr->part6, M / 128, G + L.b5, G + L.b2e2,
+                                                       G + L.b1, G + L.w1, G + L.b6, G + L.bh1);
         ape::count_launch();
         if ((rc = ape::check_launch("fold_partials"))) return rc;
     }

@@ -225,8 +225,9 @@ def _bf(x):
 def refiner_train_bf16_emulation(sd, new_points, emb, obj, num_obj, d_r, d_t):
     """Test infrastructure: PoseRefineNet forward + backward (network.py:151-206 and its autograd) for ONE object in
     fp32 arithmetic with bf16 ROUNDING at exactly the points where the B200 training path stores bf16 (csrc/train.cuh):
-    trunk weights conv2/e_conv2/conv5/conv6, the activations x1|e1|x2|e2 and h5, the pooled-layer gradient g6, and the
-    activation gradients dZ5, dZ2|dZe2, the conv5 share of dX1|dE1, dZ1|dZe1.  Heads stay fp32.  Separates "the
+    trunk weights conv2/e_conv2/conv5/conv6 and head weights conv1_{r,t}/conv2_{r,t}, the activations x1|e1|x2|e2, h5 and
+    the head activations ap/g1/g2, the pooled-layer gradient, and the activation gradients dZ5, dZ2|dZe2, the conv5 share
+    of dX1|dE1, dZ1|dZe1 and the head gradients.  conv3_{r,t}, the loss and the first-layer weight gradients stay fp32.  Separates "the
     kernels compute what they are meant to" (tight tolerance against this) from "bf16 differs from fp32" (loose
     tolerance against plain autograd).  new_points [1,N,3], emb [1,32,N], d_r [4], d_t [3] ->
     (r [4], t [3], {state_dict key: gradient})."""
@@ -247,21 +248,25 @@ def refiner_train_bf16_emulation(sd, new_points, emb, obj, num_obj, d_r, d_t):
     ap = y6.mean(0, keepdim=True)                            # [1,1024]
     g = {}
     r_t, dz1h = [], []
+    ap_b = _bf(ap)                                           # heads run on the tensor cores too: bf16 operands, fp32 accumulate
     for h, width, d in (('r', 4, d_r), ('t', 3, d_t)):
-        g1 = F.relu(ap @ W['conv1_%s.weight' % h].t() + W['conv1_%s.bias' % h])
-        g2 = F.relu(g1 @ W['conv2_%s.weight' % h].t() + W['conv2_%s.bias' % h])
+        Wa, Wb = _bf(W['conv1_%s.weight' % h]), _bf(W['conv2_%s.weight' % h])
+        g1 = _bf(F.relu(ap_b @ Wa.t() + W['conv1_%s.bias' % h]))
+        g2 = _bf(F.relu(g1 @ Wb.t() + W['conv2_%s.bias' % h]))
         w3 = W['conv3_%s.weight' % h][o * width:(o + 1) * width]
         r_t.append((g2 @ w3.t() + W['conv3_%s.bias' % h][o * width:(o + 1) * width])[0])
         d = d.reshape(1, width).to(torch.float32)
         gw3 = torch.zeros_like(W['conv3_%s.weight' % h]); gb3 = torch.zeros_like(W['conv3_%s.bias' % h])
         gw3[o * width:(o + 1) * width] = d.t() @ g2; gb3[o * width:(o + 1) * width] = d[0]
-        dz2 = (d @ w3) * (g2 > 0)
-        dz1 = (dz2 @ W['conv2_%s.weight' % h]) * (g1 > 0)
+        dz2_f = (d @ w3) * (g2 > 0)
+        dz2 = _bf(dz2_f)
+        dz1_f = (dz2 @ Wb) * (g1 > 0)
+        dz1 = _bf(dz1_f)
         g['conv3_%s.weight' % h], g['conv3_%s.bias' % h] = gw3, gb3
-        g['conv2_%s.weight' % h], g['conv2_%s.bias' % h] = dz2.t() @ g1, dz2[0]
-        g['conv1_%s.weight' % h], g['conv1_%s.bias' % h] = dz1.t() @ ap, dz1[0]
-        dz1h.append(dz1 @ W['conv1_%s.weight' % h])
-    g6 = _bf((dz1h[0] + dz1h[1]) / float(n))                 # [1,1024]
+        g['conv2_%s.weight' % h], g['conv2_%s.bias' % h] = dz2.t() @ g1, dz2_f[0]
+        g['conv1_%s.weight' % h], g['conv1_%s.bias' % h] = dz1.t() @ ap_b, dz1_f[0]
+        dz1h.append(dz1 @ Wa)
+    g6 = _bf(_bf(dz1h[0] + dz1h[1]) * (1.0 / float(n)))      # dAP stored as bf16, AvgPool1d's 1/N applied where dY6 is formed
     dy6 = (y6 > 0).to(torch.float32) * g6                    # [N,1024]
     g['feat.conv6.weight'], g['feat.conv6.bias'] = dy6.t() @ h5, dy6.sum(0)
     dz5_f = (dy6 @ W6) * (h5 > 0)
