@@ -5,7 +5,8 @@ numpy restatements of
   * mask / choose             pipeline/utils.py:524-539 (= dataset.py:239-257)
   * fp32 back-projection      pipeline/utils.py:542-553
   * get_surface projection    pc_reconstruction/open3d_utils.py:171-192
-PARITY UNPINNED by reference-run vectors (see oracle/__init__.py).
+Pinned by tests/golden/geometry_ref.npz = outputs of the reference's own dataset.py / open3d_utils.py run on seeded
+frames (oracle/gen_golden_geometry.py; tests/test_oracle_pinned.py).
 """
 import numpy as np
 

@@ -194,3 +194,56 @@ def test_mask_bbox_choose_on_device_vs_oracle(num_points):
         out2 = ops.mask_bbox_choose(_dev(label), _dev(depth.view(np.int16)), _dev(cam), num_points, frame_of=_dev(frame_of),
                                     label_value=_dev(values), seeds=_dev(seeds + 1))
         assert not np.array_equal(out2['choose'].cpu().numpy()[0], choose[0])
+
+
+# ---- against vectors produced by the reference's own code (oracle/gen_golden_geometry.py)
+def test_backproject_choose_vs_reference_run(golden_dir):
+    """DenseFusion/datasets/myDatasetAugmented/dataset.py:236-275 executed by the reference: fp32 cloud bit-exact for
+    the reference's own `choose`, in one batched launch over the three frames."""
+    import os
+    from autoposeestimation_b200 import ops
+    g = np.load(os.path.join(golden_dir, 'geometry_ref.npz'))
+    ppx, ppy, fx, fy = (float(v) for v in g['intr'])
+    F = len(g['seeds'])
+    cam = np.tile(np.array([[ppx, ppy, fx, fy, float(g['depth_scale'])]], np.float32), (F, 1))
+    out = ops.backproject_choose(_u16(g['depth']), _dev(g['bbox'].astype(np.int32)), _dev(g['choose'].astype(np.int64)), _dev(cam),
+                                 frame_of=_dev(np.arange(F, dtype=np.int32))).cpu().numpy()
+    assert np.array_equal(out.view(np.uint32), g['cloud'].view(np.uint32))
+
+
+def test_surface_backproject_vs_reference_run(golden_dir):
+    """pc_reconstruction/open3d_utils.py:171-192 executed by the reference: same number of points, same order, 1e-9 mm."""
+    import os
+    from autoposeestimation_b200 import ops
+    g = np.load(os.path.join(golden_dir, 'geometry_ref.npz'))
+    F = len(g['surf_n'])
+    cam = np.tile(g['intr'][None].astype(np.float64), (F, 1))
+    T = np.tile(g['robot2cam'][None], (F, 1, 1))
+    pts, pix, cnt = ops.surface_backproject(_dev(g['label']), _u16(g['depth']), _dev(cam), _dev(T), capacity=int(g['surf_n'].max()) + 8)
+    off = np.concatenate([[0], np.cumsum(g['surf_n'])])
+    cnt = cnt.cpu().numpy(); pts = pts.cpu().numpy()
+    for i in range(F):
+        assert int(cnt[i]) == int(g['surf_n'][i])
+        assert np.abs(pts[i, :cnt[i]] - g['surf_pts'][off[i]:off[i + 1]]).max() < 1e-9
+
+
+def test_mask_bbox_choose_on_device_vs_reference_run(golden_dir):
+    """Device-side mask -> bbox -> choose (csrc/choose.cu) on the reference-run frames: the bbox equals the reference's
+    get_bbox; in the 'wrap' branch (frame 2: fewer candidates than num_pt) choose and cloud equal the reference's bit
+    for bit; in the subset branch the chosen pixels are an ascending num_pt-subset of the reference's candidates."""
+    import os
+    from autoposeestimation_b200 import ops
+    g = np.load(os.path.join(golden_dir, 'geometry_ref.npz'))
+    ppx, ppy, fx, fy = (float(v) for v in g['intr'])
+    F, N = len(g['seeds']), int(g['num_pt'])
+    cam = np.tile(np.array([[ppx, ppy, fx, fy, float(g['depth_scale'])]], np.float32), (F, 1))
+    res = ops.mask_bbox_choose(_dev(g['label']), _u16(g['depth']), _dev(cam), N, frame_of=_dev(np.arange(F, dtype=np.int32)),
+                               seeds=_dev(np.array([9, 10, 11], np.int64)))
+    bbox, choose, cloud = res['bbox'].cpu().numpy(), res['choose'].cpu().numpy(), res['cloud'].cpu().numpy()
+    assert np.array_equal(bbox, g['bbox'].astype(bbox.dtype))
+    assert np.array_equal(choose[2], g['choose'][2]) and np.array_equal(cloud[2].view(np.uint32), g['cloud'][2].view(np.uint32))
+    for i in (0, 1):
+        mask = (g['label'][i] == 255) & (g['depth'][i] != 0)
+        r0, r1, c0, c1 = (int(v) for v in g['bbox'][i])
+        cand = np.flatnonzero(mask[r0:r1, c0:c1].ravel())
+        assert len(np.unique(choose[i])) == N and np.all(np.diff(choose[i]) > 0) and np.isin(choose[i], cand).all()

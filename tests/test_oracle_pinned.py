@@ -152,3 +152,53 @@ def test_voxel_down_sample_oracle():
     v = oicp.voxel_down_sample(p, 2.0)
     assert v.shape == (3, 3)
     assert np.allclose(sorted(v[:, 0]), sorted([0.15, 4.3, 9.9]))
+
+
+# ---- (d) geometry oracle against vectors produced by the reference's OWN dataset / get_surface code
+#      (oracle/gen_golden_geometry.py: DenseFusion/datasets/myDatasetAugmented/dataset.py, pc_reconstruction/open3d_utils.py)
+def test_geometry_bbox_golden(golden_dir):
+    from oracle import geometry as og
+    g = _g(golden_dir, 'geometry_ref.npz')
+    for (r0, r1, c0, c1), want in zip(g['rects'], g['rect_bbox']):
+        m = np.zeros((480, 640), bool); m[r0:r1, c0:c1] = True
+        assert tuple(int(v) for v in og.get_bbox(m)) == tuple(int(v) for v in want)
+    for i in range(len(g['bbox'])):
+        assert tuple(int(v) for v in og.get_bbox(g['label'][i] == 255)) == tuple(int(v) for v in g['bbox'][i])
+
+
+def test_geometry_choose_and_backprojection_golden(golden_dir):
+    """dataset.py:236-275 run by the reference itself (np.random.seed(s) before each sample): the oracle must reproduce
+    `choose` exactly (shuffle branch for frames 0/1, 'wrap' branch for frame 2) and the fp32 cloud bit for bit."""
+    from oracle import geometry as og
+    g = _g(golden_dir, 'geometry_ref.npz')
+    ppx, ppy, fx, fy = (float(v) for v in g['intr'])
+    N = int(g['num_pt'])
+    branches = set()
+    for i, s in enumerate(g['seeds']):
+        depth, mask = g['depth'][i], g['label'][i] == 255
+        bbox = og.get_bbox(mask)
+        cand = og.choose_candidates(mask, depth, bbox)
+        keep = og.make_keep(len(cand), N, np.random.RandomState(int(s))) if len(cand) > N else None
+        branches.add(keep is None)
+        choose = og.choose_fixed(cand, N, keep)
+        assert np.array_equal(choose, g['choose'][i])
+        cloud = og.backproject_choose(depth, bbox, choose, ppx, ppy, fx, fy, float(g['depth_scale']))
+        assert cloud.dtype == np.float32 and np.array_equal(cloud.view(np.uint32), g['cloud'][i].view(np.uint32))
+    assert branches == {True, False}
+
+
+def test_geometry_surface_golden(golden_dir):
+    """open3d_utils.py:171-192 run by the reference itself: same points, same (row-major) order, bit for bit in fp64 for
+    the literal restatement; the vectorised form (what the GPU tests use at full size) within 1e-9 mm."""
+    from oracle import geometry as og
+    g = _g(golden_dir, 'geometry_ref.npz')
+    intr = dict(zip(('ppx', 'ppy', 'fx', 'fy'), (float(v) for v in g['intr'])))
+    off = np.concatenate([[0], np.cumsum(g['surf_n'])])
+    for i in range(len(g['surf_n'])):
+        want = g['surf_pts'][off[i]:off[i + 1]]
+        depth = g['depth'][i].astype(np.float64)
+        vec, pix = og.surface_backproject(g['label'][i], depth, intr, g['robot2cam'])
+        assert vec.shape == want.shape and np.abs(vec - want).max() < 1e-9
+        if i == 2:      # small frame: the literal per-pixel loop is cheap
+            lit, pix_l = og.surface_backproject_literal(g['label'][i], depth, intr, g['robot2cam'])
+            assert np.array_equal(lit, want) and np.array_equal(pix, pix_l)
