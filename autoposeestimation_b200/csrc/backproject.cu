@@ -41,20 +41,28 @@ backproject_choose_kernel(const uint16_t* __restrict__ depth, int n_frames, int 
 }
 
 // ---------------------------------------------------------------------------------- a4
-// Two embarrassingly parallel kernels, no inter-CTA waiting:
+// Three kernels, no inter-CTA waiting:
 //   surface_mask_kernel : pure stream over label + depth (the 921 600 B/frame of SURVEY 8d).  Each thread owns 32
 //                         consecutive pixels (2 x 16 B of label, 4 x 16 B of depth, streaming loads), builds a 32-bit
-//                         validity mask, writes it (4 B per 96 B read) and the CTA writes its chunk's pop-count.
-//   surface_emit_kernel : per 8192-pixel chunk with at least one valid pixel: base offset = sum of the counts of the
-//                         chunks before it in the same view (<= 37 words), block scan of the mask pop-counts, compaction
-//                         of the in-chunk offsets into shared memory (row-major = np.where order), then ALL threads
-//                         convert the compacted pixels (balanced fp64 work, contiguous 24-byte point stores).  Depth is
-//                         re-read only for valid pixels.
+//                         validity mask and writes it (4 B per 96 B read); each WARP writes the pop-count of its
+//                         1024-pixel span ("sub-chunk").  5.9 TB/s = 89 % of the measured HBM peak.
+//   surface_scan_kernel : one warp per view: exclusive prefix of the view's sub-chunk counts (= first output slot of
+//                         every sub-chunk), the view total, and a global list of the NON-EMPTY sub-chunks (3 of 4 are
+//                         empty: the object covers a fraction of the frame).
+//   surface_emit_kernel : persistent warps over that list, one task = one non-empty sub-chunk, no block-level state,
+//                         no compaction list: lane l converts pixel 32 w + l of word w when its bit is set and writes
+//                         it to slot = first slot + (valid pixels before word w) + (set bits below l) -- the row-major
+//                         order of np.where.  Depth is re-read only for non-empty 32-pixel words.
 // History (profiles/): one CTA per view walking the frame = 1.35 TB/s (latency-bound); single-pass chunked kernels
-// with a decoupled look-back = 1.5 TB/s, and 0.16 TB/s when made persistent (convoy on the look-back flags).
+// with a decoupled look-back = 1.5 TB/s, and 0.16 TB/s when made persistent (convoy on the look-back flags); mask +
+// one emit CTA per 8192-pixel chunk with a shared-memory compaction list (3 of 4 CTAs empty, two block barriers, two
+// fp64 divisions and one integer division per pixel: 69 us of emit for 512 frames) = 3.5 TB/s; this version (40 us of
+// emit: the prologue of the empty CTAs / warps was 40 % of all stall samples) = 4.7 TB/s for the whole call.
 constexpr int kSurfThreads = 256;
-constexpr int kSurfPix = 32;                       // pixels per thread
-constexpr int kSurfChunk = kSurfThreads * kSurfPix;   // 8192 pixels = 24 KB of input per CTA
+constexpr int kSurfPix = 32;                          // pixels per thread
+constexpr int kSurfSub = 32 * kSurfPix;               // 1024 pixels per warp = one sub-chunk
+constexpr int kSurfChunk = kSurfThreads * kSurfPix;   // 8192 pixels = 24 KB of input per mask CTA
+constexpr int kSurfWarps = kSurfThreads / 32;
 
 struct SurfRegs { uint4 l0, l1, d0, d1, d2, d3; };
 
@@ -82,26 +90,27 @@ __device__ __forceinline__ void surf_load(SurfRegs& r, const uint8_t* lab, const
     }
 }
 
-// 4 label bytes -> 4 bits (bit i set when byte i matches: != 0 if want == 0 else == want), SIMD-in-register
+// 4 label bytes -> 4 bits (bit i set when byte i matches: == want, or != 0 when want == 0).  Exact zero-byte test on
+// x = w ^ want4: ((x & 0x7f..) + 0x7f..) | x has the top bit of a byte clear only when the byte is zero (no carries
+// between bytes); plain integer ops instead of the emulated SIMD-video intrinsics.
 __device__ __forceinline__ uint32_t label_bits(uint32_t w, uint32_t want4) {
-    // __vcmpeq4 gives 0xff per equal byte; want4 = want replicated (0 -> "byte == 0", inverted below)
-    const uint32_t eq = __vcmpeq4(w, want4);
-    const uint32_t hit = want4 ? eq : ~eq;                 // want == 0: label != 0
-    // gather the top bit of each byte into bits 0..3
-    return ((hit & 0x80808080u) * 0x00204081u) >> 28;
+    const uint32_t x = w ^ want4;
+    const uint32_t nz = (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;      // 0x80 per NON-zero byte of x
+    const uint32_t hit = want4 ? (nz ^ 0x80808080u) : nz;                          // want == 0: label != 0
+    return (hit * 0x00204081u) >> 28;                                              // top bits of the 4 bytes -> bits 0..3
 }
 __device__ __forceinline__ uint32_t depth_bits(uint32_t w) {
-    const uint32_t nz = ~__vcmpeq2(w, 0u);                 // 0xffff per non-zero half
-    return ((nz >> 15) & 1u) | ((nz >> 30) & 2u);
+    const uint32_t nz = (((w & 0x7fff7fffu) + 0x7fff7fffu) | w) & 0x80008000u;      // 0x8000 per non-zero half
+    return ((nz >> 15) | (nz >> 30)) & 3u;
 }
 
-// work layout: counts [n_views * n_chunks] int32, then masks [n_views * n_chunks * 256] u32 (one bit per pixel)
+// work layout: sub_count [n_views * n_chunks * 8] int32 (valid pixels per 1024-pixel span), then
+//              masks [n_views * n_chunks * 256] u32 (one bit per pixel)
 __global__ void __launch_bounds__(kSurfThreads, 4)
 surface_mask_kernel(const uint8_t* __restrict__ label, const uint16_t* __restrict__ depth, int npix,
                     const int32_t* __restrict__ frame_of, const uint8_t* __restrict__ label_value,
-                    int32_t* __restrict__ chunk_count, uint32_t* __restrict__ masks, int n_chunks)
+                    int32_t* __restrict__ sub_count, uint32_t* __restrict__ masks, int n_chunks, int32_t* __restrict__ n_tasks)
 {
-    __shared__ int s_warp_tot[kSurfThreads / 32];
     const int tile = blockIdx.x;
     const int v = tile / n_chunks, c = tile - v * n_chunks;
     const int f = frame_of ? frame_of[v] : v;
@@ -119,90 +128,149 @@ surface_mask_kernel(const uint8_t* __restrict__ label, const uint16_t* __restric
     for (int i = 0; i < 16; ++i) dmask |= depth_bits(dw[i]) << (2 * i);
     mask &= dmask;
     masks[(size_t)tile * kSurfThreads + threadIdx.x] = mask;
+    if (tile == 0 && threadIdx.x == 0) *n_tasks = 0;        // consumed by surface_scan_kernel (next launch on the stream)
     const int cnt = warp_sum(__popc(mask));
-    if ((threadIdx.x & 31) == 0) s_warp_tot[threadIdx.x >> 5] = cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-#pragma unroll
-        for (int w = 0; w < kSurfThreads / 32; ++w) t += s_warp_tot[w];
-        chunk_count[tile] = t;
-    }
+    if ((threadIdx.x & 31) == 0) sub_count[(size_t)tile * kSurfWarps + (threadIdx.x >> 5)] = cnt;
 }
 
-__global__ void __launch_bounds__(kSurfThreads)
-surface_emit_kernel(const uint16_t* __restrict__ depth, int H, int W, const int32_t* __restrict__ frame_of,
-                    const double* __restrict__ cam, const double* __restrict__ robot2cam, int capacity,
-                    double* __restrict__ points, int32_t* __restrict__ pixel_index, int32_t* __restrict__ counts,
-                    const int32_t* __restrict__ chunk_count, const uint32_t* __restrict__ masks, int n_chunks)
+// One warp per view: exclusive prefix of the view's sub-chunk counts -> the view total, and one task record
+// {view, sub-chunk, first output slot, valid pixels} per NON-EMPTY sub-chunk appended to a global list (the order of the
+// list does not matter: every task knows its output slots).  work[0] (task counter) is zeroed by the mask kernel.
+__global__ void __launch_bounds__(256)
+surface_scan_kernel(const int32_t* __restrict__ sub_count, int32_t* __restrict__ counts, int32_t* __restrict__ n_tasks,
+                    int4* __restrict__ tasks, int n_sub, int n_views)
 {
-    __shared__ uint16_t s_list[kSurfChunk];                // compacted in-chunk offsets of the valid pixels
-    __shared__ int s_warp_tot[kSurfThreads / 32];
-    __shared__ int s_base;
-    __shared__ double s_par[16];                           // robot2cam rows 0..2 (12) + ppx, ppy, fx, fy
-    const int tile = blockIdx.x;
-    const int v = tile / n_chunks, c = tile - v * n_chunks;
-    const int total = chunk_count[tile];
-    if (total == 0 && c != n_chunks - 1) return;           // nothing to emit (uniform across the CTA)
+    __shared__ int s_ne[8], s_base;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int v = blockIdx.x * 8 + warp;
+    const bool live = v < n_views;                          // (whole warps; dead warps still meet the block barriers)
+    const int32_t* c = sub_count + (size_t)(live ? v : 0) * n_sub;
+    // all counts of the view are fetched up front (independent loads: one memory round trip); frames of more than
+    // 32 * kScanRegs sub-chunks (512 Ki pixels) read the rest inside the loops
+    constexpr int kScanRegs = 16;
+    int xr[kScanRegs];
+#pragma unroll
+    for (int k = 0; k < kScanRegs; ++k) xr[k] = (live && 32 * k + lane < n_sub) ? c[32 * k + lane] : 0;
+    // number of non-empty sub-chunks per view -> ONE atomic per CTA reserves the task slots of its 8 views
+    // (same-address atomics with a return value serialise: one per view cost 8 us for 512 views)
+    int ne = 0;
+#pragma unroll
+    for (int k = 0; k < kScanRegs; ++k) ne += xr[k] != 0;
+    if (live) for (int j = 32 * kScanRegs + lane; j < n_sub; j += 32) ne += c[j] != 0;
+    ne = warp_sum(ne);
+    if (lane == 0) s_ne[warp] = ne;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += s_ne[w];
+        s_base = tot ? atomicAdd(n_tasks, tot) : 0;
+    }
+    __syncthreads();
+    if (!live) return;
+    int tbase = s_base;
+    for (int w = 0; w < warp; ++w) tbase += s_ne[w];
+    int carry = 0;
+    auto round = [&](int j, int x) {
+        int incl = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t nz = __ballot_sync(0xffffffffu, x != 0);
+        if (x) tasks[tbase + __popc(nz & ((1u << lane) - 1u))] = make_int4(v, j, carry + incl - x, x);
+        tbase += __popc(nz);
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    };
+#pragma unroll
+    for (int k = 0; k < kScanRegs; ++k)
+        if (32 * k < n_sub) round(32 * k + lane, xr[k]);
+    for (int j0 = 32 * kScanRegs; j0 < n_sub; j0 += 32) round(j0 + lane, j0 + lane < n_sub ? c[j0 + lane] : 0);
+    if (lane == 0) counts[v] = carry;
+}
+
+// Persistent warps over the task list (one task = one non-empty 1024-pixel sub-chunk), no block-level state.  Two
+// dependent memory round trips per task: (task record + mask word), then the depth of the non-empty 32-pixel words
+// (64 B per lane, all in flight together, parked in shared memory); the conversion loop itself touches no global memory
+// except its stores.
+// Word by word (non-empty words only, warp-uniform): lane l converts pixel 32 w + l when its bit is set and writes it
+// to slot = offset + pre(w) + (set bits below l) -- the row-major order of np.where without a compaction list.  Object
+// interiors are dense, so most words keep all 32 lanes busy.
+constexpr int kEmitWarps = 8;
+__global__ void __launch_bounds__(kEmitWarps * 32)
+surface_emit_kernel(const uint16_t* __restrict__ depth, int npix, int W, const int32_t* __restrict__ frame_of,
+                    const double* __restrict__ cam, const double* __restrict__ robot2cam, int capacity,
+                    double* __restrict__ points, int32_t* __restrict__ pixel_index,
+                    const int32_t* __restrict__ n_tasks_p, const int4* __restrict__ tasks, const uint32_t* __restrict__ masks, int n_sub)
+{
+    __shared__ __align__(16) uint16_t s_dep[kEmitWarps][kSurfSub];
+    __shared__ double s_parw[kEmitWarps][16];              // robot2cam rows 0..2 (12) + ppx, ppy, fx, fy
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (warp == 0) {                                       // base = valid pixels of the chunks before this one
-        int sum = 0;
-        for (int j = lane; j < c; j += 32) sum += chunk_count[v * n_chunks + j];
-        sum = warp_sum(sum);
-        if (lane == 0) {
-            s_base = sum;
-            if (c == n_chunks - 1) counts[v] = sum + total;
+    const int n_tasks = *n_tasks_p;
+    const uint32_t w_inv = (uint32_t)(0x100000000ull / (uint32_t)W);   // floor(2^32 / W): row estimate is exact or one short
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const double* par = s_parw[warp];
+    for (int t = blockIdx.x * kEmitWarps + warp; t < n_tasks; t += gridDim.x * kEmitWarps) {
+        const int4 task = tasks[t];
+        const int v = task.x, j = task.y, off = task.z;
+        if (off >= capacity) continue;                      // warp-uniform
+        const uint32_t mk = masks[((size_t)v * n_sub + j) * 32 + lane];   // lane l: validity of pixels [32 l, 32 l + 32)
+        const int f = frame_of ? frame_of[v] : v;
+        const uint16_t* dep = depth + (size_t)f * npix;
+        const int p0 = j * kSurfSub;
+        __syncwarp();                                       // previous task's readers of s_dep / s_parw are done
+        if (mk) {
+            const int p = p0 + 32 * lane;
+            uint4* dst = reinterpret_cast<uint4*>(&s_dep[warp][32 * lane]);
+            if (p + 32 <= npix) {
+                const uint4 a = ld_stream16(dep + p), b = ld_stream16(dep + p + 8), c = ld_stream16(dep + p + 16), d = ld_stream16(dep + p + 24);
+                dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d;
+            } else {
+                for (int i = 0; i < 32; ++i) s_dep[warp][32 * lane + i] = p + i < npix ? dep[p + i] : (uint16_t)0;
+            }
         }
-    } else if (warp == 1 && lane < 16) {
-        s_par[lane] = lane < 12 ? robot2cam[16 * v + lane] : cam[4 * v + (lane - 12)];
-    }
-    if (total == 0) return;
-    const uint32_t mask = masks[(size_t)tile * kSurfThreads + threadIdx.x];
-    const int cnt = __popc(mask);
-    int incl = cnt;                                        // warp inclusive scan
+        if (lane < 16) s_parw[warp][lane] = lane < 12 ? robot2cam[16 * (size_t)v + lane] : cam[4 * (size_t)v + (lane - 12)];
+        __syncwarp();
+        const double ppx = par[12], ppy = par[13], fx = par[14], fy = par[15];
+        const double rfx = 1.0 / fx, rfy = 1.0 / fy;
+        double* out = points + (size_t)v * capacity * 3;
+        int32_t* opix = pixel_index ? pixel_index + (size_t)v * capacity : nullptr;
+        const int pc = __popc(mk);
+        int incl = pc;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp_tot[warp] = incl;
-    __syncthreads();
-    int before = 0;
-#pragma unroll
-    for (int w = 0; w < kSurfThreads / 32; ++w) before += (w < warp) ? s_warp_tot[w] : 0;
-    {
-        int slot = before + incl - cnt;
-        uint32_t m = mask;
-        while (m) {
-            const int i = __ffs(m) - 1;
-            m &= m - 1;
-            s_list[slot++] = (uint16_t)(threadIdx.x * kSurfPix + i);
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
         }
-    }
-    __syncthreads();
-    const int f = frame_of ? frame_of[v] : v;
-    const uint16_t* dep = depth + (size_t)f * H * W;
-    const int p0 = c * kSurfChunk;
-    const int base = s_base;
-    const double* T = s_par;
-    const double ppx = s_par[12], ppy = s_par[13], fx = s_par[14], fy = s_par[15];
-    double* out = points + (size_t)v * capacity * 3;
-    int32_t* opix = pixel_index ? pixel_index + (size_t)v * capacity : nullptr;
-    for (int i = threadIdx.x; i < total; i += kSurfThreads) {
-        const int slot = base + i;
-        if (slot >= capacity) break;
-        const int pix = p0 + (int)s_list[i];
-        const int r = pix / W, col = pix - r * W;
-        const double z = (double)dep[pix];
-        // open3d_utils.py:185-189: p0 = ((px-ppx)*z)/fx, p1 = ((py-ppy)*z)/fy (fp64, rounded per op)
-        const double x = __ddiv_rn(__dmul_rn(__dsub_rn((double)col, ppx), z), fx);
-        const double y = __ddiv_rn(__dmul_rn(__dsub_rn((double)r, ppy), z), fy);
-        // robot2cam * [x y z 1]^T (:190-192)
-        double* o = out + (size_t)slot * 3;
-        o[0] = fma(T[0], x, fma(T[1], y, fma(T[2], z, T[3])));
-        o[1] = fma(T[4], x, fma(T[5], y, fma(T[6], z, T[7])));
-        o[2] = fma(T[8], x, fma(T[9], y, fma(T[10], z, T[11])));
-        if (opix) opix[slot] = pix;
+        const int pre = incl - pc;                          // valid pixels of the span before word `lane`
+        uint32_t words = __ballot_sync(0xffffffffu, pc != 0);
+        while (words) {
+            const int w = __ffs(words) - 1;
+            words &= words - 1;
+            const uint32_t wd = __shfl_sync(0xffffffffu, mk, w);
+            const int slot = off + __shfl_sync(0xffffffffu, pre, w) + __popc(wd & lt_mask);
+            if (!((wd >> lane) & 1u) || slot >= capacity) continue;
+            const int pix = p0 + 32 * w + lane;
+            const double z = (double)s_dep[warp][32 * w + lane];
+            uint32_t r = __umulhi((uint32_t)pix, w_inv);
+            uint32_t col = (uint32_t)pix - r * (uint32_t)W;
+            if (col >= (uint32_t)W) { col -= (uint32_t)W; ++r; }
+            // open3d_utils.py:185-189: p0 = ((px-ppx)*z)/fx, p1 = ((py-ppy)*z)/fy (fp64, rounded per op).  The two
+            // divisions by the per-view constants are reciprocal + two fma residual corrections (the second one starts
+            // from a faithful quotient, so the result is the correctly rounded quotient)
+            const double ax = __dmul_rn(__dsub_rn((double)col, ppx), z);
+            const double ay = __dmul_rn(__dsub_rn((double)r, ppy), z);
+            double x = ax * rfx, y = ay * rfy;
+            x = fma(fma(-x, fx, ax), rfx, x); y = fma(fma(-y, fy, ay), rfy, y);
+            x = fma(fma(-x, fx, ax), rfx, x); y = fma(fma(-y, fy, ay), rfy, y);
+            // robot2cam * [x y z 1]^T (:190-192)
+            double* o = out + (size_t)slot * 3;
+            o[0] = fma(par[0], x, fma(par[1], y, fma(par[2], z, par[3])));
+            o[1] = fma(par[4], x, fma(par[5], y, fma(par[6], z, par[7])));
+            o[2] = fma(par[8], x, fma(par[9], y, fma(par[10], z, par[11])));
+            if (opix) opix[slot] = pix;
+        }
     }
 }
 
@@ -229,7 +297,8 @@ extern "C" __attribute__((visibility("default"))) size_t ape_surface_work_bytes(
 {
     const size_t chunks = ((size_t)(height > 0 ? height : 0) * (size_t)(width > 0 ? width : 0) + ape::kSurfChunk - 1) / ape::kSurfChunk;
     const size_t tiles = (size_t)(n_views > 0 ? n_views : 0) * chunks;
-    return 4 * tiles + 4 * tiles * ape::kSurfThreads;        // chunk counts + one mask bit per pixel
+    // task counter (16 B) + one int4 task record and one count per 1024-pixel span + one mask bit per pixel
+    return 16 + (16 + 4) * tiles * ape::kSurfWarps + 4 * tiles * ape::kSurfThreads;
 }
 
 extern "C" __attribute__((visibility("default"))) int ape_surface_backproject(const uint8_t* label, const uint16_t* depth, int n_frames, int height,
@@ -244,25 +313,37 @@ extern "C" __attribute__((visibility("default"))) int ape_surface_backproject(co
     APE_REQUIRE((size_t)height * width < (1u << 30), "ape_surface_backproject: frame too large");
     APE_REQUIRE((((uintptr_t)label) & 15) == 0 && (((uintptr_t)depth) & 15) == 0,
                 "ape_surface_backproject: label/depth must be 16-byte aligned");
-    APE_REQUIRE((((uintptr_t)work) & 3) == 0, "ape_surface_backproject: work must be 4-byte aligned");
+    APE_REQUIRE((((uintptr_t)work) & 15) == 0, "ape_surface_backproject: work must be 16-byte aligned");
     if (n_views == 0) return APE_OK;
     const int n_chunks = (int)(((size_t)height * width + ape::kSurfChunk - 1) / ape::kSurfChunk);
     APE_REQUIRE((size_t)n_views * n_chunks < (1u << 31), "ape_surface_backproject: too many views (split the batch)");
     cudaStream_t s = (cudaStream_t)stream;
     const int n_tiles = n_views * n_chunks;
-    int32_t* chunk_count = reinterpret_cast<int32_t*>(work);
-    uint32_t* masks = reinterpret_cast<uint32_t*>(work) + n_tiles;
+    // work: [task counter + 3 pad words | task records int4 | sub-chunk counts | mask words]
+    const int n_sub = n_chunks * ape::kSurfWarps;            // 1024-pixel spans per view (the last ones may be empty padding)
+    const size_t n_span = (size_t)n_views * n_sub;
+    int32_t* n_tasks = reinterpret_cast<int32_t*>(work);
+    int4* tasks = reinterpret_cast<int4*>(work) + 1;
+    int32_t* sub_count = reinterpret_cast<int32_t*>(tasks + n_span);
+    uint32_t* masks = reinterpret_cast<uint32_t*>(sub_count + n_span);
     {
         ape::ProfScope prof_("surface_mask", s);
         ape::surface_mask_kernel<<<n_tiles, ape::kSurfThreads, 0, s>>>(label, depth, height * width, frame_of, label_value,
-                                                                       chunk_count, masks, n_chunks);
+                                                                       sub_count, masks, n_chunks, n_tasks);
         ape::count_launch();
     }
     int rc = ape::check_launch("ape_surface_backproject (mask)");
     if (rc) return rc;
+    {
+        ape::ProfScope prof_("surface_scan", s);
+        ape::surface_scan_kernel<<<(n_views + 7) / 8, 256, 0, s>>>(sub_count, counts, n_tasks, tasks, n_sub, n_views);
+        ape::count_launch();
+    }
     ape::ProfScope prof_("surface_emit", s);
-    ape::surface_emit_kernel<<<n_tiles, ape::kSurfThreads, 0, s>>>(depth, height, width, frame_of, cam, robot2cam, capacity, points,
-                                                                   pixel_index, counts, chunk_count, masks, n_chunks);
+    const size_t want_ctas = (n_span + ape::kEmitWarps - 1) / ape::kEmitWarps;      // at most one task per warp is ever needed
+    const size_t max_ctas = (size_t)ape::sm_count() * 8;
+    ape::surface_emit_kernel<<<(unsigned)(want_ctas < max_ctas ? want_ctas : max_ctas), ape::kEmitWarps * 32, 0, s>>>(
+        depth, height * width, width, frame_of, cam, robot2cam, capacity, points, pixel_index, n_tasks, tasks, masks, n_sub);
     ape::count_launch();
     return ape::check_launch("ape_surface_backproject (emit)");
 }

@@ -206,12 +206,20 @@ def icp_leg(torch, ops, lib, peaks, steps):
         pts, _, cnt = ops.surface_backproject(label, depth, cam, r2c, capacity=cap, want_pixels=False)
     torch.cuda.synchronize()
     rep = profile_report(lib); lib.ape_profile_enable(0)
-    ms_bp = (rep['surface_mask'][1] + rep['surface_emit'][1]) / rep['surface_mask'][0]      # two kernels per call
-    ms_mask = rep['surface_mask'][1] / rep['surface_mask'][0]
+    ms_kernels = {k: rep[k][1] / rep[k][0] for k in ('surface_mask', 'surface_scan', 'surface_emit') if k in rep}
+    # the launch as a whole (mask + scan + emit back to back, gaps included), CUDA events on the launching stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_bp = min(max(steps, 4), 50)
+    e0.record()
+    for _ in range(n_bp):
+        pts, _, cnt = ops.surface_backproject(label, depth, cam, r2c, capacity=cap, want_pixels=False)
+    e1.record(); torch.cuda.synchronize()
+    ms_bp = e0.elapsed_time(e1) / n_bp
     nvalid = int(cnt.sum())
     bytes_bp = F * H * W * 3 + nvalid * 24
-    bp = dict(frames_per_s=F / ms_bp * 1e3, ms_per_launch=ms_bp, ms_mask_kernel=ms_mask, frames_per_launch=F,
-              kernels='surface_mask_kernel (stream label+depth -> validity bits) + surface_emit_kernel (ordered compaction, fp64 points)',
+    bp = dict(frames_per_s=F / ms_bp * 1e3, ms_per_launch=ms_bp, ms_per_kernel=ms_kernels, frames_per_launch=F,
+              kernels='surface_mask_kernel (stream label+depth -> validity bits) + surface_scan_kernel (slot prefix, list of non-empty '
+                      '1024-pixel spans) + surface_emit_kernel (persistent warps, ordered fp64 points)',
               roofline=dict(bound='hbm', achieved=bytes_bp / ms_bp / 1e6, peak=peaks['hbm'], unit='GB/s',
                             frac=bytes_bp / ms_bp / 1e6 / peaks['hbm'], traffic=None, peak_source=peaks['src'],
                             algorithmic_bytes_per_launch=bytes_bp))

@@ -95,7 +95,7 @@ int ape_mask_bbox_choose(const uint8_t* label, const uint16_t* depth, int n_fram
  *   pixel_index  [n_views,capacity] int32 flat pixel index of every emitted point, or NULL
  *   counts       [n_views] int32 out: number of valid pixels (may exceed capacity: the excess is dropped,
  *                the caller checks)
- *   work         scratch of ape_surface_work_bytes(n_views, height, width) bytes (4-byte aligned; the call
+ *   work         scratch of ape_surface_work_bytes(n_views, height, width) bytes (16-byte aligned; the call
  *                does not need it initialised): per-chunk valid-pixel counts + one validity bit per pixel           */
 size_t ape_surface_work_bytes(int n_views, int height, int width);
 int ape_surface_backproject(const uint8_t* label, const uint16_t* depth, int n_frames, int height, int width,
