@@ -3,10 +3,12 @@
 // pc_reconstruction/open3d_utils.py:76-104 (open3d 0.9.0 semantics restated in oracle/icp.py).
 //
 // Per registration:
-//   build   : uniform grid over the (fixed) target cloud, cell >= threshold, counting sort of the
+//   build   : uniform grid over the (fixed) target cloud, cells of half the threshold (two-cell reach) when that fits
+//             the 4096-cell budget, else cells >= threshold (one-cell reach); counting sort of the
 //             target into cell order (scratch in global memory: read-only afterwards, L1/L2-resident)
-//   iterate : [apply update to the working source cloud] -> nearest target point in the 27
-//             neighbouring cells (fp64, d2=(dx*dx+dy*dy)+dz*dz, strict d2<r2, lowest original index on
+//   iterate : [apply update to the working source cloud] -> nearest target point: own cell first, then the
+//             neighbouring cells that can still beat the running best
+//             (fp64, d2=(dx*dx+dy*dy)+dz*dz, strict d2<r2, lowest original index on
 //             exact ties) -> block reduction of n, sum d2, sum p, sum q -> fitness / rmse / stop rule
 //             -> centred 3x3 covariance (second pass over the stored correspondences) -> one-thread
 //             fp64 Jacobi SVD (Kabsch / Eigen::umeyama without scaling) -> T = update * T
@@ -16,9 +18,16 @@
 
 namespace ape {
 
-// (dy, dz) of the nine x-runs around a cell, centre first, then faces, then edges
-__constant__ signed char c_run_dy[9] = {0, -1, 1, 0, 0, -1, 1, -1, 1};
-__constant__ signed char c_run_dz[9] = {0, 0, 0, -1, 1, -1, -1, 1, 1};
+// Search steps around the query's cell, nearest first.  Step 0 = the query's own cell, 1 / 2 = the cells to its left /
+// right in the same x-row, 3.. = the other x-rows (dy, dz), ordered by distance; steps 0..10 are the 3 x 3 neighbourhood
+// (one-cell reach), 11..26 complete the 5 x 5 neighbourhood (two-cell reach).
+constexpr int kIcpSteps = 27;
+constexpr int kIcpSteps1 = 11;
+// bit k set when step k has dy (dz) == the given offset; index = offset + 2
+__host__ __device__ constexpr uint32_t steps_dy(int i) { return i == 0 ? 0x2818800u : i == 1 ? 0x0280288u : i == 2 ? 0x0006067u : i == 3 ? 0x0500510u : 0x5061000u; }
+__host__ __device__ constexpr uint32_t steps_dz(int i) { return i == 0 ? 0x1982000u : i == 1 ? 0x00281A0u : i == 2 ? 0x000181Fu : i == 3 ? 0x0050640u : 0x6604000u; }
+__constant__ signed char c_run_dy[kIcpSteps] = {0, 0, 0,  -1, 1, 0, 0,  -1, 1, -1, 1,  -2, 2, 0, 0,  -2, -2, 2, 2, -1, 1, -1, 1,  -2, 2, -2, 2};
+__constant__ signed char c_run_dz[kIcpSteps] = {0, 0, 0,  0, 0, -1, 1,  -1, -1, 1, 1,  0, 0, -2, 2,  -1, 1, -1, 1, -2, -2, 2, 2,  -2, -2, 2, 2};
 
 constexpr int kIcpThreads = 128;      // small CTAs, several registrations per SM: one CTA's serial Kabsch/SVD step overlaps the others' searches
 constexpr int kIcpWarps = kIcpThreads / 32;
@@ -33,6 +42,7 @@ struct IcpSmem {
     double T[12];          // accumulated transform (3x4 row-major)
     double bbmin[3], bbmax[3];
     int scan_carry;
+    signed char run_dy[32], run_dz[32];   // copy of c_run_* (lanes index it with different steps: no constant-cache replays)
 };
 
 template <int K>
@@ -167,6 +177,7 @@ icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ sr
     IcpSmem& s = *reinterpret_cast<IcpSmem*>(smem_raw);
     const int tid = threadIdx.x;
     const double r2 = threshold * threshold;
+    if (tid < kIcpSteps) { s.run_dy[tid] = c_run_dy[tid]; s.run_dz[tid] = c_run_dz[tid]; }   // visible after the first barrier below
 
     for (int reg = blockIdx.x; reg < n_reg; reg += gridDim.x) {
         const int s0 = src_offset[reg], Ns = src_offset[reg + 1] - s0;
@@ -207,8 +218,12 @@ icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ sr
             s.bbmin[tid] = l; s.bbmax[tid] = h;
         }
         __syncthreads();
-        // grid geometry (uniform across the CTA)
-        double h = threshold;
+        // grid geometry (uniform across the CTA).  Cells of half the threshold with a two-cell reach when that fits the
+        // cell budget (the candidates of a query shrink from a 30 x 10 x 10 mm run to little more than its own
+        // 5 mm cell), else cells of the threshold with a one-cell reach, widened until the grid fits.
+        // reach * h > threshold by a hair, so a target within the threshold is never more than `reach` cells away.
+        int reach = 2;
+        double h = threshold * (0.5 + 1e-9);
         int dim[3];
         for (;;) {
             long cells = 1;
@@ -221,7 +236,8 @@ icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ sr
                 cells *= dim[a];
             }
             if (cells <= kIcpMaxCells) break;
-            h *= 1.25;
+            if (reach == 2) { reach = 1; h = threshold * (1.0 + 1e-9); }
+            else h *= 1.25;
         }
         const double inv_h = 1.0 / h;
         const int ncell = dim[0] * dim[1] * dim[2];
@@ -283,9 +299,7 @@ icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ sr
         bool first = true;
         for (;;) {
             // ---- (re)evaluate correspondences; the working cloud is updated in place by s.U
-            double U[12];
-#pragma unroll
-            for (int k = 0; k < 12; ++k) U[k] = s.U[k];
+            const double* U = s.U;                                // (broadcast reads: keeps 24 registers free)
             double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};            // n, sum d2, sum p(3), sum q(3)
             // The point loop is warp-uniform (every lane runs every trip, lanes past Ns are masked) so that the lanes can
             // be brought back together with a warp vote before each scan: without it each lane scanned its runs on its
@@ -303,40 +317,73 @@ icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ sr
                     wsrc[3 * i] = px; wsrc[3 * i + 1] = py; wsrc[3 * i + 2] = pz;
                 }
                 const int cx = cell_coord(px, g0, inv_h), cy = cell_coord(py, g1, inv_h), cz = cell_coord(pz, g2, inv_h);
-                // best starts at r^2: only candidates with d2 < r^2 can be accepted (open3d's strict radius test), and a
-                // run of cells whose bounding box is farther than the current best is skipped.  The centre run is
-                // scanned first, so in the common case (nearest neighbour a few mm away, 10 mm cells) the other eight
-                // runs are rejected by the box test.  Skipping needs boxdist^2 > best strictly (an exact tie in a skipped
-                // run could otherwise win on original index); delta widens the boxes against binning round-off.
+                // best starts at r^2: only candidates with d2 < r^2 can be accepted (open3d's strict radius test).  The
+                // query's own cell is scanned first; every other step is an x-row of cells that is skipped when its
+                // distance in (y, z) already exceeds the current best, and otherwise trimmed in x to the cells that can
+                // still hold a point within the best.  In the common case (nearest neighbour 1-2 mm away, 5 mm cells)
+                // that leaves the own cell and one or two neighbours.  Skipping needs boxdist^2 > best strictly (an exact
+                // tie in a skipped cell could otherwise win on original index); delta widens the cells against binning
+                // round-off; the (y, z) gaps are kept as float LOWER bounds (round-down), the x gaps in fp64.
                 double best = r2; int bpos = -1, borig = 0x7fffffff;
-                const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, dim[0] - 1);
                 const double delta = 1e-6 * h;
-                const double gx = fmax(fmax((g0 + x_lo * h - delta) - px, px - (g0 + (x_hi + 1) * h + delta)), 0.0);
-                const double gx2 = gx * gx;
-                uint32_t need = 0;                                // the runs this lane may still have to scan
-                if (live && Nt > 0 && cx >= -1 && cx <= dim[0] && cy >= -1 && cy <= dim[1] && cz >= -1 && cz <= dim[2] && x_lo <= x_hi) {
+                float sy_l1, sy_l2, sy_r1, sy_r2, sz_l1, sz_l2, sz_r1, sz_r2;
+                {
+                    const double yl = fmax(py - (g1 + cy * h) - delta, 0.0), yr = fmax((g1 + (cy + 1) * h) - py - delta, 0.0);
+                    const double zl = fmax(pz - (g2 + cz * h) - delta, 0.0), zr = fmax((g2 + (cz + 1) * h) - pz - delta, 0.0);
+                    float t;
+                    t = __double2float_rd(yl); sy_l1 = __fmul_rd(t, t); t = __double2float_rd(yl + h); sy_l2 = __fmul_rd(t, t);
+                    t = __double2float_rd(yr); sy_r1 = __fmul_rd(t, t); t = __double2float_rd(yr + h); sy_r2 = __fmul_rd(t, t);
+                    t = __double2float_rd(zl); sz_l1 = __fmul_rd(t, t); t = __double2float_rd(zl + h); sz_l2 = __fmul_rd(t, t);
+                    t = __double2float_rd(zr); sz_r1 = __fmul_rd(t, t); t = __double2float_rd(zr + h); sz_r2 = __fmul_rd(t, t);
+                }
+                const double xl = fmax(px - (g0 + cx * h) - delta, 0.0), xr = fmax((g0 + (cx + 1) * h) - px - delta, 0.0);
+                const double xl1 = xl * xl, xl2 = (xl + h) * (xl + h), xr1 = xr * xr, xr2 = (xr + h) * (xr + h);
+                uint32_t need = 0;                                // the steps this lane may still have to take
+                if (live && Nt > 0 && cx >= -reach && cx < dim[0] + reach && cy >= -reach && cy < dim[1] + reach &&
+                    cz >= -reach && cz < dim[2] + reach) {
+                    need = reach == 2 ? (1u << kIcpSteps) - 1u : (1u << kIcpSteps1) - 1u;
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) {
-                        const int yy = cy + c_run_dy[k], zz = cz + c_run_dz[k];
-                        need |= (uint32_t)(yy >= 0 && yy < dim[1] && zz >= 0 && zz < dim[2]) << k;
+                    for (int d = -2; d <= 2; ++d) {               // rows outside the grid
+                        if (cy + d < 0 || cy + d >= dim[1]) need &= ~steps_dy(d + 2);
+                        if (cz + d < 0 || cz + d >= dim[2]) need &= ~steps_dz(d + 2);
                     }
                 }
+                double pruned_at = DBL_MAX;                       // the best the bulk pruning below was last done for
                 for (;;) {
-                    // every lane advances to ITS next run that survives the box test (short loop) ...
+                    // every lane advances to ITS next step that survives the box test and holds points (short loop) ...
                     int jb = 0, je = 0;
+                    if (best < pruned_at) {                       // drop every row whose y gap or z gap alone exceeds the best
+                        pruned_at = best;
+                        if ((double)sy_l1 > best) need &= ~steps_dy(1);
+                        if ((double)sy_r1 > best) need &= ~steps_dy(3);
+                        if ((double)sy_l2 > best) need &= ~steps_dy(0);
+                        if ((double)sy_r2 > best) need &= ~steps_dy(4);
+                        if ((double)sz_l1 > best) need &= ~steps_dz(1);
+                        if ((double)sz_r1 > best) need &= ~steps_dz(3);
+                        if ((double)sz_l2 > best) need &= ~steps_dz(0);
+                        if ((double)sz_r2 > best) need &= ~steps_dz(4);
+                    }
                     while (need) {
                         const int k = __ffs(need) - 1;
                         need &= need - 1;
-                        const int yy = cy + c_run_dy[k], zz = cz + c_run_dz[k];
-                        const double gy = fmax(fmax((g1 + yy * h - delta) - py, py - (g1 + (yy + 1) * h + delta)), 0.0);
-                        const double gz = fmax(fmax((g2 + zz * h - delta) - pz, pz - (g2 + (zz + 1) * h + delta)), 0.0);
-                        if (!(gx2 + gy * gy + gz * gz > best)) {
-                            const int row = (zz * dim[1] + yy) * dim[0];
-                            jb = s.cell_start[row + x_lo]; je = s.cell_start[row + x_hi + 1];   // x-run is contiguous
-                            break;
-                        }
+                        const int dy = s.run_dy[k], dz = s.run_dz[k];
+                        const float fy = dy == 0 ? 0.f : (dy == -1 ? sy_l1 : (dy == 1 ? sy_r1 : (dy == -2 ? sy_l2 : sy_r2)));
+                        const float fz = dz == 0 ? 0.f : (dz == -1 ? sz_l1 : (dz == 1 ? sz_r1 : (dz == -2 ? sz_l2 : sz_r2)));
+                        const double lower = (double)fy + (double)fz;
+                        if (lower > best) continue;
+                        const double rem = best - lower;          // what is left for the x gap
+                        const int nl = (xl1 <= rem) + (reach == 2 && xl2 <= rem);
+                        const int nr = (xr1 <= rem) + (reach == 2 && xr2 <= rem);
+                        int xa = k == 0 ? cx : (k == 2 ? cx + 1 : cx - nl);
+                        int xb = k == 0 ? cx : (k == 1 ? cx - 1 : cx + nr);
+                        xa = max(xa, 0); xb = min(xb, dim[0] - 1);
+                        if (xa > xb) continue;
+                        const int row = ((cz + dz) * dim[1] + (cy + dy)) * dim[0];
+                        jb = s.cell_start[row + xa]; je = s.cell_start[row + xb + 1];   // cells of an x-row are contiguous
+                        if (je > jb) break;
                     }
                     // ... and the warp meets here, so the scans of the 32 lanes run side by side
+                    // (measured: working in rounds of four candidates across steps instead of whole runs is 8 % slower)
                     if (!__any_sync(0xffffffffu, je > jb || need != 0u)) break;
                     // groups of four candidates are reduced with min first (independent chains, no branch);
                     // only a group that reaches the running best takes the slow path with the tie rule
@@ -459,7 +506,8 @@ extern "C" __attribute__((visibility("default"))) int ape_icp_p2p(const double* 
         APE_CUDA(cudaFuncSetAttribute(ape::icp_p2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    const int grid = n_reg < ape::sm_count() * 4 ? n_reg : ape::sm_count() * 4;   // 4 resident CTAs per SM (registers); 6 with spills measured slower
+    // 4 resident CTAs per SM (128 registers); 5 / 6 with spills measured 19 % / 10 % slower
+    const int grid = n_reg < ape::sm_count() * 4 ? n_reg : ape::sm_count() * 4;
     ape::ProfScope prof_("icp_p2p", (cudaStream_t)stream);
     ape::icp_p2p_kernel<<<grid, ape::kIcpThreads, smem, (cudaStream_t)stream>>>(
         source, src_offset, target, tgt_offset, n_reg, threshold, rel_fitness, rel_rmse, max_iter, init, transform, info,
