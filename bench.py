@@ -121,7 +121,7 @@ def dist_env():
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
-def cpu_pose_frames_per_s(n_objects, threads=None, seed=7):
+def cpu_pose_frames_per_s(n_objects, threads=None, seed=7, min_seconds=0.0):
     """The reference's CPU path for this workload: per-sample torch-CPU PoseNet geometry + 2 canonical refine
     iterations + numpy pose composition (oracle port of DenseFusion/lib/network.py, tools/utils.py,
     tools/eval_linemod.py:81-114).  Returns (frames/s, seconds, threads)."""
@@ -137,12 +137,17 @@ def cpu_pose_frames_per_s(n_objects, threads=None, seed=7):
     with torch.no_grad():
         odf.canonical_prediction(sd_e, sd_r, t[0][:1], t[1][:1], t[2][:1], t[3][:1], NUM_OBJ, iterations=REFINE_ITERS)   # warm-up
         t0 = time.perf_counter()
-        for i in range(n_objects):
-            b = i % nb
-            odf.canonical_prediction(sd_e, sd_r, t[0][b:b + 1], t[1][b:b + 1], t[2][b:b + 1], t[3][b:b + 1], NUM_OBJ,
-                                     iterations=REFINE_ITERS)
-        dt = time.perf_counter() - t0
-    return n_objects / dt, dt, threads
+        done = 0
+        while True:                                            # whole multiples of n_objects until min_seconds of CPU work are in
+            for i in range(n_objects):
+                b = i % nb
+                odf.canonical_prediction(sd_e, sd_r, t[0][b:b + 1], t[1][b:b + 1], t[2][b:b + 1], t[3][b:b + 1], NUM_OBJ,
+                                         iterations=REFINE_ITERS)
+            done += n_objects
+            dt = time.perf_counter() - t0
+            if dt >= min_seconds:
+                break
+    return done / dt, dt, threads
 
 
 def run_reference(args):
@@ -183,13 +188,18 @@ def profile_report(lib):
     return out
 
 
-def icp_leg(torch, ops, lib, peaks, steps):
-    """Extra leg (BASELINE configs 1/4): (a) masked back-projection over 512 distinct 640x480 frames (HBM roofline),
-    (b) voxel grid + point-to-point ICP of 1184 registrations built from 32 rendered frames."""
+def icp_leg(torch, ops, lib, peaks, steps, rank=0, world=1, sync=None, reduce_max=None):
+    """Extra leg (BASELINE configs 1/4), run by EVERY rank on its own frames (frames are independent: no collective on the
+    data path; `sync` = barrier + device synchronize, `reduce_max` = max over ranks of a list of floats):
+    (a) masked back-projection over 512 distinct 640x480 frames per rank (HBM roofline),
+    (b) voxel grid + point-to-point ICP of 1184 registrations per rank built from 32 rendered frames.
+    Whole-job rates = world * per-rank units / max-over-ranks device time."""
     from autoposeestimation_b200 import synthetic as synth
-    dev = 'cuda'
+    sync = sync or torch.cuda.synchronize
+    reduce_max = reduce_max or (lambda v: v)
+    dev = torch.device('cuda', torch.cuda.current_device())
     F, H, W = 512, 480, 640                                   # 512 * 921 600 B = 472 MB > L2
-    g = torch.Generator(device=dev).manual_seed(3)
+    g = torch.Generator(device=dev).manual_seed(3 + rank)
     yy = torch.arange(H, device=dev).view(1, H, 1).float(); xx = torch.arange(W, device=dev).view(1, 1, W).float()
     cy = torch.randint(100, 380, (F, 1, 1), device=dev, generator=g).float(); cx = torch.randint(120, 520, (F, 1, 1), device=dev, generator=g).float()
     label = ((((yy - cy) / 45.0) ** 2 + ((xx - cx) / 60.0) ** 2) < 1.0).to(torch.uint8) * 255       # ~8.5 k px per frame
@@ -210,22 +220,15 @@ def icp_leg(torch, ops, lib, peaks, steps):
     # the launch as a whole (mask + scan + emit back to back, gaps included), CUDA events on the launching stream
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_bp = min(max(steps, 4), 50)
+    sync()
     e0.record()
     for _ in range(n_bp):
         pts, _, cnt = ops.surface_backproject(label, depth, cam, r2c, capacity=cap, want_pixels=False)
-    e1.record(); torch.cuda.synchronize()
-    ms_bp = e0.elapsed_time(e1) / n_bp
-    nvalid = int(cnt.sum())
-    bytes_bp = F * H * W * 3 + nvalid * 24
-    bp = dict(frames_per_s=F / ms_bp * 1e3, ms_per_launch=ms_bp, ms_per_kernel=ms_kernels, frames_per_launch=F,
-              kernels='surface_mask_kernel (stream label+depth -> validity bits) + surface_scan_kernel (slot prefix, list of non-empty '
-                      '1024-pixel spans) + surface_emit_kernel (persistent warps, ordered fp64 points)',
-              roofline=dict(bound='hbm', achieved=bytes_bp / ms_bp / 1e6, peak=peaks['hbm'], unit='GB/s',
-                            frac=bytes_bp / ms_bp / 1e6 / peaks['hbm'], traffic=None, peak_source=peaks['src'],
-                            algorithmic_bytes_per_launch=bytes_bp))
+    e1.record(); sync()
+    ms_bp_rank = e0.elapsed_time(e1) / n_bp
     # (b) registrations: 32 rendered frames -> clouds -> 2 mm voxel grid -> ICP against the 2000-pt model
     n_src = 32
-    frames = [synth.render_ellipsoid_frame(100 + i) for i in range(n_src)]
+    frames = [synth.render_ellipsoid_frame(100 + n_src * rank + i) for i in range(n_src)]
     lab = torch.from_numpy(np.stack([f['label'] for f in frames])).to(dev)
     dep = torch.from_numpy(np.stack([f['depth'] for f in frames]).view(np.int16)).to(dev)
     cam2 = cam[:n_src]; r2c2 = r2c[:n_src]
@@ -247,26 +250,62 @@ def icp_leg(torch, ops, lib, peaks, steps):
     tgt = torch.from_numpy(np.concatenate([f['model'] for f in frames])).to(dev).repeat(reps, 1)
     to = torch.arange(0, nreg + 1, device=dev, dtype=torch.int32) * 2000
     T, info = ops.icp_p2p(src, so, tgt, to, 10.0)             # warm-up
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
     n_icp = min(10, max(1, steps // 4))
+    sync()
+    e0.record()
     for _ in range(n_icp):
         T, info = ops.icp_p2p(src, so, tgt, to, 10.0)
-    e1.record(); torch.cuda.synchronize()
-    ms_icp = e0.elapsed_time(e1) / n_icp
+    e1.record(); sync()
+    ms_icp_rank = e0.elapsed_time(e1) / n_icp
+    ms_bp, ms_icp = reduce_max([ms_bp_rank, ms_icp_rank])    # max over ranks; every rank did the same amount of work
+    nvalid = int(cnt.sum())
+    bytes_bp = F * H * W * 3 + nvalid * 24                     # per rank
     iters = float(info[:, 2].mean()); ns_mean = float(np.mean(vc_h))
     bytes_icp = nreg * (24 * (ns_mean + 2000) + 128)
+    # pair evaluations a brute-force NN would need (iters * Ns * Nt), the work the grid search avoids
     t0 = time.perf_counter(); once(); torch.cuda.synchronize(); prep_ms = (time.perf_counter() - t0) * 1e3
-    return dict(backprojection=bp,
-                icp=dict(registrations_per_s=nreg / ms_icp * 1e3, ms_per_launch=ms_icp, registrations_per_launch=nreg,
-                         mean_source_points=ns_mean, target_points=2000, mean_iterations=iters,
-                         mean_fitness=float(info[:, 0].mean()), mean_rmse_mm=float(info[:, 1].mean()),
-                         roofline=dict(bound='hbm', achieved=bytes_icp / ms_icp / 1e6, peak=peaks['hbm'], unit='GB/s',
-                                       frac=bytes_icp / ms_icp / 1e6 / peaks['hbm'], traffic=None, peak_source=peaks['src'],
-                                       note='compulsory bytes 24*(Ns+Nt)+128 per registration; the NN stage is FP64-ALU bound '
-                                            '(SURVEY 8d), so this fraction is expected to be small')),
-                label_path_32_frames_ms=prep_ms)
+    out = dict(backprojection=dict(
+                   frames_per_s=world * F / ms_bp * 1e3, ms_per_launch=ms_bp, ms_per_kernel=ms_kernels, frames_per_launch=F, n_gpus=world,
+                   kernels='surface_mask_kernel (stream label+depth -> validity bits) + surface_scan_kernel (slot prefix, list of non-empty '
+                           '1024-pixel spans) + surface_emit_kernel (persistent warps, ordered fp64 points)',
+                   roofline=dict(bound='hbm', achieved=bytes_bp / ms_bp / 1e6, peak=peaks['hbm'], unit='GB/s',
+                                 frac=bytes_bp / ms_bp / 1e6 / peaks['hbm'], traffic=measured_traffic('surface_backproject'),
+                                 peak_source=peaks['src'], algorithmic_bytes_per_launch=bytes_bp,
+                                 note='per GPU; achieved = algorithmic bytes (921 600 B per frame + 24 B per valid pixel) / whole-call time')),
+               icp=dict(registrations_per_s=world * nreg / ms_icp * 1e3, ms_per_launch=ms_icp, registrations_per_launch=nreg, n_gpus=world,
+                        mean_source_points=ns_mean, target_points=2000, mean_iterations=iters,
+                        mean_fitness=float(info[:, 0].mean()), mean_rmse_mm=float(info[:, 1].mean()),
+                        roofline=dict(bound='hbm', achieved=bytes_icp / ms_icp / 1e6, peak=peaks['hbm'], unit='GB/s',
+                                      frac=bytes_icp / ms_icp / 1e6 / peaks['hbm'], traffic=measured_traffic('icp_p2p'), peak_source=peaks['src'],
+                                      note='per GPU; compulsory bytes 24*(Ns+Nt)+128 per registration; the NN stage is FP64-ALU / latency '
+                                           'bound (SURVEY 8d), so this fraction is expected to be small')),
+               label_path_32_frames_ms=prep_ms)
+    if world == 1:                                            # the reference's CPU path beside it (bounded sample, oracle port)
+        out['cpu_baseline'] = cpu_label_path(frames[:4])
+    return out
+
+
+def cpu_label_path(frames):
+    """CPU arm of the label path on a bounded sample (oracle restatement: open3d 0.9 is not installable here): per frame the
+    get_surface back-projection (vectorised numpy form of open3d_utils.py:172-192; the reference's literal per-pixel loop is
+    timed on one frame), the 2 mm voxel grid and the point-to-point ICP against the 2000-point model (scipy cKDTree)."""
+    from oracle import geometry as og, icp as oicp
+    t_bp = t_icp = 0.0
+    for fr in frames:
+        t0 = time.perf_counter()
+        pts, _ = og.surface_backproject(fr['label'], fr['depth'].astype(np.float64), fr['intr'], fr['robot2cam'])
+        t1 = time.perf_counter()
+        src = oicp.voxel_down_sample(pts, 2.0)
+        oicp.registration_icp_p2p(src, fr['model'], 10.0)
+        t2 = time.perf_counter()
+        t_bp += t1 - t0; t_icp += t2 - t1
+    fr = frames[0]
+    t0 = time.perf_counter()
+    og.surface_backproject_literal(fr['label'], fr['depth'].astype(np.float64), fr['intr'], fr['robot2cam'])
+    t_lit = time.perf_counter() - t0
+    return dict(kind='port', cores=1, sample='%d frames: numpy back-projection + voxel grid + ICP (oracle, one thread); literal per-pixel loop on 1 frame' % len(frames),
+                backprojection_frames_per_s=len(frames) / t_bp, backprojection_literal_loop_frames_per_s=1.0 / t_lit,
+                registrations_per_s=len(frames) / t_icp)
 
 
 def live_leg(torch, ops, steps):
@@ -463,6 +502,22 @@ def run_b200(args):
             train = train_leg(torch, dist, lib, peaks, world, rank, dev, args.steps)
         except Exception as ex:                               # an extra leg must never take the headline down
             train = dict(error=repr(ex))
+    # ---- label path (BASELINE configs 1/4): every rank works on its own frames, whole-job rates on rank 0
+    label_leg = None
+    if not args.no_icp:
+        def reduce_max(vals):
+            t = torch.tensor(vals, dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return [float(v) for v in t]
+        if world == 1:
+            try:
+                label_leg = icp_leg(torch, ops, lib, peaks, args.steps, 0, 1, barrier, reduce_max)
+            except Exception as ex:
+                label_leg = dict(error=repr(ex))
+        else:
+            # no try/except here: a rank that dropped out of the leg would leave the others waiting in its collectives
+            label_leg = icp_leg(torch, ops, lib, peaks, args.steps, rank, world, barrier, reduce_max)
 
     line = None
     if rank == 0:
@@ -497,13 +552,9 @@ def run_b200(args):
                  'summed GEMM kernel time; executed = 3 split-bf16 passes on padded rows with the global feature hoisted')
         # ---- CPU baseline beside it (bounded sample)
         # rank 0 at N=1 only (under torchrun OMP_NUM_THREADS=1 would make it a 1-thread number that looks like a regression)
-        cpu_fps, cpu_s, cpu_threads = cpu_pose_frames_per_s(32) if world == 1 else (None, 0.0, 0)
-        extra = None
-        if not args.no_icp:
-            try:
-                extra = icp_leg(torch, ops, lib, peaks, args.steps)
-            except Exception as ex:                           # the extra leg must never take the headline down
-                extra = dict(error=repr(ex))
+        cpu_fps, cpu_s, cpu_threads = cpu_pose_frames_per_s(32, min_seconds=10.0) if world == 1 else (None, 0.0, 0)
+        cpu_n = int(round(cpu_fps * cpu_s)) if cpu_fps else 0
+        extra = label_leg
         if train is not None:
             extra = dict(extra or {}, refiner_training=train)
         try:
@@ -521,7 +572,7 @@ def run_b200(args):
                              api='autoposeestimation_b200.densefusion.estimate_poses.Runner (pinned host buffers, copy/compute double-buffered)'),
                     gpu_launches=launches, clocks=clocks, roofline=roofline,
                     cpu_baseline=(dict(value=cpu_fps, unit='frames/s', cores=cpu_threads, kind='port',
-                                       sample='32 objects of the same workload, per-sample torch-CPU oracle port (%.1f s)' % cpu_s)
+                                       sample='%d objects of the same workload, per-sample torch-CPU oracle port (%.1f s)' % (cpu_n, cpu_s))
                                   if cpu_fps is not None else None),
                     extra=extra, checksum=float(out_host.sum()))
     if world > 1:
