@@ -247,3 +247,36 @@ def test_mask_bbox_choose_on_device_vs_reference_run(golden_dir):
         r0, r1, c0, c1 = (int(v) for v in g['bbox'][i])
         cand = np.flatnonzero(mask[r0:r1, c0:c1].ravel())
         assert len(np.unique(choose[i])) == N and np.all(np.diff(choose[i]) > 0) and np.isin(choose[i], cand).all()
+
+
+def test_surface_backproject_large_and_odd_frames():
+    """Frames larger than 512 Ki pixels (the scan kernel keeps 16 x 32 sub-chunk counts in registers and loops over the
+    rest), a frame whose size is not a multiple of the 8192-pixel chunk (ragged last chunk), several labels per frame and
+    a capacity smaller than the number of valid pixels: indices bit-exact, points within 1e-9 of the oracle."""
+    from autoposeestimation_b200 import ops
+    rng = np.random.RandomState(11)
+    for (H, W) in ((1200, 1600), (72, 1000), (16, 16)):
+        label = np.zeros((2, H, W), np.uint8)
+        label[0, H // 5:H // 2, W // 4:W // 2] = 255
+        label[0, -3:, :] = 255                                        # last rows: the ragged tail of the frame
+        label[0, 0, :7] = 255
+        label[1, H // 3:, : W // 3] = 9
+        depth = rng.randint(0, 3000, size=(2, H, W)).astype(np.uint16)
+        depth[rng.rand(2, H, W) < 0.1] = 0
+        intr = dict(ppx=W / 2 - 0.3, ppy=H / 2 + 0.2, fx=611.5, fy=612.25)
+        r2c = synth.hand_eye()
+        views = [(0, 255), (1, 9), (0, 9)]                             # the last one has no pixel at all
+        cam = np.tile(np.array([[intr['ppx'], intr['ppy'], intr['fx'], intr['fy']]]), (len(views), 1))
+        want = [og.surface_backproject(label[f] == v, depth[f].astype(np.float64), intr, r2c) for f, v in views]
+        cap = max(len(w[1]) for w in want) + 5
+        for capacity in (cap, max(1, len(want[0][1]) // 2)):
+            pts, pix, cnt = ops.surface_backproject(_dev(label), _u16(depth), _dev(cam), _dev(np.tile(r2c[None], (len(views), 1, 1))),
+                                                    capacity=capacity, frame_of=_dev(np.array([f for f, _ in views], np.int32)),
+                                                    label_value=_dev(np.array([v for _, v in views], np.uint8)))
+            pts = pts.cpu().numpy(); pix = pix.cpu().numpy(); cnt = cnt.cpu().numpy()
+            for i, (wp, wi) in enumerate(want):
+                assert cnt[i] == len(wi)                                # the count is the full number of valid pixels
+                n = min(len(wi), capacity)
+                assert np.array_equal(pix[i, :n], wi[:n].astype(np.int32))
+                if n:
+                    assert np.abs(pts[i, :n] - wp[:n]).max() < 1e-9

@@ -91,6 +91,28 @@ def test_icp_large_grid_and_small_threshold():
     assert np.abs(T.cpu().numpy()[0] - T_ref).max() < 1e-5
 
 
+@pytest.mark.parametrize('box,threshold,n_t', [(60.0, 10.0, 1500), (60.0, 10.0, 60), (200.0, 10.0, 4000), (30.0, 3.0, 800)])
+def test_icp_correspondence_search_exact(box, threshold, n_t):
+    """The nearest-neighbour stage alone (max_iter=0: one evaluation of the correspondences) on clouds that stress the grid
+    search: uniform targets in a box (nearest neighbours anywhere between 0 and the threshold, many queries with an empty own
+    cell, queries outside the target's bounding box by less and by more than the threshold), for the half-threshold grid
+    with a two-cell reach (60 mm and 30 mm boxes) and for the widened one-cell grid (200 mm box: too many cells).  The
+    number of correspondences must equal the oracle's brute-force count exactly and the inlier rmse to 1e-12."""
+    from autoposeestimation_b200 import ops
+    rng = np.random.RandomState(int(box) + n_t)
+    tgt = rng.uniform(0, box, size=(n_t, 3))
+    src = rng.uniform(-1.5 * threshold, box + 1.5 * threshold, size=(3000, 3))
+    src[:50] = tgt[:50] + rng.standard_normal((50, 3)) * 1e-3          # near-coincident points
+    src[50:60] = tgt[50:60]                                            # exact hits (d = 0)
+    idx, hit, fit, rmse = oicp._evaluate(src, tgt, threshold, oicp.nn_within)
+    T, info = ops.icp_p2p(_dev(src), _dev(np.array([0, len(src)], np.int32)), _dev(tgt), _dev(np.array([0, n_t], np.int32)),
+                          threshold, max_iter=0)
+    info = info.cpu().numpy()[0]
+    assert int(info[3]) == int(hit.sum()) and 0 < int(hit.sum()) < len(src)
+    assert abs(info[0] - fit) < 1e-15 and abs(info[1] - rmse) < 1e-12
+    assert np.array_equal(T.cpu().numpy()[0], np.identity(4))
+
+
 def test_icp_batch_property_identical_registrations():
     """592 copies of one registration in a single launch (4 CTAs per SM) give bit-identical transforms."""
     from autoposeestimation_b200 import ops
