@@ -277,6 +277,45 @@ dense_batch_kernel(const float* __restrict__ in, int in_ld, int in_gs, const flo
     }
 }
 
+// The same layer for SMALL batches (one live frame = a handful of objects, main.py option 6): one warp per output,
+// lanes stride K with 16-byte loads, one accumulator per object, butterfly reduction (fixed order).  The batched kernel
+// above always works on slabs of 64 objects and eight dependent K-chunks: 24 us per launch even for 5 objects, five
+// launches per frame = 30 % of the live-frame latency.
+constexpr int kGemvMaxB = 16;
+__global__ void __launch_bounds__(256)
+dense_gemv_kernel(const float* __restrict__ in, int in_ld, int in_gs, const float* __restrict__ W,
+                  const float* __restrict__ bias, float* __restrict__ out, int out_ld, int B, int K, int npg, int n_out, int relu)
+{
+    const int lane = threadIdx.x & 31;
+    const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (o >= n_out) return;
+    const float* w = W + (size_t)o * K;
+    const int b0 = blockIdx.y * kGemvMaxB;                    // grid.y walks the batch in groups of 16 objects
+    const float* x = in + (size_t)(o / npg) * in_gs + (size_t)b0 * in_ld;
+    out += (size_t)b0 * out_ld;
+    B = min(B - b0, kGemvMaxB);
+    float acc[kGemvMaxB];
+#pragma unroll
+    for (int b = 0; b < kGemvMaxB; ++b) acc[b] = 0.f;
+    for (int k = lane * 4; k < K; k += 128) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + k));
+#pragma unroll
+        for (int b = 0; b < kGemvMaxB; ++b) {
+            if (b < B) {
+                const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)b * in_ld + k);
+                acc[b] = fmaf(wv.w, xv.w, fmaf(wv.z, xv.z, fmaf(wv.y, xv.y, fmaf(wv.x, xv.x, acc[b]))));
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < kGemvMaxB; ++b) {
+        if (b < B) {                                          // warp-uniform
+            const float v = warp_sum(acc[b]) + bias[o];
+            if (lane == 0) out[(size_t)b * out_ld + o] = relu ? fmaxf(v, 0.f) : v;
+        }
+    }
+}
+
 // PoseNet last layer: conv4_{r,t,c} restricted to the object's class (network.py:119-130), sigmoid on c.
 // One warp per point; H3 row = [r128 | t128 | c128] split-bf16.
 __global__ void __launch_bounds__(256)
@@ -760,6 +799,13 @@ static int dense(const float* in, int in_ld, int in_gs, const DevF32& W, const D
     if (!attr_set) {
         APE_CUDA(cudaFuncSetAttribute(ape::dense_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         attr_set = true;
+    }
+    // small batches only: at B = 64 (four groups of 16) the GEMV form re-reads W four times and measured 2.4x slower
+    if (B <= ape::kGemvMaxB && (in_ld % 4) == 0 && (in_gs % 4) == 0) {
+        ape::ProfScope prof_("dense_gemv", s);
+        ape::dense_gemv_kernel<<<dim3((n_out + 7) / 8, (B + ape::kGemvMaxB - 1) / ape::kGemvMaxB), 256, 0, s>>>(in, in_ld, in_gs, W.p, bias.p, out, out_ld, B, K, npg, n_out, relu);
+        ape::count_launch();
+        return ape::check_launch("dense_gemv");
     }
     ape::ProfScope prof_("dense_batch", s);
     const int chunks = (B + ape::kDenseObj - 1) / ape::kDenseObj;

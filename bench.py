@@ -312,7 +312,7 @@ def live_leg(torch, ops, steps):
     """Extra leg: ONE live frame as main.py option 6 sees it (pipeline/utils.py:517-574): 5 detected objects x 1000 sampled
     points (the fork's num_points, :520), PoseNet + 2 canonical refine iterations, as launch-by-launch stream work and as
     one CUDA-graph replay (the whole block is graph-capturable: no host sync, no allocation inside ape_pose_pipeline)."""
-    from autoposeestimation_b200 import synthetic as synth
+    from autoposeestimation_b200 import _lib, synthetic as synth
     B, N = 5, 1000
     dev = torch.device('cuda', torch.cuda.current_device())
     est = ops.NetHandle(ops.NET_POSENET, synth.posenet_state_dict(7, NUM_OBJ), NUM_OBJ, B, N)
@@ -348,8 +348,19 @@ def live_leg(torch, ops, steps):
     graph.replay(); torch.cuda.synchronize()
     same = bool(torch.equal(ref_pose, poses))
     us_graph = timed(graph.replay, n)
+    lib = _lib.load()
+    lib.ape_profile_enable(1)
+    for _ in range(10):
+        run()
+    torch.cuda.synchronize()
+    rep = profile_report(lib); lib.ape_profile_enable(0)
+    kern = {}
+    for k, v in rep.items():
+        kk = 'gemm (tcgen05, all layers)' if k.startswith('gemm.') else k
+        kern[kk] = kern.get(kk, 0.0) + v[1] / 10 * 1e3
     est.close(); ref.close()
     return dict(objects=B, points=N, refine_iters=REFINE_ITERS, us_per_frame_stream=us_stream, us_per_frame_cuda_graph=us_graph,
+                kernel_us_per_frame=kern,
                 frames_per_s_cuda_graph=1e6 / us_graph, graph_matches_stream_bitwise=same,
                 note='device-resident inputs; one frame = 5 objects; latency mode of the same kernels as the headline')
 

@@ -48,6 +48,54 @@ def report(path, out):
     print('wrote', out)
 
 
+def _mb(row, hdr, name):
+    for i, h in enumerate(hdr):
+        if h.startswith(name):
+            v = float(row[i].replace(',', ''))
+            unit = h[h.index('[') + 1:h.index(']')] if '[' in h else 'byte'
+            return v * {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[unit]
+    raise KeyError(name)
+
+
+def traffic(tag):
+    """profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch (per call for the three-kernel
+    back-projection) from the tag's ncu --set full summaries; bench.py copies these into roofline.traffic."""
+    import json
+    out = {}
+    pg = os.path.join(ROOT, 'profiles', tag + '_ncu_gemm.csv')
+    if os.path.exists(pg):
+        rows = list(csv.reader(open(pg))); hdr = rows[0]
+        b = [_mb(r, hdr, 'dram__bytes_read.sum') + _mb(r, hdr, 'dram__bytes_write.sum') for r in rows[1:] if r and 'gemm_split' in r[0]]
+        g = [r for r in rows[1:] if r and 'gemm_split' in r[0]]
+        ti = [i for i, h in enumerate(hdr) if h.startswith('gpu__time_duration.sum')][0]
+        pi = [i for i, h in enumerate(hdr) if h.startswith('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')][0]
+        tw = sum(float(r[ti]) * float(r[pi]) for r in g) / sum(float(r[ti]) for r in g)
+        out['gemm'] = dict(kernel='tc2::gemm_split_bf16_persistent_kernel', launches_captured=len(b), dram_bytes_per_launch=sum(b) / len(b),
+                           tensor_pipe_active_pct_time_weighted=tw,
+                           dram_bytes_per_step=sum(b), source='profiles/%s_ncu_gemm.csv (ncu --set full, one bench step: %d GEMM launches)' % (tag, len(b)))
+    per = collections.OrderedDict()
+    for name in ('label', 'icp'):                      # ncu picks the byte unit per report: one summary file per report
+        pl = os.path.join(ROOT, 'profiles', '%s_ncu_%s.csv' % (tag, name))
+        if os.path.exists(pl):
+            rows = list(csv.reader(open(pl))); hdr = rows[0]
+            for r in rows[1:]:
+                if r:
+                    per.setdefault(r[0].strip(), []).append(_mb(r, hdr, 'dram__bytes_read.sum') + _mb(r, hdr, 'dram__bytes_write.sum'))
+    if per:
+        avg = {k: sum(v) / len(v) for k, v in per.items()}
+        surf = [k for k in avg if k.startswith('surface_')]
+        if surf:
+            out['surface_backproject'] = dict(kernels={k: avg[k] for k in surf}, dram_bytes_per_launch=sum(avg[k] for k in surf),
+                                              source='profiles/%s_ncu_label.csv (mask + scan + emit of one 512-frame call)' % tag)
+        icp = [k for k in avg if k.startswith('icp_p2p')]
+        if icp:
+            out['icp_p2p'] = dict(kernel=icp[0], dram_bytes_per_launch=avg[icp[0]],
+                                  source='profiles/%s_ncu_icp.csv (1184 registrations per launch)' % tag)
+    with open(os.path.join(ROOT, 'profiles', 'traffic.json'), 'w') as f:
+        json.dump(out, f, indent=1)
+    print('wrote profiles/traffic.json', {k: round(v['dram_bytes_per_launch'] / 1e6, 1) for k, v in out.items()}, 'MB per launch')
+
+
 if __name__ == '__main__':
     tag = sys.argv[1]
     args = sys.argv[2:]
@@ -56,6 +104,8 @@ if __name__ == '__main__':
     while i < len(args):
         if args[i] == '--launches':
             launches(args[i + 1], os.path.join(ROOT, 'profiles', tag + '_launches.csv')); i += 2
+        elif args[i] == '--traffic':
+            traffic(tag); i += 1
         elif args[i] == '--rep':
             name, path = args[i + 1].split('=')
             report(path, os.path.join(ROOT, 'profiles', '%s_ncu_%s.csv' % (tag, name))); i += 2
