@@ -308,6 +308,74 @@ def cpu_label_path(frames):
                 registrations_per_s=len(frames) / t_icp)
 
 
+def adds_leg(torch, ops, peaks, steps, rank=0, world=1, sync=None, reduce_max=None):
+    """Extra leg (BASELINE config 3): ADD / ADD-S evaluation with kNN for symmetric objects, 500 predicted points against a
+    2 600-point model cloud, 100 k object instances sharded over 8 GPUs = 12 500 instances per rank (instances are
+    independent: no collective; the final means are 2 scalars per rank).  Every instance has its own GT-posed target cloud
+    (31 KB) and its own 500-point sample, as eval_linemod.py:118-130 sees them.  Timed twice: with the dataset's mix of
+    symmetric classes (5 of 21) and with every instance symmetric (the kNN path for all)."""
+    from autoposeestimation_b200 import synthetic as synth
+    sync = sync or torch.cuda.synchronize
+    reduce_max = reduce_max or (lambda v: v)
+    dev = torch.device('cuda', torch.cuda.current_device())
+    n_inst, n_model, n_pred = 12500, 2600, 500
+    d = synth.adds_instances(2 + rank, n_inst, n_model_pts=n_model, n_pred_pts=n_pred)
+    sub_np = d['subsample']; rest_np = np.setdiff1d(np.arange(n_model), sub_np)
+    # the sampled 500 points first: row i of the GT-posed target is the partner of predicted point i (non-symmetric ADD)
+    models = torch.from_numpy(np.concatenate([d['models'][:, sub_np], d['models'][:, rest_np]], axis=1)).to(dev)
+    cls = torch.from_numpy(d['cls']).long().to(dev)
+    q_gt = torch.from_numpy(d['q_gt']).to(dev); t_gt = torch.from_numpy(d['t_gt']).to(dev)
+    w, x, y, z = q_gt.unbind(1)
+    R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
+                     2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+                     2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], 1).view(-1, 3, 3)
+    target = torch.empty((n_inst, n_model, 3), dtype=torch.float32, device=dev)
+    for c0 in range(0, n_inst, 2500):                          # setup only (untimed): GT-posed model cloud per instance
+        sl = slice(c0, c0 + 2500)
+        target[sl] = torch.bmm(models[cls[sl]], R[sl].transpose(1, 2)) + t_gt[sl, None, :]
+    model_points = models[:, :n_pred][cls].contiguous()        # [B,500,3]
+    q_pr = torch.from_numpy(d['q_pred']).to(dev); t_pr = torch.from_numpy(d['t_pred']).to(dev)
+    sym_mix = torch.from_numpy(d['sym']).to(dev)[cls].contiguous()
+    sym_all = torch.ones_like(sym_mix)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = max(3, min(steps // 10, 10))
+    res = {}
+    for name, sym in (('mixed', sym_mix), ('all_symmetric', sym_all)):
+        dis = ops.add_metric(q_pr, t_pr, model_points, target, sym)     # warm-up
+        sync()
+        e0.record()
+        for _ in range(n):
+            dis = ops.add_metric(q_pr, t_pr, model_points, target, sym)
+        e1.record(); sync()
+        res[name] = (e0.elapsed_time(e1) / n, float(dis.double().mean()), float((dis < 0.02).double().mean()))
+    ms_mix, ms_all = reduce_max([res['mixed'][0], res['all_symmetric'][0]])
+    bytes_inst = (n_model + n_pred) * 12 + 2 * 28 + 4           # SURVEY 8d: clouds + poses in, one distance out
+    pair_flops = 8.0 * n_model * n_pred                          # brute-force pair evaluations x 8 FLOP (SURVEY 8d)
+    fp32_peak = 148 * 128 * 2 * peaks.get('sm_max_mhz', 1965.0) * 1e6 / 1e12
+    out = dict(instances_per_s=world * n_inst / ms_mix * 1e3, instances_per_s_all_symmetric=world * n_inst / ms_all * 1e3,
+               ms_per_launch=ms_mix, ms_per_launch_all_symmetric=ms_all, instances_per_launch=n_inst, n_gpus=world,
+               pred_points=n_pred, model_points=n_model, symmetric_fraction=float(sym_mix.float().mean()),
+               mean_add_m=res['mixed'][1], below_2cm=res['mixed'][2],
+               roofline=dict(bound='hbm', achieved=n_inst * bytes_inst / ms_mix / 1e6, peak=peaks['hbm'], unit='GB/s',
+                             frac=n_inst * bytes_inst / ms_mix / 1e6 / peaks['hbm'], traffic=measured_traffic('add_metric'), peak_source=peaks['src'],
+                             note='per GPU; compulsory bytes %d per instance; the symmetric (kNN) instances are FP32-ALU bound: all-symmetric run = '
+                                  '%.1f TFLOP/s of brute-force pair arithmetic against ~%.0f TFLOP/s nominal fp32' %
+                                  (bytes_inst, n_inst * pair_flops / ms_all / 1e9, fp32_peak)))
+    if world == 1:
+        from oracle import clib
+        k = 512
+        qs, ts_, mp, tg, sy = (a[:k].cpu().numpy() for a in (q_pr, t_pr, model_points, target, sym_mix))
+        t0 = time.perf_counter(); done = 0
+        while time.perf_counter() - t0 < 5.0:
+            for i in range(k):
+                clib.add_metric(qs[i], ts_[i], mp[i], tg[i], bool(sy[i]))
+            done += k
+        dt = time.perf_counter() - t0; k = done
+        out['cpu_baseline'] = dict(kind='port', cores=1, sample='%d instances, C restatement of eval_linemod.py:118-130 + knn_cpu.cpp (one thread, %.1f s)' % (k, dt),
+                                   instances_per_s=k / dt)
+    return out
+
+
 def live_leg(torch, ops, steps):
     """Extra leg: ONE live frame as main.py option 6 sees it (pipeline/utils.py:517-574): 5 detected objects x 1000 sampled
     points (the fork's num_points, :520), PoseNet + 2 canonical refine iterations, as launch-by-launch stream work and as
@@ -529,6 +597,14 @@ def run_b200(args):
         else:
             # no try/except here: a rank that dropped out of the leg would leave the others waiting in its collectives
             label_leg = icp_leg(torch, ops, lib, peaks, args.steps, rank, world, barrier, reduce_max)
+        # ---- ADD / ADD-S evaluation (BASELINE config 3), same sharding rule
+        if world == 1:
+            try:
+                label_leg = dict(label_leg, add_metric=adds_leg(torch, ops, peaks, args.steps, 0, 1, barrier, reduce_max))
+            except Exception as ex:
+                label_leg = dict(label_leg, add_metric=dict(error=repr(ex)))
+        else:
+            label_leg = dict(label_leg, add_metric=adds_leg(torch, ops, peaks, args.steps, rank, world, barrier, reduce_max))
 
     line = None
     if rank == 0:
