@@ -12,6 +12,7 @@
 // Kernels: front-end (gather + K=3 / K=32 convs, SIMT), tcgen05 split-bf16 GEMM (gemm_tc.cuh) for every
 // K>=64 layer, small dense layers / heads (SIMT fp32), final conv4 + sigmoid + class select.
 #include "gemm_tc3.cuh"
+#include "gemm_tc4.cuh"
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -682,7 +683,7 @@ extern "C" __attribute__((visibility("default")))
 int ape_net_set_gemm(ape_net* net, int gemm_impl)
 {
     APE_REQUIRE(net, "ape_net_set_gemm: null handle");
-    APE_REQUIRE(gemm_impl >= APE_GEMM_TCGEN05 && gemm_impl <= APE_GEMM_TCGEN05_PAIR, "ape_net_set_gemm: unknown implementation");
+    APE_REQUIRE(gemm_impl >= APE_GEMM_TCGEN05 && gemm_impl <= APE_GEMM_TCGEN05_B2B, "ape_net_set_gemm: unknown implementation");
     net->gemm_impl = gemm_impl;
     return APE_OK;
 }
@@ -712,7 +713,7 @@ static int run_gemm(ape_net* net, const SplitMat& A, const SplitMat& W, const Sp
         const SplitMat& O = out ? *out : A;          // EPI_RELU_COLSUM never touches the store maps
         ape::tc3::gemm_split_bf16_pair_kernel<<<2 * pairs, ape::tc3::kThreads3, ape::tc3::kSmemBytes3, s>>>(
             A.map_hi, A.map_lo, W.w64_hi, W.w64_lo, O.st_hi, O.st_lo, p, bn_full);
-    } else if (net->gemm_impl == APE_GEMM_TCGEN05) {
+    } else if (net->gemm_impl == APE_GEMM_TCGEN05 || net->gemm_impl == APE_GEMM_TCGEN05_B2B) {
         const int bn_full = (wide && p.N >= 256) ? 256 : 128;
         const int tiles = p.groups * (p.M / ape::tc::BM) * ((p.N + bn_full - 1) / bn_full);
         const int grid = tiles < ape::sm_count() ? tiles : ape::sm_count();
@@ -831,14 +832,35 @@ int ape_posenet_forward(ape_net* net, const float* out_img, int hw, const float*
     if (rc) return rc;
     // global-feature half of conv1_{r,t,c} folded into a per-object bias: GB = b + Wg * AP
     if ((rc = dense(net->AP.p, 1024, 0, net->Wg, net->b_h1, net->GB.p, 1920, B, 1024, 1920, 1, 0, s))) return rc;
+    ape::tc::Params p;
+    if (net->gemm_impl == APE_GEMM_TCGEN05_B2B) {
+        // conv1_{r,t,c} -> conv2_{r,t,c} back to back in one kernel: the [R,1920] intermediate never leaves the SM
+        static bool attr_set = false;
+        if (!attr_set) {
+            APE_CUDA(cudaFuncSetAttribute(ape::tc4::heads12_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ape::tc4::kSmemBytesF));
+            attr_set = true;
+        }
+        ape::tc4::FusedParams fp;
+        fp.M = M; fp.gb = net->GB.p; fp.rows_per_obj = Np; fp.b2 = net->b_h2.p;
+        const int items = (M / 128) * 3;
+        ape::ProfScope prof_("gemm.pn.heads12", s);
+        const int fgrid = items < ape::sm_count() ? items : ape::sm_count();
+        // (the double-buffered-A2 / 3-stage variant <2> measured 1.5 % slower than <1>)
+        ape::tc4::heads12_fused_kernel<1><<<fgrid, ape::tc::kThreads, ape::tc4::kSmemBytesF, s>>>(
+                net->PF.map_hi, net->PF.map_lo, net->W_h1.map_hi, net->W_h1.map_lo, net->W_h2.map_hi, net->W_h2.map_lo,
+                net->H2.st_hi, net->H2.st_lo, fp);
+        ape::count_launch();
+        if ((rc = ape::check_launch("heads12 fused"))) return rc;
+    } else {
     // conv1_{r,t,c} on [pointfeat_1 | pointfeat_2] (K=384), N = 3*640, per-object bias
-    ape::tc::Params p = split_layer(M, 1920, 384, 1, 0, 0, net->GB.p, net->H1, 0);
+    p = split_layer(M, 1920, 384, 1, 0, 0, net->GB.p, net->H1, 0);
     p.bias_obj_rows = Np;
     if ((rc = run_gemm(net, net->PF, net->W_h1, &net->H1, p, wide_layer(3), s, "gemm.pn.heads1"))) return rc;
     p = split_layer(M, 256, 640, 3, 0, 640, net->b_h2.p, net->H2, 0);          // conv2_{r,t,c}
     if ((rc = run_gemm(net, net->H1, net->W_h2, &net->H2, p, wide_layer(4), s, "gemm.pn.heads2"))) return rc;
+    }
     p = split_layer(M, 128, 256, 3, 0, 256, net->b_h3.p, net->H3, 0);          // conv3_{r,t,c}
-    if (net->gemm_impl == APE_GEMM_TCGEN05) {
+    if (net->gemm_impl == APE_GEMM_TCGEN05 || net->gemm_impl == APE_GEMM_TCGEN05_B2B) {
         // conv4_{r,t,c} of the object's class + sigmoid folded into the conv3 epilogue: H3 is never written
         p.mode = ape::tc::EPI_HEAD_OUT; p.rows_per_obj = Np; p.valid_rows = N; p.obj = obj; p.num_obj = net->num_obj; p.batch = B;
         p.w4[0] = net->w4r.p; p.w4[1] = net->w4t.p; p.w4[2] = net->w4c.p;

@@ -263,7 +263,7 @@ def pose_compose(pose_in, r2, t2, cloud=None):
 
 # ------------------------------------------------------------------------------------------ networks
 NET_POSENET, NET_REFINER = 0, 1
-GEMM_TCGEN05, GEMM_SIMT, GEMM_TCGEN05_V1, GEMM_TCGEN05_PAIR = 0, 1, 2, 3
+GEMM_TCGEN05, GEMM_SIMT, GEMM_TCGEN05_V1, GEMM_TCGEN05_PAIR, GEMM_TCGEN05_B2B = 0, 1, 2, 3, 4
 
 _POSENET_ORDER = ['feat.conv1', 'feat.e_conv1', 'feat.conv2', 'feat.e_conv2', 'feat.conv5', 'feat.conv6',
                   'conv1_r', 'conv1_t', 'conv1_c', 'conv2_r', 'conv2_t', 'conv2_c', 'conv3_r', 'conv3_t', 'conv3_c',

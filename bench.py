@@ -622,11 +622,15 @@ def run_b200(args):
         alg = sum(GEMM_FLOPS_PER_PT[k] * refine[k] for k in GEMM_FLOPS_PER_PT) * BATCH * NPTS
         rows = BATCH * ((NPTS + 127) // 128 * 128)
         exe = sum(GEMM_EXEC_PER_ROW[k] * refine[k] for k in GEMM_EXEC_PER_ROW) * rows
+        fpt = dict(GEMM_FLOPS_PER_PT); epr = dict(GEMM_EXEC_PER_ROW)
+        # the back-to-back heads kernel (gemm_tc4.cuh) does the work of two layers in one launch
+        fpt['gemm.pn.heads12'] = fpt['gemm.pn.heads1'] + fpt['gemm.pn.heads2']
+        epr['gemm.pn.heads12'] = epr['gemm.pn.heads1'] + epr['gemm.pn.heads2']
         layers = {k: dict(launches_per_step=rep[k][0] / args.steps, ms_per_step=rep[k][1] / args.steps,
-                          algorithmic_tflops=GEMM_FLOPS_PER_PT[k] * BATCH * NPTS * (rep[k][0] / args.steps) / (rep[k][1] / args.steps) / 1e9,
-                          executed_bf16_tflops=GEMM_EXEC_PER_ROW[k] * rows * (rep[k][0] / args.steps) / (rep[k][1] / args.steps) / 1e9)
-                  for k in GEMM_FLOPS_PER_PT if k in rep}
-        roofline = dict(bound='tensor', kernel='gemm_split_bf16_kernel (tcgen05, %d launches/step)' % sum(
+                          algorithmic_tflops=fpt[k] * BATCH * NPTS * (rep[k][0] / args.steps) / (rep[k][1] / args.steps) / 1e9,
+                          executed_bf16_tflops=epr[k] * rows * (rep[k][0] / args.steps) / (rep[k][1] / args.steps) / 1e9)
+                  for k in fpt if k in rep}
+        roofline = dict(bound='tensor', kernel='tcgen05 split-bf16 GEMM kernels (gemm_tc2 / gemm_tc4, %d launches/step)' % sum(
             round(rep[k][0] / args.steps) for k in rep if k.startswith('gemm.')),
             achieved=alg / gemm_ms / 1e9, peak=peaks['bf16'], unit='TFLOP/s', frac=alg / gemm_ms / 1e9 / peaks['bf16'],
             traffic=measured_traffic('gemm'), traffic_source='profiles/traffic.json (ncu --set full, bytes per GEMM launch)',

@@ -186,8 +186,11 @@ enum { APE_NET_POSENET = 0, APE_NET_REFINER = 1 };
 enum { APE_GEMM_TCGEN05 = 0,      /* persistent tcgen05 kernel, 128x256 tiles (gemm_tc2.cuh): the product path */
        APE_GEMM_SIMT = 1,         /* fp32 SIMT validation kernels (tests only) */
        APE_GEMM_TCGEN05_V1 = 2,   /* first generation: non-persistent 128x128 tiles (A/B runs only) */
-       APE_GEMM_TCGEN05_PAIR = 3 };/* CTA-pair variant, tcgen05.mma.cta_group::2 (gemm_tc3.cuh); measured 5 % slower than the
+       APE_GEMM_TCGEN05_PAIR = 3, /* CTA-pair variant, tcgen05.mma.cta_group::2 (gemm_tc3.cuh); measured 5 % slower than the
                                      product path on this workload (profiles/), kept for A/B runs */
+       APE_GEMM_TCGEN05_B2B = 4 };/* product path with PoseNet conv1_{r,t,c} -> conv2_{r,t,c} fused back to back in one kernel
+                                     (gemm_tc4.cuh): the [R,1920] intermediate never leaves the SM (0.5 GB less HBM traffic per
+                                     step); measured 11 % slower on these two layers, kept selectable */
 
 /* weights_host: array of n_tensors host pointers to fp32 tensors in the canonical order listed in
  * DESIGN.md ("weight order"); num_obj as in the reference constructor; max_batch/max_points size the

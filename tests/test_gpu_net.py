@@ -24,7 +24,7 @@ def _handles(seed, nobj, max_batch, max_points):
     return est, ref, synth.to_torch(sd_e), synth.to_torch(sd_r)
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tcgen05', 'tcgen05_v1', 'tcgen05_pair'])
+@pytest.mark.parametrize('impl', ['simt', 'tcgen05', 'tcgen05_v1', 'tcgen05_pair', 'tcgen05_b2b'])
 @pytest.mark.parametrize('case', [0, 1, 2])
 def test_posenet_refiner_golden(golden_dir, case, impl):
     """Raw network outputs vs the reference's own PoseNet / PoseRefineNet (tests/golden)."""
@@ -33,7 +33,8 @@ def test_posenet_refiner_golden(golden_dir, case, impl):
     seed, npts, nobj = int(g['seed']), int(g['npts']), int(g['nobj'])
     hw = tuple(int(v) for v in g['hw'])
     est, ref, _, _ = _handles(seed, nobj, 2, npts)
-    gi = {'simt': ops.GEMM_SIMT, 'tcgen05': ops.GEMM_TCGEN05, 'tcgen05_v1': ops.GEMM_TCGEN05_V1, 'tcgen05_pair': ops.GEMM_TCGEN05_PAIR}[impl]
+    gi = {'simt': ops.GEMM_SIMT, 'tcgen05': ops.GEMM_TCGEN05, 'tcgen05_v1': ops.GEMM_TCGEN05_V1, 'tcgen05_pair': ops.GEMM_TCGEN05_PAIR,
+          'tcgen05_b2b': ops.GEMM_TCGEN05_B2B}[impl]
     est.set_gemm(gi); ref.set_gemm(gi)
     out_img, cloud, choose, idx = synth.posenet_inputs(seed, npts, hw, nobj)
     r, t, c, emb = est.posenet_forward(_dev(out_img), _dev(cloud), _dev(choose), _dev(idx))
@@ -103,16 +104,17 @@ def test_tcgen05_matches_simt_batch64():
     out_img, cloud, choose, idx = synth.posenet_inputs(52, N, (120, 160), nobj, batch=B)
     d = [_dev(a) for a in (out_img, cloud, choose, idx)]
     outs = {}
-    for name, gi in (('simt', ops.GEMM_SIMT), ('tc', ops.GEMM_TCGEN05)):
+    for name, gi in (('simt', ops.GEMM_SIMT), ('tc', ops.GEMM_TCGEN05), ('b2b', ops.GEMM_TCGEN05_B2B)):
         est.set_gemm(gi); ref.set_gemm(gi)
         outs[name] = [x.clone() for x in est.posenet_forward(*d)]
         poses, _ = ops.pose_pipeline(est, ref, *d, iterations=2, canonical=True)
         outs[name].append(poses.clone())
-    for a, b in zip(outs['simt'][:3], outs['tc'][:3]):
-        assert float((a - b).abs().max()) < 5e-5 * max(1.0, float(a.abs().max()))
-    dq = (outs['simt'][4][:, :4] - outs['tc'][4][:, :4]).abs().max(dim=1).values
-    dt = (outs['simt'][4][:, 4:] - outs['tc'][4][:, 4:]).abs().max(dim=1).values
-    assert int(((dq < 1e-4) & (dt < 1e-4)).sum()) >= B - 1      # at most one arg-max near-tie flip
+    for other in ('tc', 'b2b'):                                  # b2b: conv1 -> conv2 of the heads fused back to back (gemm_tc4.cuh)
+        for a, b in zip(outs['simt'][:3], outs[other][:3]):
+            assert float((a - b).abs().max()) < 5e-5 * max(1.0, float(a.abs().max()))
+        dq = (outs['simt'][4][:, :4] - outs[other][4][:, :4]).abs().max(dim=1).values
+        dt = (outs['simt'][4][:, 4:] - outs[other][4][:, 4:]).abs().max(dim=1).values
+        assert int(((dq < 1e-4) & (dt < 1e-4)).sum()) >= B - 1  # at most one arg-max near-tie flip
 
 
 def test_net_errors_are_loud():
