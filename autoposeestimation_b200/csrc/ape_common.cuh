@@ -47,6 +47,28 @@ struct ProfScope {
         }                                                                           \
     } while (0)
 
+// ---- programmatic dependent launch ------------------------------------------------------------
+// The kernels of the per-frame pipeline are launched with the stream-serialization attribute: a kernel's CTAs may be
+// scheduled while the previous kernel on the stream is still draining its last CTAs, and every such kernel calls
+// pdl_sync() before it touches global memory, which waits for the COMPLETION (and memory flush) of that previous kernel:
+// the semantics of a normal launch, minus the launch gap.  pdl_sync() also lets the next kernel be scheduled early.
+// APE_PDL=0 turns the attribute off (normal launches; pdl_sync() is then a no-op).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---- device helpers ------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -126,6 +126,12 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: when this grid was launched with the stream-serialization attribute its CTAs may
+    // start (barrier init, TMEM allocation, descriptor prefetch above) while the previous kernel on the stream is still
+    // draining its last tiles; everything below reads or overwrites that kernel's buffers, so all threads wait here for its
+    // completion (a no-op for a normal launch).  launch_dependents lets the NEXT kernel do the same with this one.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         // ===== TMA producer =====

@@ -36,6 +36,7 @@ frontend_kernel(const float* __restrict__ feat_src /*GATHER: out_img [B,32,hw]; 
                 int N, int Np, bf16* __restrict__ pf_hi, bf16* __restrict__ pf_lo, int pf_ld,
                 float* __restrict__ emb_out)
 {
+    pdl_sync();                                           // programmatic dependent launch: see ape_common.cuh
     // fw = [e_conv1^T 32x64 | conv1^T 3x64 | b1 64 | be1 64] packed once at ape_net_create: straight float4 copy
     __shared__ __align__(16) float s_fw[32 * 64 + 3 * 64 + 128];
     float (*s_we1)[64] = reinterpret_cast<float (*)[64]>(s_fw);
@@ -187,6 +188,7 @@ gemm_simt_kernel(const bf16* __restrict__ a_hi, const bf16* __restrict__ a_lo, i
 __global__ void pool_finish_kernel(const float* __restrict__ cs, int tiles_per_obj, int C, float inv_n, float* __restrict__ ap,
                                    bf16* __restrict__ ap_b16 /* training: bf16 copy for the tensor-core heads, or NULL */)
 {
+    pdl_sync();                                           // programmatic dependent launch: see ape_common.cuh
     const int b = blockIdx.y;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -210,6 +212,7 @@ dense_batch_kernel(const float* __restrict__ in, int in_ld, int in_gs, const flo
                    const float* __restrict__ bias, float* __restrict__ out, int out_ld, int B, int K, int npg, int n_out,
                    int relu)
 {
+    pdl_sync();                                           // programmatic dependent launch: see ape_common.cuh
     extern __shared__ __align__(16) float s_dense[];
     float* s_w = s_dense;                                   // [8][K]
     float* s_x = s_w + kDenseOut * K;                       // [2][64][4*32 + 4]   (cp.async double buffer)
@@ -287,6 +290,7 @@ __global__ void __launch_bounds__(256)
 dense_gemv_kernel(const float* __restrict__ in, int in_ld, int in_gs, const float* __restrict__ W,
                   const float* __restrict__ bias, float* __restrict__ out, int out_ld, int B, int K, int npg, int n_out, int relu)
 {
+    pdl_sync();                                           // programmatic dependent launch: see ape_common.cuh
     const int lane = threadIdx.x & 31;
     const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (o >= n_out) return;
@@ -326,6 +330,7 @@ posenet_out_kernel(const bf16* __restrict__ h_hi, const bf16* __restrict__ h_lo,
                    const int64_t* __restrict__ obj, int num_obj, float* __restrict__ pred_r, float* __restrict__ pred_t,
                    float* __restrict__ pred_c)
 {
+    pdl_sync();                                           // programmatic dependent launch: see ape_common.cuh
     __shared__ float s_w[8][128];
     __shared__ float s_b[8];
     const int b = blockIdx.y;
@@ -379,6 +384,7 @@ refiner_out_kernel(const float* __restrict__ g2, const bf16* __restrict__ g2_b16
                    const float* __restrict__ w3t, const float* __restrict__ b3t, const int64_t* __restrict__ obj,
                    int num_obj, float* __restrict__ r2, float* __restrict__ t2)
 {
+    pdl_sync();                                           // programmatic dependent launch: see ape_common.cuh
     const int b = blockIdx.x, lane = threadIdx.x & 31, j = threadIdx.x >> 5;      // 8 warps, 7 outputs
     if (j >= 7) return;
     int o = (int)obj[b];
@@ -721,12 +727,22 @@ static int run_gemm(ape_net* net, const SplitMat& A, const SplitMat& W, const Sp
         const int kblocks = (p.passes == 1 ? 1 : 3) * (p.K / ape::tc::BK);
         static int epi8_max = -1;
         if (epi8_max < 0) { const char* e = getenv("APE_GEMM_EPI8_MAX_KB"); epi8_max = e ? (int)strtol(e, nullptr, 0) : 3; }
-        if (p.mode != ape::tc::EPI_HEAD_OUT && (p.passes == 1 || kblocks <= epi8_max))     // short mainloop: 8 epilogue warps
-            ape::tc2::gemm_split_bf16_persistent_kernel<true><<<grid, ape::tc2::kThreadsEpi8, ape::tc2::kSmemBytes2, s>>>(
-                A.map_hi, A.map_lo, W.map_hi, W.map_lo, O.st_hi, O.st_lo, p, bn_full);
+        const bool epi8 = p.mode != ape::tc::EPI_HEAD_OUT && (p.passes == 1 || kblocks <= epi8_max);   // short mainloop: 8 epilogue warps
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(epi8 ? ape::tc2::kThreadsEpi8 : ape::tc::kThreads);
+        cfg.dynamicSmemBytes = ape::tc2::kSmemBytes2; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = ape::pdl_enabled() ? 1 : 0;   // programmatic dependent launch: see ape_common.cuh
+        cudaError_t le;
+        if (epi8)
+            le = cudaLaunchKernelEx(&cfg, ape::tc2::gemm_split_bf16_persistent_kernel<true>, A.map_hi, A.map_lo, W.map_hi, W.map_lo,
+                                    O.st_hi, O.st_lo, p, bn_full);
         else
-            ape::tc2::gemm_split_bf16_persistent_kernel<false><<<grid, ape::tc::kThreads, ape::tc2::kSmemBytes2, s>>>(
-                A.map_hi, A.map_lo, W.map_hi, W.map_lo, O.st_hi, O.st_lo, p, bn_full);
+            le = cudaLaunchKernelEx(&cfg, ape::tc2::gemm_split_bf16_persistent_kernel<false>, A.map_hi, A.map_lo, W.map_hi, W.map_lo,
+                                    O.st_hi, O.st_lo, p, bn_full);
+        if (le != cudaSuccess) { ape::set_error("GEMM launch failed: %s", cudaGetErrorString(le)); return APE_ERR_CUDA; }
     } else if (net->gemm_impl == APE_GEMM_TCGEN05_V1) {
         dim3 grid(p.N / ape::tc::BN, p.M / ape::tc::BM, p.groups);
         ape::tc::gemm_split_bf16_kernel<<<grid, ape::tc::kThreads, ape::tc::kSmemBytes, s>>>(A.map_hi, A.map_lo, W.map_hi,
@@ -761,9 +777,9 @@ static int run_trunk(ape_net* net, const float* feat_src, int hw, const float* c
     {
     ape::ProfScope prof_("frontend", s);
     if (net->kind == APE_NET_POSENET)
-        ape::frontend_kernel<true><<<gf, 256, 0, s>>>(feat_src, hw, cloud, choose, net->fw.p, N, Np, net->PF.hi, net->PF.lo, 384, emb_out);
+        APE_CUDA(ape::launch_pdl(ape::frontend_kernel<true>, gf, dim3(256), 0, s, feat_src, hw, cloud, choose, net->fw.p, N, Np, net->PF.hi, net->PF.lo, 384, emb_out));
     else
-        ape::frontend_kernel<false><<<gf, 256, 0, s>>>(feat_src, hw, cloud, nullptr, net->fw.p, N, Np, net->PF.hi, net->PF.lo, 384, nullptr);
+        APE_CUDA(ape::launch_pdl(ape::frontend_kernel<false>, gf, dim3(256), 0, s, feat_src, hw, cloud, (const int64_t*)nullptr, net->fw.p, N, Np, net->PF.hi, net->PF.lo, 384, (float*)nullptr));
     }
     ape::count_launch();
     int rc = ape::check_launch("frontend");
@@ -785,7 +801,7 @@ static int run_trunk(ape_net* net, const float* feat_src, int hw, const float* c
     if ((rc = run_gemm(net, net->H5, net->W_c6, nullptr, p, wide_layer(2), s, pn ? "gemm.pn.conv6" : "gemm.rf.conv6"))) return rc;
     dim3 gp(1024 / 256, B);
     ape::ProfScope prof_("pool_finish", s);
-    ape::pool_finish_kernel<<<gp, 256, 0, s>>>(net->CS.p, Np / 128, 1024, (float)N, net->AP.p, net->train ? net->APb.hi : nullptr);
+    APE_CUDA(ape::launch_pdl(ape::pool_finish_kernel, gp, dim3(256), 0, s, net->CS.p, Np / 128, 1024, (float)N, net->AP.p, net->train ? net->APb.hi : (bf16*)nullptr));
     ape::count_launch();
     return ape::check_launch("pool_finish");
 }
@@ -804,14 +820,14 @@ static int dense(const float* in, int in_ld, int in_gs, const DevF32& W, const D
     // small batches only: at B = 64 (four groups of 16) the GEMV form re-reads W four times and measured 2.4x slower
     if (B <= ape::kGemvMaxB && (in_ld % 4) == 0 && (in_gs % 4) == 0) {
         ape::ProfScope prof_("dense_gemv", s);
-        ape::dense_gemv_kernel<<<dim3((n_out + 7) / 8, (B + ape::kGemvMaxB - 1) / ape::kGemvMaxB), 256, 0, s>>>(in, in_ld, in_gs, W.p, bias.p, out, out_ld, B, K, npg, n_out, relu);
+        APE_CUDA(ape::launch_pdl(ape::dense_gemv_kernel, dim3((n_out + 7) / 8, (B + ape::kGemvMaxB - 1) / ape::kGemvMaxB), dim3(256), 0, s, in, in_ld, in_gs, W.p, bias.p, out, out_ld, B, K, npg, n_out, relu));
         ape::count_launch();
         return ape::check_launch("dense_gemv");
     }
     ape::ProfScope prof_("dense_batch", s);
     const int chunks = (B + ape::kDenseObj - 1) / ape::kDenseObj;
     dim3 grid((n_out + ape::kDenseOut - 1) / ape::kDenseOut, chunks < 8 ? chunks : 8);
-    ape::dense_batch_kernel<<<grid, 256, smem, s>>>(in, in_ld, in_gs, W.p, bias.p, out, out_ld, B, K, npg, n_out, relu);
+    APE_CUDA(ape::launch_pdl(ape::dense_batch_kernel, grid, dim3(256), smem, s, in, in_ld, in_gs, W.p, bias.p, out, out_ld, B, K, npg, n_out, relu));
     ape::count_launch();
     return ape::check_launch("dense_batch");
 }
@@ -871,8 +887,8 @@ int ape_posenet_forward(ape_net* net, const float* out_img, int hw, const float*
     if ((rc = run_gemm(net, net->H2, net->W_h3, &net->H3, p, wide_layer(5), s, "gemm.pn.heads3"))) return rc;
     dim3 go((N + 7) / 8 < 64 ? (N + 7) / 8 : 64, B);
     ape::ProfScope prof_("posenet_out", s);
-    ape::posenet_out_kernel<<<go, 256, 0, s>>>(net->H3.hi, net->H3.lo, 384, N, Np, net->w4r.p, net->b4r.p, net->w4t.p,
-                                              net->b4t.p, net->w4c.p, net->b4c.p, obj, net->num_obj, pred_r, pred_t, pred_c);
+    APE_CUDA(ape::launch_pdl(ape::posenet_out_kernel, go, dim3(256), 0, s, net->H3.hi, net->H3.lo, 384, N, Np, net->w4r.p, net->b4r.p, net->w4t.p,
+                             net->b4t.p, net->w4c.p, net->b4c.p, obj, net->num_obj, pred_r, pred_t, pred_c));
     ape::count_launch();
     return ape::check_launch("posenet_out");
 }
@@ -903,8 +919,8 @@ int ape_refiner_forward(ape_net* net, const float* new_points, const float* emb,
         if ((rc = dense(net->G1.p, 1024, 512, net->Wr2, net->br2, net->G2.p, 256, B, 512, 128, 2, 1, s))) return rc;    // conv2_{r,t}
     }
     ape::ProfScope prof_("refiner_out", s);
-    ape::refiner_out_kernel<<<B, 256, 0, s>>>(net->G2.p, net->train ? net->G2b.hi : nullptr, net->w3r.p, net->b3r.p, net->w3t.p,
-                                              net->b3t.p, obj, net->num_obj, r2, t2);
+    APE_CUDA(ape::launch_pdl(ape::refiner_out_kernel, dim3(B), dim3(256), 0, s, net->G2.p, net->train ? net->G2b.hi : (bf16*)nullptr, net->w3r.p,
+                             net->b3r.p, net->w3t.p, net->b3t.p, obj, net->num_obj, r2, t2));
     ape::count_launch();
     return ape::check_launch("refiner_out");
 }

@@ -55,6 +55,7 @@ pose_select_kernel(const float* __restrict__ pred_r, const float* __restrict__ p
                    const float* __restrict__ cloud, int N, int32_t* __restrict__ which_max, float* __restrict__ my_r,
                    float* __restrict__ my_t, float* __restrict__ new_points, double* __restrict__ pose)
 {
+    pdl_sync();                                           // programmatic dependent launch: see ape_common.cuh
     __shared__ float s_v[kSelThreads / 32];
     __shared__ int s_i[kSelThreads / 32];
     __shared__ float s_pose[16];
@@ -120,6 +121,7 @@ pose_compose_kernel(const double* __restrict__ pose_in, const float* __restrict_
                     double* __restrict__ pose_out, const float* __restrict__ cloud, int N,
                     float* __restrict__ next_points)
 {
+    pdl_sync();                                           // programmatic dependent launch: see ape_common.cuh
     __shared__ float s_R[9];
     __shared__ float s_T[3];
     const int b = blockIdx.x;
@@ -178,8 +180,8 @@ extern "C" __attribute__((visibility("default"))) int ape_pose_select(const floa
     APE_REQUIRE(B >= 0 && N > 0, "ape_pose_select: bad sizes");
     if (B == 0) return APE_OK;
     ape::ProfScope prof_("pose_select", (cudaStream_t)stream);
-    ape::pose_select_kernel<<<B, ape::kSelThreads, 0, (cudaStream_t)stream>>>(pred_r, pred_t, pred_c, cloud, N, which_max,
-                                                                             my_r, my_t, new_points, pose);
+    APE_CUDA(ape::launch_pdl(ape::pose_select_kernel, dim3(B), dim3(ape::kSelThreads), 0, (cudaStream_t)stream, pred_r, pred_t, pred_c, cloud, N,
+                             which_max, my_r, my_t, new_points, pose));
     ape::count_launch();
     return ape::check_launch("ape_pose_select");
 }
@@ -192,8 +194,8 @@ extern "C" __attribute__((visibility("default"))) int ape_pose_compose(const dou
     APE_REQUIRE(!next_points || (cloud && N > 0), "ape_pose_compose: next_points needs cloud and N");
     if (B == 0) return APE_OK;
     ape::ProfScope prof_("pose_compose", (cudaStream_t)stream);
-    ape::pose_compose_kernel<<<B, ape::kSelThreads, 0, (cudaStream_t)stream>>>(pose_in, r2, t2, pose_out, cloud, N,
-                                                                              next_points);
+    APE_CUDA(ape::launch_pdl(ape::pose_compose_kernel, dim3(B), dim3(ape::kSelThreads), 0, (cudaStream_t)stream, pose_in, r2, t2, pose_out, cloud, N,
+                             next_points));
     ape::count_launch();
     return ape::check_launch("ape_pose_compose");
 }

@@ -1,6 +1,7 @@
 // Library-level plumbing: version, error message, launch counter, device properties.
 #include "ape_common.cuh"
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -38,6 +39,12 @@ bool prof_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
 void prof_push(const char* label, cudaEvent_t e0, cudaEvent_t e1) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof.push_back({label, e0, e1});
+}
+
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("APE_PDL"); on = e ? (atoi(e) != 0) : 1; }
+    return on != 0;
 }
 
 int sm_count() {
