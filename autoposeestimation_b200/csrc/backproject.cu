@@ -111,6 +111,7 @@ surface_mask_kernel(const uint8_t* __restrict__ label, const uint16_t* __restric
                     const int32_t* __restrict__ frame_of, const uint8_t* __restrict__ label_value,
                     int32_t* __restrict__ sub_count, uint32_t* __restrict__ masks, int n_chunks, int32_t* __restrict__ n_tasks)
 {
+    pdl_sync();                                           // programmatic dependent launch: see ape_common.cuh
     const int tile = blockIdx.x;
     const int v = tile / n_chunks, c = tile - v * n_chunks;
     const int f = frame_of ? frame_of[v] : v;
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(256)
 surface_scan_kernel(const int32_t* __restrict__ sub_count, int32_t* __restrict__ counts, int32_t* __restrict__ n_tasks,
                     int4* __restrict__ tasks, int n_sub, int n_views)
 {
+    pdl_sync();                                           // programmatic dependent launch: see ape_common.cuh
     __shared__ int s_ne[8], s_base;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int v = blockIdx.x * 8 + warp;
@@ -204,6 +206,7 @@ surface_emit_kernel(const uint16_t* __restrict__ depth, int npix, int W, const i
                     double* __restrict__ points, int32_t* __restrict__ pixel_index,
                     const int32_t* __restrict__ n_tasks_p, const int4* __restrict__ tasks, const uint32_t* __restrict__ masks, int n_sub)
 {
+    pdl_sync();                                           // programmatic dependent launch: see ape_common.cuh
     __shared__ __align__(16) uint16_t s_dep[kEmitWarps][kSurfSub];
     __shared__ double s_parw[kEmitWarps][16];              // robot2cam rows 0..2 (12) + ppx, ppy, fx, fy
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -328,22 +331,22 @@ extern "C" __attribute__((visibility("default"))) int ape_surface_backproject(co
     uint32_t* masks = reinterpret_cast<uint32_t*>(sub_count + n_span);
     {
         ape::ProfScope prof_("surface_mask", s);
-        ape::surface_mask_kernel<<<n_tiles, ape::kSurfThreads, 0, s>>>(label, depth, height * width, frame_of, label_value,
-                                                                       sub_count, masks, n_chunks, n_tasks);
+        APE_CUDA(ape::launch_pdl(ape::surface_mask_kernel, dim3(n_tiles), dim3(ape::kSurfThreads), 0, s, label, depth, height * width, frame_of,
+                                 label_value, sub_count, masks, n_chunks, n_tasks));
         ape::count_launch();
     }
     int rc = ape::check_launch("ape_surface_backproject (mask)");
     if (rc) return rc;
     {
         ape::ProfScope prof_("surface_scan", s);
-        ape::surface_scan_kernel<<<(n_views + 7) / 8, 256, 0, s>>>(sub_count, counts, n_tasks, tasks, n_sub, n_views);
+        APE_CUDA(ape::launch_pdl(ape::surface_scan_kernel, dim3((n_views + 7) / 8), dim3(256), 0, s, sub_count, counts, n_tasks, tasks, n_sub, n_views));
         ape::count_launch();
     }
     ape::ProfScope prof_("surface_emit", s);
     const size_t want_ctas = (n_span + ape::kEmitWarps - 1) / ape::kEmitWarps;      // at most one task per warp is ever needed
     const size_t max_ctas = (size_t)ape::sm_count() * 8;
-    ape::surface_emit_kernel<<<(unsigned)(want_ctas < max_ctas ? want_ctas : max_ctas), ape::kEmitWarps * 32, 0, s>>>(
-        depth, height * width, width, frame_of, cam, robot2cam, capacity, points, pixel_index, n_tasks, tasks, masks, n_sub);
+    APE_CUDA(ape::launch_pdl(ape::surface_emit_kernel, dim3((unsigned)(want_ctas < max_ctas ? want_ctas : max_ctas)), dim3(ape::kEmitWarps * 32), 0, s,
+                             depth, height * width, width, frame_of, cam, robot2cam, capacity, points, pixel_index, n_tasks, tasks, masks, n_sub));
     ape::count_launch();
     return ape::check_launch("ape_surface_backproject (emit)");
 }
