@@ -29,7 +29,7 @@ __host__ __device__ constexpr uint32_t steps_dz(int i) { return i == 0 ? 0x19820
 __constant__ signed char c_run_dy[kIcpSteps] = {0, 0, 0,  -1, 1, 0, 0,  -1, 1, -1, 1,  -2, 2, 0, 0,  -2, -2, 2, 2, -1, 1, -1, 1,  -2, 2, -2, 2};
 __constant__ signed char c_run_dz[kIcpSteps] = {0, 0, 0,  0, 0, -1, 1,  -1, -1, 1, 1,  0, 0, -2, 2,  -1, 1, -1, 1, -2, -2, 2, 2,  -2, -2, 2, 2};
 
-constexpr int kIcpThreads = 128;      // small CTAs, several registrations per SM: one CTA's serial Kabsch/SVD step overlaps the others' searches
+constexpr int kIcpThreads = 128;      // small CTAs, 4 or 6 registrations per SM: one CTA's serial Kabsch/SVD step overlaps the others' searches
 constexpr int kIcpWarps = kIcpThreads / 32;
 constexpr int kIcpMaxCells = 4096;
 
@@ -165,7 +165,8 @@ __device__ __forceinline__ int cell_coord(double v, double lo, double inv_h) {
     return (int)floor((v - lo) * inv_h);
 }
 
-__global__ void __launch_bounds__(kIcpThreads, 4)
+template <int MINB>
+__global__ void __launch_bounds__(kIcpThreads, MINB)
 icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ src_offset,
                const double* __restrict__ target, const int32_t* __restrict__ tgt_offset, int n_reg,
                double threshold, double rel_fitness, double rel_rmse, int max_iter,
@@ -500,18 +501,31 @@ extern "C" __attribute__((visibility("default"))) int ape_icp_p2p(const double* 
     double* wtgt = wsrc + 3 * (size_t)total_source_points;
     int32_t* worig = reinterpret_cast<int32_t*>(wtgt + 3 * (size_t)total_target_points);
     int32_t* wcorr = worig + total_target_points;
-    static bool attr_set = false;
     const int smem = (int)sizeof(ape::IcpSmem);
+    static bool attr_set = false;
     if (!attr_set) {
-        APE_CUDA(cudaFuncSetAttribute(ape::icp_p2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        APE_CUDA(cudaFuncSetAttribute(ape::icp_p2p_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        APE_CUDA(cudaFuncSetAttribute(ape::icp_p2p_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    // 4 resident CTAs per SM (128 registers); 5 / 6 with spills measured 19 % / 10 % slower
-    const int grid = n_reg < ape::sm_count() * 4 ? n_reg : ape::sm_count() * 4;
+    // Resident CTAs per SM: 4 (128 registers, no spills) or 6 (80 registers, a few spills).  The search is latency-bound
+    // (fixed-latency fp64 chains, 4 warps per scheduler), so 6 per SM deliver 15 % more registrations per second when the
+    // grid stays full (measured: 3552 registrations, 245 k/s against 213 k/s), but a CTA then takes 1.3x as long per
+    // registration: pick the one with the shorter makespan for this batch (1184 registrations: 2 rounds of 4 per SM beat
+    // 1.33 -> 2 rounds of 6 per SM).
+    const int sms = ape::sm_count();
+    const double t4 = (double)((n_reg + 4 * sms - 1) / (4 * sms)), t6 = 1.30 * (double)((n_reg + 6 * sms - 1) / (6 * sms));
+    const int minb = (n_reg > 4 * sms && t6 < t4) ? 6 : 4;
+    const int grid = n_reg < sms * minb ? n_reg : sms * minb;
     ape::ProfScope prof_("icp_p2p", (cudaStream_t)stream);
-    ape::icp_p2p_kernel<<<grid, ape::kIcpThreads, smem, (cudaStream_t)stream>>>(
-        source, src_offset, target, tgt_offset, n_reg, threshold, rel_fitness, rel_rmse, max_iter, init, transform, info,
-        wsrc, wtgt, worig, wcorr);
+    if (minb == 6)
+        ape::icp_p2p_kernel<6><<<grid, ape::kIcpThreads, smem, (cudaStream_t)stream>>>(
+            source, src_offset, target, tgt_offset, n_reg, threshold, rel_fitness, rel_rmse, max_iter, init, transform, info,
+            wsrc, wtgt, worig, wcorr);
+    else
+        ape::icp_p2p_kernel<4><<<grid, ape::kIcpThreads, smem, (cudaStream_t)stream>>>(
+            source, src_offset, target, tgt_offset, n_reg, threshold, rel_fitness, rel_rmse, max_iter, init, transform, info,
+            wsrc, wtgt, worig, wcorr);
     ape::count_launch();
     return ape::check_launch("ape_icp_p2p");
 }

@@ -52,12 +52,16 @@ GEMM_EXEC_PER_ROW = {
 }
 
 
-def measured_traffic(kernel):
+def measured_traffic(kernel, units=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
     (profiles/traffic.json, written by tools/summarize_profiles.py); None when there is no capture."""
     p = os.path.join(ROOT, 'profiles', 'traffic.json')
     try:
-        return json.load(open(p))[kernel]['dram_bytes_per_launch']
+        e = json.load(open(p))[kernel]
+        b = e['dram_bytes_per_launch']
+        if units is not None and e.get('registrations_per_launch'):      # captured at another launch size: scale per unit
+            b = b / e['registrations_per_launch'] * units
+        return b
     except Exception:
         return None
 
@@ -192,7 +196,7 @@ def icp_leg(torch, ops, lib, peaks, steps, rank=0, world=1, sync=None, reduce_ma
     """Extra leg (BASELINE configs 1/4), run by EVERY rank on its own frames (frames are independent: no collective on the
     data path; `sync` = barrier + device synchronize, `reduce_max` = max over ranks of a list of floats):
     (a) masked back-projection over 512 distinct 640x480 frames per rank (HBM roofline),
-    (b) voxel grid + point-to-point ICP of 1184 registrations per rank built from 32 rendered frames.
+    (b) voxel grid + point-to-point ICP of 3552 registrations per rank built from 32 rendered frames.
     Whole-job rates = world * per-rank units / max-over-ranks device time."""
     from autoposeestimation_b200 import synthetic as synth
     sync = sync or torch.cuda.synchronize
@@ -232,7 +236,7 @@ def icp_leg(torch, ops, lib, peaks, steps, rank=0, world=1, sync=None, reduce_ma
     lab = torch.from_numpy(np.stack([f['label'] for f in frames])).to(dev)
     dep = torch.from_numpy(np.stack([f['depth'] for f in frames]).view(np.int16)).to(dev)
     cam2 = cam[:n_src]; r2c2 = r2c[:n_src]
-    reps = 37                                                 # 32 * 37 = 1184 registrations = 148 SMs * 8
+    reps = 111                                                # 32 * 111 = 3552 registrations = 148 SMs * 24 (whole rounds at 4, 6 or 8 CTAs per SM)
     nreg = n_src * reps
 
     def once():
@@ -276,7 +280,7 @@ def icp_leg(torch, ops, lib, peaks, steps, rank=0, world=1, sync=None, reduce_ma
                         mean_source_points=ns_mean, target_points=2000, mean_iterations=iters,
                         mean_fitness=float(info[:, 0].mean()), mean_rmse_mm=float(info[:, 1].mean()),
                         roofline=dict(bound='hbm', achieved=bytes_icp / ms_icp / 1e6, peak=peaks['hbm'], unit='GB/s',
-                                      frac=bytes_icp / ms_icp / 1e6 / peaks['hbm'], traffic=measured_traffic('icp_p2p'), peak_source=peaks['src'],
+                                      frac=bytes_icp / ms_icp / 1e6 / peaks['hbm'], traffic=measured_traffic('icp_p2p', nreg), peak_source=peaks['src'],
                                       note='per GPU; compulsory bytes 24*(Ns+Nt)+128 per registration; the NN stage is FP64-ALU / latency '
                                            'bound (SURVEY 8d), so this fraction is expected to be small')),
                label_path_32_frames_ms=prep_ms)

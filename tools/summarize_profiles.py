@@ -89,8 +89,9 @@ def traffic(tag):
                                               source='profiles/%s_ncu_label.csv (mask + scan + emit of one 512-frame call)' % tag)
         icp = [k for k in avg if k.startswith('icp_p2p')]
         if icp:
-            out['icp_p2p'] = dict(kernel=icp[0], dram_bytes_per_launch=avg[icp[0]],
-                                  source='profiles/%s_ncu_icp.csv (1184 registrations per launch)' % tag)
+            out['icp_p2p'] = dict(kernel=icp[0], dram_bytes_per_launch=avg[icp[0]], registrations_per_launch=1184,
+                                  source='profiles/%s_ncu_icp.csv (captured with 1184 registrations per launch; bench.py scales it to '
+                                         'its own launch size)' % tag)
     with open(os.path.join(ROOT, 'profiles', 'traffic.json'), 'w') as f:
         json.dump(out, f, indent=1)
     print('wrote profiles/traffic.json', {k: round(v['dram_bytes_per_launch'] / 1e6, 1) for k, v in out.items()}, 'MB per launch')
