@@ -319,7 +319,7 @@ extern "C" __attribute__((visibility("default"))) int ape_surface_backproject(co
     APE_REQUIRE((((uintptr_t)work) & 15) == 0, "ape_surface_backproject: work must be 16-byte aligned");
     if (n_views == 0) return APE_OK;
     const int n_chunks = (int)(((size_t)height * width + ape::kSurfChunk - 1) / ape::kSurfChunk);
-    APE_REQUIRE((size_t)n_views * n_chunks < (1u << 31), "ape_surface_backproject: too many views (split the batch)");
+    APE_REQUIRE((size_t)n_views * n_chunks * ape::kSurfWarps < (1u << 31), "ape_surface_backproject: too many views (split the batch)");
     cudaStream_t s = (cudaStream_t)stream;
     const int n_tiles = n_views * n_chunks;
     // work: [task counter + 3 pad words | task records int4 | sub-chunk counts | mask words]
