@@ -113,11 +113,12 @@ def test_icp_correspondence_search_exact(box, threshold, n_t):
     assert np.array_equal(T.cpu().numpy()[0], np.identity(4))
 
 
-def test_icp_batch_property_identical_registrations():
-    """592 copies of one registration in a single launch (4 CTAs per SM) give bit-identical transforms."""
+@pytest.mark.parametrize('R', [592, 1776])
+def test_icp_batch_property_identical_registrations(R):
+    """Copies of one registration in a single launch give bit-identical transforms: 592 = one round at 4 CTAs per SM,
+    1776 = the batch size at which the host switches to the 6-CTAs-per-SM build of the kernel (two rounds of 888)."""
     from autoposeestimation_b200 import ops
     src, tgt = _surface(4)
-    R = 592
     S = np.tile(src, (R, 1)); Tg = np.tile(tgt, (R, 1))
     so = (np.arange(R + 1) * len(src)).astype(np.int32); to = (np.arange(R + 1) * len(tgt)).astype(np.int32)
     T, info = ops.icp_p2p(_dev(S), _dev(so), _dev(Tg), _dev(to), 10.0)
