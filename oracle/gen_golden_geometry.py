@@ -11,6 +11,7 @@ Reference code exercised:
       PoseDataset.__getitem__ (:157-318), mode 'test', add_noise=False: mask, bbox, `choose` with
       np.random.shuffle of the 0/1 vector or np.pad(...,'wrap'), fp32 back-projection (:236-275)   -> rows a2, a3
       (this is the same code as pipeline/utils.py:524-553, which lives inside full_prediction)
+      PoseDataset.__init__ (:119-141): the .xyz model parser (= pipeline/utils.py:667-684)          -> row (f)-4
   pc_reconstruction/open3d_utils.py
       get_surface (:171-192): the per-pixel fp64 loop; the open3d calls that follow it (:194-212) are
       stand-ins that return the cloud unchanged, so the fixture holds the raw back-projected points   -> row a4
@@ -151,6 +152,8 @@ def main():
     try:
         ds_name = _write_tree(root, frames, intr, depth_scale, model_mm)
         ds = dataset.PoseDataset('test', num_pt, False, 0.0, False, ds_name, root)
+        xyz_text = open(os.path.join(root, 'pc_reconstruction/data/ellipsoid/ellipsoid.xyz')).read()
+        parsed_model = np.array(ds.cld[0], np.float64)            # the reference's own .xyz parser (dataset.py:119-141)
         clouds, chooses, bboxes, targets, models = [], [], [], [], []
         for i, s in enumerate(seeds):
             np.random.seed(s); random.seed(s)
@@ -187,7 +190,8 @@ def main():
         robot2cam=np.asarray(robot2cam, np.float64), num_pt=np.int64(num_pt), seeds=np.array(seeds, np.int64),
         bbox=np.array(bboxes, np.int64), choose=np.stack(chooses), cloud=np.stack(clouds),
         rects=np.array(rects, np.int64), rect_bbox=np.array(rect_bbox, np.int64),
-        surf_n=np.array([len(p) for p in surf_pts], np.int64), surf_pts=np.concatenate(surf_pts))
+        surf_n=np.array([len(p) for p in surf_pts], np.int64), surf_pts=np.concatenate(surf_pts),
+        xyz_text=np.array(xyz_text), xyz_written=np.asarray(model_mm, np.float64), xyz_parsed_m=parsed_model)
     print('wrote', path, os.path.getsize(path), 'bytes;', 'candidates per frame:',
           [int(((f[1] == 255) & (f[0] != 0)).sum()) for f in frames], 'bbox', bboxes)
 

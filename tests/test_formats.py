@@ -87,3 +87,19 @@ def test_frame_batch_loader(tmp_path):
         assert np.allclose(b['cam'][k].numpy(), [frames[idx]['intr'][q] for q in ('ppx', 'ppy', 'fx', 'fy')])
     with pytest.raises(ValueError):
         formats.load_depth_png(str(labels / '000003.new_pred.label.png'))                          # 8-bit file is not a depth image
+
+
+def test_xyz_parser_matches_reference_run(tmp_path):
+    """The .xyz text written as create_pointcloud.py:373-376 writes it and parsed by the REFERENCE's own parser
+    (dataset.py:119-141 = pipeline/utils.py:667-684, run by oracle/gen_golden_geometry.py): read_xyz reproduces the parsed
+    model bit for bit (including the dropped last character of unpadded z columns), and write_xyz reproduces the text."""
+    import os
+    from autoposeestimation_b200 import formats
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'geometry_ref.npz'))
+    path = tmp_path / 'ellipsoid.xyz'
+    path.write_text(str(g['xyz_text']))
+    got = formats.read_xyz(str(path), to_meter=True)
+    assert got.shape == g['xyz_parsed_m'].shape and np.array_equal(got, g['xyz_parsed_m'])
+    path2 = tmp_path / 'again.xyz'
+    formats.write_xyz(str(path2), g['xyz_written'])
+    assert path2.read_text() == str(g['xyz_text'])
