@@ -57,7 +57,8 @@ backproject_choose_kernel(const uint16_t* __restrict__ depth, int n_frames, int 
 // with a decoupled look-back = 1.5 TB/s, and 0.16 TB/s when made persistent (convoy on the look-back flags); mask +
 // one emit CTA per 8192-pixel chunk with a shared-memory compaction list (3 of 4 CTAs empty, two block barriers, two
 // fp64 divisions and one integer division per pixel: 69 us of emit for 512 frames) = 3.5 TB/s; this version (40 us of
-// emit: the prologue of the empty CTAs / warps was 40 % of all stall samples) = 4.7 TB/s for the whole call.
+// emit: the prologue of the empty CTAs / warps was 40 % of all stall samples) = 4.7 TB/s for the whole call, 4.8 TB/s with
+// programmatic dependent launch between the three kernels.
 constexpr int kSurfThreads = 256;
 constexpr int kSurfPix = 32;                          // pixels per thread
 constexpr int kSurfSub = 32 * kSurfPix;               // 1024 pixels per warp = one sub-chunk
