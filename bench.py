@@ -664,6 +664,9 @@ def run_b200(args):
                                    % (n_sets, h2d / 1e6), sharding='frames partitioned across ranks, no collective on the inference path'),
                     e2e=dict(value=e2e_value, unit='frames/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=float(ms2) / args.steps, wall_s=wall_e2e,
+                             h2d_gbs_per_gpu=h2d * args.steps / float(ms2) / 1e6,
+                             note='PCIe-bound: the step moves the fp32 encoder output of the batch (the reference interface of PoseNet.forward) '
+                                  'from pinned host memory; compute is hidden behind the copy',
                              api='autoposeestimation_b200.densefusion.estimate_poses.Runner (pinned host buffers, copy/compute double-buffered)'),
                     gpu_launches=launches, clocks=clocks, roofline=roofline,
                     cpu_baseline=(dict(value=cpu_fps, unit='frames/s', cores=cpu_threads, kind='port',
