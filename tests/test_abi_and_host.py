@@ -134,3 +134,24 @@ def test_host_quaternion_helpers(golden_dir):
         assert np.allclose(tf.quaternion_from_matrix(R, True), q, atol=1e-15)
         q2 = tf.quaternion_from_matrix(R, False)
         assert min(np.abs(q2 - q).max(), np.abs(q2 + q).max()) < 1e-8
+
+
+def test_committed_profiles_feed_the_bench_roofline():
+    """bench.py reads roofline.traffic (and the ncu tensor-pipe utilisation) from profiles/traffic.json: the committed file
+    must hold the three kernels the bench line reports, consistent with the committed ncu summaries it was derived from."""
+    import csv
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    t = json.load(open(os.path.join(root, 'profiles', 'traffic.json')))
+    for k in ('gemm', 'surface_backproject', 'icp_p2p'):
+        assert t[k]['dram_bytes_per_launch'] > 0 and os.path.exists(os.path.join(root, t[k]['source'].split(' ')[0]))
+    assert 40.0 <= t['gemm']['tensor_pipe_active_pct_time_weighted'] <= 100.0      # BASELINE target: >= 40 % tensor-pipe utilisation
+    rows = list(csv.reader(open(os.path.join(root, t['gemm']['source'].split(' ')[0]))))
+    assert len(rows) - 1 == t['gemm']['launches_captured'] == 12
+    import bench
+    assert bench.measured_traffic('gemm') == t['gemm']['dram_bytes_per_launch']
+    assert abs(bench.measured_traffic('icp_p2p', 2 * t['icp_p2p']['registrations_per_launch']) - 2 * t['icp_p2p']['dram_bytes_per_launch']) < 1.0
+    # back-projection: measured DRAM traffic must not exceed the algorithmic bytes by more than a few per cent
+    # (512 frames x 921 600 B + 24 B per valid pixel ~ 574 MB): no wasted re-reads
+    assert t['surface_backproject']['dram_bytes_per_launch'] < 1.05 * 574e6
