@@ -39,6 +39,12 @@ SIGNATURES = {
     'ape_refiner_forward': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
     'ape_pose_pipeline': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
                                   c_vp, c_vp, c_vp]),
+    'ape_posenet_forward_ex': (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'ape_pose_pipeline_ex': (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
+                                     c_vp, c_vp, c_vp]),
+    'ape_gather_emb': (c_int, [c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp]),
+    'ape_host_gather_begin': (c_int, [c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp, c_int]),
+    'ape_host_gather_wait': (c_int, []),
     'ape_radius_outlier': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_dbl, c_vp, c_vp, c_vp]),
     'ape_mahalanobis': (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     'ape_statistical_outlier': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_dbl, c_vp, c_vp, c_vp, c_vp]),

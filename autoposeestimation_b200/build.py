@@ -20,8 +20,13 @@ FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-li
          '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']
 
 
+CXX = os.environ.get('CXX', 'g++')
+CXXFLAGS = ['-O3', '-std=c++17', '-fPIC', '-fvisibility=hidden', '-pthread']
+
+
 def _sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cu'))
+    """csrc/*.cu (nvcc, sm_100a) and csrc/*.cpp (host-only plumbing: g++)."""
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cpp')))
 
 
 def _headers_mtime():
@@ -31,13 +36,16 @@ def _headers_mtime():
 
 
 def _compile(src, force, hdr_m, verbose):
-    obj = os.path.join(OBJ, os.path.basename(src)[:-3] + '.o')
+    obj = os.path.join(OBJ, os.path.splitext(os.path.basename(src))[0] + '.o')
     if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_m):
         return obj, ''
-    cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+    if src.endswith('.cpp'):
+        cmd = [CXX] + CXXFLAGS + ['-c', src, '-o', obj]
+    else:
+        cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError('nvcc failed for %s:\n%s\n%s' % (src, r.stdout, r.stderr))
+        raise RuntimeError('compile failed for %s:\n%s\n%s' % (src, r.stdout, r.stderr))
     return obj, r.stderr
 
 
@@ -53,7 +61,7 @@ def build(force=False, verbose=False):
             if log:
                 print(log)
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(o) for o in objs):
-        cmd = [NVCC, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB] + objs + ['-lcudart']
+        cmd = [NVCC, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB] + objs + ['-lcudart', '-lpthread']
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))

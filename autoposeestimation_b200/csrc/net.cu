@@ -30,7 +30,7 @@ typedef __nv_bfloat16 bf16;
 constexpr int kFrontPts = 8;
 template <bool GATHER>
 __global__ void __launch_bounds__(256)
-frontend_kernel(const float* __restrict__ feat_src /*GATHER: out_img [B,32,hw]; else emb [B,32,N]*/, int hw,
+frontend_kernel(const float* __restrict__ feat_src /*GATHER: out_img [B,32,hw] (hw > 0) or channels-last [B,-hw,32] (hw < 0); else emb [B,32,N]*/, int hw,
                 const float* __restrict__ cloud, const int64_t* __restrict__ choose,
                 const float* __restrict__ fw,                                    // packed front-end weights (see below)
                 int N, int Np, bf16* __restrict__ pf_hi, bf16* __restrict__ pf_lo, int pf_ld,
@@ -64,13 +64,16 @@ frontend_kernel(const float* __restrict__ feat_src /*GATHER: out_img [B,32,hw]; 
     // ---- loads (all in flight together)
     float e[kFrontPts];                                 // lane = channel
     if (GATHER) {
+        const bool nhwc = hw < 0;                        // channels-last map: one point = one contiguous 128-byte line
+        const int hwp = nhwc ? -hw : hw;
         int64_t ci = 0;
         if (lane < npts) ci = choose[(size_t)b * N + n0 + lane];
-        const float* src = feat_src + ((size_t)b * 32 + lane) * hw;
+        ci = ci < 0 ? 0 : (ci >= hwp ? hwp - 1 : ci);    // torch.gather would raise (network.py:102); never read outside the map
+        const float* src = nhwc ? feat_src + (size_t)b * hwp * 32 + lane : feat_src + ((size_t)b * 32 + lane) * hwp;
 #pragma unroll
         for (int j = 0; j < kFrontPts; ++j) {
             const int64_t c = __shfl_sync(0xffffffffu, ci, j);
-            e[j] = j < npts ? __ldg(src + c) : 0.f;
+            e[j] = j < npts ? __ldg(src + (nhwc ? c * 32 : c)) : 0.f;
         }
     } else {
         const float* src = feat_src + ((size_t)b * 32 + lane) * N + n0;
@@ -79,7 +82,7 @@ frontend_kernel(const float* __restrict__ feat_src /*GATHER: out_img [B,32,hw]; 
     }
     float cv = 0.f;                                     // lanes 0..23: the 8 points' xyz
     if (lane < 3 * npts) cv = cloud[((size_t)b * N + n0) * 3 + lane];
-    if (GATHER) {                                       // emb [B,32,N]: lane = channel writes its 8 consecutive points
+    if (GATHER && emb_out) {                            // emb [B,32,N]: lane = channel writes its 8 consecutive points
         float* dst = emb_out + ((size_t)b * 32 + lane) * N + n0;
 #pragma unroll
         for (int j = 0; j < kFrontPts; ++j) if (j < npts) dst[j] = e[j];
@@ -768,6 +771,8 @@ static ape::tc::Params split_layer(int M, int N, int K, int groups, int a_k0, in
 }
 
 // front end + conv2/e_conv2 + conv5 + conv6 (+AvgPool) shared by both networks; leaves AP [B,1024]
+// PoseNet: `choose` != NULL gathers from the encoder map (hw > 0: [B,32,hw]; hw < 0: channels-last [B,-hw,32]);
+// `choose` == NULL: feat_src is the already gathered emb [B,32,N] (as for the refiner).
 static int run_trunk(ape_net* net, const float* feat_src, int hw, const float* cloud, const int64_t* choose, int B, int N,
                      float* emb_out, cudaStream_t s)
 {
@@ -776,7 +781,7 @@ static int run_trunk(ape_net* net, const float* feat_src, int hw, const float* c
     dim3 gf((Np + 63) / 64, B);
     {
     ape::ProfScope prof_("frontend", s);
-    if (net->kind == APE_NET_POSENET)
+    if (net->kind == APE_NET_POSENET && choose)
         APE_CUDA(ape::launch_pdl(ape::frontend_kernel<true>, gf, dim3(256), 0, s, feat_src, hw, cloud, choose, net->fw.p, N, Np, net->PF.hi, net->PF.lo, 384, emb_out));
     else
         APE_CUDA(ape::launch_pdl(ape::frontend_kernel<false>, gf, dim3(256), 0, s, feat_src, hw, cloud, (const int64_t*)nullptr, net->fw.p, N, Np, net->PF.hi, net->PF.lo, 384, (float*)nullptr));
@@ -832,20 +837,29 @@ static int dense(const float* in, int in_ld, int in_gs, const DevF32& W, const D
     return ape::check_launch("dense_batch");
 }
 
+// emb_layout: APE_EMB_NCHW  out_img [B,32,hw] (the encoder's own layout), gathered at `choose` (network.py:100-102);
+//             APE_EMB_NHWC  out_img [B,hw,32] (torch channels_last memory format of the same tensor);
+//             APE_EMB_GATHERED  out_img is emb [B,32,N] already gathered (ape_gather_emb / ape_host_gather_*): hw and
+//                               choose are ignored, `emb` may be NULL (or receives a copy).
 extern "C" __attribute__((visibility("default")))
-int ape_posenet_forward(ape_net* net, const float* out_img, int hw, const float* cloud, const int64_t* choose,
-                        const int64_t* obj, int B, int N, float* pred_r, float* pred_t, float* pred_c, float* emb,
-                        void* stream)
+int ape_posenet_forward_ex(ape_net* net, const float* out_img, int hw, int emb_layout, const float* cloud, const int64_t* choose,
+                           const int64_t* obj, int B, int N, float* pred_r, float* pred_t, float* pred_c, float* emb,
+                           void* stream)
 {
     APE_REQUIRE(net && net->kind == APE_NET_POSENET, "ape_posenet_forward: not a PoseNet handle");
-    APE_REQUIRE(out_img && cloud && choose && obj && pred_r && pred_t && pred_c && emb, "ape_posenet_forward: null pointer");
-    APE_REQUIRE(B > 0 && N > 0 && hw > 0, "ape_posenet_forward: bad sizes");
+    APE_REQUIRE(emb_layout == APE_EMB_NCHW || emb_layout == APE_EMB_NHWC || emb_layout == APE_EMB_GATHERED, "ape_posenet_forward: unknown emb_layout");
+    const bool gathered = emb_layout == APE_EMB_GATHERED;
+    APE_REQUIRE(out_img && cloud && obj && pred_r && pred_t && pred_c, "ape_posenet_forward: null pointer");
+    APE_REQUIRE(gathered || (choose && emb), "ape_posenet_forward: null pointer");
+    APE_REQUIRE(B > 0 && N > 0 && (gathered || hw > 0), "ape_posenet_forward: bad sizes");
     APE_REQUIRE(B <= net->max_batch && N <= net->max_points, "ape_posenet_forward: B=%d N=%d exceed the handle's workspace (%d, %d)",
                 B, N, net->max_batch, net->max_points);
     cudaStream_t s = (cudaStream_t)stream;
     const int Np = (N + 127) / 128 * 128, M = (B * Np + 255) / 256 * 256;
-    int rc = run_trunk(net, out_img, hw, cloud, choose, B, N, emb, s);
+    int rc = run_trunk(net, out_img, emb_layout == APE_EMB_NHWC ? -hw : hw, cloud, gathered ? nullptr : choose, B, N, emb, s);
     if (rc) return rc;
+    if (gathered && emb && emb != out_img)
+        APE_CUDA(cudaMemcpyAsync(emb, out_img, (size_t)B * 32 * N * sizeof(float), cudaMemcpyDeviceToDevice, s));
     // global-feature half of conv1_{r,t,c} folded into a per-object bias: GB = b + Wg * AP
     if ((rc = dense(net->AP.p, 1024, 0, net->Wg, net->b_h1, net->GB.p, 1920, B, 1024, 1920, 1, 0, s))) return rc;
     ape::tc::Params p;
@@ -894,6 +908,14 @@ int ape_posenet_forward(ape_net* net, const float* out_img, int hw, const float*
 }
 
 extern "C" __attribute__((visibility("default")))
+int ape_posenet_forward(ape_net* net, const float* out_img, int hw, const float* cloud, const int64_t* choose,
+                        const int64_t* obj, int B, int N, float* pred_r, float* pred_t, float* pred_c, float* emb,
+                        void* stream)
+{
+    return ape_posenet_forward_ex(net, out_img, hw, APE_EMB_NCHW, cloud, choose, obj, B, N, pred_r, pred_t, pred_c, emb, stream);
+}
+
+extern "C" __attribute__((visibility("default")))
 int ape_refiner_forward(ape_net* net, const float* new_points, const float* emb, const int64_t* obj, int B, int N,
                         float* r2, float* t2, void* stream)
 {
@@ -931,14 +953,17 @@ int ape_refiner_forward(ape_net* net, const float* new_points, const float* emb,
 //   canonical == 0 : pipeline/utils.py:564-571 as written (the refiner input is never updated, so its
 //                    `iterations` calls are identical: it runs once and one composition follows)
 extern "C" __attribute__((visibility("default")))
-int ape_pose_pipeline(ape_net* est, ape_net* ref, const float* out_img, int hw, const float* cloud, const int64_t* choose,
-                      const int64_t* obj, int B, int N, int iterations, int canonical, double* poses, int32_t* which_max,
-                      void* stream)
+int ape_pose_pipeline_ex(ape_net* est, ape_net* ref, const float* out_img, int hw, int emb_layout, const float* cloud,
+                         const int64_t* choose, const int64_t* obj, int B, int N, int iterations, int canonical, double* poses,
+                         int32_t* which_max, void* stream)
 {
     APE_REQUIRE(est && est->kind == APE_NET_POSENET, "ape_pose_pipeline: estimator handle required");
     APE_REQUIRE(iterations == 0 || (ref && ref->kind == APE_NET_REFINER), "ape_pose_pipeline: refiner handle required");
     APE_REQUIRE(poses, "ape_pose_pipeline: null output");
-    int rc = ape_posenet_forward(est, out_img, hw, cloud, choose, obj, B, N, est->s_r.p, est->s_t.p, est->s_c.p, est->s_emb.p, stream);
+    const bool gathered = emb_layout == APE_EMB_GATHERED;
+    const float* emb = gathered ? out_img : est->s_emb.p;           // pre-gathered: the input IS the refiner's emb
+    int rc = ape_posenet_forward_ex(est, out_img, hw, emb_layout, cloud, choose, obj, B, N, est->s_r.p, est->s_t.p, est->s_c.p,
+                                    gathered ? nullptr : est->s_emb.p, stream);
     if (rc) return rc;
     int32_t* wm = which_max ? which_max : est->s_which;
     double* cur = iterations == 0 ? poses : est->s_pose_a;
@@ -946,7 +971,7 @@ int ape_pose_pipeline(ape_net* est, ape_net* ref, const float* out_img, int hw, 
     if (rc) return rc;
     const int n_eff = canonical ? iterations : (iterations > 0 ? 1 : 0);
     for (int it = 0; it < n_eff; ++it) {
-        rc = ape_refiner_forward(ref, est->s_newp.p, est->s_emb.p, obj, B, N, est->s_r2.p, est->s_t2.p, stream);
+        rc = ape_refiner_forward(ref, est->s_newp.p, emb, obj, B, N, est->s_r2.p, est->s_t2.p, stream);
         if (rc) return rc;
         const bool last = it == n_eff - 1;
         double* nxt = last ? poses : (cur == est->s_pose_a ? est->s_pose_b : est->s_pose_a);
@@ -956,6 +981,15 @@ int ape_pose_pipeline(ape_net* est, ape_net* ref, const float* out_img, int hw, 
         cur = nxt;
     }
     return APE_OK;
+}
+
+extern "C" __attribute__((visibility("default")))
+int ape_pose_pipeline(ape_net* est, ape_net* ref, const float* out_img, int hw, const float* cloud, const int64_t* choose,
+                      const int64_t* obj, int B, int N, int iterations, int canonical, double* poses, int32_t* which_max,
+                      void* stream)
+{
+    return ape_pose_pipeline_ex(est, ref, out_img, hw, APE_EMB_NCHW, cloud, choose, obj, B, N, iterations, canonical, poses,
+                                which_max, stream);
 }
 
 #include "train.cuh"

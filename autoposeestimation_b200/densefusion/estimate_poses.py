@@ -1,9 +1,26 @@
 """Batched option-6 geometry block from HOST buffers (the call a user of the drop-in makes).
 
-`Runner` double-buffers: the H2D copy of batch i+1 (pinned host memory, copy stream) overlaps the
-kernels of batch i; the poses of every batch are copied back to pinned host memory.  No CPU fallback.
-Replaces the per-object loop of pipeline/utils.py:556-571 (three H2D + three D2H syncs per object).
+Replaces the per-object loop of pipeline/utils.py:556-571 (three H2D + three D2H syncs per object).  `Runner`
+double-buffers: the hand-over of batch i+1 overlaps the kernels of batch i; the poses of every batch are copied back to
+pinned host memory.  No CPU fallback: the networks and the pose math only ever run on the sm_100a kernels.
+
+Hand-over of the colour-encoder output.  The kernels need 32 channels at the N sampled pixels of every object
+(network.py:100-102), i.e. 4.1 MB of a 157 MB [64,32,120,160] fp32 map.  Shipping the whole map (round 1) made the call
+PCIe-bound (2.9 ms per batch against 0.76 ms of kernels).  `transfer=`
+  'gather' (default)  only the sampled columns cross the bus.  For a pinned [B,32,H,W] map the batch is SPLIT between
+                      (a) the zero-copy gather kernel reading the map in place over PCIe (ops.gather_emb, 1.26 ms for a
+                      whole batch) and (b) the host thread pool gathering into a pinned staging buffer + one small H2D
+                      (ops.host_gather_*, 0.93 ms on 16 cores): they draw on different resources (PCIe read requests /
+                      host DRAM bandwidth), the split is calibrated on the first batch.  A channels_last map
+                      (`t.contiguous(memory_format=torch.channels_last)`: one point = one 128-byte line) goes through the
+                      zero-copy kernel alone (0.09 ms); a pageable (unpinned) map through the host pool alone.
+  'full'              cudaMemcpyAsync of the whole map, gather in the front-end kernel (the round-1 path; also what a
+                      DEVICE-resident map gets, without the copy).
+The step's kernels are replayed from a CUDA graph per buffer slot, so the host thread spends its time in the gather, not
+in ~40 launches.
 """
+import time
+
 import numpy as np
 import torch
 
@@ -11,41 +28,130 @@ from .. import ops
 
 
 class Runner:
-    def __init__(self, estimator, refiner, max_batch, n_points, crop_pixels, iterations=2, canonical=True, device=None):
+    def __init__(self, estimator, refiner, max_batch, n_points, crop_pixels, iterations=2, canonical=True, device=None,
+                 transfer='gather', zero_copy_fraction=None, host_threads=0, use_graph=True):
+        assert transfer in ('gather', 'full')
         self.est, self.ref = estimator, refiner
         self.iterations, self.canonical = iterations, canonical
         dev = device or torch.device('cuda', torch.cuda.current_device())
         self.dev = dev
-        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.transfer, self.zc_fraction, self.host_threads, self.use_graph = transfer, zero_copy_fraction, host_threads, use_graph
+        self.copy_stream = torch.cuda.Stream(device=dev, priority=-1)
         mk = lambda shape, dt: [torch.empty(shape, dtype=dt, device=dev) for _ in range(2)]
-        self.d_img = mk((max_batch, 32, crop_pixels), torch.float32)
+        self.d_img = mk((max_batch, 32, crop_pixels), torch.float32) if transfer == 'full' else None
+        self.d_emb = mk((max_batch, 32, n_points), torch.float32)
         self.d_cloud = mk((max_batch, n_points, 3), torch.float32)
         self.d_choose = mk((max_batch, n_points), torch.int64)
         self.d_idx = mk((max_batch,), torch.int64)
         self.d_pose = mk((max_batch, 7), torch.float64)
         self.h_pose = [torch.empty((max_batch, 7), dtype=torch.float64).pin_memory() for _ in range(2)]
+        self.h_stage = [torch.empty((max_batch, 32, n_points), dtype=torch.float32).pin_memory() for _ in range(2)]
         self.copied = [torch.cuda.Event() for _ in range(2)]
         self.done = [torch.cuda.Event() for _ in range(2)]
+        self.graphs = {}
         self.i = 0
         self.last = None
+        self.calibration = None
+
+    # ------------------------------------------------------------------------------------------------
+    def calibrate(self, out_img, choose, reps=3):
+        """Time the two gather paths on this batch and split objects so that both finish together.
+        -> dict(zero_copy_ms, host_ms, zero_copy_fraction)."""
+        B = out_img.shape[0]
+        N = self.d_choose[0].shape[1]
+        torch.cuda.synchronize(self.dev)
+        with torch.cuda.stream(self.copy_stream):
+            self.d_choose[0][:B].copy_(choose.reshape(B, -1), non_blocking=True)
+            ops.gather_emb(out_img, self.d_choose[0][:B], out=self.d_emb[0][:B])        # warm-up (page tables, kernel load)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.copy_stream)
+            for _ in range(reps):
+                ops.gather_emb(out_img, self.d_choose[0][:B], out=self.d_emb[0][:B])
+            e1.record(self.copy_stream)
+        e1.synchronize()
+        t_zc = e0.elapsed_time(e1) / reps
+        ch = choose.reshape(B, -1).contiguous()
+        ops.host_gather_begin(out_img, ch, self.h_stage[0], 0, B, self.host_threads); ops.host_gather_wait()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ops.host_gather_begin(out_img, ch, self.h_stage[0], 0, B, self.host_threads); ops.host_gather_wait()
+        t_host = (time.perf_counter() - t0) / reps * 1e3
+        self.zc_fraction = t_host / (t_host + t_zc)
+        self.calibration = dict(zero_copy_ms=t_zc, host_ms=t_host, zero_copy_fraction=self.zc_fraction)
+        return self.calibration
+
+    def _compute(self, s, B, gathered):
+        """The step's kernels on the current stream (a CUDA-graph replay once the slot / batch size has been seen)."""
+        src = self.d_emb[s][:B] if gathered else self.d_img[s][:B]
+
+        def launch():
+            ops.pose_pipeline(self.est, self.ref, src, self.d_cloud[s][:B], None if gathered else self.d_choose[s][:B], self.d_idx[s][:B],
+                              iterations=self.iterations, canonical=self.canonical, out=self.d_pose[s][:B], gathered=gathered)
+        key = (s, B, gathered)
+        g = self.graphs.get(key)
+        if g is None and self.use_graph and self.i >= 2:         # the first use of each slot runs (and warms up) eagerly
+            try:
+                cap = torch.cuda.Stream(device=self.dev)
+                cap.wait_stream(torch.cuda.current_stream(self.dev))
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=cap):
+                    launch()
+                torch.cuda.current_stream(self.dev).wait_stream(cap)
+            except Exception:                                     # capture not possible (e.g. profiling hooks on): plain launches
+                g = False
+            self.graphs[key] = g
+        if g:
+            g.replay()
+        else:
+            launch()
 
     def submit(self, out_img, cloud, choose, idx):
-        """Host tensors (pinned for true async): out_img [B,32,H,W] fp32, cloud [B,N,3] fp32,
-        choose [B,1,N] int64, idx [B,1] int64.  Returns immediately."""
+        """out_img [B,32,H,W] fp32: pinned host tensor (contiguous or channels_last), pageable host tensor or CUDA tensor;
+        cloud [B,N,3] fp32, choose [B,1,N] int64, idx [B,1] int64 host (pinned for true async) or CUDA.  Returns immediately."""
         s = self.i % 2
         B = cloud.shape[0]
         main = torch.cuda.current_stream(self.dev)
         if self.i >= 2:
             self.copy_stream.wait_event(self.done[s])         # device slot s is free again
+            self.copied[s].synchronize()                      # ... and so is the pinned staging buffer of slot s
+        on_dev = out_img.is_cuda
+        gathered = self.transfer == 'gather' and not on_dev
         with torch.cuda.stream(self.copy_stream):
-            self.d_img[s][:B].copy_(out_img.reshape(B, 32, -1), non_blocking=True)
             self.d_cloud[s][:B].copy_(cloud, non_blocking=True)
             self.d_choose[s][:B].copy_(choose.reshape(B, -1), non_blocking=True)
             self.d_idx[s][:B].copy_(idx.reshape(B), non_blocking=True)
-            self.copied[s].record(self.copy_stream)
+        if gathered:
+            nhwc = out_img.dim() == 4 and not out_img.is_contiguous() and out_img.is_contiguous(memory_format=torch.channels_last)
+            if not out_img.is_pinned():
+                k = 0                                          # pageable memory cannot be read by a kernel
+            elif nhwc:
+                k = B                                          # 128-byte lines: the kernel alone is PCIe-efficient
+            else:
+                if self.zc_fraction is None:
+                    self.calibrate(out_img, choose)
+                k = int(round(B * self.zc_fraction))
+            keep = None
+            if k < B:
+                ch = choose.reshape(B, -1)
+                keep = ops.host_gather_begin(out_img, ch if ch.is_contiguous() else ch.contiguous(), self.h_stage[s], k, B, self.host_threads)
+            if k > 0:
+                with torch.cuda.stream(self.copy_stream):
+                    ops.gather_emb(out_img[:k], self.d_choose[s][:k], out=self.d_emb[s][:k])
+            if k < B:
+                ops.host_gather_wait()
+                del keep
+                with torch.cuda.stream(self.copy_stream):
+                    self.d_emb[s][k:B].copy_(self.h_stage[s][k:B], non_blocking=True)
+        elif not on_dev:
+            with torch.cuda.stream(self.copy_stream):
+                self.d_img[s][:B].copy_(out_img.reshape(B, 32, -1), non_blocking=True)
+        self.copied[s].record(self.copy_stream)
         main.wait_event(self.copied[s])
-        ops.pose_pipeline(self.est, self.ref, self.d_img[s][:B], self.d_cloud[s][:B], self.d_choose[s][:B], self.d_idx[s][:B],
-                          iterations=self.iterations, canonical=self.canonical, out=self.d_pose[s][:B])
+        if on_dev:                                             # device-resident map: gather inside the front-end kernel
+            ops.pose_pipeline(self.est, self.ref, out_img, self.d_cloud[s][:B], self.d_choose[s][:B], self.d_idx[s][:B],
+                              iterations=self.iterations, canonical=self.canonical, out=self.d_pose[s][:B])
+        else:
+            self._compute(s, B, gathered)
         self.h_pose[s][:B].copy_(self.d_pose[s][:B], non_blocking=True)
         self.done[s].record(main)
         self.last = (s, B)
@@ -60,10 +166,10 @@ class Runner:
         return self.h_pose[s][:B].clone()
 
 
-def estimate_poses(estimator, refiner, out_img, cloud, choose, idx, iterations=2, canonical=True):
+def estimate_poses(estimator, refiner, out_img, cloud, choose, idx, iterations=2, canonical=True, transfer='gather'):
     """One-shot convenience wrapper: numpy / CPU tensors in, numpy poses [B,7] (wxyz, t; metres) out."""
     t = [torch.as_tensor(np.ascontiguousarray(a)) if not isinstance(a, torch.Tensor) else a for a in (out_img, cloud, choose, idx)]
     B, N = t[1].shape[0], t[1].shape[1]
-    r = Runner(estimator, refiner, B, N, int(np.prod(t[0].shape[2:])), iterations, canonical)
+    r = Runner(estimator, refiner, B, N, int(np.prod(t[0].shape[2:])), iterations, canonical, transfer=transfer, use_graph=False)
     r.submit(*t)
     return r.drain().numpy()

@@ -314,18 +314,22 @@ class NetHandle:
         except Exception:
             pass
 
-    def posenet_forward(self, out_img, cloud, choose, obj):
-        """out_img [B,32,hw] (or [B,32,H,W]), cloud [B,N,3], choose [B,N] (or [B,1,N]) int64, obj [B] (or [B,1]) int64
-        -> pred_r [B,N,4], pred_t [B,N,3], pred_c [B,N,1], emb [B,32,N]"""
+    def posenet_forward(self, out_img, cloud, choose, obj, gathered=False):
+        """out_img [B,32,hw] / [B,32,H,W] (contiguous, or 4-D in torch.channels_last memory format), cloud [B,N,3],
+        choose [B,N] (or [B,1,N]) int64, obj [B] (or [B,1]) int64 -> pred_r [B,N,4], pred_t [B,N,3], pred_c [B,N,1], emb [B,32,N].
+        gathered=True: out_img IS emb [B,32,N] (already gathered, choose ignored) and is returned as emb."""
         require_cuda(out_img, cloud, choose, obj)
         B, N = cloud.shape[0], cloud.shape[1]
-        out_img = _c(out_img, torch.float32).reshape(B, 32, -1)
-        cloud = _c(cloud, torch.float32); choose = _c(choose, torch.int64).reshape(B, N); obj = _c(obj, torch.int64).reshape(B)
+        img, hw, layout = _emb_input(out_img, B, N, gathered)
+        cloud = _c(cloud, torch.float32); obj = _c(obj, torch.int64).reshape(B)
+        choose = None if gathered else _c(choose, torch.int64).reshape(B, N)
         dev = cloud.device
         r = torch.empty((B, N, 4), dtype=torch.float32, device=dev); t = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
-        c = torch.empty((B, N, 1), dtype=torch.float32, device=dev); emb = torch.empty((B, 32, N), dtype=torch.float32, device=dev)
-        check(_lib.load().ape_posenet_forward(self._h, ptr(out_img), out_img.shape[2], ptr(cloud), ptr(choose), ptr(obj), B, N,
-                                              ptr(r), ptr(t), ptr(c), ptr(emb), stream_ptr()), 'ape_posenet_forward')
+        c = torch.empty((B, N, 1), dtype=torch.float32, device=dev)
+        emb = img if gathered else torch.empty((B, 32, N), dtype=torch.float32, device=dev)
+        check(_lib.load().ape_posenet_forward_ex(self._h, img.data_ptr(), hw, layout, ptr(cloud), ptr(choose), ptr(obj), B, N,
+                                                 ptr(r), ptr(t), ptr(c), None if gathered else ptr(emb), stream_ptr()),
+              'ape_posenet_forward_ex')
         return r, t, c, emb
 
     def refiner_forward(self, new_points, emb, obj):
@@ -340,17 +344,71 @@ class NetHandle:
         return r2, t2
 
 
-def pose_pipeline(est, ref, out_img, cloud, choose, obj, iterations=2, canonical=True, out=None):
-    """Whole option-6 geometry block: -> (poses [B,7] fp64 (wxyz, t), which_max [B] int32).  No host sync."""
+EMB_NCHW, EMB_NHWC, EMB_GATHERED = 0, 1, 2
+
+
+def _emb_input(out_img, B, N, gathered):
+    """-> (fp32 tensor whose data_ptr is handed over, hw, APE_EMB_* layout) for an encoder map / a gathered embedding."""
+    if out_img.dtype != torch.float32:
+        out_img = out_img.float()
+    if gathered:
+        assert tuple(out_img.shape) == (B, 32, N), 'gathered embedding must be [B,32,N]'
+        return out_img.contiguous(), 0, EMB_GATHERED
+    if out_img.dim() == 4 and not out_img.is_contiguous() and out_img.is_contiguous(memory_format=torch.channels_last):
+        return out_img, out_img.shape[2] * out_img.shape[3], EMB_NHWC
+    out_img = out_img.contiguous().reshape(B, 32, -1)
+    return out_img, out_img.shape[2], EMB_NCHW
+
+
+def gather_emb(out_img, choose, out=None):
+    """network.py:100-102 as a stand-alone kernel.  out_img [B,32,hw] / [B,32,H,W] fp32: a CUDA tensor, or a PINNED host
+    tensor (read zero-copy over PCIe: only the sampled columns cross the bus); contiguous or channels_last.
+    choose [B,N] int64 CUDA -> emb [B,32,N] fp32 CUDA."""
+    require_cuda(choose)
+    if not out_img.is_cuda and not out_img.is_pinned():
+        raise _lib.ApeError('gather_emb: a host encoder map must be pinned (torch.Tensor.pin_memory) for zero-copy access')
+    B = out_img.shape[0]
+    choose = _c(choose, torch.int64).reshape(B, -1)
+    N = choose.shape[1]
+    img, hw, layout = _emb_input(out_img, B, N, False)
+    emb = out if out is not None else torch.empty((B, 32, N), dtype=torch.float32, device=choose.device)
+    check(_lib.load().ape_gather_emb(img.data_ptr(), hw, layout, ptr(choose), B, N, ptr(emb), stream_ptr()), 'ape_gather_emb')
+    return emb
+
+
+def host_gather_begin(out_img, choose, emb_host, obj_begin=0, obj_end=None, threads=0):
+    """Start gathering objects [obj_begin, obj_end) of a HOST encoder map into the (pinned) staging tensor emb_host
+    [B,32,N] on the library's thread pool; returns immediately, host_gather_wait() blocks until it is complete."""
+    assert not out_img.is_cuda and not choose.is_cuda and not emb_host.is_cuda
+    B = out_img.shape[0]
+    choose = choose.reshape(B, -1)
+    assert choose.dtype == torch.int64 and choose.is_contiguous() and emb_host.is_contiguous() and emb_host.dtype == torch.float32
+    N = choose.shape[1]
+    img, hw, layout = _emb_input(out_img, B, N, False)
+    check(_lib.load().ape_host_gather_begin(img.data_ptr(), hw, layout, choose.data_ptr(), int(obj_begin),
+                                            int(B if obj_end is None else obj_end), N, emb_host.data_ptr(), int(threads)),
+          'ape_host_gather_begin')
+    return img                                                   # keep alive until host_gather_wait()
+
+
+def host_gather_wait():
+    check(_lib.load().ape_host_gather_wait(), 'ape_host_gather_wait')
+
+
+def pose_pipeline(est, ref, out_img, cloud, choose, obj, iterations=2, canonical=True, out=None, gathered=False):
+    """Whole option-6 geometry block: -> (poses [B,7] fp64 (wxyz, t), which_max [B] int32).  No host sync.
+    out_img: encoder map [B,32,hw] / [B,32,H,W] (contiguous or channels_last), or with gathered=True the already
+    gathered emb [B,32,N] (choose may then be None)."""
     require_cuda(out_img, cloud, choose, obj)
     B, N = cloud.shape[0], cloud.shape[1]
-    out_img = _c(out_img, torch.float32).reshape(B, 32, -1)
-    cloud = _c(cloud, torch.float32); choose = _c(choose, torch.int64).reshape(B, N); obj = _c(obj, torch.int64).reshape(B)
+    img, hw, layout = _emb_input(out_img, B, N, gathered)
+    cloud = _c(cloud, torch.float32); obj = _c(obj, torch.int64).reshape(B)
+    choose = None if gathered else _c(choose, torch.int64).reshape(B, N)
     poses = out if out is not None else torch.empty((B, 7), dtype=torch.float64, device=cloud.device)
     wm = torch.empty((B,), dtype=torch.int32, device=cloud.device)
-    check(_lib.load().ape_pose_pipeline(est._h, ref._h if ref is not None else None, ptr(out_img), out_img.shape[2], ptr(cloud),
-                                        ptr(choose), ptr(obj), B, N, int(iterations), int(bool(canonical)), ptr(poses), ptr(wm),
-                                        stream_ptr()), 'ape_pose_pipeline')
+    check(_lib.load().ape_pose_pipeline_ex(est._h, ref._h if ref is not None else None, img.data_ptr(), hw, layout, ptr(cloud),
+                                           ptr(choose), ptr(obj), B, N, int(iterations), int(bool(canonical)), ptr(poses), ptr(wm),
+                                           stream_ptr()), 'ape_pose_pipeline_ex')
     return poses, wm
 
 

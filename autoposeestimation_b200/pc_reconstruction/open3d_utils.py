@@ -173,11 +173,15 @@ def icp_regression_batch(targets, sources, voxel_size=5, threshold=100, max_iter
 
 def icp_regression(target, source, voxel_size=5, threshold=100, global_regression=False, icp_point2point=True,
                    icp_point2plane=True, plot=False):
-    """open3d_utils.py:63-122 with the reference's signature.  Only the configuration the reference runs is
-    grafted (point-to-point; main.py:177-179 disables the FPFH/RANSAC and point-to-plane branches).
+    """open3d_utils.py:63-122 with the reference's signature AND defaults.  Only the configuration the reference runs is
+    grafted (point-to-point; main.py:177-179 and create_labels.py:229-231 pass global_regression=False,
+    icp_point2point=True, icp_point2plane=False).  The signature default icp_point2plane=True (:66-67) would run a
+    point-to-plane refinement after the point-to-point one (:106-117): that is never silently skipped -- every call with
+    icp_point2plane=True (or global_regression=True) raises, so pass icp_point2plane=False as the reference's callers do.
     Returns (target_down, source_down, T 4x4 numpy fp64)."""
-    if global_regression or (icp_point2plane and not icp_point2point):
-        raise NotImplementedError('global (FPFH/RANSAC) and point-to-plane registration are disabled by the '
-                                  'reference configuration and are not grafted')
+    if global_regression or icp_point2plane:
+        raise NotImplementedError('icp_regression: global (FPFH/RANSAC) registration and point-to-plane ICP are disabled by the '
+                                  'reference configuration (main.py:177-179) and are not grafted; call with '
+                                  'global_regression=False, icp_point2plane=False')
     td, sd, T, _ = icp_regression_batch([target], [source], voxel_size, threshold)
     return td[0], sd[0], (T[0] if icp_point2point else np.identity(4))

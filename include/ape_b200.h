@@ -222,6 +222,34 @@ int ape_pose_pipeline(ape_net* estimator, ape_net* refiner, const float* out_img
                       const int64_t* choose, const int64_t* obj, int B, int N, int iterations, int canonical,
                       double* poses, int32_t* which_max, void* stream);
 
+/* Layout of the colour-encoder output handed to the PoseNet entry points (`_ex` variants below). */
+enum { APE_EMB_NCHW = 0,      /* out_img [B,32,hw]: the reference encoder's own layout (network.py:98-102)            */
+       APE_EMB_NHWC = 1,      /* out_img [B,hw,32]: the same tensor in torch's channels_last memory format (one sampled
+                                 point = one contiguous 128-byte line)                                                   */
+       APE_EMB_GATHERED = 2 };/* out_img is emb [B,32,N], already gathered at `choose` (ape_gather_emb /
+                                 ape_host_gather_*); hw and choose are ignored                                           */
+int ape_posenet_forward_ex(ape_net* net, const float* out_img, int hw, int emb_layout, const float* cloud,
+                           const int64_t* choose, const int64_t* obj, int B, int N, float* pred_r, float* pred_t,
+                           float* pred_c, float* emb /* may be NULL with APE_EMB_GATHERED */, void* stream);
+int ape_pose_pipeline_ex(ape_net* estimator, ape_net* refiner, const float* out_img, int hw, int emb_layout,
+                         const float* cloud, const int64_t* choose, const int64_t* obj, int B, int N, int iterations,
+                         int canonical, double* poses, int32_t* which_max, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Embedding hand-over for HOST-resident encoder maps (network.py:100-102 `torch.gather(emb, 2, choose)` done where the
+ * map lives, so that only the sampled columns cross PCIe: 4.1 MB instead of 157 MB per batch of 64 x 500 points).
+ * ape_gather_emb: gather kernel; `out_img` is a device pointer OR a pointer into mapped pinned host memory (zero-copy
+ *   reads over PCIe); layout APE_EMB_NCHW or APE_EMB_NHWC; choose [B,N] int64 (device); emb [B,32,N] fp32 out (device).
+ *   Indices are clamped to [0, hw).
+ * ape_host_gather_begin / _wait: the same gather on the HOST for objects [obj_begin, obj_end) into a (pinned) staging
+ *   buffer emb_host [B,32,N], on a persistent thread pool (`threads` <= 0: all hardware threads); begin returns at once,
+ *   wait blocks until the staging buffer is complete.  One gather in flight per process.  Pure data movement: the
+ *   caller then copies emb_host[obj_begin:obj_end] to the device and calls the APE_EMB_GATHERED entry points.         */
+int ape_gather_emb(const float* out_img, int hw, int layout, const int64_t* choose, int B, int N, float* emb, void* stream);
+int ape_host_gather_begin(const float* out_img_host, int hw, int layout, const int64_t* choose_host, int obj_begin,
+                          int obj_end, int n_points, float* emb_host, int threads);
+int ape_host_gather_wait(void);
+
 /* Candidate-pose distances of the estimator loss `Loss` (DenseFusion/lib/loss.py:30-50):
  * as ape_add_metric for B = the N per-point candidate poses of an object (pass model / target with stride 0
  * to share them), plus std_out[i] = unbiased std of the per-point distances (torch.std, loss.py:50).

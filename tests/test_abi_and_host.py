@@ -44,6 +44,27 @@ def test_no_cuda_means_loud_failure_not_fallback():
         ops.NetHandle(ops.NET_REFINER, synth.refiner_state_dict(0, 2), 2, 1, 128)
 
 
+def test_host_gather_pool_matches_torch_gather():
+    """ape_host_gather_* is host-side data movement (no GPU involved): NCHW and channels-last maps, sub-ranges of objects,
+    out-of-range indices clamped, repeated jobs on the persistent pool."""
+    from autoposeestimation_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    B, hw, N = 7, (24, 40), 300
+    img = torch.randn((B, 32) + hw, generator=g)
+    choose = torch.sort(torch.randint(0, hw[0] * hw[1], (B, 1, N), generator=g), dim=2).values
+    choose[0, 0, 0] = -3; choose[1, 0, -1] = 10 ** 8
+    want = torch.gather(img.reshape(B, 32, -1), 2, choose.clamp(0, hw[0] * hw[1] - 1).expand(B, 32, N))
+    for threads in (1, 3, 0):
+        for src in (img, img.contiguous(memory_format=torch.channels_last)):
+            for lo, hi in ((0, B), (2, 5), (4, 4)):
+                out = torch.full((B, 32, N), -1.0)
+                keep = ops.host_gather_begin(src, choose.reshape(B, N).contiguous(), out, lo, hi, threads)
+                ops.host_gather_wait()
+                assert torch.equal(out[lo:hi], want[lo:hi])
+                assert bool((out[:lo] == -1).all()) and bool((out[hi:] == -1).all())
+                del keep
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, 'autoposeestimation_b200')
     for dp, _, fs in os.walk(pkg):

@@ -173,7 +173,9 @@ def test_get_surface_and_icp_regression():
     assert len(tgt_d) == len(t_ref) and len(src_d) == len(s_ref)
     assert np.abs(T - T_ref).max() < 1e-5
     with pytest.raises(NotImplementedError):
-        icp_regression(PointCloud(fr['model']), surf, global_regression=True)
+        icp_regression(PointCloud(fr['model']), surf, global_regression=True, icp_point2plane=False)
+    with pytest.raises(NotImplementedError):                      # the signature default icp_point2plane=True is never silently skipped
+        icp_regression(PointCloud(fr['model']), surf, voxel_size=2, threshold=10)
     with pytest.raises(ValueError):
         get_surface(fr['label'], fr['depth'] + 0.5, fr['intr'], fr['robot2cam'], 20, 5, 20, voxel_size=2)
     with pytest.raises(ValueError):

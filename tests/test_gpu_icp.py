@@ -41,6 +41,26 @@ def test_icp_c1_vs_oracle(seed):
     assert np.allclose(T[3], [0, 0, 0, 1])
 
 
+def test_icp_kabsch_update_matches_reference_fixture(golden_dir):
+    """ONE iteration of the ICP kernel on correspondences that are the identity pairing = its Kabsch / Umeyama update,
+    against the reference's own rigid SVD fit (transformations.py:889-995, tests/golden/kabsch_ref.npz): exact and noisy
+    pairs, the reflection branch, rank-2 clouds."""
+    import os
+    from autoposeestimation_b200 import ops
+    g = np.load(os.path.join(golden_dir, 'kabsch_ref.npz'))
+    idx = [i for i, ok in enumerate(g['identity_nn']) if ok]
+    assert len(idx) >= 9
+    srcs, tgts = [g['v0_%d' % i] for i in idx], [g['v1_%d' % i] for i in idx]
+    S, so = _ragged(srcs); Tg, to = _ragged(tgts)
+    T, info = ops.icp_p2p(_dev(S), _dev(so), _dev(Tg), _dev(to), 10.0, max_iter=1)
+    T = T.cpu().numpy(); info = info.cpu().numpy()
+    for k, i in enumerate(idx):
+        M = g['M_%d' % i]
+        assert int(info[k, 2]) == 1
+        assert np.abs(T[k] - M).max() < 1e-9, (str(g['names'][i]), np.abs(T[k] - M).max())
+        assert abs(np.linalg.det(T[k][:3, :3]) - 1.0) < 1e-9
+
+
 def test_icp_ragged_batch_init_and_edge_cases():
     from autoposeestimation_b200 import ops
     rng = np.random.RandomState(21)
