@@ -35,6 +35,8 @@ SIGNATURES = {
     'ape_net_create': (c_int, [c_int, ctypes.POINTER(c_vp), c_int, c_int, c_int, c_int, ctypes.POINTER(c_vp)]),
     'ape_net_destroy': (c_int, [c_vp]),
     'ape_net_set_gemm': (c_int, [c_vp, c_int]),
+    'ape_net_set_passes': (c_int, [c_vp, c_vp]),
+    'ape_net_get_passes': (c_int, [c_vp, c_vp]),
     'ape_posenet_forward': (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'ape_refiner_forward': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
     'ape_pose_pipeline': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,

@@ -9,6 +9,7 @@
 // ascending, so neighbouring lanes fall into the same 128-byte line now and then and the requests merge); channels-last
 // ([B,hw,32]: one point = one contiguous 128-byte read) 0.089 ms.
 #include "ape_common.cuh"
+#include <cstdlib>
 
 namespace ape {
 
@@ -65,6 +66,18 @@ int ape_gather_emb(const float* out_img, int hw, int layout, const int64_t* choo
     APE_REQUIRE(B > 0 && N > 0 && hw > 0, "ape_gather_emb: bad sizes");
     APE_REQUIRE(layout == APE_EMB_NCHW || layout == APE_EMB_NHWC, "ape_gather_emb: layout must be APE_EMB_NCHW or APE_EMB_NHWC");
     cudaStream_t s = (cudaStream_t)stream;
+    {   // experiment knob: shared-memory carve-out preference of the gather kernels (a kernel that is to run BESIDE the
+        // persistent GEMM CTAs, which configure their SM for the maximum shared memory)
+        static int carve = -2;
+        if (carve == -2) {
+            const char* e = getenv("APE_GATHER_CARVEOUT");
+            carve = e ? atoi(e) : -1;
+            if (carve >= 0) {
+                cudaFuncSetAttribute(ape::gather_emb_nchw_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+                cudaFuncSetAttribute(ape::gather_emb_nhwc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            }
+        }
+    }
     ape::ProfScope prof_("gather_emb", s);
     if (layout == APE_EMB_NCHW)
         ape::gather_emb_nchw_kernel<8><<<dim3((N + 127) / 128, B, 4), 128, 0, s>>>(out_img, hw, choose, N, emb);

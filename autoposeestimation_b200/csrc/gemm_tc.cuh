@@ -50,6 +50,7 @@ struct Params {
     // training forward (gemm_tc2.cuh only; csrc/train.cu): plain bf16 = the A_hi*W_hi pass alone, no lo stores, and the
     // ReLU sign bits of the pooled layer kept for the backward pass
     int passes;                   // 1: A_hi*W_hi only;  0 or 3: the three split-bf16 passes
+    int pass_mask;                // gemm_tc2.cuh: when != 0 it overrides `passes`: bit 0 = A_lo*W_hi, bit 1 = A_hi*W_lo, bit 2 = A_hi*W_hi
     int hi_only;                  // EPI_RELU_SPLIT: skip the lo store
     uint32_t* relu_bits;          // EPI_RELU_COLSUM: [M, groups*N/32] bit j of word c/32 = (valid row && relu(x)[c] > 0)
 };

@@ -108,7 +108,9 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
     int full_tiles;
     const int total_tiles = tail_split(p.groups * m_tiles * n_tiles, (int)gridDim.x, bn_full, p.N, &full_tiles);
     const int kb_per_pass = p.K / BK;
-    const int n_pass = p.passes == 1 ? 1 : 3;
+    // which of the three split-bf16 products run (small terms first): bit 0 = A_lo*W_hi, bit 1 = A_hi*W_lo, bit 2 = A_hi*W_hi
+    const int pass_mask = p.pass_mask ? (p.pass_mask & 7) : (p.passes == 1 ? 4 : 7);
+    const int n_pass = __popc(pass_mask);
     const int iters_per_tile = n_pass * kb_per_pass;
 
     if (warp == 0 && lane == 0) {
@@ -149,7 +151,10 @@ gemm_split_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, 
                     mbar_wait(&empty_bar[s], ph ^ 1u);
                     const int pass_i = i / kb_per_pass, kb = i - pass_i * kb_per_pass;
                     // pass 0: A_lo*W_hi, pass 1: A_hi*W_lo, pass 2: A_hi*W_hi (small terms first); plain bf16 = pass 2 alone
-                    const int pass = n_pass == 1 ? 2 : pass_i;
+                    // = the pass_i-th set bit of pass_mask
+                    int pass = 0;
+                    for (int seen = 0; pass < 3; ++pass)
+                        if ((pass_mask >> pass) & 1) { if (seen == pass_i) break; ++seen; }
                     const CUtensorMap* ma = (pass == 0) ? &map_a_lo : &map_a_hi;
                     const CUtensorMap* mw = (pass == 1) ? &map_w_lo : &map_w_hi;
                     unsigned char* sa = smem + s * kStage;

@@ -463,6 +463,10 @@ struct DevF32 { float* p = nullptr; size_t n = 0; };
 struct ape_net {
     int kind = 0, num_obj = 0, max_batch = 0, max_points = 0, np_max = 0;
     int gemm_impl = APE_GEMM_TCGEN05;
+    // split-bf16 products per GEMM layer (conv2|e_conv2, conv5, conv6, heads1, heads2, heads3): bit 0 = A_lo*W_hi,
+    // bit 1 = A_hi*W_lo, bit 2 = A_hi*W_hi.  Defaults: kDefaultPasses* below (per-layer error budget in DESIGN.md 5).
+    int pass_mask[6] = {7, 7, 7, 7, 7, 7};
+    int full_mask[6] = {7, 7, 7, 7, 7, 7};   // what calls with fewer than kMinPointsReduced points per object use
     std::vector<void*> allocs;
     // fp32 parameters
     DevF32 fw;                               // front end: [e_conv1^T 32x64 | conv1^T 3x64 | b1 | be1]
@@ -582,6 +586,26 @@ int ape_net_create(int kind, const float* const* w, int n_tensors, int num_obj, 
     {
         const char* e = getenv("APE_GEMM_IMPL");          // bring-up / A-B knob; the default is the product path
         if (e) net->gemm_impl = (int)strtol(e, nullptr, 0);
+        // Product configuration from the per-layer error budget (tools/pass_study.py, profiles/r02_pass_study.json: 256
+        // objects x 2 weight sets against the fp32 restatement of the reference; gates 1e-3 rad / 1e-4 m).  The layers
+        // whose output is only ever POOLED over the N points of an object (conv5 -> conv6 -> AvgPool1d of PoseNet; the whole
+        // refiner trunk, whose heads see nothing but the pooled vector) run without the A_lo*W_hi product: the rounding
+        // error of an activation's high half is independent from point to point and averages out as 1/sqrt(N)
+        // (measured at N = 500: 9.2e-5 rad / 5.5e-6 m worst case, no arg-max flip).  The weight's low half must stay (its
+        // error is the same for every point: conv6 without W_lo flips an arg-max) and so must all three products of the
+        // per-point layers conv2 and heads1-3 (every variant of them fails the gate).
+        static const int kDefaultPassesPoseNet[6] = {7, 6, 6, 7, 7, 7};
+        static const int kDefaultPassesRefiner[6] = {6, 6, 6, 7, 7, 7};
+        for (int i = 0; i < 6; ++i) net->pass_mask[i] = (kind == APE_NET_POSENET ? kDefaultPassesPoseNet : kDefaultPassesRefiner)[i];
+        // error-budget knob: "APE_GEMM_PASSES_PN=7,7,6,7,7,7" / "APE_GEMM_PASSES_RF=6,6,6"
+        e = getenv(kind == APE_NET_POSENET ? "APE_GEMM_PASSES_PN" : "APE_GEMM_PASSES_RF");
+        for (int i = 0; e && *e && i < 6; ++i) {
+            char* end = nullptr;
+            const long v = strtol(e, &end, 0);
+            if (end == e) break;
+            if (v >= 1 && v <= 7 && (v & 4)) net->pass_mask[i] = (int)v;
+            e = (*end == ',') ? end + 1 : end;
+        }
     }
 #define TRY(x) do { if ((rc = (x)) != APE_OK) { ape_net_destroy(net); return rc; } } while (0)
     {   // front-end weights transposed to [k][c] so the kernel's shared-memory fill is a straight copy
@@ -697,6 +721,24 @@ int ape_net_set_gemm(ape_net* net, int gemm_impl)
     return APE_OK;
 }
 
+extern "C" __attribute__((visibility("default")))
+int ape_net_set_passes(ape_net* net, const int* masks6)
+{
+    APE_REQUIRE(net && masks6, "ape_net_set_passes: null pointer");
+    for (int i = 0; i < 6; ++i)
+        APE_REQUIRE(masks6[i] >= 4 && masks6[i] <= 7, "ape_net_set_passes: mask %d of layer %d must contain A_hi*W_hi (4..7)", masks6[i], i);
+    for (int i = 0; i < 6; ++i) net->pass_mask[i] = masks6[i];
+    return APE_OK;
+}
+
+extern "C" __attribute__((visibility("default")))
+int ape_net_get_passes(const ape_net* net, int* masks6)
+{
+    APE_REQUIRE(net && masks6, "ape_net_get_passes: null pointer");
+    for (int i = 0; i < 6; ++i) masks6[i] = net->pass_mask[i];
+    return APE_OK;
+}
+
 // One GEMM layer: out = relu(A[:, a_k0 + g*a_kg : +K] * W_g^T + bias)
 // Tile-width choice per layer (bit i of APE_GEMM_WIDE_MASK; layers: conv2, conv5, conv6, heads1, heads2, heads3).
 // Tuning knob only: both widths give bit-identical results (same K order, same accumulator arithmetic).
@@ -727,7 +769,8 @@ static int run_gemm(ape_net* net, const SplitMat& A, const SplitMat& W, const Sp
         const int tiles = p.groups * (p.M / ape::tc::BM) * ((p.N + bn_full - 1) / bn_full);
         const int grid = tiles < ape::sm_count() ? tiles : ape::sm_count();
         const SplitMat& O = out ? *out : A;          // EPI_RELU_COLSUM never touches the store maps
-        const int kblocks = (p.passes == 1 ? 1 : 3) * (p.K / ape::tc::BK);
+        const int pm = p.pass_mask ? (p.pass_mask & 7) : (p.passes == 1 ? 4 : 7);
+        const int kblocks = __builtin_popcount(pm) * (p.K / ape::tc::BK);
         static int epi8_max = -1;
         if (epi8_max < 0) { const char* e = getenv("APE_GEMM_EPI8_MAX_KB"); epi8_max = e ? (int)strtol(e, nullptr, 0) : 3; }
         const bool epi8 = p.mode != ape::tc::EPI_HEAD_OUT && (p.passes == 1 || kblocks <= epi8_max);   // short mainloop: 8 epilogue warps
@@ -771,6 +814,15 @@ static ape::tc::Params split_layer(int M, int N, int K, int groups, int a_k0, in
 }
 
 // front end + conv2/e_conv2 + conv5 + conv6 (+AvgPool) shared by both networks; leaves AP [B,1024]
+// The reduced pass table relies on averaging over the points of an object (error ~ 1/sqrt(N)): small clouds get all
+// three products everywhere.
+constexpr int kMinPointsReduced = 256;
+static const int* ape_net_masks(const ape_net* net, int N) {
+    // only the product GEMM kernel (gemm_tc2.cuh) implements the masks; the A/B and validation kernels always read hi + lo
+    const bool masked = net->gemm_impl == APE_GEMM_TCGEN05 || net->gemm_impl == APE_GEMM_TCGEN05_B2B;
+    return (masked && N >= kMinPointsReduced) ? net->pass_mask : net->full_mask;
+}
+
 // PoseNet: `choose` != NULL gathers from the encoder map (hw > 0: [B,32,hw]; hw < 0: channels-last [B,-hw,32]);
 // `choose` == NULL: feat_src is the already gathered emb [B,32,N] (as for the refiner).
 static int run_trunk(ape_net* net, const float* feat_src, int hw, const float* cloud, const int64_t* choose, int B, int N,
@@ -791,18 +843,22 @@ static int run_trunk(ape_net* net, const float* feat_src, int hw, const float* c
     if (rc) return rc;
     const bool pn = net->kind == APE_NET_POSENET, pn_ = pn;
     // conv2 (PF[:,0:64] -> PF[:,128:256]) and e_conv2 (PF[:,64:128] -> PF[:,256:384]) as two groups
+    const int* pm = ape_net_masks(net, N);
     ape::tc::Params p = split_layer(M, 128, 64, 2, 0, 64, net->b_c2e2.p, net->PF, 128);
     if (net->train) { p.passes = 1; p.hi_only = 1; }
+    else { p.pass_mask = pm[0]; p.hi_only = !((pm[1] & 1) || (pn_ && (pm[3] & 1))); }   // lo halves only where a consumer multiplies by them
     if ((rc = run_gemm(net, net->PF, net->W_c2e2, &net->PF, p, wide_layer(0), s, pn_ ? "gemm.pn.conv2" : "gemm.rf.conv2"))) return rc;
     // conv5: PoseNet reads pointfeat_2 = PF[:,128:384] (network.py:62); refiner reads pointfeat_3 = PF[:,0:384] (:162)
     p = split_layer(M, 512, pn ? 256 : 384, 1, pn ? 128 : 0, 0, net->b_c5.p, net->H5, 0);
     if (net->train) { p.passes = 1; p.hi_only = 1; }
+    else { p.pass_mask = pm[1]; p.hi_only = !(pm[2] & 1); }
     if ((rc = run_gemm(net, net->PF, net->W_c5, &net->H5, p, wide_layer(1), s, pn ? "gemm.pn.conv5" : "gemm.rf.conv5"))) return rc;
     // conv6 + ReLU + AvgPool1d: masked per-tile column sums, never materialising [1024, N]
     memset(&p, 0, sizeof(p));
     p.M = M; p.N = 1024; p.K = 512; p.groups = 1; p.bias = net->b_c6.p; p.mode = ape::tc::EPI_RELU_COLSUM;
     p.colsum = net->CS.p; p.rows_per_obj = Np; p.valid_rows = N;
     if (net->train) { p.passes = 1; p.relu_bits = net->relu_bits; }
+    else p.pass_mask = pm[2];
     if ((rc = run_gemm(net, net->H5, net->W_c6, nullptr, p, wide_layer(2), s, pn ? "gemm.pn.conv6" : "gemm.rf.conv6"))) return rc;
     dim3 gp(1024 / 256, B);
     ape::ProfScope prof_("pool_finish", s);
@@ -883,13 +939,16 @@ int ape_posenet_forward_ex(ape_net* net, const float* out_img, int hw, int emb_l
         if ((rc = ape::check_launch("heads12 fused"))) return rc;
     } else {
     // conv1_{r,t,c} on [pointfeat_1 | pointfeat_2] (K=384), N = 3*640, per-object bias
+    const int* pmh = ape_net_masks(net, N);
     p = split_layer(M, 1920, 384, 1, 0, 0, net->GB.p, net->H1, 0);
-    p.bias_obj_rows = Np;
+    p.bias_obj_rows = Np; p.pass_mask = pmh[3]; p.hi_only = !(pmh[4] & 1);
     if ((rc = run_gemm(net, net->PF, net->W_h1, &net->H1, p, wide_layer(3), s, "gemm.pn.heads1"))) return rc;
     p = split_layer(M, 256, 640, 3, 0, 640, net->b_h2.p, net->H2, 0);          // conv2_{r,t,c}
+    p.pass_mask = pmh[4]; p.hi_only = !(pmh[5] & 1);
     if ((rc = run_gemm(net, net->H1, net->W_h2, &net->H2, p, wide_layer(4), s, "gemm.pn.heads2"))) return rc;
     }
     p = split_layer(M, 128, 256, 3, 0, 256, net->b_h3.p, net->H3, 0);          // conv3_{r,t,c}
+    p.pass_mask = ape_net_masks(net, N)[5];
     if (net->gemm_impl == APE_GEMM_TCGEN05 || net->gemm_impl == APE_GEMM_TCGEN05_B2B) {
         // conv4_{r,t,c} of the object's class + sigmoid folded into the conv3 epilogue: H3 is never written
         p.mode = ape::tc::EPI_HEAD_OUT; p.rows_per_obj = Np; p.valid_rows = N; p.obj = obj; p.num_obj = net->num_obj; p.batch = B;

@@ -52,32 +52,46 @@ class Runner:
         self.i = 0
         self.last = None
         self.calibration = None
+        self.cpu_ms = None                                    # set to {} to accumulate host-side time per phase (diagnostics)
 
     # ------------------------------------------------------------------------------------------------
-    def calibrate(self, out_img, choose, reps=3):
-        """Time the two gather paths on this batch and split objects so that both finish together.
-        -> dict(zero_copy_ms, host_ms, zero_copy_fraction)."""
+    def calibrate(self, out_img, cloud, choose, idx, reps=3):
+        """Time the two gather paths and the step's kernels on this batch and choose how many objects go through the
+        zero-copy kernel.  The host pool costs host time, the zero-copy kernel costs DEVICE time (it shares the SMs with
+        the step's kernels: measured, about half of its stand-alone duration shows up in the step), so: everything through
+        the host pool while that keeps the host faster than the device; otherwise the fraction that balances the two.
+        -> dict(zero_copy_ms, host_ms, compute_ms, zero_copy_fraction)."""
         B = out_img.shape[0]
-        N = self.d_choose[0].shape[1]
         torch.cuda.synchronize(self.dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         with torch.cuda.stream(self.copy_stream):
+            self.d_cloud[0][:B].copy_(cloud, non_blocking=True)
+            self.d_idx[0][:B].copy_(idx.reshape(B), non_blocking=True)
             self.d_choose[0][:B].copy_(choose.reshape(B, -1), non_blocking=True)
             ops.gather_emb(out_img, self.d_choose[0][:B], out=self.d_emb[0][:B])        # warm-up (page tables, kernel load)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(self.copy_stream)
+            ev[0].record(self.copy_stream)
             for _ in range(reps):
                 ops.gather_emb(out_img, self.d_choose[0][:B], out=self.d_emb[0][:B])
-            e1.record(self.copy_stream)
-        e1.synchronize()
-        t_zc = e0.elapsed_time(e1) / reps
+            ev[1].record(self.copy_stream)
+            run = lambda: ops.pose_pipeline(self.est, self.ref, self.d_emb[0][:B], self.d_cloud[0][:B], None, self.d_idx[0][:B],
+                                            iterations=self.iterations, canonical=self.canonical, out=self.d_pose[0][:B], gathered=True)
+            run()
+            ev[2].record(self.copy_stream)
+            for _ in range(reps):
+                run()
+            ev[3].record(self.copy_stream)
+        ev[3].synchronize()
+        t_zc, t_gpu = ev[0].elapsed_time(ev[1]) / reps, ev[2].elapsed_time(ev[3]) / reps
         ch = choose.reshape(B, -1).contiguous()
         ops.host_gather_begin(out_img, ch, self.h_stage[0], 0, B, self.host_threads); ops.host_gather_wait()
         t0 = time.perf_counter()
         for _ in range(reps):
             ops.host_gather_begin(out_img, ch, self.h_stage[0], 0, B, self.host_threads); ops.host_gather_wait()
         t_host = (time.perf_counter() - t0) / reps * 1e3
-        self.zc_fraction = t_host / (t_host + t_zc)
-        self.calibration = dict(zero_copy_ms=t_zc, host_ms=t_host, zero_copy_fraction=self.zc_fraction)
+        host_overhead, zc_visible = 0.15, 0.5                  # ms of launches / events per step on the host; see docstring
+        f = (t_host + host_overhead - t_gpu) / (t_host + zc_visible * t_zc)
+        self.zc_fraction = min(1.0, max(0.0, f))
+        self.calibration = dict(zero_copy_ms=t_zc, host_ms=t_host, compute_ms=t_gpu, zero_copy_fraction=self.zc_fraction)
         return self.calibration
 
     def _compute(self, s, B, gathered):
@@ -111,15 +125,16 @@ class Runner:
         s = self.i % 2
         B = cloud.shape[0]
         main = torch.cuda.current_stream(self.dev)
-        if self.i >= 2:
-            self.copy_stream.wait_event(self.done[s])         # device slot s is free again
-            self.copied[s].synchronize()                      # ... and so is the pinned staging buffer of slot s
+        prof = self.cpu_ms
+        t_ = time.perf_counter() if prof is not None else 0.0
+
+        def lap(name):
+            nonlocal t_
+            if prof is not None:
+                t1 = time.perf_counter(); prof[name] = prof.get(name, 0.0) + (t1 - t_) * 1e3; t_ = t1
         on_dev = out_img.is_cuda
         gathered = self.transfer == 'gather' and not on_dev
-        with torch.cuda.stream(self.copy_stream):
-            self.d_cloud[s][:B].copy_(cloud, non_blocking=True)
-            self.d_choose[s][:B].copy_(choose.reshape(B, -1), non_blocking=True)
-            self.d_idx[s][:B].copy_(idx.reshape(B), non_blocking=True)
+        k, keep = B, None
         if gathered:
             nhwc = out_img.dim() == 4 and not out_img.is_contiguous() and out_img.is_contiguous(memory_format=torch.channels_last)
             if not out_img.is_pinned():
@@ -128,32 +143,42 @@ class Runner:
                 k = B                                          # 128-byte lines: the kernel alone is PCIe-efficient
             else:
                 if self.zc_fraction is None:
-                    self.calibrate(out_img, choose)
+                    self.calibrate(out_img, cloud, choose, idx)
                 k = int(round(B * self.zc_fraction))
-            keep = None
-            if k < B:
+            if self.i >= 2:
+                self.copied[s].synchronize()                  # the pinned staging buffer of slot s has been shipped
+            if k < B:                                          # the pool starts first: everything below overlaps it
                 ch = choose.reshape(B, -1)
                 keep = ops.host_gather_begin(out_img, ch if ch.is_contiguous() else ch.contiguous(), self.h_stage[s], k, B, self.host_threads)
-            if k > 0:
-                with torch.cuda.stream(self.copy_stream):
-                    ops.gather_emb(out_img[:k], self.d_choose[s][:k], out=self.d_emb[s][:k])
-            if k < B:
-                ops.host_gather_wait()
-                del keep
-                with torch.cuda.stream(self.copy_stream):
-                    self.d_emb[s][k:B].copy_(self.h_stage[s][k:B], non_blocking=True)
-        elif not on_dev:
-            with torch.cuda.stream(self.copy_stream):
+        if self.i >= 2:
+            self.copy_stream.wait_event(self.done[s])         # device slot s is free again
+        with torch.cuda.stream(self.copy_stream):
+            self.d_cloud[s][:B].copy_(cloud, non_blocking=True)
+            self.d_choose[s][:B].copy_(choose.reshape(B, -1), non_blocking=True)
+            self.d_idx[s][:B].copy_(idx.reshape(B), non_blocking=True)
+            if gathered and k > 0:
+                ops.gather_emb(out_img[:k], self.d_choose[s][:k], out=self.d_emb[s][:k])
+            elif not gathered and not on_dev:
                 self.d_img[s][:B].copy_(out_img.reshape(B, 32, -1), non_blocking=True)
+        lap('enqueue_h2d')
+        if gathered and k < B:
+            ops.host_gather_wait()
+            lap('host_gather_wait')
+            del keep
+            with torch.cuda.stream(self.copy_stream):
+                self.d_emb[s][k:B].copy_(self.h_stage[s][k:B], non_blocking=True)
         self.copied[s].record(self.copy_stream)
         main.wait_event(self.copied[s])
+        lap('events')
         if on_dev:                                             # device-resident map: gather inside the front-end kernel
             ops.pose_pipeline(self.est, self.ref, out_img, self.d_cloud[s][:B], self.d_choose[s][:B], self.d_idx[s][:B],
                               iterations=self.iterations, canonical=self.canonical, out=self.d_pose[s][:B])
         else:
             self._compute(s, B, gathered)
+        lap('compute_launch')
         self.h_pose[s][:B].copy_(self.d_pose[s][:B], non_blocking=True)
         self.done[s].record(main)
+        lap('d2h')
         self.last = (s, B)
         self.i += 1
 

@@ -303,6 +303,20 @@ class NetHandle:
     def set_gemm(self, impl):
         check(_lib.load().ape_net_set_gemm(self._h, impl), 'ape_net_set_gemm')
 
+    def set_passes(self, masks):
+        """Split-bf16 products per tensor-core layer (conv2, conv5, conv6, heads1, heads2, heads3): 7 = all three,
+        6 = activation low half dropped, 5 = weight low half dropped, 4 = plain bf16."""
+        import ctypes
+        m = list(masks) + [7] * (6 - len(masks))
+        arr = (ctypes.c_int * 6)(*m)
+        check(_lib.load().ape_net_set_passes(self._h, arr), 'ape_net_set_passes')
+
+    def get_passes(self):
+        import ctypes
+        arr = (ctypes.c_int * 6)()
+        check(_lib.load().ape_net_get_passes(self._h, arr), 'ape_net_get_passes')
+        return list(arr)
+
     def close(self):
         if getattr(self, '_h', None):
             _lib.load().ape_net_destroy(self._h)

@@ -44,12 +44,23 @@ GEMM_FLOPS_PER_PT = {
     'gemm.pn.heads1': 3 * 2 * 1408 * 640, 'gemm.pn.heads2': 3 * 2 * 640 * 256, 'gemm.pn.heads3': 3 * 2 * 256 * 128,
     'gemm.rf.conv2': 2 * 2 * 64 * 128, 'gemm.rf.conv5': 2 * 384 * 512, 'gemm.rf.conv6': 2 * 512 * 1024,
 }
-# executed MMA FLOPs per padded row: 3 split-bf16 passes, global-feature part of heads1 hoisted (K=384)
-GEMM_EXEC_PER_ROW = {
-    'gemm.pn.conv2': 3 * 2 * 2 * 64 * 128, 'gemm.pn.conv5': 3 * 2 * 256 * 512, 'gemm.pn.conv6': 3 * 2 * 512 * 1024,
-    'gemm.pn.heads1': 3 * 2 * 384 * 1920, 'gemm.pn.heads2': 3 * 3 * 2 * 640 * 256, 'gemm.pn.heads3': 3 * 3 * 2 * 256 * 128,
-    'gemm.rf.conv2': 3 * 2 * 2 * 64 * 128, 'gemm.rf.conv5': 3 * 2 * 384 * 512, 'gemm.rf.conv6': 3 * 2 * 512 * 1024,
+# executed MMA FLOPs per padded row and bf16 product: global-feature part of heads1 hoisted (K=384); multiplied by the
+# number of split-bf16 products the layer runs (ape_net_get_passes: 3 for the per-point layers, 2 for the pooled ones)
+GEMM_EXEC_PER_ROW_PASS = {
+    'gemm.pn.conv2': 2 * 2 * 64 * 128, 'gemm.pn.conv5': 2 * 256 * 512, 'gemm.pn.conv6': 2 * 512 * 1024,
+    'gemm.pn.heads1': 2 * 384 * 1920, 'gemm.pn.heads2': 3 * 2 * 640 * 256, 'gemm.pn.heads3': 3 * 2 * 256 * 128,
+    'gemm.rf.conv2': 2 * 2 * 64 * 128, 'gemm.rf.conv5': 2 * 384 * 512, 'gemm.rf.conv6': 2 * 512 * 1024,
 }
+GEMM_LAYER_ORDER = ['conv2', 'conv5', 'conv6', 'heads1', 'heads2', 'heads3']
+
+
+def gemm_exec_per_row(est, ref):
+    pn, rf = est.get_passes(), ref.get_passes()
+    out = {}
+    for k, v in GEMM_EXEC_PER_ROW_PASS.items():
+        net, layer = k.split('.')[1:]
+        out[k] = v * bin((pn if net == 'pn' else rf)[GEMM_LAYER_ORDER.index(layer)]).count('1')
+    return out
 
 
 def measured_traffic(kernel, units=None):
@@ -744,8 +755,9 @@ def run_b200(args):
         refine = {k: (REFINE_ITERS if k.startswith('gemm.rf') else 1) for k in GEMM_FLOPS_PER_PT}
         alg = sum(GEMM_FLOPS_PER_PT[k] * refine[k] for k in GEMM_FLOPS_PER_PT) * BATCH * NPTS
         rows = BATCH * ((NPTS + 127) // 128 * 128)
-        exe = sum(GEMM_EXEC_PER_ROW[k] * refine[k] for k in GEMM_EXEC_PER_ROW) * rows
-        fpt = dict(GEMM_FLOPS_PER_PT); epr = dict(GEMM_EXEC_PER_ROW)
+        epr = gemm_exec_per_row(est, ref)
+        exe = sum(epr[k] * refine[k] for k in epr) * rows
+        fpt = dict(GEMM_FLOPS_PER_PT)
         # the back-to-back heads kernel (gemm_tc4.cuh) does the work of two layers in one launch
         fpt['gemm.pn.heads12'] = fpt['gemm.pn.heads1'] + fpt['gemm.pn.heads2']
         epr['gemm.pn.heads12'] = epr['gemm.pn.heads1'] + epr['gemm.pn.heads2']
@@ -762,8 +774,11 @@ def run_b200(args):
             executed_frac=exe / gemm_ms / 1e9 / peaks['bf16'], gemm_ms_per_step=gemm_ms, all_kernels_ms_per_step=all_ms,
             gemm_share_of_kernel_time=gemm_ms / all_ms, layers=layers,
             other_kernels_ms_per_step={k: v[1] / args.steps for k, v in rep.items() if not k.startswith('gemm.')},
+            split_bf16_products=dict(posenet=est.get_passes(), refiner=ref.get_passes()[:3], layers=GEMM_LAYER_ORDER,
+                                     key='7 = A_lo*W_hi + A_hi*W_lo + A_hi*W_hi, 6 = without A_lo*W_hi (layers whose output is pooled over the points)'),
             note='achieved = reference-formulation FLOPs (SURVEY 8d: 7.94 MFLOP/pt PoseNet + 1.48 MFLOP/pt per refine iter, GEMM layers) / '
-                 'summed GEMM kernel time; executed = 3 split-bf16 passes on padded rows with the global feature hoisted')
+                 'summed GEMM kernel time; executed = the split-bf16 products actually run (3 per-point layers, 2 pooled layers) on padded rows '
+                 'with the global feature hoisted')
         # ---- CPU baseline beside it (bounded sample)
         # rank 0 at N=1 only (under torchrun OMP_NUM_THREADS=1 would make it a 1-thread number that looks like a regression)
         cpu_fps, cpu_s, cpu_threads, cpu_kind, cpu_impl = cpu_pose_frames_per_s(32, min_seconds=10.0) if world == 1 else (None, 0.0, 0, None, None)

@@ -199,6 +199,12 @@ int ape_net_create(int kind, const float* const* weights_host, int n_tensors, in
                    int max_batch, int max_points, ape_net** out);
 int ape_net_destroy(ape_net* net);
 int ape_net_set_gemm(ape_net* net, int gemm_impl);
+/* Split-bf16 products per tensor-core layer, in the order conv2|e_conv2, conv5, conv6, heads1, heads2, heads3 (the refiner
+ * uses the first three): bit 0 = A_lo*W_hi, bit 1 = A_hi*W_lo, bit 2 = A_hi*W_hi (always set).  7 = all three (fp32-grade
+ * products), 6 = the activation's low half dropped, 5 = the weight's low half dropped, 4 = plain bf16.  The defaults are
+ * the product configuration chosen from the per-layer error budget; tests and A/B runs change it here.   */
+int ape_net_set_passes(ape_net* net, const int* masks6);
+int ape_net_get_passes(const ape_net* net, int* masks6);
 
 /* PoseNet geometry forward for B objects.
  *   out_img [B,32,hw] fp32 colour-encoder output per object crop (hw = crop pixels, same for the batch)

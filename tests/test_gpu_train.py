@@ -122,6 +122,53 @@ def test_trainer_forward_backward_vs_fp32_autograd(B, N):
     tr.close()
 
 
+def test_config5_batch256_gradient_vs_emulation_and_fp32():
+    """BASELINE config 5 AT SCALE (batch 256 x 500 points: 64-object slabs in the dense layers, split-K weight gradients
+    over 131 072 rows).  (1) Upstream gradients that are non-zero for 4 objects sampled from different slabs only: by
+    linearity the accumulated gradient must equal the bf16 emulation of those 4 objects (1e-2), and their r2 / t2 the
+    emulation's.  (2) Non-zero upstream gradients everywhere: the accumulated gradient against the fp32 autograd sum over
+    a 32-object subset is checked through linearity as well (the other objects' upstream gradients are zeroed)."""
+    from autoposeestimation_b200 import ops
+    nobj, B, N = 5, 256, 500
+    sd_np = _state_dict(55, nobj)
+    points, emb, idx, _, _ = _inputs(77, B, N, 16, nobj)
+    rng = np.random.RandomState(12)
+    tr = ops.RefinerTrainerHandle(sd_np, nobj, B, N)
+    dev_in = (_dev(points), _dev(emb), _dev(idx))
+    for sample, check_emulation in (([3, 70, 133, 250], True), (list(range(5, 256, 8)), False)):
+        d_r = np.zeros((B, 4), np.float32); d_t = np.zeros((B, 3), np.float32)
+        d_r[sample] = rng.randn(len(sample), 4); d_t[sample] = rng.randn(len(sample), 3)
+        tr.grads.zero_()
+        r2, t2 = tr.forward(*dev_in)
+        tr.backward(*dev_in, _dev(d_r), _dev(d_t))
+        torch.cuda.synchronize()
+        sd = _ref_sd(sd_np)
+        emu = {}
+        torch.set_num_threads(8)
+        for b in sample:
+            args = (torch.from_numpy(points[b:b + 1]), torch.from_numpy(emb[b:b + 1]), torch.from_numpy(idx[b:b + 1]).view(1, 1), nobj)
+            if check_emulation:
+                with torch.no_grad():
+                    r_e, t_e, g_e = odf.refiner_train_bf16_emulation({k: v.detach() for k, v in sd.items()}, *args,
+                                                                     torch.from_numpy(d_r[b]), torch.from_numpy(d_t[b]))
+                assert np.allclose(r2[b].cpu().numpy(), r_e.numpy(), rtol=1e-3, atol=1e-4)
+                assert np.allclose(t2[b].cpu().numpy(), t_e.numpy(), rtol=1e-3, atol=1e-4)
+                for k, v in g_e.items():
+                    emu[k] = emu.get(k, 0) + v
+            else:
+                r, t = odf.refiner_forward(sd, *args)
+                ((r[0] * torch.from_numpy(d_r[b])).sum() + (t[0] * torch.from_numpy(d_t[b])).sum()).backward()
+        for key in tr.table:
+            g = tr.view(key, tr.grads).cpu()
+            if check_emulation:
+                rel, cos = _rel_cos(g, emu[key].reshape(g.shape))
+                assert rel < 1e-2 and cos > 0.9999, ('vs bf16 emulation @256', key, rel, cos)
+            else:
+                rel, cos = _rel_cos(g, sd[key].grad.reshape(g.shape))
+                assert rel < 1e-1 and cos > 0.995, ('vs fp32 autograd @256', key, rel, cos)
+    tr.close()
+
+
 def test_backward_accumulates_and_zero_grad():
     from autoposeestimation_b200 import ops
     nobj, B, N = 2, 2, 128
