@@ -7,9 +7,11 @@
 // Measured on this pool's B200 (PCIe 5 x16, tools/zc_bench.cu): full-map cudaMemcpyAsync 2.83 ms; zero-copy gather
 // with lane = channel 2.58 ms (every lane its own 32-byte PCIe read), with lane = POINT 1.26 ms (`choose` is
 // ascending, so neighbouring lanes fall into the same 128-byte line now and then and the requests merge); channels-last
-// ([B,hw,32]: one point = one contiguous 128-byte read) 0.089 ms.
+// ([B,hw,32]: one point = one contiguous 128-byte read) 0.089 ms.  Run beside the step's kernels the NCHW zero-copy gather
+// is not free: about half of its stand-alone duration shows up in the step time (its CTAs wait microseconds for every PCIe
+// read and share the SMs with the persistent GEMM CTAs; the shared-memory carve-out preference makes no difference), which
+// is why the Runner prefers the host pool while the host keeps up (densefusion/estimate_poses.py).
 #include "ape_common.cuh"
-#include <cstdlib>
 
 namespace ape {
 
@@ -66,18 +68,6 @@ int ape_gather_emb(const float* out_img, int hw, int layout, const int64_t* choo
     APE_REQUIRE(B > 0 && N > 0 && hw > 0, "ape_gather_emb: bad sizes");
     APE_REQUIRE(layout == APE_EMB_NCHW || layout == APE_EMB_NHWC, "ape_gather_emb: layout must be APE_EMB_NCHW or APE_EMB_NHWC");
     cudaStream_t s = (cudaStream_t)stream;
-    {   // experiment knob: shared-memory carve-out preference of the gather kernels (a kernel that is to run BESIDE the
-        // persistent GEMM CTAs, which configure their SM for the maximum shared memory)
-        static int carve = -2;
-        if (carve == -2) {
-            const char* e = getenv("APE_GATHER_CARVEOUT");
-            carve = e ? atoi(e) : -1;
-            if (carve >= 0) {
-                cudaFuncSetAttribute(ape::gather_emb_nchw_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-                cudaFuncSetAttribute(ape::gather_emb_nhwc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-            }
-        }
-    }
     ape::ProfScope prof_("gather_emb", s);
     if (layout == APE_EMB_NCHW)
         ape::gather_emb_nchw_kernel<8><<<dim3((N + 127) / 128, B, 4), 128, 0, s>>>(out_img, hw, choose, N, emb);

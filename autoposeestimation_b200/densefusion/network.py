@@ -217,7 +217,8 @@ class _RefinerTrainFn(torch.autograd.Function):
     def forward(ctx, module, x, emb, obj, *params):
         tr = module._trainer(x.shape[0], x.shape[1])
         r, t = tr.forward(x, emb, obj)
-        ctx.module = module
+        module._fwd_id += 1                       # the trainer workspace now holds THIS forward's activations
+        ctx.module, ctx.fwd_id, ctx.tr = module, module._fwd_id, tr
         ctx.save_for_backward(x, emb, obj)
         return r, t
 
@@ -225,8 +226,15 @@ class _RefinerTrainFn(torch.autograd.Function):
     def backward(ctx, d_r, d_t):
         x, emb, obj = ctx.saved_tensors
         m = ctx.module
+        tr = m._trainer(x.shape[0], x.shape[1])
+        if m._fwd_id != ctx.fwd_id or tr is not ctx.tr:
+            # another forward ran in between (e.g. `(dis_0 + dis_1).backward()`, a loss summed over several objects):
+            # the workspace holds ITS activations, so the forward being differentiated is re-run from the saved inputs
+            # first (same kernels, same result) -- the patterns autograd supports stay correct, at the cost of a recompute
+            tr.forward(x, emb, obj)
+            m._fwd_id += 1
         m._attach_grads()
-        m._tr.backward(x, emb, obj, d_r.contiguous(), d_t.contiguous())
+        tr.backward(x, emb, obj, d_r.contiguous(), d_t.contiguous())
         return (None,) * (4 + len(list(m.parameters())))
 
 
@@ -241,6 +249,7 @@ class PoseRefineNet(_Grafted):
         self.conv2_r, self.conv2_t = nn.Linear(512, 128), nn.Linear(512, 128)
         self.conv3_r, self.conv3_t = nn.Linear(128, num_obj * 4), nn.Linear(128, num_obj * 3)
         self._tr = None
+        self._fwd_id = 0
 
     # -- training plumbing -------------------------------------------------------------------------
     def _trainer(self, batch, n_points):
@@ -296,6 +305,7 @@ class PoseRefineNet(_Grafted):
             raise ops._lib.ApeError('PoseRefineNet: tensors must be on a CUDA device (no CPU fallback)')
         if self._needs_autograd():
             return _RefinerTrainFn.apply(self, x.detach(), emb.detach(), obj, *self.parameters())
-        if self._tr is not None:                      # parameters live in the trainer's flat vector: keep one source of truth
-            return self._trainer(B, N).forward(x, emb, obj)
+        # inference always runs the split-bf16 kernels on their own handle / workspace (re-derived from the parameters when
+        # an optimizer step changed them): it neither disturbs the activations a pending backward needs nor drops to the
+        # plain-bf16 accuracy of the training forward
         return self._handle(B, N).refiner_forward(x, emb, obj)

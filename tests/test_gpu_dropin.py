@@ -156,6 +156,43 @@ def test_refiner_dropin_trains_like_reference_loop(golden_dir):
     assert float((r_after - r_before).abs().max()) > 0               # the bf16 weight copies follow the in-place update
 
 
+def test_refiner_autograd_patterns_other_than_the_reference_loop():
+    """Patterns autograd supports but train.py does not use: a loss summed over two forwards before ONE backward, and an
+    eval / no_grad forward between a training forward and its backward.  Both must give the gradient of the plain
+    forward -> backward sequence (the backward re-runs its own forward when the workspace was overwritten)."""
+    from autoposeestimation_b200 import synthetic as synth
+    from autoposeestimation_b200.densefusion import network
+    nobj, N = 3, 200
+    sd = synth.refiner_state_dict(91, nobj)
+    rng = np.random.RandomState(6)
+    pts = [torch.from_numpy((rng.randn(1, N, 3) * 0.05).astype(np.float32)).cuda() for _ in range(2)]
+    emb = [torch.from_numpy(rng.randn(1, 32, N).astype(np.float32)).cuda() for _ in range(2)]
+    idx = torch.zeros((1, 1), dtype=torch.long, device='cuda')
+    w = [torch.from_numpy(rng.randn(7).astype(np.float32)).cuda() for _ in range(2)]
+
+    def loss_of(refiner, i):
+        r, t = refiner(pts[i], emb[i], idx)
+        return (torch.cat([r.view(-1), t.view(-1)]) * w[i]).sum()
+
+    def fresh():
+        m = network.PoseRefineNet(N, nobj).cuda(); m.load_state_dict(synth.to_torch(sd)); m.train()
+        return m
+    a = fresh()
+    loss_of(a, 0).backward(); loss_of(a, 1).backward()                # the reference's pattern
+    want = a.flat_gradient().clone()
+    b = fresh()
+    (loss_of(b, 0) + loss_of(b, 1)).backward()                         # summed loss, one backward
+    rel = float((b.flat_gradient() - want).norm() / want.norm())
+    assert rel < 2e-3, rel
+    c = fresh()
+    l0 = loss_of(c, 0)
+    with torch.no_grad():
+        c(pts[1], emb[1], idx)                                         # inference in between (own workspace)
+    l0.backward(); loss_of(c, 1).backward()
+    rel = float((c.flat_gradient() - want).norm() / want.norm())
+    assert rel < 2e-3, rel
+
+
 def test_get_surface_and_icp_regression():
     from autoposeestimation_b200.pc_reconstruction.open3d_utils import PointCloud, get_surface, icp_regression, icp_regression_batch
     fr = synth.render_ellipsoid_frame(6)
