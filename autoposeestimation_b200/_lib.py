@@ -47,6 +47,7 @@ SIGNATURES = {
     'ape_gather_emb': (c_int, [c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp]),
     'ape_host_gather_begin': (c_int, [c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp, c_int]),
     'ape_host_gather_wait': (c_int, []),
+    'ape_estimator_loss': (c_int, [c_vp] * 6 + [c_int, c_int, c_int, ctypes.c_float] + [c_vp] * 12),
     'ape_radius_outlier': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_dbl, c_vp, c_vp, c_vp]),
     'ape_mahalanobis': (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     'ape_statistical_outlier': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_dbl, c_vp, c_vp, c_vp, c_vp]),

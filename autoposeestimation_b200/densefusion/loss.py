@@ -1,70 +1,48 @@
-"""Drop-in `Loss` (reference: DenseFusion/lib/loss.py:12-85): per-point candidate poses, ADD / ADD-S with the
-fork's `(dis + 2 std) c - w log c` objective, and the cloud / target in the frame of the most confident point.
-Returns the reference's 5-tuple (loss, dis, new_points, new_target, pred).  kNN (symmetric objects, not-refine
-branch) runs on the sm_100a kernel; the rest is differentiable torch glue on the device."""
+"""Drop-in `Loss` (reference: DenseFusion/lib/loss.py:12-85): per-point candidate poses, ADD / ADD-S with the fork's
+`(dis + 2 std) c - w log c` objective, and the cloud / target in the frame of the most confident point.  Returns the
+reference's 5-tuple (loss, dis, new_points, new_target, pred).
+
+Everything -- the candidate transforms, the nearest-neighbour targets of symmetric objects, the mean / std distances, the
+objective, its GRADIENT w.r.t. pred_r / pred_t / pred_c, the arg-max and the re-expressed clouds -- runs in two sm_100a
+kernels (csrc/knn.cu: estimator_loss_kernel, estimator_loss_finish_kernel) behind one autograd node; there is no torch
+arithmetic on this path.  The reference materialises pred [N,M,3], repeats model / target N times and runs an N*M-query kNN
+with an (N*M) x M distance matrix (4 GB at 1000 x 1000, knn.h:33); here `pred` is written once only because it is part of
+the returned tuple.  As in the reference the kNN indices are constants of the backward pass (`inds.detach()`, :45),
+`new_points` / `new_target` are detached (:73); `dis` and `pred` are returned as values (train.py back-propagates `loss`
+only, :222 / :216).  The reference's batch size is 1 (`idx[0]`, `which_max[0]`, :41, :60): other batch sizes raise."""
 import torch
 from torch.nn.modules.loss import _Loss
 
 from .. import ops
-from .knn import KNearestNeighbor
-from .loss_refiner import quat_to_base
+
+
+class _EstimatorLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred_r, pred_t, pred_c, target, model_points, points, w, symmetric, want_grad):
+        out = ops.estimator_loss(pred_r, pred_t, pred_c, points, model_points, target, symmetric, w, want_grad=want_grad)
+        ctx.shapes = (pred_r.shape, pred_t.shape, pred_c.shape)
+        if want_grad:
+            ctx.save_for_backward(out['d_r'], out['d_t'], out['d_c'])
+        dis_best, newp, newt, pred = out['dis_best'].clone(), out['new_points'], out['new_target'], out['pred']
+        ctx.mark_non_differentiable(dis_best, newp, newt, pred)
+        return out['loss'].clone(), dis_best, newp, newt, pred
+
+    @staticmethod
+    def backward(ctx, g_loss, *unused):
+        d_r, d_t, d_c = ctx.saved_tensors
+        sr, st, sc = ctx.shapes
+        return (g_loss * d_r).reshape(sr), (g_loss * d_t).reshape(st), (g_loss * d_c).reshape(sc), None, None, None, None, None, None
 
 
 def loss_calculation(pred_r, pred_t, pred_c, target, model_points, idx, points, w, refine, num_point_mesh, sym_list):
     if not pred_r.is_cuda:
         raise ops._lib.ApeError('Loss: tensors must be on a CUDA device (no CPU fallback)')
     bs, num_p, _ = pred_c.size()
-    m = num_point_mesh
-    if bs == 1 and m <= 2048 and not (torch.is_grad_enabled() and (pred_r.requires_grad or pred_t.requires_grad or pred_c.requires_grad)):
-        return _fused_forward(pred_r, pred_t, pred_c, target, model_points, idx, points, w, refine, m, sym_list)
-    knn = KNearestNeighbor(1)
-    q = pred_r.reshape(bs * num_p, 4)
-    q = q / torch.norm(q, dim=1, keepdim=True)
-    ori_base = quat_to_base(q)
-    mp = model_points.reshape(bs, 1, m, 3).expand(bs, num_p, m, 3).reshape(bs * num_p, m, 3)
-    tg = target.reshape(bs, 1, m, 3).expand(bs, num_p, m, 3).reshape(bs * num_p, m, 3)
-    pt = pred_t.reshape(bs * num_p, 1, 3)
-    ps = points.reshape(bs * num_p, 1, 3)
-    c = pred_c.reshape(bs * num_p)
-    pred = torch.bmm(mp, ori_base.transpose(2, 1)) + (ps + pt)                              # :38
-    tg_used = tg
-    if (not refine) and int(idx.reshape(-1)[0]) in sym_list:                                 # :40-47
-        t0 = target.reshape(bs, m, 3)[0]
-        inds = knn(t0.t().unsqueeze(0), pred.reshape(-1, 3).t().unsqueeze(0)).view(-1) - 1
-        tg_used = t0[inds.to(t0.device)].view(bs * num_p, m, 3)
-    d = torch.norm(pred - tg_used, dim=2)
-    dis, std = d.mean(dim=1), d.std(dim=1)
-    loss = torch.mean((dis + 2 * std) * c - w * torch.log(c), dim=0)                         # :53
-    which = torch.argmax(c.view(bs, num_p), dim=1)[0]
-    t = (pt[which] + ps[which]).view(1, 1, 3)
-    b = ori_base[which].view(1, 3, 3)
-    new_points = torch.bmm(points.reshape(1, bs * num_p, 3) - t, b).contiguous()
-    new_target = torch.bmm(tg[0].view(1, m, 3) - t, b).contiguous()
-    return loss, dis.view(bs, num_p)[0][which], new_points.detach(), new_target.detach(), pred
-
-
-def _fused_forward(pred_r, pred_t, pred_c, target, model_points, idx, points, w, refine, m, sym_list):
-    """Forward-only path (evaluation, and the refine phase of train.py:205-216 where `loss` is not back-propagated): the
-    per-candidate mean / std distances come from ONE fused kernel (csrc/knn.cu: add_metric_kernel with B = num_p candidate
-    poses, shared model / target) -- no [N,M,3] gather, no N*M-query kNN, no N x M distance matrix."""
-    num_p = pred_c.shape[1]
-    with torch.no_grad():
-        q = pred_r.reshape(num_p, 4)
-        trans = (points.reshape(num_p, 3) + pred_t.reshape(num_p, 3)).contiguous()
-        sym = torch.full((num_p,), 1 if ((not refine) and int(idx.reshape(-1)[0]) in sym_list) else 0, dtype=torch.uint8, device=q.device)
-        dis, std = ops.add_metric_std(q, trans, model_points.reshape(m, 3), target.reshape(m, 3), sym)
-        c = pred_c.reshape(num_p)
-        loss = torch.mean((dis + 2 * std) * c - w * torch.log(c), dim=0)                        # :53
-        which = torch.argmax(c)
-        qn = q / torch.norm(q, dim=1, keepdim=True)
-        ori_base = quat_to_base(qn)
-        t = trans[which].view(1, 1, 3)
-        b = ori_base[which].view(1, 3, 3)
-        new_points = torch.bmm(points.reshape(1, num_p, 3) - t, b).contiguous()
-        new_target = torch.bmm(target.reshape(1, m, 3) - t, b).contiguous()
-        # `pred` (:38) is part of the returned tuple; it is cheap to form once the distances no longer depend on it
-        pred = torch.bmm(model_points.reshape(1, m, 3).expand(num_p, m, 3), ori_base.transpose(2, 1)) + trans.view(num_p, 1, 3)
-    return loss, dis[which], new_points, new_target, pred
+    if bs != 1:
+        raise NotImplementedError('Loss: the reference evaluates one object per call (batch size 1: loss.py:41, :60, train.py:216)')
+    symmetric = (not refine) and int(idx.reshape(-1)[0]) in sym_list                        # :40-41
+    want_grad = torch.is_grad_enabled() and (pred_r.requires_grad or pred_t.requires_grad or pred_c.requires_grad)
+    return _EstimatorLossFn.apply(pred_r, pred_t, pred_c, target, model_points, points, float(w), symmetric, want_grad)
 
 
 class Loss(_Loss):

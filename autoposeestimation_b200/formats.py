@@ -151,3 +151,92 @@ class FrameBatchLoader:
         import torch
         dev = device or torch.device('cuda', torch.cuda.current_device())
         return {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+
+
+# ----------------------------------------------------------------------------------------------------- .ply / .pcd clouds
+def write_ply(path, points):
+    """`o3d.io.write_point_cloud(path.ply, cloud)` (create_pointcloud.py:324-354): binary little-endian PLY, one vertex
+    element with double x, y, z (what open3d writes for a cloud without colours / normals)."""
+    pts = np.ascontiguousarray(np.asarray(points, np.float64).reshape(-1, 3))
+    header = ('ply\nformat binary_little_endian 1.0\ncomment written by autoposeestimation_b200\nelement vertex %d\n'
+              'property double x\nproperty double y\nproperty double z\nend_header\n' % len(pts))
+    with open(path, 'wb') as f:
+        f.write(header.encode('ascii'))
+        f.write(pts.astype('<f8').tobytes())
+
+
+_PLY_TYPES = {'char': 'i1', 'uchar': 'u1', 'short': 'i2', 'ushort': 'u2', 'int': 'i4', 'uint': 'u4', 'float': 'f4', 'double': 'f8',
+              'int8': 'i1', 'uint8': 'u1', 'int16': 'i2', 'uint16': 'u2', 'int32': 'i4', 'uint32': 'u4', 'float32': 'f4', 'float64': 'f8'}
+
+
+def read_ply(path):
+    """`o3d.io.read_point_cloud(path.ply)` (create_labels.py:331, :346-347): the x, y, z of the vertex element as fp64 [n,3];
+    ascii and binary (little / big endian) files, extra vertex properties (colours, normals) are skipped."""
+    with open(path, 'rb') as f:
+        if f.readline().strip() != b'ply':
+            raise ValueError('%s: not a PLY file' % path)
+        fmt, n, props, in_vertex = None, 0, [], False
+        while True:
+            line = f.readline()
+            if not line:
+                raise ValueError('%s: truncated PLY header' % path)
+            tok = line.decode('ascii', 'replace').split()
+            if not tok:
+                continue
+            if tok[0] == 'format':
+                fmt = tok[1]
+            elif tok[0] == 'element':
+                in_vertex = tok[1] == 'vertex'
+                if in_vertex:
+                    n = int(tok[2])
+            elif tok[0] == 'property' and in_vertex:
+                if tok[1] == 'list':
+                    raise ValueError('%s: list property in the vertex element' % path)
+                props.append((tok[2], _PLY_TYPES[tok[1]]))
+            elif tok[0] == 'end_header':
+                break
+        names = [p[0] for p in props]
+        if not all(a in names for a in 'xyz'):
+            raise ValueError('%s: vertex element without x, y, z' % path)
+        if fmt == 'ascii':
+            rows = np.loadtxt(f, max_rows=n, ndmin=2) if n else np.zeros((0, len(props)))
+            return np.ascontiguousarray(rows[:, [names.index(a) for a in 'xyz']], dtype=np.float64)
+        order = '<' if fmt == 'binary_little_endian' else '>'
+        rec = np.dtype([(nm, order + ty) for nm, ty in props])
+        data = np.frombuffer(f.read(n * rec.itemsize), dtype=rec, count=n)
+        return np.stack([data[a].astype(np.float64) for a in 'xyz'], axis=1)
+
+
+def write_pcd(path, points):
+    """`o3d.io.write_point_cloud(path.pcd, cloud)`: PCD v0.7, float32 x y z, binary (written for the user's viewers only;
+    nothing on the path reads it back)."""
+    pts = np.ascontiguousarray(np.asarray(points, np.float64).reshape(-1, 3).astype('<f4'))
+    n = len(pts)
+    header = ('# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\n'
+              'WIDTH %d\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA binary\n' % (n, n))
+    with open(path, 'wb') as f:
+        f.write(header.encode('ascii'))
+        f.write(pts.tobytes())
+
+
+# ----------------------------------------------------------------------------------------------------- Euler angles
+_EPS4 = np.finfo(float).eps * 4.0
+
+
+def mat2euler(M):
+    """transforms3d.euler.mat2euler(M) with its default axes 'sxyz' (create_labels.py:344, :363-366): static x-y-z angles
+    of a rotation matrix (the closed form of Gohlke's euler_from_matrix, DenseFusion/lib/transformations.py:1057-1112)."""
+    M = np.asarray(M, np.float64)[:3, :3]
+    cy = np.sqrt(M[0, 0] * M[0, 0] + M[1, 0] * M[1, 0])
+    if cy > _EPS4:
+        return (float(np.arctan2(M[2, 1], M[2, 2])), float(np.arctan2(-M[2, 0], cy)), float(np.arctan2(M[1, 0], M[0, 0])))
+    return (float(np.arctan2(-M[1, 2], M[1, 1])), float(np.arctan2(-M[2, 0], cy)), 0.0)
+
+
+def euler2mat(ax, ay, az):
+    """transforms3d.euler.euler2mat(ai, aj, ak) with axes 'sxyz' (create_labels.py:372): R = Rz(az) Ry(ay) Rx(ax)."""
+    sx, sy, sz = np.sin(ax), np.sin(ay), np.sin(az)
+    cx, cy, cz = np.cos(ax), np.cos(ay), np.cos(az)
+    return np.array([[cy * cz, sy * sx * cz - cx * sz, sy * cx * cz + sx * sz],
+                     [cy * sz, sy * sx * sz + cx * cz, sy * cx * sz - sx * cz],
+                     [-sy, cy * sx, cy * cx]])

@@ -135,6 +135,32 @@ def add_metric_std(quat, trans, model_points, target, symmetric):
     return dis, std
 
 
+def estimator_loss(pred_r, pred_t, pred_c, points, model_points, target, symmetric, w, want_grad=True, want_pred=True):
+    """a12.  `Loss` (lib/loss.py:12-73) forward + backward for the N candidate poses of one object.  pred_r [N,4], pred_t [N,3],
+    pred_c [N], points [N,3], model_points / target [M,3] fp32 CUDA ->
+    dict(loss [] , dis_best [], which_max [1] int32, dis [N], std [N], d_r [N,4], d_t [N,3], d_c [N] (d loss / d inputs, or None),
+    new_points [1,N,3], new_target [1,M,3], pred [N,M,3] or None)."""
+    require_cuda(pred_r, pred_t, pred_c, points, model_points, target)
+    pred_r = _c(pred_r, torch.float32).reshape(-1, 4); N = pred_r.shape[0]
+    pred_t = _c(pred_t, torch.float32).reshape(N, 3); pred_c = _c(pred_c, torch.float32).reshape(N)
+    points = _c(points, torch.float32).reshape(N, 3)
+    model_points = _c(model_points, torch.float32).reshape(-1, 3); M = model_points.shape[0]
+    target = _c(target, torch.float32).reshape(M, 3)
+    dev = pred_r.device
+    f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    loss_dis, which = f(2), torch.empty((1,), dtype=torch.int32, device=dev)
+    dis, std, term = f(N), f(N), f(N)
+    d_r, d_t, d_c = (f(N, 4), f(N, 3), f(N)) if want_grad else (None, None, None)
+    newp, newt = f(1, N, 3), f(1, M, 3)
+    pred = f(N, M, 3) if want_pred else None
+    check(_lib.load().ape_estimator_loss(ptr(pred_r), ptr(pred_t), ptr(pred_c), ptr(points), ptr(model_points), ptr(target), N, M,
+                                         int(bool(symmetric)), float(w), ptr(loss_dis), ptr(which), ptr(dis), ptr(std), ptr(term),
+                                         ptr(d_r), ptr(d_t), ptr(d_c), ptr(newp), ptr(newt), ptr(pred), stream_ptr()),
+          'ape_estimator_loss')
+    return dict(loss=loss_dis[0], dis_best=loss_dis[1], which_max=which, dis=dis, std=std, d_r=d_r, d_t=d_t, d_c=d_c,
+                new_points=newp, new_target=newt, pred=pred)
+
+
 def icp_p2p(source, src_offset, target, tgt_offset, threshold, rel_fitness=1e-2, rel_rmse=1e-2, max_iter=100, init=None):
     """a5.  Ragged batch: source [S,3] fp64 with src_offset [R+1] int32, target [T,3] fp64 with tgt_offset [R+1].
     Returns (transform [R,4,4] fp64, info [R,4] fp64 = fitness, rmse, iterations, n_corr)."""

@@ -121,7 +121,8 @@ int ape_knn(const float* ref, const float* query, int64_t* idx, int B, int D, in
  *   model_points: instance b reads  model_points + b*model_stride  ([n_model,3] fp32; stride in floats, 0 = shared)
  *   target:       instance b reads  target + b*target_stride      ([n_target,3] fp32)
  *   symmetric [B] u8: 1 -> ADD-S (nearest target point per predicted point, APE_KNN_ARITH_CPU
- *   arithmetic), 0 -> ADD (requires n_model == n_target)
+ *   arithmetic), 0 -> ADD: model point i is paired with target row i (requires n_target >= n_model; an instance that
+ *   violates it gets dis = NaN, nothing is read out of bounds)
  *   dis [B] fp32 out; nn_index [B,n_model] int32 out (0-based) or NULL                          */
 int ape_add_metric(const float* quat, const float* trans, const float* model_points, int64_t model_stride,
                    int n_model, const float* target, int64_t target_stride, int n_target,
@@ -263,6 +264,20 @@ int ape_host_gather_wait(void);
 int ape_add_metric_std(const float* quat, const float* trans, const float* model_points, int64_t model_stride,
                        int n_model, const float* target, int64_t target_stride, int n_target,
                        const uint8_t* symmetric, int B, float* dis, float* std_out, void* stream);
+
+/* a12. Estimator loss `Loss` (DenseFusion/lib/loss.py:12-73), forward AND backward, for the n_cand per-point candidate
+ * poses of one object (the reference's batch size is 1, train.py:216): pred_r [n_cand,4] raw quaternions, pred_t
+ * [n_cand,3], pred_c [n_cand], points [n_cand,3], model_points / target [n_mesh,3] fp32; symmetric != 0 selects the
+ * nearest-neighbour target (the caller passes `idx in sym_list and not refine`, loss.py:40-41).
+ *   loss_dis [2] out: loss = mean_i[(dis_i + 2 std_i) c_i - w log c_i] (:53) and dis of the most confident candidate (:73)
+ *   which_max [1] out; dis / std_out / term [n_cand] out (per-candidate mean distance, unbiased std, loss term)
+ *   d_r [n_cand,4], d_t [n_cand,3], d_c [n_cand] out: d loss / d (pred_r, pred_t, pred_c), or NULL (forward only)
+ *   new_points [n_cand,3], new_target [n_mesh,3] out or NULL (:55-69); pred_out [n_cand,n_mesh,3] out or NULL (:38)
+ * Neither the [N,M,3] gather nor the N*M-query kNN of the reference is materialised (unless pred_out is requested).  */
+int ape_estimator_loss(const float* pred_r, const float* pred_t, const float* pred_c, const float* points,
+                       const float* model_points, const float* target, int n_cand, int n_mesh, int symmetric, float w,
+                       float* loss_dis, int32_t* which_max, float* dis, float* std_out, float* term, float* d_r, float* d_t,
+                       float* d_c, float* new_points, float* new_target, float* pred_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Point-cloud outlier filters, open3d 0.9.0 semantics, ragged batches

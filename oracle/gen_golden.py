@@ -166,5 +166,27 @@ def main():
         print('  %-28s %8d B' % (f, os.path.getsize(os.path.join(OUT, f))))
 
 
+def loss_grads():
+    """tests/golden/loss_grads.npz: the REFERENCE's own `Loss` (lib/loss.py:12-73) differentiated by autograd -- loss value
+    and d loss / d (pred_r, pred_t, pred_c) for a symmetric and a non-symmetric class (inputs: tests/golden/losses.npz)."""
+    network, tools, tf, loss_m, lossr_m = _import_reference()
+    g = np.load(os.path.join(OUT, 'losses.npz'))
+    res = {}
+    for tag, sym in (('sym', [0]), ('nosym', [])):
+        pr = torch.from_numpy(g['pr_n']).requires_grad_(True); pt = torch.from_numpy(g['pt_n']).requires_grad_(True)
+        pc = torch.from_numpy(g['pc_n']).requires_grad_(True)
+        L = loss_m.Loss(g['model'].shape[1], sym)
+        lo, dis, npn, ntg, pred = L(pr, pt, pc, torch.from_numpy(g['target']), torch.from_numpy(g['model']), torch.LongTensor([[0]]),
+                                    torch.from_numpy(g['points']), 0.015, False)
+        lo.backward()
+        res.update({'loss_' + tag: lo.detach().numpy(), 'd_r_' + tag: pr.grad.numpy(), 'd_t_' + tag: pt.grad.numpy(),
+                    'd_c_' + tag: pc.grad.numpy(), 'pred_' + tag: pred.detach().numpy()})
+    np.savez_compressed(os.path.join(OUT, 'loss_grads.npz'), **res)
+    print('loss_grads.npz written', {k: v.shape for k, v in res.items()})
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'grads':
+        loss_grads()
+    else:
+        main()

@@ -92,21 +92,56 @@ def test_loss_dropins_nonsymmetric_match_reference(golden_dir):
         assert np.allclose(N(npn), g['l_newp_' + tag], atol=1e-6) and np.allclose(N(ntg), g['l_newt_' + tag], atol=1e-6)
 
 
-def test_loss_fused_forward_equals_differentiable_path(golden_dir):
-    """`Loss` has two implementations of loss.py:12-73: the fused forward-only kernel path and the
-    differentiable torch glue around the kNN kernel; both must give the reference's numbers."""
+def test_loss_forward_and_gradient_match_reference_autograd(golden_dir):
+    """`Loss` on the kernels (csrc/knn.cu: estimator_loss_kernel) against the reference's own lib/loss.py differentiated by
+    torch autograd (tests/golden/loss_grads.npz, oracle/gen_golden.py): loss, `pred`, and d loss / d (pred_r, pred_t, pred_c)
+    for a symmetric class (nearest-neighbour targets, indices detached) and a non-symmetric one; a no-grad call returns
+    the same values."""
     from autoposeestimation_b200.densefusion.loss import Loss
     g = np.load(os.path.join(golden_dir, 'losses.npz'))
+    gg = np.load(os.path.join(golden_dir, 'loss_grads.npz'))
     T = lambda k: torch.from_numpy(g[k]).cuda()
     idx = torch.zeros((1, 1), dtype=torch.long, device='cuda')
-    for sym, refine in (([0], False), ([], False), ([0], True)):
-        fused = Loss(120, sym)(T('pr_n'), T('pt_n'), T('pc_n'), T('target'), T('model'), idx, T('points'), 0.015, refine)
-        pr = T('pr_n').requires_grad_(True)
-        glue = Loss(120, sym)(pr, T('pt_n'), T('pc_n'), T('target'), T('model'), idx, T('points'), 0.015, refine)
-        for a, b in zip(fused, glue):
-            assert a.shape == b.shape and torch.allclose(a, b.detach(), atol=2e-6, rtol=1e-5)
-        glue[0].backward()
-        assert pr.grad is not None and float(pr.grad.abs().sum()) > 0
+    for tag, sym in (('sym', [0]), ('nosym', [])):
+        pr, pt, pc = T('pr_n').requires_grad_(True), T('pt_n').requires_grad_(True), T('pc_n').requires_grad_(True)
+        lo, dis, npn, ntg, pred = Loss(120, sym)(pr, pt, pc, T('target'), T('model'), idx, T('points'), 0.015, False)
+        assert abs(float(lo) - float(gg['loss_' + tag])) < 1e-6
+        assert np.allclose(pred.cpu().numpy(), gg['pred_' + tag], atol=1e-6)
+        assert np.allclose(npn.cpu().numpy(), g['l_newp_' + tag], atol=1e-6) and np.allclose(ntg.cpu().numpy(), g['l_newt_' + tag], atol=1e-6)
+        assert abs(float(dis) - float(g['l_dis_' + tag])) < 1e-6 and not dis.requires_grad and not npn.requires_grad
+        (2.0 * lo).backward()
+        for got, key in ((pr.grad, 'd_r_'), (pt.grad, 'd_t_'), (pc.grad, 'd_c_')):
+            want = 2.0 * gg[key + tag]
+            assert got.shape == want.shape
+            assert np.allclose(got.cpu().numpy(), want, rtol=2e-4, atol=1e-7), (tag, key, np.abs(got.cpu().numpy() - want).max())
+        with torch.no_grad():
+            lo2, dis2, *_ = Loss(120, sym)(T('pr_n'), T('pt_n'), T('pc_n'), T('target'), T('model'), idx, T('points'), 0.015, False)
+        assert float(lo2) == float(lo) and float(dis2) == float(dis)
+    with pytest.raises(NotImplementedError):
+        Loss(120, [])(T('pr_n').repeat(2, 1, 1), T('pt_n').repeat(2, 1, 1), T('pc_n').repeat(2, 1, 1), T('target').repeat(2, 1, 1),
+                      T('model').repeat(2, 1, 1), idx, T('points').repeat(2, 1, 1), 0.015, False)
+
+
+def test_loss_large_mesh_and_many_candidates():
+    """Shapes of the reference's training configs: 1000 candidates x 1000 mesh points (this fork) and a 2600-point mesh (YCB
+    refine phase), symmetric: per-candidate dis / std against the ADD-S kernel pinned elsewhere, finite gradients."""
+    from autoposeestimation_b200 import ops
+    rng = np.random.RandomState(4)
+    for N, M in ((1000, 1000), (300, 2600)):
+        model = torch.from_numpy(rng.uniform(-0.1, 0.1, (M, 3)).astype(np.float32)).cuda()
+        target = model + 0.003 * torch.randn_like(model)
+        pr = torch.from_numpy(rng.standard_normal((N, 4)).astype(np.float32)).cuda(); pr[:, 0] += 3.0
+        pt = torch.from_numpy((rng.standard_normal((N, 3)) * 0.01).astype(np.float32)).cuda()
+        pc = torch.from_numpy(rng.uniform(0.1, 0.9, N).astype(np.float32)).cuda()
+        pts = torch.from_numpy((rng.standard_normal((N, 3)) * 0.01).astype(np.float32)).cuda()
+        out = ops.estimator_loss(pr, pt, pc, pts, model, target, True, 0.015)
+        dis = ops.add_metric(pr, pts + pt, model, target, torch.ones(N, dtype=torch.uint8, device='cuda'))
+        assert torch.allclose(out['dis'], dis, atol=1e-6)
+        want = torch.mean((out['dis'] + 2 * out['std']) * pc - 0.015 * torch.log(pc))
+        assert abs(float(out['loss']) - float(want)) < 1e-6
+        assert int(out['which_max'][0]) == int(torch.argmax(pc))
+        for k in ('d_r', 'd_t', 'd_c'):
+            assert bool(torch.isfinite(out[k]).all()) and float(out[k].abs().sum()) > 0
 
 
 def test_refiner_dropin_trains_like_reference_loop(golden_dir):
