@@ -85,3 +85,108 @@ def rotate_about_center(cloud, R):
     c = cloud.points.mean(dim=0, keepdim=True)
     cloud.points = ((cloud.points - c) @ R.T + c).contiguous()
     return cloud
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Entry point of main.py option 4 with the reference's signature (create_pointcloud.py:181-378)
+def bbox_center(cloud):
+    """`utils.get_my_source_center` (open3d_utils.py:273-290): centre of the axis-aligned bounding box."""
+    p = cloud.points
+    return ((p.min(dim=0).values + p.max(dim=0).values) / 2).cpu().numpy()
+
+
+def get_view_distribution(data_path, d, n, n_viewpoints, plot=False, l_arrow=30, reference_point=np.array([0, 0, 0])):
+    """create_pointcloud.py:46-179 (view selection; the 3-D plot is outside the graft): camera positions of the n frames
+    of rotation run `d` -> voxel grid whose cell size is grown / shrunk by 1 mm until n_viewpoints cells are occupied ->
+    the frame nearest to each cell mean -> greedy nearest-neighbour chain starting at the view closest to the robot origin.
+    Returns frame indices in visiting order.  (When the grid cannot hit n_viewpoints exactly the reference draws a random
+    subset of the cells, :99-104; the draw comes from np.random here as well, over cells in sorted instead of hash order.)"""
+    import json
+    import os
+    pos = []
+    for idx in range(n):
+        with open(os.path.join(data_path, d, '{:06d}.meta.json'.format(idx))) as f:
+            meta = json.load(f)
+        r2c = np.dot(np.array(meta.get('robot2endEff_tf'), np.float64).reshape(4, 4),
+                     np.array(meta.get('hand_eye_calibration'), np.float64).reshape(4, 4))
+        pos.append(r2c[:3, 3])
+    pos = np.array(pos)
+    diff = np.linalg.norm(pos[:, None, :] - pos[None, :, :], axis=2)
+    voxel = int(diff[~np.eye(len(pos), dtype=bool)].min()) if len(pos) > 1 else 1
+    cams = PointCloud(pos)
+    while True:
+        cells = cams.voxel_down_sample(max(voxel, 1e-9)).numpy() if voxel > 0 else pos
+        if len(cells) == n_viewpoints:
+            centres = cells
+            break
+        if len(cells) < n_viewpoints:
+            voxel -= 1
+            cells = cams.voxel_down_sample(voxel).numpy() if voxel > 0 else pos
+            centres = cells[np.random.choice(np.arange(len(cells)), replace=False, size=n_viewpoints)]
+            break
+        voxel += 1
+    nearest = [int(np.argmin(np.linalg.norm(pos - c, axis=1))) for c in centres]
+    chosen = pos[nearest]
+    order = [int(np.argmin(np.linalg.norm(chosen, axis=1)))]
+    while len(order) != n_viewpoints:
+        rest = [j for j in range(len(chosen)) if j not in order]
+        order.append(rest[int(np.argmin([np.linalg.norm(chosen[j] - chosen[order[-1]]) for j in rest]))])
+    return np.array(nearest)[order]
+
+
+def load_point_cloud(object_name, save_dir, root, reference_point=np.array([0, 0, 0]), mode='gen', n_viewpoints=10, min_friends=10,
+                     voxel_size=5, voxel_size_out=10, threshold=50, min_dist=10, nb_neighbors=5, l_arrow=30,
+                     global_regression=False, icp_point2point=True, icp_point2plane=True, plot=False):
+    """Drop-in for create_pointcloud.py:181-378 (same arguments, same files written, returns the aligned cloud).
+
+    Per rotation run under `label_generator/data/<object>/`: select n_viewpoints views, decode them into pinned buffers
+    (formats.FrameBatchLoader), run `get_surface` for ALL of them in one pass of batched launches, register-and-merge them
+    sequentially (`reconstruct_run`), rotate by the run's object pose, write `<run>.pcd/.ply`; then align the runs
+    (`align_point_clouds`) and write `<object>_out`, the down-sampled centred `<object>` cloud and the `.xyz` model the
+    pose networks train on (>= 1000 points, :363-376).  As in the reference, `icp_point2plane=True` is not grafted and
+    raises inside icp_regression (main.py:177-179 passes False); plots are outside the graft."""
+    import os
+    from .. import formats
+    from .open3d_utils import align_point_clouds
+    label_root = os.path.join(root, 'label_generator/data', object_name)
+    runs = [d for d in os.listdir(label_root) if d != 'extra']
+    if not runs:
+        raise ValueError('no labels obtained yet')
+    data_root = os.path.join(root, 'data_generation/data', object_name)
+    out_dir = os.path.join(save_dir, object_name)
+    os.makedirs(out_dir, exist_ok=True)
+    n = len([f for f in os.listdir(os.path.join(label_root, runs[0])) if '.{}.label.png'.format(mode) in f])
+    run_clouds = []
+    for d in runs:
+        views = get_view_distribution(data_root, d, n, n_viewpoints, plot=False, l_arrow=l_arrow, reference_point=reference_point)
+        loader = formats.FrameBatchLoader(os.path.join(data_root, d), os.path.join(label_root, d), mode=mode)
+        batch = loader.to_device(loader.load([int(v) for v in views]))
+        surfaces = get_surfaces_batch(batch['label'], batch['depth'], batch['cam'], batch['robot2cam'], min_friends, min_dist,
+                                      nb_neighbors, voxel_size)
+        cloud = reconstruct_run(surfaces, voxel_size, threshold, global_regression=global_regression,
+                                icp_point2point=icp_point2point, icp_point2plane=icp_point2plane)
+        rot = batch['meta'][-1]['object_rotation']                 # the last view's object_pose, as :246-247 leaves it
+        if len(cloud):
+            rotate_about_center(cloud, rot)
+        formats.write_pcd(os.path.join(out_dir, '{}.pcd'.format(d)), cloud.numpy())
+        formats.write_ply(os.path.join(out_dir, '{}.ply'.format(d)), cloud.numpy())
+        run_clouds.append(PointCloud(cloud.points.clone()))
+    cloud = align_point_clouds(run_clouds, min_friends=min_friends, min_dist=min_dist, nb_neighbors=nb_neighbors, plot=False,
+                               global_regression=global_regression, icp_point2point=icp_point2point,
+                               icp_point2plane=icp_point2plane, voxel_size=voxel_size, threshold=threshold)
+    formats.write_pcd(os.path.join(out_dir, '{}_out.pcd'.format(object_name)), cloud.numpy())
+    formats.write_ply(os.path.join(out_dir, '{}_out.ply'.format(object_name)), cloud.numpy())
+    down = cloud.voxel_down_sample(voxel_size_out)
+    down.translate(-bbox_center(down))
+    formats.write_pcd(os.path.join(out_dir, '{}.pcd'.format(object_name)), down.numpy())
+    formats.write_ply(os.path.join(out_dir, '{}.ply'.format(object_name)), down.numpy())
+    big = PointCloud(cloud.points.clone())
+    big.translate(-bbox_center(big))
+    v = voxel_size                                             # coarsen in 0.1 mm steps while at least 1000 points remain (:363-370)
+    while True:
+        v += 0.1
+        if len(big.voxel_down_sample(v)) < 1000:
+            big = big.voxel_down_sample(v - 0.1)
+            break
+    formats.write_xyz(os.path.join(out_dir, '{}.xyz'.format(object_name)), big.numpy())
+    return cloud

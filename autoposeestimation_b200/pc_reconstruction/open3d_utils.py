@@ -139,7 +139,8 @@ def align_point_clouds(point_clouds, min_friends, min_dist, nb_neighbors, plot=F
         if diff[1] > -30:                                                         # :141-143
             source.translate([0, -30 - diff[1], 0])
         target, source, init_tf = icp_regression(target, source, voxel_size=voxel_size, threshold=threshold,
-                                                 global_regression=global_regression, icp_point2point=True, icp_point2plane=False)
+                                                 global_regression=global_regression, icp_point2point=icp_point2point,
+                                                 icp_point2plane=icp_point2plane)
         source = source.transform(init_tf)
         target = PointCloud(torch.cat((source.points, target.points)))            # :156-157 (source first)
         target = target.voxel_down_sample(voxel_size)

@@ -179,3 +179,83 @@ def encoder_state_dict(seed, shapes):
             fan_in = int(np.prod(shp[1:]))
             sd[k] = (rng.standard_normal(shp) * math.sqrt(2.0 / fan_in)).astype(np.float32)
     return sd
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Multi-object scene seen from many camera poses ("10 000 random camera poses on a hemisphere r in
+# [450,700] mm looking at the table centre; each frame contains all 5 objects' labels")
+SCENE_AXES = ((40.0, 30.0, 20.0), (35.0, 35.0, 25.0), (50.0, 25.0, 20.0), (30.0, 30.0, 28.0), (45.0, 22.0, 26.0))
+SCENE_CENTER = np.array([0.0, -500.0, 60.0])                  # table centre in the robot frame (mm)
+
+
+class Scene:
+    """n_objects ellipsoids with distinct semi-axes at fixed poses around SCENE_CENTER (robot frame, mm).
+    `object_rotation` (optional 3x3) rotates every object about its own centre (a "rotation run" of the turntable)."""
+
+    def __init__(self, seed=3, n_objects=5, n_model=2000, object_rotation=None):
+        rng = np.random.RandomState(seed)
+        self.n = n_objects
+        self.axes = np.array(SCENE_AXES[:n_objects])
+        ang = np.arange(n_objects) * (2 * math.pi / max(n_objects, 1)) + rng.uniform(0, 1)
+        radius = 0.0 if n_objects == 1 else 115.0
+        self.centers = SCENE_CENTER + np.stack([radius * np.cos(ang), radius * np.sin(ang), np.zeros(n_objects)], 1)
+        self.R = np.stack([random_rotation(rng, math.pi) for _ in range(n_objects)])
+        if object_rotation is not None:
+            self.R = np.stack([np.asarray(object_rotation) @ r for r in self.R])
+        # model clouds (true surface, robot frame) and perturbed copies (<= 10 deg, <= 5 mm) that ICP has to bring back
+        self.models, self.models_pert = [], []
+        for k in range(n_objects):
+            m = ellipsoid_cloud(rng, n_model, self.axes[k]) @ self.R[k].T + self.centers[k]
+            dR = random_rotation(rng, math.radians(10.0)); dt = rng.uniform(-5.0, 5.0, size=3) / math.sqrt(3.0)
+            self.models.append(m)
+            self.models_pert.append((m - self.centers[k]) @ dR.T + self.centers[k] + dt)
+
+    def camera_poses(self, seed, n):
+        """n camera->robot transforms [n,4,4]: positions on the upper hemisphere around SCENE_CENTER (r in [450,700] mm,
+        elevation 35..80 deg), optical axis through the centre, small in-plane roll."""
+        rng = np.random.RandomState(seed)
+        r = rng.uniform(450.0, 700.0, n); el = np.radians(rng.uniform(35.0, 80.0, n)); az = rng.uniform(0, 2 * math.pi, n)
+        roll = np.radians(rng.uniform(-10.0, 10.0, n))
+        pos = SCENE_CENTER + np.stack([r * np.cos(el) * np.cos(az), r * np.cos(el) * np.sin(az), r * np.sin(el)], 1)
+        T = np.tile(np.identity(4), (n, 1, 1))
+        for i in range(n):
+            z = SCENE_CENTER - pos[i]; z /= np.linalg.norm(z)
+            x = np.cross(z, [0.0, 0.0, 1.0]); x /= np.linalg.norm(x)
+            y = np.cross(z, x)
+            c, s = math.cos(roll[i]), math.sin(roll[i])
+            T[i, :3, 0], T[i, :3, 1], T[i, :3, 2], T[i, :3, 3] = c * x + s * y, -s * x + c * y, z, pos[i]
+        return T
+
+    def render(self, robot2cam, seed=0, device='cpu', noise_mm=0.5, dropout=0.02, H=480, W=640, only_object=None):
+        """Analytic ray casting of a batch of frames with torch (CPU or CUDA): robot2cam [F,4,4] ->
+        label [F,H,W] uint8 (0 = background, k+1 = object k; `only_object` k renders object k alone as 255),
+        depth [F,H,W] int16 storage of the uint16 millimetres (background 900..1100 mm, `dropout` zeros)."""
+        import torch
+        dev = torch.device(device)
+        T = torch.as_tensor(np.asarray(robot2cam), dtype=torch.float64, device=dev)
+        F = T.shape[0]
+        g = torch.Generator(device=dev).manual_seed(int(seed))
+        vv, uu = torch.meshgrid(torch.arange(H, device=dev, dtype=torch.float64), torch.arange(W, device=dev, dtype=torch.float64), indexing='ij')
+        d_cam = torch.stack([(uu - INTR['ppx']) / INTR['fx'], (vv - INTR['ppy']) / INTR['fy'], torch.ones_like(uu)], -1)   # [H,W,3]
+        best = torch.full((F, H, W), float('inf'), dtype=torch.float64, device=dev)
+        label = torch.zeros((F, H, W), dtype=torch.uint8, device=dev)
+        objs = range(self.n) if only_object is None else [only_object]
+        for k in objs:
+            A = torch.as_tensor((self.R[k] / self.axes[k]).T, dtype=torch.float64, device=dev)        # rows (R[:,i] / a_i)^T
+            M = A @ T[:, :3, :3]                                                                       # [F,3,3]: robot dir -> scaled object frame
+            dd = torch.einsum('fij,hwj->fhwi', M, d_cam)
+            cc = torch.einsum('ij,fj->fi', A, torch.as_tensor(self.centers[k], dtype=torch.float64, device=dev) - T[:, :3, 3])
+            qa = (dd * dd).sum(-1); qb = -2.0 * torch.einsum('fhwi,fi->fhw', dd, cc); qc = (cc * cc).sum(-1)[:, None, None] - 1.0
+            disc = qb * qb - 4 * qa * qc
+            s = torch.where(disc > 0, (-qb - torch.sqrt(disc.clamp_min(0))) / (2 * qa), torch.full_like(qa, float('inf')))
+            s = torch.where(s > 0, s, torch.full_like(s, float('inf')))
+            closer = s < best
+            best = torch.where(closer, s, best)
+            label = torch.where(closer, torch.full_like(label, 255 if only_object is not None else k + 1), label)
+        hit = torch.isfinite(best)
+        z = best + torch.randn((F, H, W), dtype=torch.float64, device=dev, generator=g) * noise_mm
+        bg = torch.rand((F, H, W), dtype=torch.float64, device=dev, generator=g) * 200.0 + 900.0
+        depth = torch.where(hit, z.clamp(1, 65535), bg).round().to(torch.int32)
+        depth[torch.rand((F, H, W), device=dev, generator=g) < dropout] = 0
+        depth16 = torch.where(depth >= 32768, depth - 65536, depth).to(torch.int16)
+        return label, depth16

@@ -1,0 +1,238 @@
+"""GPU: the reference's option-4 / option-6 ENTRY POINTS with their own signatures -- full_prediction,
+get_prediction_models (pipeline/utils.py:410-718), load_point_cloud (create_pointcloud.py:181-378), create_pose_label
+(create_labels.py:292-440) -- against the same flows assembled from the oracle pieces, on synthetic dataset trees written
+in the reference's on-disk formats."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import densefusion as odf, geometry as og, icp as oicp, pose_math as pm, synth
+
+pytestmark = pytest.mark.gpu
+
+
+class _Segmentor(torch.nn.Module):
+    """Stand-in for the smp U-Net (outside the graft): logits that reproduce a given label map, with a per-component
+    confidence so that the connected-component selection has something to decide."""
+
+    def __init__(self, label_map, n_classes, weak=None):
+        super().__init__()
+        self.label_map, self.n, self.weak = label_map, n_classes, weak
+
+    def predict(self, x):
+        lab = torch.from_numpy(self.label_map.astype(np.int64)).to(x.device)
+        logits = torch.full((1, self.n) + lab.shape, -4.0, device=x.device)
+        logits.scatter_(1, lab[None, None], 4.0)
+        if self.weak is not None:
+            logits[0, :, self.weak[0], self.weak[1]] *= 0.25            # a less confident blob of the same class
+        return logits
+
+
+def _modules(seed, N, nobj):
+    from autoposeestimation_b200.densefusion import network
+    est = network.PoseNet(N, nobj); est.load_state_dict(synth.to_torch(synth.posenet_state_dict(seed, nobj)), strict=False)
+    ref = network.PoseRefineNet(N, nobj); ref.load_state_dict(synth.to_torch(synth.refiner_state_dict(seed + 1000, nobj)))
+    enc_w = torch.randn(32, 3, generator=torch.Generator().manual_seed(seed)).cuda() * 0.01
+
+    class _Enc(torch.nn.Module):                                       # per-pixel linear stand-in for the colour encoder
+        def forward(self, crops):
+            return torch.einsum('oc,bchw->bohw', enc_w, crops)
+    est.cnn = _Enc()
+    return est.cuda().eval(), ref.cuda().eval()
+
+
+def test_full_prediction_matches_reference_flow():
+    from torchvision import transforms
+    from autoposeestimation_b200.pipeline.utils import full_prediction
+    H, W, N, nobj = 480, 640, 1000, 3
+    rng = np.random.RandomState(3)
+    image = rng.randint(0, 256, size=(H, W, 3)).astype(np.uint8)
+    depth = rng.randint(400, 900, size=(H, W)).astype(np.uint16); depth[rng.rand(H, W) < 0.05] = 0
+    lab = np.zeros((H, W), np.int64)
+    lab[100:190, 150:260] = 1                                          # > 1000 candidate pixels -> random subset
+    lab[300:320, 400:430] = 3                                          # < 1000 -> wrap padding
+    lab[20:34, 20:34] = 1                                              # second, weaker blob of class 1 -> dropped by the CCA
+    lab[400:404, 600:604] = 2                                          # 16 px < 100 -> ignored
+    depth[300:320, 400:430] = np.maximum(depth[300:320, 400:430], 1)
+    seg = _Segmentor(lab, nobj + 1, weak=(slice(20, 34), slice(20, 34)))
+    est, ref = _modules(9, N, nobj)
+    names = ['bolt', 'nut', 'gear']
+    meta = {'intr': dict(ppx=320.0, ppy=240.0, fx=615.0, fy=615.0), 'depth_scale': 0.001}
+    to_tensor, normalize = transforms.ToTensor(), transforms.Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])
+    color_dict = {n: {'value': (255, 0, 0), 'tag': 'red'} for n in names}
+    np.random.seed(123)
+    out = full_prediction(image, depth, meta, seg, est, ref, to_tensor, normalize, torch.device('cuda:0'), True, color_dict,
+                          class_names=names, point_clouds=[rng.rand(50, 3) * 0.05] * 3, color_prediction=True, bbox=True, put_text=True)
+    assert sorted(out['predictions']) == ['bolt', 'gear']
+    assert set(out['elapsed_times']) == {'segmentation', 'pose_estimation', 'total'}
+    assert out['segmented_prediction'].shape == (H, W, 3) and out['pose_prediction'].dtype == np.uint8
+    m = out['predictions']['bolt']['mask']
+    assert m.dtype == np.uint8 and m[100:190, 150:260].min() == 255 and m[20:34, 20:34].max() == 0 and int((m == 255).sum()) == 90 * 110
+    # the reference flow per object (pipeline/utils.py:522-571) from the oracle pieces, same global RNG stream
+    sd_e = synth.to_torch(synth.posenet_state_dict(9, nobj)); sd_r = synth.to_torch(synth.refiner_state_dict(1009, nobj))
+    raw = normalize(torch.from_numpy(np.transpose(image, (2, 0, 1)).astype(np.float32))).cuda()
+    np.random.seed(123)
+    for cls in ('bolt', 'gear'):
+        ml = out['predictions'][cls]['mask'] == 255
+        bbox = og.get_bbox(ml)
+        cand = og.choose_candidates(ml, depth, bbox)
+        ch = og.choose_fixed(cand, N, og.make_keep(len(cand), N, np.random) if len(cand) > N else None)
+        cloud = og.backproject_choose(depth, bbox, ch, 320.0, 240.0, 615.0, 615.0, 0.001)
+        out_img = est.cnn(raw[:, bbox[0]:bbox[1], bbox[2]:bbox[3]][None]).cpu()
+        with torch.no_grad():
+            res = odf.live_prediction(sd_e, sd_r, out_img, torch.from_numpy(cloud)[None], torch.from_numpy(ch.astype(np.int64))[None, None],
+                                      torch.tensor([[names.index(cls)]]), nobj, refine_calls=2)
+        assert pm.rotation_angle_between(out['predictions'][cls]['rotation'], res['q']) < 1e-3
+        assert np.abs(out['predictions'][cls]['position'] - res['t']).max() < 1e-4
+
+
+def test_get_prediction_models_reads_reference_layout(tmp_path):
+    from autoposeestimation_b200 import formats
+    from autoposeestimation_b200.densefusion import network
+    from autoposeestimation_b200.pipeline.utils import get_prediction_models
+    root, ds, names = str(tmp_path), 'myds', ['bolt', 'nut']
+    os.makedirs(os.path.join(root, 'label_generator', 'data_sets', 'segmentation', ds))
+    with open(os.path.join(root, 'label_generator', 'data_sets', 'segmentation', ds, 'classes.txt'), 'w') as f:
+        f.write('\n'.join(names) + '\n')
+    rng = np.random.RandomState(0)
+    clouds = []
+    for n in names:
+        os.makedirs(os.path.join(root, 'pc_reconstruction', 'data', n))
+        pts = rng.uniform(-60, 60, size=(1200, 3)); clouds.append(pts)
+        formats.write_xyz(os.path.join(root, 'pc_reconstruction', 'data', n, n + '.xyz'), pts)
+    os.makedirs(os.path.join(root, 'DenseFusion', 'trained_models', ds))
+    est = network.PoseNet(1000, 2); ref = network.PoseRefineNet(1000, 2)
+    torch.save(est.state_dict(), os.path.join(root, 'DenseFusion', 'trained_models', ds, 'pose_model.pth'))
+    torch.save(ref.state_dict(), os.path.join(root, 'DenseFusion', 'trained_models', ds, 'pose_refine_model.pth'))
+    seg, e2, r2, classes, to_tensor, normalize, cld, device, cuda = get_prediction_models(
+        root, ds, segmentor_factory=lambda r, d, n: _Segmentor(np.zeros((4, 4)), n))
+    assert classes == names and cuda and device.type == 'cuda' and isinstance(seg, _Segmentor) and seg.n == 3
+    assert not e2.training and next(e2.parameters()).is_cuda and next(r2.parameters()).is_cuda
+    for k in range(2):
+        assert cld[k].shape == (1200, 3) and np.abs(cld[k] * 1000 - clouds[k]).max() < 1.0        # metres; parser quirk <= last digit
+    assert torch.equal(e2.conv1_r.weight.cpu(), est.conv1_r.weight) and torch.equal(r2.conv3_t.bias.cpu(), ref.conv3_t.bias)
+
+
+# ------------------------------------------------------------------------------------------------ option 4
+def _write_run(root, obj, run, scene, k, poses, object_pose, render_seed):
+    """One rotation run in the reference's layout: data_generation/data/<obj>/<run>/NNNNNN.{meta.json,depth.png,color.png}
+    and label_generator/data/<obj>/<run>/NNNNNN.gen.label.png."""
+    from autoposeestimation_b200 import formats, synthetic as psynth
+    ddir = os.path.join(root, 'data_generation', 'data', obj, run); ldir = os.path.join(root, 'label_generator', 'data', obj, run)
+    os.makedirs(ddir, exist_ok=True); os.makedirs(ldir, exist_ok=True)
+    he = psynth.hand_eye()
+    lab, dep = scene.render(poses, seed=render_seed, only_object=k)
+    frames = []
+    for i in range(len(poses)):
+        r2e = poses[i] @ np.linalg.inv(he)
+        intr = dict(psynth.INTR, width=640, height=480, coeffs=[0.0] * 5)
+        meta = formats.frame_meta([0.0] * 6, {}, object_pose, r2e, intr, 0.001, False, [float(v) for v in he.reshape(-1)], i)
+        formats.write_json(os.path.join(ddir, '{:06d}.meta.json'.format(i)), meta)
+        d = dep[i].numpy().view(np.uint16); l = lab[i].numpy()
+        formats.save_png(os.path.join(ddir, '{:06d}.depth.png'.format(i)), d)
+        formats.save_png(os.path.join(ddir, '{:06d}.color.png'.format(i)), np.zeros((480, 640, 3), np.uint8))
+        formats.save_png(os.path.join(ldir, '{:06d}.gen.label.png'.format(i)), l)
+        frames.append(dict(label=l, depth=d.astype(np.float64), robot2cam=np.dot(r2e, he)))
+    return frames
+
+
+def _oracle_run(frames, order, intr, voxel, threshold, filt):
+    cloud = None
+    for i in order:
+        fr = frames[i]
+        pts, _ = og.surface_backproject(fr['label'], fr['depth'], intr, fr['robot2cam'])
+        if len(pts) == 0:
+            continue
+        src = oicp.get_surface_filters(pts, *filt, voxel)
+        if len(src) == 0:
+            continue
+        if cloud is None:
+            cloud = src
+            continue
+        td, sd, T = oicp.icp_regression(cloud, src, voxel_size=voxel, threshold=threshold)
+        cloud = oicp.voxel_down_sample(np.concatenate((sd @ T[:3, :3].T + T[:3, 3], td)), voxel)
+    return cloud
+
+
+def test_load_point_cloud_and_create_pose_label(tmp_path):
+    from autoposeestimation_b200 import formats, synthetic as psynth
+    from autoposeestimation_b200.label_generator.create_labels import create_pose_label
+    from autoposeestimation_b200.pc_reconstruction.create_pointcloud import get_view_distribution, load_point_cloud
+    root, obj = str(tmp_path), 'gear'
+    n_frames, n_views, voxel, threshold, filt = 6, 4, 2.0, 10.0, (5, 5.0, 20)
+    Rz = np.identity(4); a = np.radians(90.0)
+    Rz[:3, :3] = [[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]]
+    runs = {}
+    for run, pose, seed in (('rot0', np.identity(4), 11), ('rot1', Rz, 12)):
+        scene = psynth.Scene(5, n_objects=1, object_rotation=pose[:3, :3])
+        cams = scene.camera_poses(seed, n_frames)
+        runs[run] = (_write_run(root, obj, run, scene, 0, cams, pose, seed), pose)
+    os.makedirs(os.path.join(root, 'data_generation', 'data', obj, 'background'))
+    save_dir = os.path.join(root, 'pc_reconstruction', 'data')
+    np.random.seed(0)
+    cloud = load_point_cloud(obj, save_dir, root, mode='gen', n_viewpoints=n_views, min_friends=filt[0], voxel_size=voxel, voxel_size_out=5,
+                             threshold=threshold, min_dist=filt[1], nb_neighbors=filt[2], icp_point2plane=False)
+    out_dir = os.path.join(save_dir, obj)
+    for f in ('rot0.ply', 'rot0.pcd', 'rot1.ply', obj + '_out.ply', obj + '_out.pcd', obj + '.ply', obj + '.pcd', obj + '.xyz'):
+        assert os.path.exists(os.path.join(out_dir, f)), f
+    # the same flow from the oracle pieces
+    np.random.seed(0)
+    run_clouds = []
+    # os.listdir order is what the entry point used
+    listed = [d for d in os.listdir(os.path.join(root, 'label_generator', 'data', obj)) if d != 'extra']
+    for run in listed:
+        frames, pose = runs[run]
+        order = get_view_distribution(os.path.join(root, 'data_generation', 'data', obj), run, n_frames, n_views)
+        c = _oracle_run(frames, order, psynth.INTR, voxel, threshold, filt)
+        ctr = c.mean(axis=0)
+        c = (c - ctr) @ pose[:3, :3].T + ctr                              # point_cloud.rotate(R, center=True), :320
+        got = formats.read_ply(os.path.join(out_dir, run + '.ply'))
+        assert len(got) == len(c) and np.allclose(got, c, atol=1e-6), run
+        run_clouds.append(c)
+    tgt = run_clouds[0]
+    for src in run_clouds[1:]:                                            # align_point_clouds, open3d_utils.py:125-168
+        diff = src.mean(0) - tgt.mean(0)
+        if diff[1] > -30:
+            src = src + np.array([0, -30 - diff[1], 0])
+        td, sd, T = oicp.icp_regression(tgt, src, voxel_size=voxel, threshold=threshold)
+        tgt = oicp.voxel_down_sample(np.concatenate((sd @ T[:3, :3].T + T[:3, 3], td)), voxel)
+        tgt, _ = oicp.remove_radius_outlier(tgt, filt[0], filt[1])
+        tgt, _, _, _ = oicp.remove_statistical_outlier(tgt, filt[2], float(np.std(oicp.compute_mahalanobis_distance(tgt))))
+    assert len(cloud) == len(tgt) and np.allclose(cloud.numpy(), tgt, atol=1e-6)
+    assert np.allclose(formats.read_ply(os.path.join(out_dir, obj + '_out.ply')), tgt, atol=1e-6)
+    down = oicp.voxel_down_sample(tgt, 5)
+    down = down - (down.min(0) + down.max(0)) / 2
+    assert np.allclose(formats.read_ply(os.path.join(out_dir, obj + '.ply')), down, atol=1e-6)
+    xyz = formats.read_xyz(os.path.join(out_dir, obj + '.xyz'), to_meter=False, exact=True)
+    assert len(xyz) >= 1000 and abs(((xyz.min(0) + xyz.max(0)) / 2)).max() < 3.0      # centred model with at least 1000 points
+    with pytest.raises(NotImplementedError):                             # the signature default icp_point2plane=True is not grafted
+        load_point_cloud(obj, save_dir, root, mode='gen', n_viewpoints=n_views, min_friends=filt[0], voxel_size=voxel, threshold=threshold,
+                         min_dist=filt[1], nb_neighbors=filt[2])
+
+    # ---- create_pose_label on the files just written
+    create_pose_label(root, obj, False, True, False)
+    he = psynth.hand_eye()
+    aligned = formats.read_ply(os.path.join(out_dir, obj + '_out.ply'))
+    centre = (aligned.min(0) + aligned.max(0)) / 2
+    for run in listed:
+        frames, pose = runs[run]
+        pos, rot = centre, pose[:3, :3]
+        if run == 'rot1':                                                 # rotated run: ICP of the aligned cloud onto the run's cloud
+            target = formats.read_ply(os.path.join(out_dir, 'rot1.ply'))
+            td, sd, T = oicp.icp_regression(target, aligned, voxel_size=5, threshold=10)
+            e = np.array(formats.mat2euler(np.dot(rot, T[:3, :3])))
+            e[np.rad2deg(formats.mat2euler(rot)) == 0.0] = 0.0
+            rot = formats.euler2mat(*e)
+            pos = (sd.min(0) + sd.max(0)) / 2
+        for i in range(n_frames):
+            lab = json.load(open(os.path.join(root, 'label_generator', 'data', obj, run, '{:06d}.meta.json'.format(i))))
+            assert set(lab) == {'position', 'rotation', 'cls_name', 'cam2robot', 'robot2object'} and lab['cls_name'] == obj
+            m = formats.load_frame_meta(os.path.join(root, 'data_generation', 'data', obj, run, '{:06d}.meta.json'.format(i)))
+            want = formats.pose_label(m['hand_eye'], m['robot2endEff'], rot, pos, obj)
+            assert np.allclose(lab['position'], want['position'], atol=1e-4) and np.allclose(lab['rotation'], want['rotation'], atol=1e-4)
+    os.makedirs(os.path.join(root, 'data_generation', 'data', 'no_background', 'rot0'))
+    with pytest.raises(ValueError):                                      # create_labels.py:308-312
+        create_pose_label(root, 'no_background', False, True, False)
