@@ -13,6 +13,7 @@
 // K>=64 layer, small dense layers / heads (SIMT fp32), final conv4 + sigmoid + class select.
 #include "gemm_tc3.cuh"
 #include "gemm_tc4.cuh"
+#include "gemm_dense.cuh"
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -189,7 +190,8 @@ gemm_simt_kernel(const bf16* __restrict__ a_hi, const bf16* __restrict__ a_lo, i
 // ------------------------------------------------------------------------------------------------
 // AvgPool1d over the points of each object from the per-tile column sums: ap[b,c] = sum_t cs[b*tpo+t,c] / N
 __global__ void pool_finish_kernel(const float* __restrict__ cs, int tiles_per_obj, int C, float inv_n, float* __restrict__ ap,
-                                   bf16* __restrict__ ap_b16 /* training: bf16 copy for the tensor-core heads, or NULL */)
+                                   bf16* __restrict__ ap_b16 /* training: bf16 copy for the tensor-core heads, or NULL */,
+                                   bf16* __restrict__ ap_lo /* inference: ap_b16 = hi half, ap_lo = low half of the split-bf16 copy */)
 {
     pdl_sync();                                           // programmatic dependent launch: see ape_common.cuh
     const int b = blockIdx.y;
@@ -199,7 +201,11 @@ __global__ void pool_finish_kernel(const float* __restrict__ cs, int tiles_per_o
     for (int t = 0; t < tiles_per_obj; ++t) s += cs[((size_t)b * tiles_per_obj + t) * C + c];
     const float v = s / inv_n;           // inv_n carries N: AvgPool1d divides
     ap[(size_t)b * C + c] = v;
-    if (ap_b16) ap_b16[(size_t)b * C + c] = __float2bfloat16_rn(v);
+    if (ap_b16) {
+        const bf16 h = __float2bfloat16_rn(v);
+        ap_b16[(size_t)b * C + c] = h;
+        if (ap_lo) ap_lo[(size_t)b * C + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
 }
 
 // Small dense layer over per-object vectors (fp32 SIMT), the per-object GEMVs of both networks batched into one
@@ -478,6 +484,12 @@ struct ape_net {
     DevF32 w4r, b4r, w4t, b4t, w4c, b4c;
     // Refiner heads (fp32)
     DevF32 Wr1, br1, Wr2, br2, w3r, b3r, w3t, b3t;
+    // per-object dense layers on the tensor cores (gemm_dense.cuh): split-bf16 weights [outputs, K], split-bf16 operands
+    // [padded batch, K] (APs written by pool_finish, G1s by the conv1 launch), fp32 partial workspace, tile tickets
+    SplitMat Wd_g, Wd_r1, Wd_r2, APs, G1s;
+    float* d_partial = nullptr;
+    int* d_ticket = nullptr;
+    int bpa = 0;
     // workspace
     SplitMat PF, H5, H1, H2, H3;
     DevF32 CS, AP, GB, G1, G2;
@@ -633,11 +645,17 @@ int ape_net_create(int kind, const float* const* w, int n_tensors, int num_obj, 
     TRY(alloc_split(net, net->H5, R, 512));
     TRY(alloc_f32(net, net->CS, (R / 128) * 1024));
     TRY(alloc_f32(net, net->AP, (size_t)max_batch * 1024));
+    net->bpa = (max_batch + 127) / 128 * 128;
+    TRY(alloc_split(net, net->APs, net->bpa, 1024));
+    TRY(dev_alloc(net, (void**)&net->d_partial, (size_t)8 * 1920 * 256 * sizeof(float)));
+    TRY(dev_alloc(net, (void**)&net->d_ticket, 16 * sizeof(int)));
+    APE_CUDA(cudaMemset(net->d_ticket, 0, 16 * sizeof(int)));
     if (kind == APE_NET_POSENET) {
         TRY(upload_split(net, net->W_h1, vcat({w[12], w[14], w[16]}, {640, 640, 640}, 1408, 0, 384), 1920, 384));
         {
             std::vector<float> g = vcat({w[12], w[14], w[16]}, {640, 640, 640}, 1408, 384, 1024);
             TRY(upload_f32(net, net->Wg, g.data(), g.size()));
+            TRY(upload_split(net, net->Wd_g, g, 1920, 1024));
             std::vector<float> b(w[13], w[13] + 640); b.insert(b.end(), w[15], w[15] + 640); b.insert(b.end(), w[17], w[17] + 640);
             TRY(upload_f32(net, net->b_h1, b.data(), 1920));
         }
@@ -670,10 +688,13 @@ int ape_net_create(int kind, const float* const* w, int n_tensors, int num_obj, 
         {
             std::vector<float> W1 = vcat({w[12], w[14]}, {512, 512}, 1024, 0, 1024);
             TRY(upload_f32(net, net->Wr1, W1.data(), W1.size()));
+            TRY(upload_split(net, net->Wd_r1, W1, 1024, 1024));
             std::vector<float> b(w[13], w[13] + 512); b.insert(b.end(), w[15], w[15] + 512);
             TRY(upload_f32(net, net->br1, b.data(), 1024));
             std::vector<float> W2 = vcat({w[16], w[18]}, {128, 128}, 512, 0, 512);
             TRY(upload_f32(net, net->Wr2, W2.data(), W2.size()));
+            TRY(upload_split(net, net->Wd_r2, W2, 256, 512));
+            TRY(alloc_split(net, net->G1s, net->bpa, 1024));
             std::vector<float> b2(w[17], w[17] + 128); b2.insert(b2.end(), w[19], w[19] + 128);
             TRY(upload_f32(net, net->br2, b2.data(), 256));
         }
@@ -696,6 +717,9 @@ int ape_net_create(int kind, const float* const* w, int n_tensors, int num_obj, 
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(ape::tc3::gemm_split_bf16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      ape::tc3::kSmemBytes3);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(ape::tcd::dense_swapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     ape::tcd::kSmemDense);
         if (e != cudaSuccess) { ape::set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); ape_net_destroy(net); return APE_ERR_CUDA; }
         attr_set = true;
     }
@@ -862,7 +886,8 @@ static int run_trunk(ape_net* net, const float* feat_src, int hw, const float* c
     if ((rc = run_gemm(net, net->H5, net->W_c6, nullptr, p, wide_layer(2), s, pn ? "gemm.pn.conv6" : "gemm.rf.conv6"))) return rc;
     dim3 gp(1024 / 256, B);
     ape::ProfScope prof_("pool_finish", s);
-    APE_CUDA(ape::launch_pdl(ape::pool_finish_kernel, gp, dim3(256), 0, s, net->CS.p, Np / 128, 1024, (float)N, net->AP.p, net->train ? net->APb.hi : (bf16*)nullptr));
+    APE_CUDA(ape::launch_pdl(ape::pool_finish_kernel, gp, dim3(256), 0, s, net->CS.p, Np / 128, 1024, (float)N, net->AP.p, net->train ? net->APb.hi : net->APs.hi,
+                             net->train ? (bf16*)nullptr : net->APs.lo));
     ape::count_launch();
     return ape::check_launch("pool_finish");
 }
@@ -893,6 +918,34 @@ static int dense(const float* in, int in_ld, int in_gs, const DevF32& W, const D
     return ape::check_launch("dense_batch");
 }
 
+// Per-object dense layer on the tensor cores (gemm_dense.cuh) for batches the warp-per-output GEMV does not cover.
+static bool dense_on_tensor_cores(const ape_net* net, int B) {
+    return !net->train && (net->gemm_impl == APE_GEMM_TCGEN05 || net->gemm_impl == APE_GEMM_TCGEN05_B2B) && B > ape::kGemvMaxB && B <= 256;
+}
+static int dense_tc(ape_net* net, const SplitMat& X, int x_kg, int rows_per_group, const SplitMat& W, const float* bias, int relu,
+                    float* out, int out_ld, int B, int K, int n_out, const SplitMat* xo, cudaStream_t s)
+{
+    ape::tcd::DenseParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_out = n_out; p.K = K; p.bp = B <= 128 ? 128 : 256; p.batch = B;
+    p.x_k0 = 0; p.x_kg = x_kg; p.rows_per_group = rows_per_group;
+    p.bias = bias; p.relu = relu; p.out = out; p.out_ld = out_ld;
+    if (xo) { p.xo_hi = xo->hi; p.xo_lo = xo->lo; p.xo_ld = xo->cols; }
+    p.partial = net->d_partial; p.ticket = net->d_ticket;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_out / 128, K / ape::tcd::kSlice); cfg.blockDim = dim3(ape::tc::kThreads);
+    cfg.dynamicSmemBytes = ape::tcd::kSmemDense; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = ape::pdl_enabled() ? 1 : 0;
+    ape::ProfScope prof_("dense_tc", s);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, ape::tcd::dense_swapped_kernel, W.map_hi, W.map_lo, X.map_hi, X.map_lo, p);
+    if (le != cudaSuccess) { ape::set_error("dense_tc launch failed: %s", cudaGetErrorString(le)); return APE_ERR_CUDA; }
+    ape::count_launch();
+    return ape::check_launch("dense_tc");
+}
+
 // emb_layout: APE_EMB_NCHW  out_img [B,32,hw] (the encoder's own layout), gathered at `choose` (network.py:100-102);
 //             APE_EMB_NHWC  out_img [B,hw,32] (torch channels_last memory format of the same tensor);
 //             APE_EMB_GATHERED  out_img is emb [B,32,N] already gathered (ape_gather_emb / ape_host_gather_*): hw and
@@ -917,7 +970,9 @@ int ape_posenet_forward_ex(ape_net* net, const float* out_img, int hw, int emb_l
     if (gathered && emb && emb != out_img)
         APE_CUDA(cudaMemcpyAsync(emb, out_img, (size_t)B * 32 * N * sizeof(float), cudaMemcpyDeviceToDevice, s));
     // global-feature half of conv1_{r,t,c} folded into a per-object bias: GB = b + Wg * AP
-    if ((rc = dense(net->AP.p, 1024, 0, net->Wg, net->b_h1, net->GB.p, 1920, B, 1024, 1920, 1, 0, s))) return rc;
+    if (dense_on_tensor_cores(net, B)) {
+        if ((rc = dense_tc(net, net->APs, 0, 0, net->Wd_g, net->b_h1.p, 0, net->GB.p, 1920, B, 1024, 1920, nullptr, s))) return rc;
+    } else if ((rc = dense(net->AP.p, 1024, 0, net->Wg, net->b_h1, net->GB.p, 1920, B, 1024, 1920, 1, 0, s))) return rc;
     ape::tc::Params p;
     if (net->gemm_impl == APE_GEMM_TCGEN05_B2B) {
         // conv1_{r,t,c} -> conv2_{r,t,c} back to back in one kernel: the [R,1920] intermediate never leaves the SM
@@ -995,6 +1050,9 @@ int ape_refiner_forward(ape_net* net, const float* new_points, const float* emb,
         p = split_layer(Bp, 128, 512, 2, 0, 512, net->br2.p, net->G2b, 0);
         p.passes = 1; p.hi_only = 1;
         if ((rc = run_gemm(net, net->G1b, net->Wh2b, &net->G2b, p, false, s, "gemm.rf.head2"))) return rc;
+    } else if (dense_on_tensor_cores(net, B)) {
+        if ((rc = dense_tc(net, net->APs, 0, 0, net->Wd_r1, net->br1.p, 1, net->G1.p, 1024, B, 1024, 1024, &net->G1s, s))) return rc;   // conv1_{r,t}
+        if ((rc = dense_tc(net, net->G1s, 512, 128, net->Wd_r2, net->br2.p, 1, net->G2.p, 256, B, 512, 256, nullptr, s))) return rc;   // conv2_{r,t}
     } else {
         if ((rc = dense(net->AP.p, 1024, 0, net->Wr1, net->br1, net->G1.p, 1024, B, 1024, 1024, 1, 1, s))) return rc;   // conv1_{r,t}
         if ((rc = dense(net->G1.p, 1024, 512, net->Wr2, net->br2, net->G2.p, 256, B, 512, 128, 2, 1, s))) return rc;    // conv2_{r,t}

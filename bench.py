@@ -415,6 +415,41 @@ def adds_leg(torch, ops, peaks, steps, rank=0, world=1, sync=None, reduce_max=No
                              note='per GPU; compulsory bytes %d per instance; the symmetric (kNN) instances are FP32-ALU bound: all-symmetric run = '
                                   '%.1f TFLOP/s of brute-force pair arithmetic against ~%.0f TFLOP/s nominal fp32' %
                                   (bytes_inst, n_inst * pair_flops / ms_all / 1e9, fp32_peak)))
+    if rank == 0:
+        # the reference's own CUDA kNN (DenseFusion/lib/knn/src/cuda/knn.cu:217-263, compiled unmodified into oracle/_ref) as
+        # "the kernel to beat" (SURVEY 8d iv) beside ape_knn on the same 500 x 2600 instances: checker code, timed only here
+        try:
+            from oracle import clib
+            rlib = clib.ref_knn_cuda_lib()
+            nb = 256
+            refs = target[:nb].transpose(1, 2).contiguous()                  # [nb,3,2600]
+            qrys = model_points[:nb].transpose(1, 2).contiguous()            # [nb,3,500]
+            idx_a = ops.knn(refs, qrys, 1, ops.KNN_ARITH_FMA)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(n):
+                ops.knn(refs, qrys, 1, ops.KNN_ARITH_FMA)
+            e1.record(); torch.cuda.synchronize()
+            ms_ours = e0.elapsed_time(e1) / n
+            cmp = dict(instances=nb, shape='500 queries x 2600 references, k=1', ape_knn_ms=ms_ours, ape_knn_instances_per_s=nb / ms_ours * 1e3)
+            if rlib is not None:
+                idx_r = torch.zeros_like(idx_a)
+                scratch = torch.empty((n_model * n_pred,), dtype=torch.float32, device=dev)
+                st = torch.cuda.current_stream().cuda_stream
+                rlib.ref_knn_cuda(refs.data_ptr(), qrys.data_ptr(), idx_r.data_ptr(), scratch.data_ptr(), nb, 3, n_model, n_pred, 1, st)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(n):
+                    rlib.ref_knn_cuda(refs.data_ptr(), qrys.data_ptr(), idx_r.data_ptr(), scratch.data_ptr(), nb, 3, n_model, n_pred, 1, st)
+                e1.record(); torch.cuda.synchronize()
+                ms_ref = e0.elapsed_time(e1) / n
+                cmp.update(reference_knn_cu_ms=ms_ref, reference_knn_cu_instances_per_s=nb / ms_ref * 1e3, speedup=ms_ref / ms_ours,
+                           indices_identical=bool(torch.equal(idx_a, idx_r)),
+                           note='reference = its knn.cu recompiled for sm_100a, one instance per launch pair as knn.h:33-40 loops them, '
+                                '10.4 MB distance matrix written and re-read per instance')
+            out['knn_vs_reference_kernel'] = cmp
+        except Exception as ex:
+            out['knn_vs_reference_kernel'] = dict(error=repr(ex))
     if world == 1:
         from oracle import clib
         k = 512
@@ -841,6 +876,7 @@ def make_summary(line):
                 icp_rps=g(x, 'icp', 'registrations_per_s'), icp_hbm_frac=g(x, 'icp', 'roofline', 'frac'),
                 c4_fps=g(x, 'label_c4', 'frames_per_s'), c4_rps=g(x, 'label_c4', 'registrations_per_s'),
                 adds_ips=g(x, 'add_metric', 'instances_per_s'), adds_sym_ips=g(x, 'add_metric', 'instances_per_s_all_symmetric'),
+                knn_vs_ref=g(x, 'add_metric', 'knn_vs_reference_kernel', 'speedup'),
                 train_ms=g(x, 'refiner_training', 'ms_per_step'), train_ops=g(x, 'refiner_training', 'objects_per_s'),
                 train_ar_ms=g(x, 'refiner_training', 'allreduce_ms'), train_frac=g(x, 'refiner_training', 'roofline', 'frac'),
                 live_us=g(x, 'live_frame', 'us_per_frame_cuda_graph'))

@@ -96,10 +96,13 @@ def test_pose_pipeline_no_refine_and_n1000():
         assert pm.rotation_angle_between(poses[b, :4], res['q']) < TOL_R and np.abs(poses[b, 4:] - res['t']).max() < TOL_T
 
 
-def test_tcgen05_matches_simt_batch64():
-    """BASELINE config 2 shape (batch 64, N=500): the tcgen05 path against the SIMT fp32 kernels on the same buffers."""
+@pytest.mark.parametrize('B,N', [(64, 500), (130, 256), (17, 300)])
+def test_tcgen05_matches_simt_batch64(B, N):
+    """BASELINE config 2 shape (batch 64, N=500) and two more batch sizes (130: 256-column dense tiles; 17: the smallest batch
+    on the tensor-core dense layers): the tcgen05 path (GEMM layers + per-object dense layers, gemm_dense.cuh) against the
+    SIMT fp32 kernels on the same buffers."""
     from autoposeestimation_b200 import ops
-    nobj, B, N = 5, 64, 500
+    nobj = 5
     est, ref, _, _ = _handles(51, nobj, B, N)
     out_img, cloud, choose, idx = synth.posenet_inputs(52, N, (120, 160), nobj, batch=B)
     d = [_dev(a) for a in (out_img, cloud, choose, idx)]
