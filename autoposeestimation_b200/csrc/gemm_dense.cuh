@@ -7,12 +7,16 @@
 // the batch can be small: the WEIGHT rows are the M dimension of the MMA (128 outputs per CTA), the objects are N
 // (128 or 256 columns, zero / stale rows beyond the batch are computed and ignored), split-bf16 operands with the three
 // products A_lo*W_hi + A_hi*W_lo + A_hi*W_hi as everywhere else.  K is split into slices of 128 over the grid
-// (grid = outputs/128 x K/128: 120 CTAs for the 1024 -> 1920 layer) so that no CTA streams more than 6 operand stages;
-// every CTA writes its fp32 partial tile to a workspace and the LAST CTA to arrive at a tile (atomic ticket) adds the
-// slices in slice order -- the result does not depend on the arrival order -- applies bias / ReLU and writes the layer's
-// output transposed back to [object, output], as fp32 and optionally as split bf16 (the next dense layer's operand).
+// (grid = outputs/128 x K/128: 120 CTAs for the 1024 -> 1920 layer) so that no CTA streams more than 6 operand stages.
+// The K slices of one output tile form a thread-block CLUSTER (4 or 8 CTAs): every CTA leaves its fp32 partial tile in its
+// own shared memory (the operand ring is free by then), and after a cluster barrier each CTA sums a share of the objects
+// across all slices through distributed shared memory, in slice order (deterministic), applies bias / ReLU and writes the
+// layer's output transposed back to [object, output], as fp32 and optionally as split bf16 (the next dense layer's
+// operand).  No workspace, no atomics.  (First version: partial tiles through a global workspace + last-arriver ticket:
+// 24 us per launch, slower than the SIMT kernel it was to replace.)
 #pragma once
 #include "gemm_tc2.cuh"
+#include <cooperative_groups.h>
 
 namespace ape {
 namespace tcd {
@@ -31,8 +35,6 @@ struct DenseParams {
     int relu;
     float* out; int out_ld;                    // [batch, out_ld] fp32
     __nv_bfloat16 *xo_hi, *xo_lo; int xo_ld;   // optional split-bf16 copy of the output [*, xo_ld] (NULL: none)
-    float* partial;                            // [K / 128][n_out][bp] fp32 workspace
-    int* ticket;                               // [n_out / 128], zero before the first launch; the last CTA re-zeroes it
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -46,7 +48,9 @@ dense_swapped_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
     uint64_t* empty_bar = full_bar + kStagesD;
     uint64_t* tfull_bar = empty_bar + kStagesD;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
-    int* s_last = reinterpret_cast<int*>(tmem_slot + 1);
+    float* s_part = reinterpret_cast<float*>(smem);        // [bp objects][128 outputs] fp32, aliases the operand ring after the MMAs
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int o_tile = blockIdx.x, slice = blockIdx.y, n_slices = gridDim.y;
@@ -103,52 +107,40 @@ dense_swapped_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
             umma_commit(tfull_bar);
         }
     } else {
-        // ===== epilogue: thread = output row o (TMEM lane), columns = objects =====
+        // ===== epilogue, part 1: thread = output row (TMEM lane); partial tile -> own shared memory, object-major =====
         const int quad = warp & 3;
-        const int o = o_row + quad * 32 + lane;
-        mbar_wait(tfull_bar, 0);
+        const int ol = quad * 32 + lane;
+        mbar_wait(tfull_bar, 0);                                 // all MMAs retired: the operand ring is free
         tc_fence_after();
-        float* part = p.partial + ((size_t)slice * p.n_out + o) * p.bp;
-        for (int c0 = 0; c0 < p.bp; c0 += 32) {
+        for (int c0 = 0; c0 < p.batch; c0 += 32) {               // columns beyond the batch are never read
             uint32_t v[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-            if (c0 < p.batch) {                                  // columns beyond the batch are never read back
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<uint4*>(part + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-        }
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) *s_last = (atomicAdd(p.ticket + o_tile, 1) == n_slices - 1) ? 1 : 0;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (*s_last) {
-            __threadfence();
-            const float bias = __ldg(p.bias + o);
-            for (int c0 = 0; c0 < p.batch; c0 += 4) {
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int sl = 0; sl < n_slices; ++sl) {          // slice order: independent of which CTA arrived last
-                    const float4 q = __ldcg(reinterpret_cast<const float4*>(p.partial + ((size_t)sl * p.n_out + o) * p.bp + c0));
-                    acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
-                }
-                const float r[4] = {acc.x + bias, acc.y + bias, acc.z + bias, acc.w + bias};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int b = c0 + j;
-                    if (b < p.batch) {
-                        const float y = p.relu ? fmaxf(r[j], 0.f) : r[j];
-                        p.out[(size_t)b * p.out_ld + o] = y;      // lanes = consecutive outputs: coalesced
-                        if (p.xo_hi) {
-                            const __nv_bfloat16 h = __float2bfloat16_rn(y);
-                            p.xo_hi[(size_t)b * p.xo_ld + o] = h;
-                            p.xo_lo[(size_t)b * p.xo_ld + o] = __float2bfloat16_rn(y - __bfloat162float(h));
-                        }
-                    }
-                }
-            }
-            if (threadIdx.x == 64) p.ticket[o_tile] = 0;         // ready for the next launch (stream order)
+            for (int j = 0; j < 32; ++j) s_part[(c0 + j) * 128 + ol] = __uint_as_float(v[j]);   // lanes = consecutive outputs: no bank conflicts
         }
     }
+    cluster.sync();                                              // every slice's partial tile is in its CTA's shared memory
+    if (warp >= 2) {
+        // ===== part 2: this CTA finishes the objects b = rank, rank + n_slices, ... of the tile =====
+        const int ol = (warp & 3) * 32 + lane;
+        const int o = o_row + ol;
+        const float bias = __ldg(p.bias + o);
+        const float* peer[8];
+        for (int sl = 0; sl < n_slices; ++sl) peer[sl] = cluster.map_shared_rank(s_part, sl);
+        for (int b = (int)cluster.block_rank(); b < p.batch; b += n_slices) {
+            float acc = 0.f;
+            for (int sl = 0; sl < n_slices; ++sl) acc += peer[sl][b * 128 + ol];          // slice order: deterministic
+            acc += bias;
+            const float y = p.relu ? fmaxf(acc, 0.f) : acc;
+            p.out[(size_t)b * p.out_ld + o] = y;                  // lanes = consecutive outputs: coalesced
+            if (p.xo_hi) {
+                const __nv_bfloat16 h = __float2bfloat16_rn(y);
+                p.xo_hi[(size_t)b * p.xo_ld + o] = h;
+                p.xo_lo[(size_t)b * p.xo_ld + o] = __float2bfloat16_rn(y - __bfloat162float(h));
+            }
+        }
+    }
+    cluster.sync();                                              // peers may still be reading this CTA's partial tile
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {

@@ -485,10 +485,8 @@ struct ape_net {
     // Refiner heads (fp32)
     DevF32 Wr1, br1, Wr2, br2, w3r, b3r, w3t, b3t;
     // per-object dense layers on the tensor cores (gemm_dense.cuh): split-bf16 weights [outputs, K], split-bf16 operands
-    // [padded batch, K] (APs written by pool_finish, G1s by the conv1 launch), fp32 partial workspace, tile tickets
+    // [padded batch, K] (APs written by pool_finish, G1s by the conv1 launch)
     SplitMat Wd_g, Wd_r1, Wd_r2, APs, G1s;
-    float* d_partial = nullptr;
-    int* d_ticket = nullptr;
     int bpa = 0;
     // workspace
     SplitMat PF, H5, H1, H2, H3;
@@ -647,9 +645,6 @@ int ape_net_create(int kind, const float* const* w, int n_tensors, int num_obj, 
     TRY(alloc_f32(net, net->AP, (size_t)max_batch * 1024));
     net->bpa = (max_batch + 127) / 128 * 128;
     TRY(alloc_split(net, net->APs, net->bpa, 1024));
-    TRY(dev_alloc(net, (void**)&net->d_partial, (size_t)8 * 1920 * 256 * sizeof(float)));
-    TRY(dev_alloc(net, (void**)&net->d_ticket, 16 * sizeof(int)));
-    APE_CUDA(cudaMemset(net->d_ticket, 0, 16 * sizeof(int)));
     if (kind == APE_NET_POSENET) {
         TRY(upload_split(net, net->W_h1, vcat({w[12], w[14], w[16]}, {640, 640, 640}, 1408, 0, 384), 1920, 384));
         {
@@ -931,14 +926,15 @@ static int dense_tc(ape_net* net, const SplitMat& X, int x_kg, int rows_per_grou
     p.x_k0 = 0; p.x_kg = x_kg; p.rows_per_group = rows_per_group;
     p.bias = bias; p.relu = relu; p.out = out; p.out_ld = out_ld;
     if (xo) { p.xo_hi = xo->hi; p.xo_lo = xo->lo; p.xo_ld = xo->cols; }
-    p.partial = net->d_partial; p.ticket = net->d_ticket;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_out / 128, K / ape::tcd::kSlice); cfg.blockDim = dim3(ape::tc::kThreads);
     cfg.dynamicSmemBytes = ape::tcd::kSmemDense; cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = ape::pdl_enabled() ? 1 : 0;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;          // the K slices of an output tile reduce through DSMEM
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = K / ape::tcd::kSlice; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = ape::pdl_enabled() ? 2 : 1;
     ape::ProfScope prof_("dense_tc", s);
     cudaError_t le = cudaLaunchKernelEx(&cfg, ape::tcd::dense_swapped_kernel, W.map_hi, W.map_lo, X.map_hi, X.map_lo, p);
     if (le != cudaSuccess) { ape::set_error("dense_tc launch failed: %s", cudaGetErrorString(le)); return APE_ERR_CUDA; }
