@@ -29,6 +29,10 @@ SIGNATURES = {
     'ape_icp_work_bytes': (c_sz, [c_int, c_int]),
     'ape_icp_p2p': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_dbl, c_dbl, c_dbl, c_int,
                             c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'ape_icp_p2p_ex': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_dbl, c_dbl, c_dbl, c_int,
+                               c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'ape_surface_backproject_multi': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp,
+                                              c_vp, c_vp]),
     'ape_voxel_down_sample': (c_int, [c_vp, c_vp, c_int, c_dbl, c_vp, c_vp, c_vp]),
     'ape_pose_select': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'ape_pose_compose': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp]),

@@ -135,6 +135,70 @@ surface_mask_kernel(const uint8_t* __restrict__ label, const uint16_t* __restric
     if ((threadIdx.x & 31) == 0) sub_count[(size_t)tile * kSurfWarps + (threadIdx.x >> 5)] = cnt;
 }
 
+// Multi-label variant (BASELINE config 4: every frame carries the labels of all its objects): ONE pass over label + depth
+// of a frame produces the validity words of all L label values, so the 921 600 B are read once per FRAME instead of once
+// per (frame, object).  View v = frame * L + l.  Same work layout as above.
+struct LabelSet { int n; uint8_t value[8]; };
+__global__ void __launch_bounds__(kSurfThreads, 4)
+surface_mask_multi_kernel(const uint8_t* __restrict__ label, const uint16_t* __restrict__ depth, int npix, LabelSet labels,
+                          int32_t* __restrict__ sub_count, uint32_t* __restrict__ masks, int n_chunks, int32_t* __restrict__ n_tasks)
+{
+    pdl_sync();
+    const int tile = blockIdx.x;                            // (frame, chunk)
+    const int f = tile / n_chunks, c = tile - f * n_chunks;
+    SurfRegs cur;
+    surf_load(cur, label + (size_t)f * npix, depth + (size_t)f * npix, c * kSurfChunk + threadIdx.x * kSurfPix, npix);
+    const uint32_t lw[8] = {cur.l0.x, cur.l0.y, cur.l0.z, cur.l0.w, cur.l1.x, cur.l1.y, cur.l1.z, cur.l1.w};
+    const uint32_t dw[16] = {cur.d0.x, cur.d0.y, cur.d0.z, cur.d0.w, cur.d1.x, cur.d1.y, cur.d1.z, cur.d1.w,
+                             cur.d2.x, cur.d2.y, cur.d2.z, cur.d2.w, cur.d3.x, cur.d3.y, cur.d3.z, cur.d3.w};
+    uint32_t dmask = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dmask |= depth_bits(dw[i]) << (2 * i);
+    if (tile == 0 && threadIdx.x == 0) *n_tasks = 0;
+    for (int l = 0; l < labels.n; ++l) {
+        const uint32_t want4 = (uint32_t)labels.value[l] * 0x01010101u;
+        uint32_t mask = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mask |= label_bits(lw[i], want4) << (4 * i);
+        mask &= dmask;
+        const size_t vt = ((size_t)f * labels.n + l) * n_chunks + c;          // tile index of view (f, l)
+        masks[vt * kSurfThreads + threadIdx.x] = mask;
+        const int cnt = warp_sum(__popc(mask));
+        if ((threadIdx.x & 31) == 0) sub_count[vt * kSurfWarps + (threadIdx.x >> 5)] = cnt;
+    }
+}
+
+// Exclusive prefix of the per-view totals -> first output slot of every view in a PACKED ragged cloud (one CTA).
+__global__ void __launch_bounds__(1024)
+view_offsets_kernel(const int32_t* __restrict__ counts, int n_views, int32_t* __restrict__ offsets /* [n_views + 1] */)
+{
+    pdl_sync();
+    __shared__ int s_w[32];
+    __shared__ int s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_views; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int x = i < n_views ? counts[i] : 0;
+        int incl = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        int before = s_carry;
+        for (int w = 0; w < warp; ++w) before += s_w[w];
+        if (i < n_views) offsets[i] = before + incl - x;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[n_views] = s_carry;
+}
+
 // One warp per view: exclusive prefix of the view's sub-chunk counts -> the view total, and one task record
 // {view, sub-chunk, first output slot, valid pixels} per NON-EMPTY sub-chunk appended to a global list (the order of the
 // list does not matter: every task knows its output slots).  work[0] (task counter) is zeroed by the mask kernel.
@@ -205,7 +269,9 @@ __global__ void __launch_bounds__(kEmitWarps * 32)
 surface_emit_kernel(const uint16_t* __restrict__ depth, int npix, int W, const int32_t* __restrict__ frame_of,
                     const double* __restrict__ cam, const double* __restrict__ robot2cam, int capacity,
                     double* __restrict__ points, int32_t* __restrict__ pixel_index,
-                    const int32_t* __restrict__ n_tasks_p, const int4* __restrict__ tasks, const uint32_t* __restrict__ masks, int n_sub)
+                    const int32_t* __restrict__ n_tasks_p, const int4* __restrict__ tasks, const uint32_t* __restrict__ masks, int n_sub,
+                    const int32_t* __restrict__ view_base /* packed output: first slot of every view (capacity = total), or NULL */,
+                    int views_per_frame /* > 0: view v reads frame v / views_per_frame, cam / robot2cam are per FRAME */)
 {
     pdl_sync();                                           // programmatic dependent launch: see ape_common.cuh
     __shared__ __align__(16) uint16_t s_dep[kEmitWarps][kSurfSub];
@@ -217,10 +283,12 @@ surface_emit_kernel(const uint16_t* __restrict__ depth, int npix, int W, const i
     const double* par = s_parw[warp];
     for (int t = blockIdx.x * kEmitWarps + warp; t < n_tasks; t += gridDim.x * kEmitWarps) {
         const int4 task = tasks[t];
-        const int v = task.x, j = task.y, off = task.z;
+        const int v = task.x, j = task.y;
+        const int off = task.z + (view_base ? view_base[v] : 0);
         if (off >= capacity) continue;                      // warp-uniform
         const uint32_t mk = masks[((size_t)v * n_sub + j) * 32 + lane];   // lane l: validity of pixels [32 l, 32 l + 32)
-        const int f = frame_of ? frame_of[v] : v;
+        const int f = views_per_frame > 0 ? v / views_per_frame : (frame_of ? frame_of[v] : v);
+        const int pv = views_per_frame > 0 ? f : v;         // index of the view's camera parameters
         const uint16_t* dep = depth + (size_t)f * npix;
         const int p0 = j * kSurfSub;
         __syncwarp();                                       // previous task's readers of s_dep / s_parw are done
@@ -234,12 +302,12 @@ surface_emit_kernel(const uint16_t* __restrict__ depth, int npix, int W, const i
                 for (int i = 0; i < 32; ++i) s_dep[warp][32 * lane + i] = p + i < npix ? dep[p + i] : (uint16_t)0;
             }
         }
-        if (lane < 16) s_parw[warp][lane] = lane < 12 ? robot2cam[16 * (size_t)v + lane] : cam[4 * (size_t)v + (lane - 12)];
+        if (lane < 16) s_parw[warp][lane] = lane < 12 ? robot2cam[16 * (size_t)pv + lane] : cam[4 * (size_t)pv + (lane - 12)];
         __syncwarp();
         const double ppx = par[12], ppy = par[13], fx = par[14], fy = par[15];
         const double rfx = 1.0 / fx, rfy = 1.0 / fy;
-        double* out = points + (size_t)v * capacity * 3;
-        int32_t* opix = pixel_index ? pixel_index + (size_t)v * capacity : nullptr;
+        double* out = view_base ? points : points + (size_t)v * capacity * 3;
+        int32_t* opix = pixel_index ? (view_base ? pixel_index : pixel_index + (size_t)v * capacity) : nullptr;
         const int pc = __popc(mk);
         int incl = pc;
 #pragma unroll
@@ -347,7 +415,66 @@ extern "C" __attribute__((visibility("default"))) int ape_surface_backproject(co
     const size_t want_ctas = (n_span + ape::kEmitWarps - 1) / ape::kEmitWarps;      // at most one task per warp is ever needed
     const size_t max_ctas = (size_t)ape::sm_count() * 8;
     APE_CUDA(ape::launch_pdl(ape::surface_emit_kernel, dim3((unsigned)(want_ctas < max_ctas ? want_ctas : max_ctas)), dim3(ape::kEmitWarps * 32), 0, s,
-                             depth, height * width, width, frame_of, cam, robot2cam, capacity, points, pixel_index, n_tasks, tasks, masks, n_sub));
+                             depth, height * width, width, frame_of, cam, robot2cam, capacity, points, pixel_index, n_tasks, tasks, masks, n_sub,
+                             (const int32_t*)nullptr, 0));
     ape::count_launch();
     return ape::check_launch("ape_surface_backproject (emit)");
+}
+
+// a4 for frames that carry several object labels, packed ragged output.
+extern "C" __attribute__((visibility("default")))
+int ape_surface_backproject_multi(const uint8_t* label, const uint16_t* depth, int n_frames, int height, int width,
+                                  const uint8_t* label_values_host, int n_labels, const double* cam, const double* robot2cam,
+                                  int total_capacity, double* points, int32_t* pixel_index, int32_t* counts, int32_t* offsets,
+                                  void* work, void* stream)
+{
+    APE_REQUIRE(label && depth && label_values_host && cam && robot2cam && points && counts && offsets && work,
+                "ape_surface_backproject_multi: null pointer");
+    APE_REQUIRE(n_frames >= 0 && height > 0 && width > 0 && total_capacity > 0, "ape_surface_backproject_multi: bad sizes");
+    APE_REQUIRE(n_labels >= 1 && n_labels <= 8, "ape_surface_backproject_multi: 1..8 label values per frame");
+    APE_REQUIRE(((size_t)height * width) % 16 == 0, "ape_surface_backproject_multi: height*width must be a multiple of 16");
+    APE_REQUIRE((size_t)height * width < (1u << 30), "ape_surface_backproject_multi: frame too large");
+    APE_REQUIRE((((uintptr_t)label) & 15) == 0 && (((uintptr_t)depth) & 15) == 0 && (((uintptr_t)work) & 15) == 0,
+                "ape_surface_backproject_multi: label / depth / work must be 16-byte aligned");
+    if (n_frames == 0) return APE_OK;
+    const int n_views = n_frames * n_labels;
+    const int n_chunks = (int)(((size_t)height * width + ape::kSurfChunk - 1) / ape::kSurfChunk);
+    APE_REQUIRE((size_t)n_views * n_chunks * ape::kSurfWarps < (1u << 31), "ape_surface_backproject_multi: too many views (split the batch)");
+    cudaStream_t s = (cudaStream_t)stream;
+    ape::LabelSet ls;
+    ls.n = n_labels;
+    for (int i = 0; i < 8; ++i) ls.value[i] = i < n_labels ? label_values_host[i] : 0;
+    for (int i = 0; i < n_labels; ++i) APE_REQUIRE(ls.value[i] != 0, "ape_surface_backproject_multi: label value 0 is the background");
+    const int n_sub = n_chunks * ape::kSurfWarps;
+    const size_t n_span = (size_t)n_views * n_sub;
+    int32_t* n_tasks = reinterpret_cast<int32_t*>(work);
+    int4* tasks = reinterpret_cast<int4*>(work) + 1;
+    int32_t* sub_count = reinterpret_cast<int32_t*>(tasks + n_span);
+    uint32_t* masks = reinterpret_cast<uint32_t*>(sub_count + n_span);
+    {
+        ape::ProfScope prof_("surface_mask_multi", s);
+        APE_CUDA(ape::launch_pdl(ape::surface_mask_multi_kernel, dim3(n_frames * n_chunks), dim3(ape::kSurfThreads), 0, s, label, depth,
+                                 height * width, ls, sub_count, masks, n_chunks, n_tasks));
+        ape::count_launch();
+    }
+    int rc = ape::check_launch("ape_surface_backproject_multi (mask)");
+    if (rc) return rc;
+    {
+        ape::ProfScope prof_("surface_scan", s);
+        APE_CUDA(ape::launch_pdl(ape::surface_scan_kernel, dim3((n_views + 7) / 8), dim3(256), 0, s, sub_count, counts, n_tasks, tasks, n_sub, n_views));
+        ape::count_launch();
+    }
+    {
+        ape::ProfScope prof_("view_offsets", s);
+        APE_CUDA(ape::launch_pdl(ape::view_offsets_kernel, dim3(1), dim3(1024), 0, s, (const int32_t*)counts, n_views, offsets));
+        ape::count_launch();
+    }
+    ape::ProfScope prof_("surface_emit", s);
+    const size_t want_ctas = (n_span + ape::kEmitWarps - 1) / ape::kEmitWarps;
+    const size_t max_ctas = (size_t)ape::sm_count() * 8;
+    APE_CUDA(ape::launch_pdl(ape::surface_emit_kernel, dim3((unsigned)(want_ctas < max_ctas ? want_ctas : max_ctas)), dim3(ape::kEmitWarps * 32), 0, s,
+                             depth, height * width, width, (const int32_t*)nullptr, cam, robot2cam, total_capacity, points, pixel_index,
+                             (const int32_t*)n_tasks, (const int4*)tasks, (const uint32_t*)masks, n_sub, (const int32_t*)offsets, n_labels));
+    ape::count_launch();
+    return ape::check_launch("ape_surface_backproject_multi (emit)");
 }

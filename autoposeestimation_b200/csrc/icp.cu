@@ -167,7 +167,7 @@ __device__ __forceinline__ int cell_coord(double v, double lo, double inv_h) {
 
 template <int MINB>
 __global__ void __launch_bounds__(kIcpThreads, MINB)
-icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ src_offset,
+icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ src_offset, const int32_t* __restrict__ src_count,
                const double* __restrict__ target, const int32_t* __restrict__ tgt_offset, int n_reg,
                double threshold, double rel_fitness, double rel_rmse, int max_iter,
                const double* __restrict__ init, double* __restrict__ transform, double* __restrict__ info,
@@ -181,7 +181,7 @@ icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ sr
     if (tid < kIcpSteps) { s.run_dy[tid] = c_run_dy[tid]; s.run_dz[tid] = c_run_dz[tid]; }   // visible after the first barrier below
 
     for (int reg = blockIdx.x; reg < n_reg; reg += gridDim.x) {
-        const int s0 = src_offset[reg], Ns = src_offset[reg + 1] - s0;
+        const int s0 = src_offset[reg], Ns = src_count ? max(0, min(src_count[reg], src_offset[reg + 1] - s0)) : src_offset[reg + 1] - s0;
         const int t0 = tgt_offset[reg], Nt = tgt_offset[reg + 1] - t0;
         const double* src = source + 3 * (size_t)s0;
         const double* tgt = target + 3 * (size_t)t0;
@@ -487,8 +487,10 @@ extern "C" __attribute__((visibility("default"))) size_t ape_icp_work_bytes(int 
     return 24 * s + 24 * t + 4 * t + 4 * s + 64;
 }
 
-extern "C" __attribute__((visibility("default"))) int ape_icp_p2p(const double* source, const int32_t* src_offset, const double* target,
-                           const int32_t* tgt_offset, int n_reg, int total_source_points, int total_target_points,
+// src_count (optional): registration r uses src_count[r] points starting at src_offset[r] (a gapped ragged layout, e.g. the
+// output of ape_voxel_down_sample, without repacking on the host).
+extern "C" __attribute__((visibility("default"))) int ape_icp_p2p_ex(const double* source, const int32_t* src_offset, const int32_t* src_count,
+                           const double* target, const int32_t* tgt_offset, int n_reg, int total_source_points, int total_target_points,
                            double threshold, double rel_fitness, double rel_rmse, int max_iter, const double* init,
                            double* transform, double* info, void* work, void* stream)
 {
@@ -520,12 +522,21 @@ extern "C" __attribute__((visibility("default"))) int ape_icp_p2p(const double* 
     ape::ProfScope prof_("icp_p2p", (cudaStream_t)stream);
     if (minb == 6)
         ape::icp_p2p_kernel<6><<<grid, ape::kIcpThreads, smem, (cudaStream_t)stream>>>(
-            source, src_offset, target, tgt_offset, n_reg, threshold, rel_fitness, rel_rmse, max_iter, init, transform, info,
+            source, src_offset, src_count, target, tgt_offset, n_reg, threshold, rel_fitness, rel_rmse, max_iter, init, transform, info,
             wsrc, wtgt, worig, wcorr);
     else
         ape::icp_p2p_kernel<4><<<grid, ape::kIcpThreads, smem, (cudaStream_t)stream>>>(
-            source, src_offset, target, tgt_offset, n_reg, threshold, rel_fitness, rel_rmse, max_iter, init, transform, info,
+            source, src_offset, src_count, target, tgt_offset, n_reg, threshold, rel_fitness, rel_rmse, max_iter, init, transform, info,
             wsrc, wtgt, worig, wcorr);
     ape::count_launch();
     return ape::check_launch("ape_icp_p2p");
+}
+
+extern "C" __attribute__((visibility("default"))) int ape_icp_p2p(const double* source, const int32_t* src_offset, const double* target,
+                           const int32_t* tgt_offset, int n_reg, int total_source_points, int total_target_points,
+                           double threshold, double rel_fitness, double rel_rmse, int max_iter, const double* init,
+                           double* transform, double* info, void* work, void* stream)
+{
+    return ape_icp_p2p_ex(source, src_offset, nullptr, target, tgt_offset, n_reg, total_source_points, total_target_points, threshold,
+                          rel_fitness, rel_rmse, max_iter, init, transform, info, work, stream);
 }

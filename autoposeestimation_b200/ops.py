@@ -87,6 +87,33 @@ def surface_backproject(label, depth, cam, robot2cam, capacity, frame_of=None, l
     return points, pix, counts
 
 
+def surface_backproject_multi(label, depth, cam, robot2cam, label_values, total_capacity, want_pixels=False):
+    """a4 for frames carrying several object labels (config 4), one pass per frame, PACKED output, no host sync.
+    label [F,H,W] uint8, depth [F,H,W] uint16/int16 storage, cam [F,4] fp64, robot2cam [F,4,4] fp64 (per frame), label_values:
+    list of 1..8 non-zero label values -> dict(points [total_capacity,3] fp64, offsets [F*L+1] int32, counts [F*L] int32,
+    pixel_index [total_capacity] int32 or None): view v = f * L + l occupies points[offsets[v] : offsets[v+1])."""
+    import ctypes
+    require_cuda(label, depth, cam, robot2cam)
+    assert label.dtype == torch.uint8 and depth.dtype in (torch.uint16, torch.int16)
+    label = label.contiguous(); depth = depth.contiguous()
+    cam = _c(cam, torch.float64); robot2cam = _c(robot2cam, torch.float64)
+    F, H, W = label.shape
+    L = len(label_values)
+    V = F * L
+    dev = label.device
+    points = torch.empty((int(total_capacity), 3), dtype=torch.float64, device=dev)
+    pix = torch.empty((int(total_capacity),), dtype=torch.int32, device=dev) if want_pixels else None
+    counts = torch.empty((V,), dtype=torch.int32, device=dev)
+    offsets = torch.empty((V + 1,), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    work = torch.empty(((int(lib.ape_surface_work_bytes(V, H, W)) + 3) // 4,), dtype=torch.int32, device=dev)
+    vals = (ctypes.c_uint8 * L)(*[int(v) for v in label_values])
+    check(lib.ape_surface_backproject_multi(ptr(label), ptr(depth), F, H, W, vals, L, ptr(cam), ptr(robot2cam), int(total_capacity),
+                                            ptr(points), ptr(pix), ptr(counts), ptr(offsets), ptr(work), stream_ptr()),
+          'ape_surface_backproject_multi')
+    return dict(points=points, offsets=offsets, counts=counts, pixel_index=pix)
+
+
 def knn(ref, query, k=1, arith=KNN_ARITH_CPU, out=None):
     """a14.  ref [B,D,N], query [B,D,M] fp32 -> idx [B,k,M] int64, 1-based."""
     require_cuda(ref, query)
@@ -161,9 +188,10 @@ def estimator_loss(pred_r, pred_t, pred_c, points, model_points, target, symmetr
                 new_points=newp, new_target=newt, pred=pred)
 
 
-def icp_p2p(source, src_offset, target, tgt_offset, threshold, rel_fitness=1e-2, rel_rmse=1e-2, max_iter=100, init=None):
+def icp_p2p(source, src_offset, target, tgt_offset, threshold, rel_fitness=1e-2, rel_rmse=1e-2, max_iter=100, init=None, src_count=None):
     """a5.  Ragged batch: source [S,3] fp64 with src_offset [R+1] int32, target [T,3] fp64 with tgt_offset [R+1].
-    Returns (transform [R,4,4] fp64, info [R,4] fp64 = fitness, rmse, iterations, n_corr)."""
+    src_count [R] int32 (optional): registration r uses src_count[r] points from src_offset[r] on (gapped layout, e.g. the
+    output of voxel_down_sample, no repacking).  Returns (transform [R,4,4] fp64, info [R,4] fp64 = fitness, rmse, iterations, n_corr)."""
     require_cuda(source, target, src_offset, tgt_offset)
     source = _c(source, torch.float64); target = _c(target, torch.float64)
     src_offset = _c(src_offset, torch.int32); tgt_offset = _c(tgt_offset, torch.int32)
@@ -176,9 +204,11 @@ def icp_p2p(source, src_offset, target, tgt_offset, threshold, rel_fitness=1e-2,
     info = torch.empty((R, 4), dtype=torch.float64, device=dev)
     if init is not None:
         init = _c(init, torch.float64)
-    check(lib.ape_icp_p2p(ptr(source), ptr(src_offset), ptr(target), ptr(tgt_offset), R, S, T, float(threshold),
-                          float(rel_fitness), float(rel_rmse), int(max_iter), ptr(init), ptr(tf), ptr(info), ptr(work),
-                          stream_ptr()), 'ape_icp_p2p')
+    if src_count is not None:
+        src_count = _c(src_count, torch.int32)
+    check(lib.ape_icp_p2p_ex(ptr(source), ptr(src_offset), ptr(src_count), ptr(target), ptr(tgt_offset), R, S, T, float(threshold),
+                             float(rel_fitness), float(rel_rmse), int(max_iter), ptr(init), ptr(tf), ptr(info), ptr(work),
+                             stream_ptr()), 'ape_icp_p2p_ex')
     return tf, info
 
 

@@ -103,6 +103,20 @@ int ape_surface_backproject(const uint8_t* label, const uint16_t* depth, int n_f
                             const double* cam, const double* robot2cam, int n_views, int capacity,
                             double* points, int32_t* pixel_index, int32_t* counts, void* work, void* stream);
 
+/* a4 for frames that carry SEVERAL object labels (BASELINE config 4: 10 k frames x 5 objects): one pass over a frame's
+ * label + depth produces the validity bits of all n_labels label values, so the 921 600 B of a frame are read once per
+ * frame, not once per (frame, object).  View v = frame * n_labels + l (label value label_values_host[l], non-zero).
+ *   cam [n_frames,4], robot2cam [n_frames,16] fp64: per FRAME
+ *   points [total_capacity,3] fp64 out, PACKED: view v occupies points[offsets[v] : offsets[v+1]) in row-major pixel order;
+ *   counts [n_views] / offsets [n_views+1] int32 out (device); points past total_capacity are dropped (the caller checks
+ *   offsets[n_views] <= total_capacity); pixel_index [total_capacity] int32 out or NULL;
+ *   work: ape_surface_work_bytes(n_views, height, width) bytes.  No host synchronisation: offsets feed
+ *   ape_voxel_down_sample and ape_icp_p2p_ex directly.                                                              */
+int ape_surface_backproject_multi(const uint8_t* label, const uint16_t* depth, int n_frames, int height, int width,
+                                  const uint8_t* label_values_host, int n_labels, const double* cam, const double* robot2cam,
+                                  int total_capacity, double* points, int32_t* pixel_index, int32_t* counts, int32_t* offsets,
+                                  void* work, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a14. Brute-force k nearest neighbours.
  * Replaces `int knn(ref, query, idx)` DenseFusion/lib/knn/src/knn.h:12 (python:
@@ -145,6 +159,13 @@ int ape_icp_p2p(const double* source, const int32_t* src_offset, const double* t
                 int n_reg, int total_source_points, int total_target_points,
                 double threshold, double rel_fitness, double rel_rmse, int max_iter,
                 const double* init, double* transform, double* info, void* work, void* stream);
+
+/* As ape_icp_p2p; src_count [n_reg] int32 or NULL: registration r uses src_count[r] points starting at src_offset[r]
+ * (gapped ragged source, e.g. straight from ape_voxel_down_sample's out_points / out_counts).                         */
+int ape_icp_p2p_ex(const double* source, const int32_t* src_offset, const int32_t* src_count, const double* target,
+                   const int32_t* tgt_offset, int n_reg, int total_source_points, int total_target_points,
+                   double threshold, double rel_fitness, double rel_rmse, int max_iter,
+                   const double* init, double* transform, double* info, void* work, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a5/a6. Voxel-grid down-sampling (open3d 0.9 PointCloud::voxel_down_sample semantics; output

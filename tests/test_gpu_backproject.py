@@ -280,3 +280,50 @@ def test_surface_backproject_large_and_odd_frames():
                 assert np.array_equal(pix[i, :n], wi[:n].astype(np.int32))
                 if n:
                     assert np.abs(pts[i, :n] - wp[:n]).max() < 1e-9
+
+
+def test_surface_backproject_multi_label_packed_pipeline():
+    """BASELINE config 4 building block: frames carrying the labels of 5 objects.  ONE pass per frame (multi-label mask
+    kernel, packed ragged output) == the per-(frame, label) views of the single-label path, bit for bit, == the oracle's
+    per-pixel loop; the packed offsets feed the voxel grid and (through src_count, without repacking) the ICP kernel, whose
+    transforms equal those of the repacked call and the oracle's."""
+    from autoposeestimation_b200 import ops, synthetic as psynth
+    from oracle import icp as oicp
+    scene = psynth.Scene(3)
+    F, L = 4, 5
+    T = scene.camera_poses(2, F)
+    lab, dep = scene.render(T, seed=1, device='cuda')
+    cam = torch.tensor([[psynth.INTR['ppx'], psynth.INTR['ppy'], psynth.INTR['fx'], psynth.INTR['fy']]], dtype=torch.float64, device='cuda').repeat(F, 1)
+    r2c = torch.from_numpy(T).cuda()
+    cap = 16384
+    out = ops.surface_backproject_multi(lab, dep, cam, r2c, [1, 2, 3, 4, 5], total_capacity=F * L * 8192, want_pixels=True)
+    frame_of = torch.arange(F, device='cuda', dtype=torch.int32).repeat_interleave(L)
+    values = torch.arange(1, L + 1, device='cuda', dtype=torch.uint8).repeat(F)
+    pts, pix, cnt = ops.surface_backproject(lab, dep, cam[frame_of.long()], r2c[frame_of.long()], capacity=cap, frame_of=frame_of, label_value=values)
+    off = out['offsets'].cpu().numpy(); cn = cnt.cpu().numpy()
+    assert np.array_equal(out['counts'].cpu().numpy(), cn) and np.array_equal(np.diff(off), cn) and off[0] == 0
+    assert cn.min() > 500                                               # every object is visible in every frame
+    for v in range(F * L):
+        assert torch.equal(out['points'][off[v]:off[v + 1]], pts[v, :cn[v]]) and torch.equal(out['pixel_index'][off[v]:off[v + 1]], pix[v, :cn[v]])
+    f, l = 2, 3
+    want, wpix = og.surface_backproject(((lab[f] == l + 1).cpu().numpy() * 255).astype(np.uint8), dep[f].cpu().numpy().view(np.uint16).astype(np.float64),
+                                        psynth.INTR, T[f])
+    v = f * L + l
+    assert np.array_equal(out['pixel_index'][off[v]:off[v + 1]].cpu().numpy(), wpix.astype(np.int32))
+    assert np.allclose(out['points'][off[v]:off[v + 1]].cpu().numpy(), want, rtol=0, atol=1e-9)
+    # voxel grid on the packed cloud, ICP straight from its gapped output
+    vox, vc = ops.voxel_down_sample(out['points'], out['offsets'], 2.0)
+    tgt = torch.from_numpy(np.concatenate([scene.models_pert[v % L] for v in range(F * L)])).cuda()
+    to = torch.arange(0, F * L + 1, device='cuda', dtype=torch.int32) * 2000
+    T1, info1 = ops.icp_p2p(vox, out['offsets'], tgt, to, 10.0, src_count=vc)
+    vch = vc.cpu().numpy()
+    packed = torch.cat([vox[off[v]:off[v] + vch[v]] for v in range(F * L)])
+    po = np.zeros(F * L + 1, np.int32); po[1:] = np.cumsum(vch)
+    T2, info2 = ops.icp_p2p(packed, torch.from_numpy(po).cuda(), tgt, to, 10.0)
+    assert torch.equal(T1, T2) and torch.equal(info1, info2)
+    src = oicp.voxel_down_sample(want, 2.0)
+    assert np.array_equal(vox[off[v]:off[v] + vch[v]].cpu().numpy(), src)
+    T_ref = oicp.registration_icp_p2p(src, scene.models_pert[l], 10.0)
+    assert np.abs(T1[v].cpu().numpy() - T_ref).max() < 1e-5
+    # the registration brings the perturbed model back onto the observed surface: residual of the true model under T^-1
+    assert float(info1[:, 0].min()) > 0.9                                # fitness
