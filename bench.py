@@ -405,7 +405,10 @@ def c4_leg(torch, ops, peaks, steps, rank=0, world=1, sync=None, reduce_max=None
                                     roofline=dict(bound='hbm', achieved=bytes_bp / ms_bp / 1e6, peak=peaks['hbm'], unit='GB/s',
                                                   frac=bytes_bp / ms_bp / 1e6 / peaks['hbm'], peak_source=peaks['src'],
                                                   byte_model='921 600 B per FRAME (label + depth read once for all 5 objects) + 24 B per valid pixel written',
-                                                  algorithmic_bytes=bytes_bp)),
+                                                  algorithmic_bytes=bytes_bp,
+                                                  per_view_model_frac=(frames * L * H * W * 3 + n_valid * 24) / ms_bp / 1e6 / peaks['hbm'],
+                                                  note='per_view_model_frac = the same time against 921 600 B per (frame, OBJECT), the byte model of the '
+                                                       'single-label path (one scan per view): above 1 because the frame is read once for its 5 objects')),
                 note='distinct frames, no replication; host synchronisation only at the end of the timed region')
 
 
