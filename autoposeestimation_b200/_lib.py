@@ -34,6 +34,7 @@ SIGNATURES = {
     'ape_surface_backproject_multi': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp,
                                               c_vp, c_vp]),
     'ape_voxel_down_sample': (c_int, [c_vp, c_vp, c_int, c_dbl, c_vp, c_vp, c_vp]),
+    'ape_voxel_down_sample_large': (c_int, [c_vp, c_int, c_dbl, c_vp, c_vp, c_vp]),
     'ape_pose_select': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'ape_pose_compose': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp]),
     'ape_net_create': (c_int, [c_int, ctypes.POINTER(c_vp), c_int, c_int, c_int, c_int, ctypes.POINTER(c_vp)]),

@@ -212,16 +212,33 @@ def icp_p2p(source, src_offset, target, tgt_offset, threshold, rel_fitness=1e-2,
     return tf, info
 
 
-def voxel_down_sample(points, offset, voxel_size):
+VOXEL_MAX_POINTS = 16384
+
+
+def voxel_down_sample(points, offset, voxel_size, offset_host=None, max_cloud_points=None):
     """a5/a6.  Ragged batch points [P,3] fp64, offset [C+1] int32 -> (out_points [P,3] fp64 (cloud c occupies
-    out[offset[c] : offset[c]+counts[c]]), counts [C] int32)."""
+    out[offset[c] : offset[c]+counts[c]]), counts [C] int32).
+    Clouds of up to 16 384 points go through ONE batched launch (shared-memory sort); larger ones through the
+    global-memory path (ape_voxel_down_sample_large), one call per such cloud, same result bit for bit -- no cloud size
+    fails.  Routing needs the sizes on the host: pass `offset_host` (numpy) when it is at hand, or `max_cloud_points`
+    (an upper bound the caller guarantees) to skip the check; otherwise, and only when P > 16 384, `offset` is copied to
+    the host once (a synchronisation)."""
     require_cuda(points, offset)
     points = _c(points, torch.float64); offset = _c(offset, torch.int32)
     C = offset.numel() - 1
     out = torch.empty_like(points)
     counts = torch.empty((C,), dtype=torch.int32, device=points.device)
-    check(_lib.load().ape_voxel_down_sample(ptr(points), ptr(offset), C, float(voxel_size), ptr(out), ptr(counts),
-                                            stream_ptr()), 'ape_voxel_down_sample')
+    lib = _lib.load()
+    check(lib.ape_voxel_down_sample(ptr(points), ptr(offset), C, float(voxel_size), ptr(out), ptr(counts), stream_ptr()),
+          'ape_voxel_down_sample')
+    if points.shape[0] > VOXEL_MAX_POINTS and not (max_cloud_points is not None and max_cloud_points <= VOXEL_MAX_POINTS):
+        oh = offset_host if offset_host is not None else offset.cpu().numpy()
+        for c in range(C):
+            n = int(oh[c + 1]) - int(oh[c])
+            if n > VOXEL_MAX_POINTS:
+                lo = int(oh[c])
+                check(lib.ape_voxel_down_sample_large(points[lo:lo + n].data_ptr(), n, float(voxel_size), out[lo:lo + n].data_ptr(),
+                                                      counts[c:c + 1].data_ptr(), stream_ptr()), 'ape_voxel_down_sample_large')
     return out, counts
 
 

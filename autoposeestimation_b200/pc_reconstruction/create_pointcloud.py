@@ -41,7 +41,7 @@ def get_surfaces_batch(label, depth, cam, robot2cam, min_friends, min_dist, nb_n
     cnt_h = np.minimum(cnt.cpu().numpy(), cap)
     flat, off = _repack(pts.reshape(-1, 3), np.arange(V) * cap, cnt_h)
     if voxel_size and off[-1] > 0:
-        out, vc = ops.voxel_down_sample(flat, torch.from_numpy(off).to(dev), float(voxel_size))
+        out, vc = ops.voxel_down_sample(flat, torch.from_numpy(off).to(dev), float(voxel_size), offset_host=off)
         vc_h = vc.cpu().numpy()
         if (vc_h < 0).any():
             raise ops._lib.ApeError('voxel_down_sample failed for a view (status %d)' % vc_h.min())

@@ -56,10 +56,10 @@ class PointCloud:
         if n == 0:
             return PointCloud(self.points.clone())
         off = torch.tensor([0, n], dtype=torch.int32, device=self.points.device)
-        out, cnt = ops.voxel_down_sample(self.points, off, voxel_size)
+        out, cnt = ops.voxel_down_sample(self.points, off, voxel_size, offset_host=np.array([0, n]))
         c = int(cnt.cpu()[0])
         if c < 0:
-            raise ops._lib.ApeError('voxel_down_sample: cloud too large for the kernel (%d points, status %d)' % (n, c))
+            raise ops._lib.ApeError('voxel_down_sample: more voxels along an axis than the kernel indexes (%d points, status %d)' % (n, c))
         return PointCloud(out[:c].clone())
 
     def _offset(self):
@@ -160,7 +160,7 @@ def icp_regression_batch(targets, sources, voxel_size=5, threshold=100, max_iter
         return flat, off
     def down(clouds):
         flat, off = pack(clouds)
-        out, cnt = ops.voxel_down_sample(flat, torch.from_numpy(off).to(dev), voxel_size)
+        out, cnt = ops.voxel_down_sample(flat, torch.from_numpy(off).to(dev), voxel_size, offset_host=off)
         cnt = cnt.cpu().numpy()
         if (cnt < 0).any():
             raise ops._lib.ApeError('voxel_down_sample failed for a cloud (status %s)' % cnt.min())

@@ -294,7 +294,7 @@ def icp_leg(torch, ops, lib, peaks, steps, rank=0, world=1, sync=None, reduce_ma
         c_h = c.cpu().numpy()                                  # ragged sizes are needed on the host (one sync)
         off = np.zeros(n_src + 1, np.int32); off[1:] = np.cumsum(np.minimum(c_h, cap))
         flat = torch.cat([p[i, :int(min(c_h[i], cap))] for i in range(n_src)])
-        vox, vc = ops.voxel_down_sample(flat, torch.from_numpy(off).to(dev), 2.0)
+        vox, vc = ops.voxel_down_sample(flat, torch.from_numpy(off).to(dev), 2.0, offset_host=off)
         vc_h = vc.cpu().numpy()
         src = torch.cat([vox[off[i]:off[i] + vc_h[i]] for i in range(n_src)]).repeat(reps, 1)
         so = np.zeros(nreg + 1, np.int64); so[1:] = np.cumsum(np.tile(vc_h, reps))
@@ -370,7 +370,7 @@ def c4_leg(torch, ops, peaks, steps, rank=0, world=1, sync=None, reduce_max=None
     def run_chunk(c0):
         sl = slice(c0, c0 + chunk)
         out = ops.surface_backproject_multi(labels[sl], depths[sl], cam[sl], r2c[sl], [1, 2, 3, 4, 5], total_capacity=cap_total)
-        vox, vc = ops.voxel_down_sample(out['points'], out['offsets'], 2.0)
+        vox, vc = ops.voxel_down_sample(out['points'], out['offsets'], 2.0, max_cloud_points=10240)   # an object covers < 10 k pixels here
         T, info = ops.icp_p2p(vox, out['offsets'], tgt, to, 10.0, src_count=vc)
         return out, vc, T, info
 

@@ -173,10 +173,16 @@ int ape_icp_p2p_ex(const double* source, const int32_t* src_offset, const int32_
  * at pc_reconstruction/open3d_utils.py:21, :198 and create_pointcloud.py:312.
  * Ragged batch as above.  out_points has the same capacity/offsets as the input
  * (cloud c writes at most its input count starting at offset[c]); out_counts [n_clouds].
- * Clouds larger than APE_VOXEL_MAX_POINTS return APE_ERR_UNSUPPORTED.                           */
+ * The batched kernel sorts a cloud in shared memory: a cloud of more than APE_VOXEL_MAX_POINTS points is NOT processed
+ * and gets out_counts[c] = -1 (the call itself returns APE_OK: the sizes live on the device) -- run it through
+ * ape_voxel_down_sample_large; out_counts[c] = -2: more than 65 535 (large path: 8 191) voxels along an axis.       */
 #define APE_VOXEL_MAX_POINTS 16384
 int ape_voxel_down_sample(const double* points, const int32_t* offset, int n_clouds, double voxel_size,
                           double* out_points, int32_t* out_counts, void* stream);
+/* ONE cloud of any size up to 2^25 - 1 points (n_points by value), bit-identical output: chunked bitonic sort + merge-path
+ * passes + segmented means in global memory (stream-ordered scratch from cudaMallocAsync).  out_count [1] int32 (device). */
+int ape_voxel_down_sample_large(const double* points, int n_points, double voxel_size, double* out_points,
+                                int32_t* out_count, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a8/a9. Confidence arg-max, pose of the best point, cloud in the predicted frame.

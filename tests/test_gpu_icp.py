@@ -167,3 +167,25 @@ def test_voxel_down_sample_too_large_is_reported():
     P = torch.rand((16385, 3), dtype=torch.float64, device='cuda')
     out, cnt = ops.voxel_down_sample(P, torch.tensor([0, 16385], dtype=torch.int32, device='cuda'), 0.01)
     assert int(cnt[0]) == -1
+
+
+@pytest.mark.parametrize('n', [16385, 40000, 307200])
+def test_voxel_down_sample_large_clouds(n):
+    """Clouds beyond the 16 384-point shared-memory sort (a full 480 x 640 mask has 307 200 pixels): the global-memory path
+    (chunk sort + merge passes) gives the oracle's result bit for bit, alone and inside a ragged batch with small clouds."""
+    from autoposeestimation_b200 import ops
+    rng = np.random.RandomState(n)
+    big = rng.uniform(-150, 150, size=(n, 3)) * np.array([1.0, 0.6, 0.3])
+    small = rng.uniform(-40, 40, size=(3000, 3))
+    want_big, want_small = oicp.voxel_down_sample(big, 2.0), oicp.voxel_down_sample(small, 2.0)
+    pts, off = _ragged([small, big, small[:7]])
+    out, cnt = ops.voxel_down_sample(_dev(pts), _dev(off), 2.0, offset_host=off)
+    cnt = cnt.cpu().numpy(); out = out.cpu().numpy()
+    assert cnt[0] == len(want_small) and np.array_equal(out[off[0]:off[0] + cnt[0]], want_small)
+    assert cnt[1] == len(want_big) and np.array_equal(out[off[1]:off[1] + cnt[1]], want_big)
+    assert cnt[2] == len(oicp.voxel_down_sample(small[:7], 2.0))
+    out2, cnt2 = ops.voxel_down_sample(_dev(pts), _dev(off), 2.0)               # sizes fetched from the device
+    assert np.array_equal(cnt2.cpu().numpy(), cnt) and np.array_equal(out2.cpu().numpy()[off[1]:off[1] + cnt[1]], want_big)
+    from autoposeestimation_b200.pc_reconstruction.open3d_utils import PointCloud
+    pc = PointCloud(big).voxel_down_sample(5.0)                                  # the drop-in class no longer has a size limit
+    assert np.array_equal(pc.numpy(), oicp.voxel_down_sample(big, 5.0))
