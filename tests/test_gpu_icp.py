@@ -162,11 +162,17 @@ def test_voxel_down_sample_exact(voxel):
         assert np.array_equal(out[off[c]:off[c] + cnt[c]], want)               # same order, same bits as the oracle
 
 
-def test_voxel_down_sample_too_large_is_reported():
+def test_voxel_batched_entry_flags_oversize_clouds():
+    """The batched C entry itself does not process a cloud above 16 384 points: it flags it with out_counts = -1 (header
+    contract) and ops.voxel_down_sample then routes it through the large path; when the caller vouches for the sizes
+    (max_cloud_points) the flag is what comes back."""
     from autoposeestimation_b200 import ops
     P = torch.rand((16385, 3), dtype=torch.float64, device='cuda')
-    out, cnt = ops.voxel_down_sample(P, torch.tensor([0, 16385], dtype=torch.int32, device='cuda'), 0.01)
+    off = torch.tensor([0, 16385], dtype=torch.int32, device='cuda')
+    out, cnt = ops.voxel_down_sample(P, off, 0.01, max_cloud_points=16384)
     assert int(cnt[0]) == -1
+    out, cnt = ops.voxel_down_sample(P, off, 0.01)
+    assert int(cnt[0]) == len(oicp.voxel_down_sample(P.cpu().numpy(), 0.01))
 
 
 @pytest.mark.parametrize('n', [16385, 40000, 307200])
