@@ -34,15 +34,13 @@ constexpr int kIcpThreads = 128;      // small CTAs, 4 or 6 registrations per SM
 constexpr int kIcpWarps = kIcpThreads / 32;
 constexpr int kIcpMaxCells = 4096;
 
-// Targets of up to kIcpSmemTargets points can live in SHARED memory for the whole registration (cell-sorted coordinates +
-// original indices, 28 B per point behind the struct below).  The search reads scattered candidates: as global loads every
-// lane touches its own 128-byte line, 32 L1 wavefronts per instruction, and at 4-6 CTAs per SM the 50 KB working sets miss
-// the (shrunken) L1 -- the L1 queue, not the fp64 pipe, bounded the first version (ncu r01f: fp64 pipe 17 % active).  In
-// shared memory the same accesses cost a handful of bank-conflict cycles.
-constexpr int kIcpSmemTargets = 2048;
+// (Tried and dropped, profiles/r02_icp_ab.txt: the cell-sorted target copy in SHARED memory -- 28 B per point, 3 CTAs per SM --
+// 375 k registrations/s with 128 threads and 510 k with 256 against 555 k for this version: the scattered candidate loads
+// are not what bounds the search, occupancy and the serial steps are; seeding the search with the previous iteration's
+// partner: -2 %; 8 CTAs per SM at 64 registers: +1 %.)
 struct IcpSmem {
     int cell_start[kIcpMaxCells + 2];        // [c] = first cell-sorted position of cell c, [c + 1] = one past its last
-    double red[kIcpWarps][12];
+    double red[8][12];                       // up to 8 warps per CTA
     double out[12];
     double U[12];          // current update (3x4 row-major)
     double T[12];          // accumulated transform (3x4 row-major)
@@ -51,7 +49,7 @@ struct IcpSmem {
     signed char run_dy[32], run_dz[32];   // copy of c_run_* (lanes index it with different steps: no constant-cache replays)
 };
 
-template <int K>
+template <int K, int NT>
 __device__ __forceinline__ void block_sum(double (&v)[K], IcpSmem& s) {
     // result in s.out[0..K); safe to call back-to-back (leading barrier protects s.out readers)
 #pragma unroll
@@ -65,7 +63,7 @@ __device__ __forceinline__ void block_sum(double (&v)[K], IcpSmem& s) {
     if (threadIdx.x < K) {
         double a = 0.0;
 #pragma unroll
-        for (int w = 0; w < kIcpWarps; ++w) a += s.red[w][threadIdx.x];
+        for (int w = 0; w < NT / 32; ++w) a += s.red[w][threadIdx.x];
         s.out[threadIdx.x] = a;
     }
     __syncthreads();
@@ -171,8 +169,8 @@ __device__ __forceinline__ int cell_coord(double v, double lo, double inv_h) {
     return (int)floor((v - lo) * inv_h);
 }
 
-template <int MINB, bool TS /* dynamic shared memory holds kIcpSmemTargets target points */>
-__global__ void __launch_bounds__(kIcpThreads, MINB)
+template <int MINB, int NT /* threads per CTA */>
+__global__ void __launch_bounds__(NT, MINB)
 icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ src_offset, const int32_t* __restrict__ src_count,
                const double* __restrict__ target, const int32_t* __restrict__ tgt_offset, int n_reg,
                double threshold, double rel_fitness, double rel_rmse, int max_iter,
@@ -192,15 +190,13 @@ icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ sr
         const double* src = source + 3 * (size_t)s0;
         const double* tgt = target + 3 * (size_t)t0;
         double* wsrc = wrk_src + 3 * (size_t)s0;
-        // cell-sorted target copy: in shared memory when it fits (uniform per registration), else in the global scratch
-        const bool tgt_in_smem = TS && Nt <= kIcpSmemTargets;
-        double* wtgt = tgt_in_smem ? reinterpret_cast<double*>(smem_raw + sizeof(IcpSmem)) : wrk_tgt + 3 * (size_t)t0;
-        int32_t* worig = tgt_in_smem ? reinterpret_cast<int32_t*>(smem_raw + sizeof(IcpSmem) + 24 * kIcpSmemTargets) : wrk_tgt_orig + t0;
+        double* wtgt = wrk_tgt + 3 * (size_t)t0;             // cell-sorted target copy (read-only after the build, L1/L2 resident)
+        int32_t* worig = wrk_tgt_orig + t0;
         int32_t* corr = wrk_corr + s0;
 
         // ---------------- target bounding box
         double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
-        for (int j = tid; j < Nt; j += kIcpThreads) {
+        for (int j = tid; j < Nt; j += NT) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 const double v = tgt[3 * j + a];
@@ -223,7 +219,7 @@ icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ sr
         __syncthreads();
         if (tid < 3) {
             double l = DBL_MAX, h = -DBL_MAX;
-            for (int w = 0; w < kIcpWarps; ++w) { l = fmin(l, s.red[w][tid]); h = fmax(h, s.red[w][3 + tid]); }
+            for (int w = 0; w < (NT / 32); ++w) { l = fmin(l, s.red[w][tid]); h = fmax(h, s.red[w][3 + tid]); }
             s.bbmin[tid] = l; s.bbmax[tid] = h;
         }
         __syncthreads();
@@ -256,19 +252,19 @@ icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ sr
         // cell_start[c + 1] first counts cell c, becomes its first position (exclusive scan, shifted by one) and then serves
         // as the cell's write cursor: after the scatter it is one past the cell's last point = the first position of cell
         // c + 1, i.e. cell c occupies [cell_start[c], cell_start[c + 1]) without a second per-cell array.
-        for (int c = tid; c <= ncell + 1; c += kIcpThreads) s.cell_start[c] = 0;
+        for (int c = tid; c <= ncell + 1; c += NT) s.cell_start[c] = 0;
         __syncthreads();
-        for (int j = tid; j < Nt; j += kIcpThreads) {
+        for (int j = tid; j < Nt; j += NT) {
             const int cx = min(max(cell_coord(tgt[3 * j], g0, inv_h), 0), dim[0] - 1);
             const int cy = min(max(cell_coord(tgt[3 * j + 1], g1, inv_h), 0), dim[1] - 1);
             const int cz = min(max(cell_coord(tgt[3 * j + 2], g2, inv_h), 0), dim[2] - 1);
             atomicAdd(&s.cell_start[(cz * dim[1] + cy) * dim[0] + cx + 2], 1);
         }
         __syncthreads();
-        // inclusive scan of cell_start[2..ncell+1] in chunks of kIcpThreads: [c + 1] = points in cells 0..c-1 = begin of c
+        // inclusive scan of cell_start[2..ncell+1] in chunks of NT: [c + 1] = points in cells 0..c-1 = begin of c
         if (tid == 0) s.scan_carry = 0;
         __syncthreads();
-        for (int c0 = 2; c0 <= ncell + 1; c0 += kIcpThreads) {
+        for (int c0 = 2; c0 <= ncell + 1; c0 += NT) {
             const int c = c0 + tid;
             int v = (c <= ncell + 1) ? s.cell_start[c] : 0;
             int incl = v;
@@ -284,13 +280,13 @@ icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ sr
             for (int w = 0; w < (tid >> 5); ++w) before += wtot[w];
             if (c <= ncell + 1) s.cell_start[c] = before + incl;
             __syncthreads();
-            if (tid == kIcpThreads - 1) s.scan_carry = before + incl;
+            if (tid == NT - 1) s.scan_carry = before + incl;
             __syncthreads();
         }
         // now cell_start[c + 2] = points in cells 0..c = begin of cell c + 1; shift the view by one: cursor of cell c
         // is cell_start[c + 1] and must start at begin(c) = (old) cell_start[c + 1]; the scan above wrote begin(c + 1)
         // into [c + 2], so [c + 1] already holds begin(c) for c >= 1 and [1] = 0 holds begin(0).
-        for (int j = tid; j < Nt; j += kIcpThreads) {
+        for (int j = tid; j < Nt; j += NT) {
             const double x = tgt[3 * j], y = tgt[3 * j + 1], z = tgt[3 * j + 2];
             const int cx = min(max(cell_coord(x, g0, inv_h), 0), dim[0] - 1);
             const int cy = min(max(cell_coord(y, g1, inv_h), 0), dim[1] - 1);
@@ -319,7 +315,7 @@ icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ sr
             // The point loop is warp-uniform (every lane runs every trip, lanes past Ns are masked) so that the lanes can
             // be brought back together with a warp vote before each scan: without it each lane scanned its runs on its
             // own and the inner loop ran with 7.5 of 32 lanes active (profiles/r01d).
-            for (int i0 = (tid & ~31); i0 < Ns; i0 += kIcpThreads) {
+            for (int i0 = (tid & ~31); i0 < Ns; i0 += NT) {
                 const int i = i0 + (tid & 31);
                 const bool live = i < Ns;
                 double px = 0.0, py = 0.0, pz = 0.0;
@@ -431,7 +427,7 @@ icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ sr
                     }
                 }
             }
-            block_sum<8>(acc, s);
+            block_sum<8, NT>(acc, s);
             const double n = s.out[0];
             const double pfit = fitness, prmse = rmse;
             ncorr = n;
@@ -449,7 +445,7 @@ icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ sr
             const double pm[3] = {s.out[2] * inv_n, s.out[3] * inv_n, s.out[4] * inv_n};
             const double qm[3] = {s.out[5] * inv_n, s.out[6] * inv_n, s.out[7] * inv_n};
             double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-            for (int i = tid; i < Ns; i += kIcpThreads) {
+            for (int i = tid; i < Ns; i += NT) {
                 const int j = corr[i];
                 if (j >= 0) {
                     const double p0 = wsrc[3 * i] - pm[0], p1 = wsrc[3 * i + 1] - pm[1], p2 = wsrc[3 * i + 2] - pm[2];
@@ -459,7 +455,7 @@ icp_p2p_kernel(const double* __restrict__ source, const int32_t* __restrict__ sr
                     cov[6] += q2 * p0; cov[7] += q2 * p1; cov[8] += q2 * p2;
                 }
             }
-            block_sum<9>(cov, s);
+            block_sum<9, NT>(cov, s);
             if (tid == 0) {
                 double Um[12];
                 if (n > 0.0) {
@@ -518,44 +514,30 @@ extern "C" __attribute__((visibility("default"))) int ape_icp_p2p_ex(const doubl
     int32_t* worig = reinterpret_cast<int32_t*>(wtgt + 3 * (size_t)total_target_points);
     int32_t* wcorr = worig + total_target_points;
     const int smem = (int)sizeof(ape::IcpSmem);
-    const int smem_ts = smem + 28 * ape::kIcpSmemTargets;
     static bool attr_set = false;
     if (!attr_set) {
-        APE_CUDA(cudaFuncSetAttribute(ape::icp_p2p_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        APE_CUDA(cudaFuncSetAttribute(ape::icp_p2p_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        APE_CUDA(cudaFuncSetAttribute(ape::icp_p2p_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ts));
+        APE_CUDA(cudaFuncSetAttribute(ape::icp_p2p_kernel<4, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        APE_CUDA(cudaFuncSetAttribute(ape::icp_p2p_kernel<6, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    const int sms = ape::sm_count();
-    ape::ProfScope prof_("icp_p2p", (cudaStream_t)stream);
-    // Targets that fit shared memory on average (object model clouds: 2000 points): 3 CTAs per SM, each with its
-    // cell-sorted target copy in shared memory (a registration whose target is larger falls back to the global scratch
-    // inside the kernel).  APE_ICP_SMEM=0 selects the global-scratch build for A/B runs.
-    static int use_ts = -1;
-    if (use_ts < 0) { const char* e = getenv("APE_ICP_SMEM"); use_ts = e ? atoi(e) : 1; }
-    if (use_ts && (long long)total_target_points <= (long long)ape::kIcpSmemTargets * n_reg) {
-        const int grid = n_reg < sms * 3 ? n_reg : sms * 3;
-        ape::icp_p2p_kernel<3, true><<<grid, ape::kIcpThreads, smem_ts, (cudaStream_t)stream>>>(
-            source, src_offset, src_count, target, tgt_offset, n_reg, threshold, rel_fitness, rel_rmse, max_iter, init, transform, info,
-            wsrc, wtgt, worig, wcorr);
-    } else {
     // Resident CTAs per SM: 4 (128 registers, no spills) or 6 (80 registers, a few spills).  The search is latency-bound
     // (fixed-latency fp64 chains, 4 warps per scheduler), so 6 per SM deliver 15 % more registrations per second when the
     // grid stays full (measured: 3552 registrations, 245 k/s against 213 k/s), but a CTA then takes 1.3x as long per
     // registration: pick the one with the shorter makespan for this batch (1184 registrations: 2 rounds of 4 per SM beat
     // 1.33 -> 2 rounds of 6 per SM).
+    const int sms = ape::sm_count();
     const double t4 = (double)((n_reg + 4 * sms - 1) / (4 * sms)), t6 = 1.30 * (double)((n_reg + 6 * sms - 1) / (6 * sms));
     const int minb = (n_reg > 4 * sms && t6 < t4) ? 6 : 4;
     const int grid = n_reg < sms * minb ? n_reg : sms * minb;
+    ape::ProfScope prof_("icp_p2p", (cudaStream_t)stream);
     if (minb == 6)
-        ape::icp_p2p_kernel<6, false><<<grid, ape::kIcpThreads, smem, (cudaStream_t)stream>>>(
+        ape::icp_p2p_kernel<6, 128><<<grid, 128, smem, (cudaStream_t)stream>>>(
             source, src_offset, src_count, target, tgt_offset, n_reg, threshold, rel_fitness, rel_rmse, max_iter, init, transform, info,
             wsrc, wtgt, worig, wcorr);
     else
-        ape::icp_p2p_kernel<4, false><<<grid, ape::kIcpThreads, smem, (cudaStream_t)stream>>>(
+        ape::icp_p2p_kernel<4, 128><<<grid, 128, smem, (cudaStream_t)stream>>>(
             source, src_offset, src_count, target, tgt_offset, n_reg, threshold, rel_fitness, rel_rmse, max_iter, init, transform, info,
             wsrc, wtgt, worig, wcorr);
-    }
     ape::count_launch();
     return ape::check_launch("ape_icp_p2p");
 }
