@@ -1,0 +1,54 @@
+"""GPU, 2 ranks (skipped on a one-GPU box; run with `gpurun --gpus 2`): the data-parallel refiner step on the kernels --
+all-reduced flat gradient of two half-batches == whole-batch gradient (the NCCL sum is the only collective of the scope)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from autoposeestimation_b200 import synthetic as synth
+from autoposeestimation_b200.densefusion.train_refiner import RefinerTrainer
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+torch.cuda.set_device(rank)
+dist.init_process_group('nccl', device_id=torch.device('cuda', rank))
+nobj, B, N, M = 3, 8, 256, 200
+rng = np.random.RandomState(5)
+pts = torch.from_numpy((rng.randn(B, N, 3) * 0.05).astype(np.float32)).cuda()
+emb = torch.from_numpy(rng.randn(B, 32, N).astype(np.float32)).cuda()
+idx = torch.from_numpy(rng.randint(0, nobj, (B,)).astype(np.int64)).cuda()
+model = torch.from_numpy(((rng.rand(B, M, 3) - 0.5) * 0.2).astype(np.float32)).cuda()
+target = model + 0.01
+sd = synth.refiner_state_dict(77, nobj)
+sd['conv3_r.bias'] = sd['conv3_r.bias'].copy(); sd['conv3_r.bias'][0::4] += 1.0
+whole = RefinerTrainer(sd, nobj, B, N, sym_list=[1])
+whole.zero_grad(); whole.accumulate(pts, emb, idx, target, model)
+lo, hi = rank * B // world, (rank + 1) * B // world
+part = RefinerTrainer(sd, nobj, B, N, sym_list=[1])
+part.zero_grad(); part.accumulate(pts[lo:hi], emb[lo:hi], idx[lo:hi], target[lo:hi], model[lo:hi])
+part.allreduce_gradient()
+rel = float((part.h.grads - whole.h.grads).norm() / whole.h.grads.norm())
+part.optimizer_step(); whole.optimizer_step()
+drift = float((part.h.params - whole.h.params).abs().max())
+print('RESULT rank %d rel %.3e drift %.3e' % (rank, rel, drift), flush=True)
+dist.barrier(); dist.destroy_process_group()
+assert rel < 2e-3 and drift < 1e-5, (rel, drift)
+'''
+
+
+def test_two_rank_allreduced_gradient_equals_whole_batch(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs (gpurun --gpus 2)')
+    script = tmp_path / 'worker.py'
+    script.write_text(_WORKER)
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+                        '--master-port', '29617', str(script), ROOT], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count('RESULT') == 2
