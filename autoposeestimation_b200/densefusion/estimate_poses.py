@@ -7,11 +7,16 @@ pinned host memory.  No CPU fallback: the networks and the pose math only ever r
 Hand-over of the colour-encoder output.  The kernels need 32 channels at the N sampled pixels of every object
 (network.py:100-102), i.e. 4.1 MB of a 157 MB [64,32,120,160] fp32 map.  Shipping the whole map (round 1) made the call
 PCIe-bound (2.9 ms per batch against 0.76 ms of kernels).  `transfer=`
-  'gather' (default)  only the sampled columns cross the bus.  For a pinned [B,32,H,W] map the batch is SPLIT between
-                      (a) the zero-copy gather kernel reading the map in place over PCIe (ops.gather_emb, 1.26 ms for a
-                      whole batch) and (b) the host thread pool gathering into a pinned staging buffer + one small H2D
-                      (ops.host_gather_*, 0.93 ms on 16 cores): they draw on different resources (PCIe read requests /
-                      host DRAM bandwidth), the split is calibrated on the first batch.  A channels_last map
+  'gather' (default)  the whole map never crosses the bus for all objects.  For a pinned [B,32,H,W] map the OBJECTS of a
+                      batch are split three ways, by what each path costs (calibrated on the first batch):
+                      (a) the host thread pool gathers the sampled columns into a pinned staging buffer, then one small
+                          H2D (ops.host_gather_*: 0.54 ms per batch on 16 cores) -- costs HOST time;
+                      (b) the copy engine ships some objects' whole maps (cudaMemcpyAsync, 2.8 ms per batch: neither
+                          SMs nor cores) and a device gather picks the columns -- costs PCIe time only;
+                      (c) the zero-copy gather kernel reads the map in place over PCIe (ops.gather_emb, 1.26 ms per
+                          batch stand-alone) -- costs DEVICE time: about half of it shows up in the step.
+                      The host pool takes what keeps the host ahead of the device, the copy engine what fits in a step,
+                      the zero-copy kernel the rest (nothing, when enough cores are there).  A channels_last map
                       (`t.contiguous(memory_format=torch.channels_last)`: one point = one 128-byte line) goes through the
                       zero-copy kernel alone (0.09 ms); a pageable (unpinned) map through the host pool alone.
   'full'              cudaMemcpyAsync of the whole map, gather in the front-end kernel (the round-1 path; also what a
@@ -29,16 +34,18 @@ from .. import ops
 
 class Runner:
     def __init__(self, estimator, refiner, max_batch, n_points, crop_pixels, iterations=2, canonical=True, device=None,
-                 transfer='gather', zero_copy_fraction=None, host_threads=0, use_graph=True):
+                 transfer='gather', zero_copy_fraction=None, host_threads=0, use_graph=True, dma_fraction=None):
         assert transfer in ('gather', 'full')
         self.est, self.ref = estimator, refiner
         self.iterations, self.canonical = iterations, canonical
         dev = device or torch.device('cuda', torch.cuda.current_device())
         self.dev = dev
         self.transfer, self.zc_fraction, self.host_threads, self.use_graph = transfer, zero_copy_fraction, host_threads, use_graph
+        self.dma_fraction = dma_fraction if dma_fraction is not None else (0.0 if zero_copy_fraction is not None else None)
+        self.crop_pixels = crop_pixels
         self.copy_stream = torch.cuda.Stream(device=dev, priority=-1)
         mk = lambda shape, dt: [torch.empty(shape, dtype=dt, device=dev) for _ in range(2)]
-        self.d_img = mk((max_batch, 32, crop_pixels), torch.float32) if transfer == 'full' else None
+        self.d_img = mk((max_batch, 32, crop_pixels), torch.float32) if transfer == 'full' else [None, None]   # 'gather': sized on demand
         self.d_emb = mk((max_batch, 32, n_points), torch.float32)
         self.d_cloud = mk((max_batch, n_points, 3), torch.float32)
         self.d_choose = mk((max_batch, n_points), torch.int64)
@@ -57,10 +64,8 @@ class Runner:
     # ------------------------------------------------------------------------------------------------
     def calibrate(self, out_img, cloud, choose, idx, reps=3):
         """Time the two gather paths and the step's kernels on this batch and choose how many objects go through the
-        zero-copy kernel.  The host pool costs host time, the zero-copy kernel costs DEVICE time (it shares the SMs with
-        the step's kernels: measured, about half of its stand-alone duration shows up in the step), so: everything through
-        the host pool while that keeps the host faster than the device; otherwise the fraction that balances the two.
-        -> dict(zero_copy_ms, host_ms, compute_ms, zero_copy_fraction)."""
+        zero-copy kernel, the copy engine and the host pool (see the module docstring).
+        -> dict(zero_copy_ms, host_ms, dma_ms, compute_ms, zero_copy_fraction, dma_fraction, host_fraction, predicted_ms_per_step)."""
         B = out_img.shape[0]
         torch.cuda.synchronize(self.dev)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -88,10 +93,39 @@ class Runner:
         for _ in range(reps):
             ops.host_gather_begin(out_img, ch, self.h_stage[0], 0, B, self.host_threads); ops.host_gather_wait()
         t_host = (time.perf_counter() - t0) / reps * 1e3
-        host_overhead, zc_visible = 0.15, 0.5                  # ms of launches / events per step on the host; see docstring
-        f = (t_host + host_overhead - t_gpu) / (t_host + zc_visible * t_zc)
-        self.zc_fraction = min(1.0, max(0.0, f))
-        self.calibration = dict(zero_copy_ms=t_zc, host_ms=t_host, compute_ms=t_gpu, zero_copy_fraction=self.zc_fraction)
+        # copy engine: whole maps of a few objects, scaled to the batch
+        nb = max(1, min(8, B))
+        tmp = torch.empty((nb, 32, self.crop_pixels), dtype=torch.float32, device=self.dev)
+        with torch.cuda.stream(self.copy_stream):
+            tmp.copy_(out_img[:nb].reshape(nb, 32, -1), non_blocking=True)
+            ev[0].record(self.copy_stream)
+            for _ in range(reps):
+                tmp.copy_(out_img[:nb].reshape(nb, 32, -1), non_blocking=True)
+            ev[1].record(self.copy_stream)
+        ev[1].synchronize()
+        t_dma = ev[0].elapsed_time(ev[1]) / reps * B / nb
+        del tmp
+        # smallest step time T >= t_gpu with: host share f1 = (T - c0) / t_host, copy-engine share f3 = T / t_dma, the rest
+        # through the zero-copy kernel, which adds zc_visible * f2 * t_zc to the device time
+        c0, zc_visible = 0.15, 0.5                              # ms of launches / events per step on the host; see docstring
+        def shares(T):
+            f1 = min(1.0, max(0.0, (T - c0) / t_host))
+            f3 = min(1.0 - f1, max(0.0, T / t_dma))
+            return f1, f3, max(0.0, 1.0 - f1 - f3)
+        lo, hi = t_gpu, t_gpu + t_zc + t_host
+        for _ in range(40):
+            T = 0.5 * (lo + hi)
+            f2 = shares(T)[2]
+            if t_gpu + zc_visible * f2 * t_zc <= T:
+                hi = T
+            else:
+                lo = T
+        f1, f3, f2 = shares(hi)
+        if f2 == 0.0 and f1 + f3 > 1.0 - 1e-9:                 # no zero-copy needed: give the copy engine only what the host cannot take
+            f3 = 1.0 - f1
+        self.zc_fraction, self.dma_fraction = f2, f3
+        self.calibration = dict(zero_copy_ms=t_zc, host_ms=t_host, dma_ms=t_dma, compute_ms=t_gpu, zero_copy_fraction=f2,
+                                dma_fraction=f3, host_fraction=f1, predicted_ms_per_step=hi)
         return self.calibration
 
     def _compute(self, s, B, gathered):
@@ -134,7 +168,7 @@ class Runner:
                 t1 = time.perf_counter(); prof[name] = prof.get(name, 0.0) + (t1 - t_) * 1e3; t_ = t1
         on_dev = out_img.is_cuda
         gathered = self.transfer == 'gather' and not on_dev
-        k, keep = B, None
+        k, kd, keep = B, 0, None                               # objects [0,k): zero-copy kernel, [k,k+kd): copy engine, [k+kd,B): host pool
         if gathered:
             nhwc = out_img.dim() == 4 and not out_img.is_contiguous() and out_img.is_contiguous(memory_format=torch.channels_last)
             if not out_img.is_pinned():
@@ -142,31 +176,39 @@ class Runner:
             elif nhwc:
                 k = B                                          # 128-byte lines: the kernel alone is PCIe-efficient
             else:
-                if self.zc_fraction is None:
+                if self.zc_fraction is None or self.dma_fraction is None:
                     self.calibrate(out_img, cloud, choose, idx)
                 k = int(round(B * self.zc_fraction))
+                kd = min(B - k, int(round(B * self.dma_fraction)))
+            if kd > 0 and (self.d_img[s] is None or self.d_img[s].shape[0] < kd):
+                self.d_img[s] = torch.empty((max(kd, 4), 32, self.crop_pixels), dtype=torch.float32, device=self.dev)
             if self.i >= 2:
                 self.copied[s].synchronize()                  # the pinned staging buffer of slot s has been shipped
-            if k < B:                                          # the pool starts first: everything below overlaps it
+            if k + kd < B:                                     # the pool starts first: everything below overlaps it
                 ch = choose.reshape(B, -1)
-                keep = ops.host_gather_begin(out_img, ch if ch.is_contiguous() else ch.contiguous(), self.h_stage[s], k, B, self.host_threads)
+                keep = ops.host_gather_begin(out_img, ch if ch.is_contiguous() else ch.contiguous(), self.h_stage[s], k + kd, B, self.host_threads)
         if self.i >= 2:
             self.copy_stream.wait_event(self.done[s])         # device slot s is free again
         with torch.cuda.stream(self.copy_stream):
             self.d_cloud[s][:B].copy_(cloud, non_blocking=True)
             self.d_choose[s][:B].copy_(choose.reshape(B, -1), non_blocking=True)
             self.d_idx[s][:B].copy_(idx.reshape(B), non_blocking=True)
-            if gathered and k > 0:
-                ops.gather_emb(out_img[:k], self.d_choose[s][:k], out=self.d_emb[s][:k])
-            elif not gathered and not on_dev:
+            if gathered:
+                if kd > 0:                                     # whole maps of these objects by DMA, columns picked on the device
+                    self.d_img[s][:kd].copy_(out_img[k:k + kd].reshape(kd, 32, -1), non_blocking=True)
+                if k > 0:
+                    ops.gather_emb(out_img[:k], self.d_choose[s][:k], out=self.d_emb[s][:k])
+                if kd > 0:
+                    ops.gather_emb(self.d_img[s][:kd], self.d_choose[s][k:k + kd], out=self.d_emb[s][k:k + kd])
+            elif not on_dev:
                 self.d_img[s][:B].copy_(out_img.reshape(B, 32, -1), non_blocking=True)
         lap('enqueue_h2d')
-        if gathered and k < B:
+        if gathered and k + kd < B:
             ops.host_gather_wait()
             lap('host_gather_wait')
             del keep
             with torch.cuda.stream(self.copy_stream):
-                self.d_emb[s][k:B].copy_(self.h_stage[s][k:B], non_blocking=True)
+                self.d_emb[s][k + kd:B].copy_(self.h_stage[s][k + kd:B], non_blocking=True)
         self.copied[s].record(self.copy_stream)
         main.wait_event(self.copied[s])
         lap('events')

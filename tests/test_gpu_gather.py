@@ -91,6 +91,8 @@ def test_runner_transfer_modes_agree(graph):
     pin = lambda b: [t.pin_memory() for t in b]
     for name, prep, kw in (('full', pin, dict(transfer='full')),
                            ('split', pin, dict(zero_copy_fraction=0.5)),
+                           ('three-way', pin, dict(zero_copy_fraction=0.34, dma_fraction=0.33)),
+                           ('copy engine only', pin, dict(zero_copy_fraction=0.0, dma_fraction=1.0)),
                            ('auto', pin, {}),
                            ('zero-copy only', pin, dict(zero_copy_fraction=1.0)),
                            ('pageable', lambda b: list(b), {}),
@@ -100,4 +102,5 @@ def test_runner_transfer_modes_agree(graph):
         for i, o in enumerate(outs):
             assert torch.equal(o, want[i % 3]), (name, i)
         if name == 'auto':
-            assert r.calibration is not None and 0.0 <= r.calibration['zero_copy_fraction'] <= 1.0
+            c = r.calibration
+            assert c is not None and abs(c['zero_copy_fraction'] + c['dma_fraction'] + c['host_fraction'] - 1.0) < 1e-6
