@@ -1,6 +1,7 @@
 // Shared helpers for the sm_100a kernels behind include/ape_b200.h.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
@@ -18,15 +19,19 @@ int  sm_count();
 // every kernel, aggregated by label in ape_profile_report().  Disabled by default (one branch per launch).
 bool prof_enabled();
 void prof_push(const char* label, cudaEvent_t e0, cudaEvent_t e1);
+// Every launch site is also an NVTX range named after the kernel label (header-only NVTX 3: a no-op unless a tool such as
+// Nsight Systems / Compute is attached), so a timeline shows "gemm.pn.heads1", "icp_p2p", ... instead of mangled names.
 struct ProfScope {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     cudaStream_t s;
     const char* label;
     ProfScope(const char* l, cudaStream_t st) : s(st), label(l) {
+        nvtxRangePushA(l);
         if (prof_enabled()) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
     }
     ~ProfScope() {
         if (e0) { cudaEventRecord(e1, s); prof_push(label, e0, e1); }
+        nvtxRangePop();
     }
 };
 
