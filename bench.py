@@ -841,7 +841,9 @@ def run_b200(args):
             # no try/except here: a rank that dropped out of the leg would leave the others waiting in its collectives
             label_leg = icp_leg(torch, ops, lib, peaks, args.steps, rank, world, barrier, reduce_max)
         # ---- config 4 as written: 10 k frames x 5 objects sharded over the ranks
-        if world == 1:
+        if args.no_c4:
+            pass
+        elif world == 1:
             try:
                 label_leg = dict(label_leg, label_c4=c4_leg(torch, ops, peaks, args.steps, 0, 1, barrier, reduce_max))
             except Exception as ex:
@@ -850,7 +852,9 @@ def run_b200(args):
             label_leg = dict(label_leg, label_c4=c4_leg(torch, ops, peaks, args.steps, rank, world, barrier, reduce_max))
         torch.cuda.empty_cache()
         # ---- ADD / ADD-S evaluation (BASELINE config 3), same sharding rule
-        if world == 1:
+        if args.no_adds:
+            pass
+        elif world == 1:
             try:
                 label_leg = dict(label_leg, add_metric=adds_leg(torch, ops, peaks, args.steps, 0, 1, barrier, reduce_max))
             except Exception as ex:
@@ -974,6 +978,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-icp', action='store_true', help='skip the extra ICP / back-projection leg')
     ap.add_argument('--no-train', action='store_true', help='skip the extra refiner-training leg (BASELINE config 5)')
+    ap.add_argument('--no-c4', action='store_true', help='skip the 10 000-frame label-generation leg (BASELINE config 4; profiling runs)')
+    ap.add_argument('--no-adds', action='store_true', help='skip the ADD / ADD-S evaluation leg (BASELINE config 3; profiling runs)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
