@@ -28,5 +28,11 @@ echo "== ncu full: ICP / voxel grid" >> $L
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'icp_p2p|voxel_down' -c 4 -o gpurun_out/r02_prof_icp -f \
     python bench.py --steps 4 --warmup 1 --no-train --no-c4 --no-adds > gpurun_out/r02_ncu_e.log 2>&1
 tail -2 gpurun_out/r02_ncu_e.log >> $L
-ls -la gpurun_out | grep r02 >> $L
+# reduce on the box (the .ncu-rep files together exceed what gpurun brings back) and drop the reports
+mkdir -p gpurun_out/profiles_r02
+python tools/summarize_profiles.py r02 --outdir gpurun_out/profiles_r02 --launches gpurun_out/r02_launches_step.csv \
+    --rep gemm=gpurun_out/r02_prof_gemm.ncu-rep --rep adds=gpurun_out/r02_prof_adds.ncu-rep \
+    --rep label=gpurun_out/r02_prof_label.ncu-rep --rep icp=gpurun_out/r02_prof_icp.ncu-rep >> $L 2>&1
+rm -f gpurun_out/*.ncu-rep
+ls -la gpurun_out gpurun_out/profiles_r02 >> $L
 tail -30 $L

@@ -100,15 +100,20 @@ def traffic(tag):
 if __name__ == '__main__':
     tag = sys.argv[1]
     args = sys.argv[2:]
-    os.makedirs(os.path.join(ROOT, 'profiles'), exist_ok=True)
+    outdir = os.path.join(ROOT, 'profiles')
+    if '--outdir' in args:
+        outdir = args[args.index('--outdir') + 1]
+    os.makedirs(outdir, exist_ok=True)
     i = 0
     while i < len(args):
         if args[i] == '--launches':
-            launches(args[i + 1], os.path.join(ROOT, 'profiles', tag + '_launches.csv')); i += 2
+            launches(args[i + 1], os.path.join(outdir, tag + '_launches.csv')); i += 2
         elif args[i] == '--traffic':
             traffic(tag); i += 1
         elif args[i] == '--rep':
             name, path = args[i + 1].split('=')
-            report(path, os.path.join(ROOT, 'profiles', '%s_ncu_%s.csv' % (tag, name))); i += 2
+            report(path, os.path.join(outdir, '%s_ncu_%s.csv' % (tag, name))); i += 2
+        elif args[i] == '--outdir':
+            i += 2
         else:
             i += 1
