@@ -13,7 +13,20 @@ namespace ape {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int  check_launch(const char* what);     // cudaGetLastError -> APE_OK / APE_ERR_CUDA
-int  sm_count();
+int  sm_count();                         // of the CURRENT device
+// cudaFuncSetAttribute is per device: `static ape::PerDevice done; if (done.first()) { ...set attributes... }` runs the block
+// once per device of the process (the current device at the time of the call).
+struct PerDevice {
+    bool seen[64] = {};
+    bool first() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 63;
+        if (seen[dev]) return false;
+        seen[dev] = true;
+        return true;
+    }
+};
 
 // Optional per-launch device timing (bench.py roofline leg): CUDA events on the launching stream around
 // every kernel, aggregated by label in ape_profile_report().  Disabled by default (one branch per launch).

@@ -514,11 +514,10 @@ extern "C" __attribute__((visibility("default"))) int ape_icp_p2p_ex(const doubl
     int32_t* worig = reinterpret_cast<int32_t*>(wtgt + 3 * (size_t)total_target_points);
     int32_t* wcorr = worig + total_target_points;
     const int smem = (int)sizeof(ape::IcpSmem);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static ape::PerDevice attr_done;
+    if (attr_done.first()) {
         APE_CUDA(cudaFuncSetAttribute(ape::icp_p2p_kernel<4, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         APE_CUDA(cudaFuncSetAttribute(ape::icp_p2p_kernel<6, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
     }
     // Resident CTAs per SM: 4 (128 registers, no spills) or 6 (80 registers, a few spills).  The search is latency-bound
     // (fixed-latency fp64 chains, 4 warps per scheduler), so 6 per SM deliver 15 % more registrations per second when the

@@ -625,11 +625,9 @@ int ape_estimator_loss(const float* pred_r, const float* pred_t, const float* pr
     APE_REQUIRE((d_r != nullptr) == (d_t != nullptr), "ape_estimator_loss: d_r and d_t go together");
     cudaStream_t s = (cudaStream_t)stream;
     const size_t dyn = (size_t)n_mesh * sizeof(float4);
-    static size_t dyn_set = 0;
-    if (dyn > dyn_set) {
+    static ape::PerDevice attr_done;
+    if (attr_done.first())
         APE_CUDA(cudaFuncSetAttribute(ape::estimator_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * (int)sizeof(float4)));
-        dyn_set = 8192 * sizeof(float4);
-    }
     {
         ape::ProfScope prof_("estimator_loss", s);
         ape::estimator_loss_kernel<<<n_cand, ape::kLossThreads, dyn, s>>>(pred_r, pred_t, pred_c, points, model_points, target, n_mesh,

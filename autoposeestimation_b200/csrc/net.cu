@@ -699,8 +699,8 @@ int ape_net_create(int kind, const float* const* w, int n_tensors, int num_obj, 
         TRY(alloc_f32(net, net->G2, (size_t)max_batch * 256));
     }
 #undef TRY
-    static bool attr_set = false;
-    if (!attr_set) {
+    static ape::PerDevice attr_done;
+    if (attr_done.first()) {
         cudaError_t e = cudaFuncSetAttribute(ape::tc::gemm_split_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              ape::tc::kSmemBytes);
         if (e == cudaSuccess)
@@ -716,7 +716,6 @@ int ape_net_create(int kind, const float* const* w, int n_tensors, int num_obj, 
             e = cudaFuncSetAttribute(ape::tcd::dense_swapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      ape::tcd::kSmemDense);
         if (e != cudaSuccess) { ape::set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); ape_net_destroy(net); return APE_ERR_CUDA; }
-        attr_set = true;
     }
     *out = net;
     return APE_OK;
@@ -893,10 +892,9 @@ static int dense(const float* in, int in_ld, int in_gs, const DevF32& W, const D
     if (K % 128 != 0 || K > 1024 || npg % ape::kDenseOut != 0) { ape::set_error("dense: unsupported shape K=%d npg=%d", K, npg); return APE_ERR_UNSUPPORTED; }
     const int n_out = npg * groups;
     const size_t smem = sizeof(float) * ((size_t)ape::kDenseOut * K + 2 * ape::kDenseObj * ape::kDenseXld + 4 * ape::kDenseObj * ape::kDenseOut);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static ape::PerDevice attr_done;
+    if (attr_done.first()) {
         APE_CUDA(cudaFuncSetAttribute(ape::dense_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-        attr_set = true;
     }
     // small batches only: at B = 64 (four groups of 16) the GEMV form re-reads W four times and measured 2.4x slower
     if (B <= ape::kGemvMaxB && (in_ld % 4) == 0 && (in_gs % 4) == 0) {
@@ -972,10 +970,9 @@ int ape_posenet_forward_ex(ape_net* net, const float* out_img, int hw, int emb_l
     ape::tc::Params p;
     if (net->gemm_impl == APE_GEMM_TCGEN05_B2B) {
         // conv1_{r,t,c} -> conv2_{r,t,c} back to back in one kernel: the [R,1920] intermediate never leaves the SM
-        static bool attr_set = false;
-        if (!attr_set) {
+        static ape::PerDevice attr_done;
+        if (attr_done.first()) {
             APE_CUDA(cudaFuncSetAttribute(ape::tc4::heads12_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ape::tc4::kSmemBytesF));
-            attr_set = true;
         }
         ape::tc4::FusedParams fp;
         fp.M = M; fp.gb = net->GB.p; fp.rows_per_obj = Np; fp.b2 = net->b_h2.p;

@@ -48,15 +48,16 @@ bool pdl_enabled() {
 }
 
 int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
-        n = p.multiProcessorCount;
+    static int n[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    dev &= 63;
+    if (n[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+        n[dev] = v;
     }
-    return n;
+    return n[dev];
 }
 
 }  // namespace ape

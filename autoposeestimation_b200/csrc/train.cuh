@@ -441,8 +441,8 @@ int ape_refiner_trainer_create(float* params, float* grads, int num_obj, int max
     TRY(dev_alloc(net, (void**)&tr->part_w1, (size_t)ape::kW1Copies * ape::kW1Part * 4));
     TRY(dev_alloc(net, (void**)&tr->part6, (R / 128) * 1024 * 4));
 #undef TRY
-    static bool attr_set = false;
-    if (!attr_set) {
+    static ape::PerDevice attr_done;
+    if (attr_done.first()) {
         cudaError_t e = cudaFuncSetAttribute(ape::tc2::gemm_split_bf16_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              ape::tc2::kSmemBytes2);
         if (e == cudaSuccess)
@@ -451,7 +451,6 @@ int ape_refiner_trainer_create(float* params, float* grads, int num_obj, int max
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(ape::tr::gemm_bf16_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ape::tr::kSmemBytesBwd);
         if (e != cudaSuccess) { ape::set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); ape_refiner_trainer_destroy(tr); return APE_ERR_CUDA; }
-        attr_set = true;
     }
     rc = ape_refiner_trainer_sync_weights(tr, nullptr);
     if (rc) { ape_refiner_trainer_destroy(tr); return rc; }

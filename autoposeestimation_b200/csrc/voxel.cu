@@ -345,10 +345,9 @@ int ape_voxel_down_sample(const double* points, const int32_t* offset, int n_clo
     APE_REQUIRE(n_clouds >= 0 && voxel_size > 0.0, "ape_voxel_down_sample: bad sizes (open3d raises for voxel_size <= 0)");
     if (n_clouds == 0) return APE_OK;
     const int smem = ape::kVoxMax * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static ape::PerDevice attr_done;
+    if (attr_done.first()) {
         APE_CUDA(cudaFuncSetAttribute(ape::voxel_down_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
     }
     ape::ProfScope prof_("voxel_down_sample", (cudaStream_t)stream);
     ape::voxel_down_sample_kernel<<<n_clouds, ape::kVoxThreads, smem, (cudaStream_t)stream>>>(points, offset, voxel_size,
@@ -380,10 +379,9 @@ int ape_voxel_down_sample_large(const double* points, int n_points, double voxel
     int32_t* tile_count = reinterpret_cast<int32_t*>(partial + ape::kVoxPart * 3);
     int32_t* tile_base = tile_count + n_tiles;
     int* bad = reinterpret_cast<int*>(tile_base + n_tiles);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static ape::PerDevice attr_done;
+    if (attr_done.first()) {
         APE_CUDA(cudaFuncSetAttribute(ape::vox_sort_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ape::kVoxChunk * 8));
-        attr_set = true;
     }
     ape::ProfScope prof_("voxel_down_sample_large", s);
     APE_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), s));

@@ -150,7 +150,7 @@ class _Grafted(nn.Module):
                 h.close()
             sd = {k: v for k, v in self.state_dict().items() if not k.startswith('cnn.')}
             self._ape = ops.NetHandle(self._kind, sd, self.num_obj, max(batch, getattr(h, 'max_batch', 1)),
-                                      max(n_points, getattr(h, 'max_points', 1)))
+                                      max(n_points, getattr(h, 'max_points', 1)), device=ps[0].device)
             self._ape_key = key
         return self._ape
 

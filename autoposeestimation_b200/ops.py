@@ -8,8 +8,32 @@ import torch
 from . import _lib
 from ._lib import check, ptr, require_cuda, stream_ptr
 
+import functools
+
 KNN_ARITH_CPU = 0
 KNN_ARITH_FMA = 1
+
+
+def _on_tensor_device(fn):
+    """Run `fn` with the CUDA device of its first CUDA-tensor argument (or of `self.device`) current, so that allocations,
+    the stream handed to the library and the kernels all belong to the device the data lives on, whatever device is
+    current in the caller (the reference's modules follow their parameters' device the same way)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                dev = a.device
+                break
+            d = getattr(a, 'device', None)
+            if dev is None and isinstance(d, torch.device) and d.type == 'cuda' and not isinstance(a, torch.Tensor):
+                dev = d
+                break
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def _c(t, dtype):
@@ -18,6 +42,7 @@ def _c(t, dtype):
     return t.contiguous()
 
 
+@_on_tensor_device
 def backproject_choose(depth, bbox, choose, cam, frame_of=None):
     """a3.  depth [F,H,W] uint16 (torch.int16/uint16 storage accepted), bbox [B,4] int32,
     choose [B,N] int64, cam [B,5] fp32 (ppx,ppy,fx,fy,depth_scale) -> cloud [B,N,3] fp32."""
@@ -34,6 +59,7 @@ def backproject_choose(depth, bbox, choose, cam, frame_of=None):
     return cloud
 
 
+@_on_tensor_device
 def mask_bbox_choose(label, depth, cam, n_points, frame_of=None, label_value=None, seeds=None, want_cloud=True):
     """f-2 (a1+a2+a3 on the device).  label [F,H,W] uint8, depth [F,H,W] uint16/int16 storage, cam [B,5] fp32 ->
     dict(bbox [B,4] int32, n_candidates [B] int32, choose [B,N] int64, cloud [B,N,3] fp32 or None)."""
@@ -62,6 +88,7 @@ def mask_bbox_choose(label, depth, cam, n_points, frame_of=None, label_value=Non
     return dict(bbox=bbox, n_candidates=ncand, choose=choose, cloud=cloud)
 
 
+@_on_tensor_device
 def surface_backproject(label, depth, cam, robot2cam, capacity, frame_of=None, label_value=None, want_pixels=True):
     """a4.  label [F,H,W] uint8, depth [F,H,W] uint16, cam [V,4] fp64, robot2cam [V,4,4] fp64.
     Returns (points [V,capacity,3] fp64, pixel_index [V,capacity] int32 or None, counts [V] int32)."""
@@ -87,6 +114,7 @@ def surface_backproject(label, depth, cam, robot2cam, capacity, frame_of=None, l
     return points, pix, counts
 
 
+@_on_tensor_device
 def surface_backproject_multi(label, depth, cam, robot2cam, label_values, total_capacity, want_pixels=False):
     """a4 for frames carrying several object labels (config 4), one pass per frame, PACKED output, no host sync.
     label [F,H,W] uint8, depth [F,H,W] uint16/int16 storage, cam [F,4] fp64, robot2cam [F,4,4] fp64 (per frame), label_values:
@@ -114,6 +142,7 @@ def surface_backproject_multi(label, depth, cam, robot2cam, label_values, total_
     return dict(points=points, offsets=offsets, counts=counts, pixel_index=pix)
 
 
+@_on_tensor_device
 def knn(ref, query, k=1, arith=KNN_ARITH_CPU, out=None):
     """a14.  ref [B,D,N], query [B,D,M] fp32 -> idx [B,k,M] int64, 1-based."""
     require_cuda(ref, query)
@@ -126,6 +155,7 @@ def knn(ref, query, k=1, arith=KNN_ARITH_CPU, out=None):
     return out
 
 
+@_on_tensor_device
 def add_metric(quat, trans, model_points, target, symmetric, want_index=False):
     """a13/a15.  quat [B,4], trans [B,3]; model_points [B,Mq,3] or [Mq,3] (shared); target [B,Nt,3] or
     [Nt,3]; symmetric [B] uint8/bool.  Returns dis [B] fp32 (and nn_index [B,Mq] int32)."""
@@ -144,6 +174,7 @@ def add_metric(quat, trans, model_points, target, symmetric, want_index=False):
     return (dis, nn) if want_index else dis
 
 
+@_on_tensor_device
 def add_metric_std(quat, trans, model_points, target, symmetric):
     """f-3.  As add_metric, plus the unbiased std of the per-point distances: -> (dis [B], std [B]).  With 2-D
     model_points / target ([M,3]) they are shared by all B poses: the per-point candidate poses of `Loss` (loss.py:30-50)."""
@@ -162,6 +193,7 @@ def add_metric_std(quat, trans, model_points, target, symmetric):
     return dis, std
 
 
+@_on_tensor_device
 def estimator_loss(pred_r, pred_t, pred_c, points, model_points, target, symmetric, w, want_grad=True, want_pred=True):
     """a12.  `Loss` (lib/loss.py:12-73) forward + backward for the N candidate poses of one object.  pred_r [N,4], pred_t [N,3],
     pred_c [N], points [N,3], model_points / target [M,3] fp32 CUDA ->
@@ -188,6 +220,7 @@ def estimator_loss(pred_r, pred_t, pred_c, points, model_points, target, symmetr
                 new_points=newp, new_target=newt, pred=pred)
 
 
+@_on_tensor_device
 def icp_p2p(source, src_offset, target, tgt_offset, threshold, rel_fitness=1e-2, rel_rmse=1e-2, max_iter=100, init=None, src_count=None):
     """a5.  Ragged batch: source [S,3] fp64 with src_offset [R+1] int32, target [T,3] fp64 with tgt_offset [R+1].
     src_count [R] int32 (optional): registration r uses src_count[r] points from src_offset[r] on (gapped layout, e.g. the
@@ -215,6 +248,7 @@ def icp_p2p(source, src_offset, target, tgt_offset, threshold, rel_fitness=1e-2,
 VOXEL_MAX_POINTS = 16384
 
 
+@_on_tensor_device
 def voxel_down_sample(points, offset, voxel_size, offset_host=None, max_cloud_points=None):
     """a5/a6.  Ragged batch points [P,3] fp64, offset [C+1] int32 -> (out_points [P,3] fp64 (cloud c occupies
     out[offset[c] : offset[c]+counts[c]]), counts [C] int32).
@@ -247,6 +281,7 @@ def _max_cloud(offset_host):
     return int(np.diff(offset_host).max()) if len(offset_host) > 1 else 0
 
 
+@_on_tensor_device
 def radius_outlier(points, offset, nb_points, radius, offset_host=None):
     """f-1.  Ragged batch points [P,3] fp64 + offset [C+1] int32 -> keep [P] uint8 (pcd.remove_radius_outlier)."""
     require_cuda(points, offset)
@@ -258,6 +293,7 @@ def radius_outlier(points, offset, nb_points, radius, offset_host=None):
     return keep
 
 
+@_on_tensor_device
 def mahalanobis(points, offset, want_dist=True):
     """f-1.  -> (dist [P] fp64 or None, std [C] fp64 = np.std(|dist|) per cloud) (pcd.compute_mahalanobis_distance)."""
     require_cuda(points, offset)
@@ -269,6 +305,7 @@ def mahalanobis(points, offset, want_dist=True):
     return dist, std
 
 
+@_on_tensor_device
 def statistical_outlier(points, offset, nb_neighbors, std_ratio, offset_host=None):
     """f-1.  std_ratio: python float or a [C] fp64 device tensor (one ratio per cloud) ->
     (keep [P] uint8, avg_dist [P] fp64, threshold [C] fp64) (pcd.remove_statistical_outlier)."""
@@ -286,6 +323,7 @@ def statistical_outlier(points, offset, nb_neighbors, std_ratio, offset_host=Non
     return keep, avg, thr
 
 
+@_on_tensor_device
 def compact_points(points, offset, keep, want_index=False):
     """Ordered per-cloud compaction -> (out_points [P,3] (cloud c at offset[c] : offset[c]+counts[c]), counts [C][, index [P]])."""
     require_cuda(points, offset, keep)
@@ -299,6 +337,7 @@ def compact_points(points, offset, keep, want_index=False):
     return (out, counts, index) if want_index else (out, counts)
 
 
+@_on_tensor_device
 def pose_select(pred_r, pred_t, pred_c, cloud, want_new_points=True):
     """a8/a9.  pred_r [B,N,4], pred_t [B,N,3], pred_c [B,N(,1)], cloud [B,N,3] fp32 ->
     dict(which_max [B] int32, my_r [B,4], my_t [B,3], new_points [B,N,3] or None, pose [B,7] fp64)."""
@@ -317,6 +356,7 @@ def pose_select(pred_r, pred_t, pred_c, cloud, want_new_points=True):
     return dict(which_max=wm, my_r=my_r, my_t=my_t, new_points=newp, pose=pose)
 
 
+@_on_tensor_device
 def pose_compose(pose_in, r2, t2, cloud=None):
     """a11.  pose_in [B,7] fp64, r2 [B,4] fp32, t2 [B,3] fp32 -> pose_out [B,7] fp64
     (and next_points [B,N,3] if cloud [B,N,3] is given)."""
@@ -351,11 +391,14 @@ class NetHandle:
     state_dict: reference-shaped tensors/arrays (DenseFusion/lib/network.py:74-91 or :139-183);
     extra keys (e.g. the colour encoder `cnn.*`) are ignored."""
 
-    def __init__(self, kind, state_dict, num_obj, max_batch, max_points):
+    def __init__(self, kind, state_dict, num_obj, max_batch, max_points, device=None):
         import ctypes
         import numpy as np
         if not torch.cuda.is_available():
             raise _lib.ApeError('no CUDA device: the B200 path has no CPU fallback')
+        self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
         lib = _lib.load()
         order = _POSENET_ORDER if kind == NET_POSENET else _REFINER_ORDER
         host = []
@@ -367,11 +410,11 @@ class NetHandle:
                 host.append(np.ascontiguousarray(v, dtype=np.float32).reshape(-1))
         arr = (ctypes.c_void_p * len(host))(*[h.ctypes.data for h in host])
         out = ctypes.c_void_p()
-        check(lib.ape_net_create(kind, arr, len(host), int(num_obj), int(max_batch), int(max_points), ctypes.byref(out)),
-              'ape_net_create')
+        with torch.cuda.device(self.device):                  # weights and workspace live on the handle's device
+            check(lib.ape_net_create(kind, arr, len(host), int(num_obj), int(max_batch), int(max_points), ctypes.byref(out)),
+                  'ape_net_create')
         self._h = out
         self.kind, self.num_obj, self.max_batch, self.max_points = kind, num_obj, max_batch, max_points
-        self.device = torch.device('cuda', torch.cuda.current_device())
 
     def set_gemm(self, impl):
         check(_lib.load().ape_net_set_gemm(self._h, impl), 'ape_net_set_gemm')
@@ -401,6 +444,7 @@ class NetHandle:
         except Exception:
             pass
 
+    @_on_tensor_device
     def posenet_forward(self, out_img, cloud, choose, obj, gathered=False):
         """out_img [B,32,hw] / [B,32,H,W] (contiguous, or 4-D in torch.channels_last memory format), cloud [B,N,3],
         choose [B,N] (or [B,1,N]) int64, obj [B] (or [B,1]) int64 -> pred_r [B,N,4], pred_t [B,N,3], pred_c [B,N,1], emb [B,32,N].
@@ -419,6 +463,7 @@ class NetHandle:
               'ape_posenet_forward_ex')
         return r, t, c, emb
 
+    @_on_tensor_device
     def refiner_forward(self, new_points, emb, obj):
         """new_points [B,N,3], emb [B,32,N], obj [B] -> r2 [B,4], t2 [B,3]"""
         require_cuda(new_points, emb, obj)
@@ -447,6 +492,7 @@ def _emb_input(out_img, B, N, gathered):
     return out_img, out_img.shape[2], EMB_NCHW
 
 
+@_on_tensor_device
 def gather_emb(out_img, choose, out=None):
     """network.py:100-102 as a stand-alone kernel.  out_img [B,32,hw] / [B,32,H,W] fp32: a CUDA tensor, or a PINNED host
     tensor (read zero-copy over PCIe: only the sampled columns cross the bus); contiguous or channels_last.
@@ -482,6 +528,7 @@ def host_gather_wait():
     check(_lib.load().ape_host_gather_wait(), 'ape_host_gather_wait')
 
 
+@_on_tensor_device
 def pose_pipeline(est, ref, out_img, cloud, choose, obj, iterations=2, canonical=True, out=None, gathered=False):
     """Whole option-6 geometry block: -> (poses [B,7] fp64 (wxyz, t), which_max [B] int32).  No host sync.
     out_img: encoder map [B,32,hw] / [B,32,H,W] (contiguous or channels_last), or with gathered=True the already
@@ -500,6 +547,7 @@ def pose_pipeline(est, ref, out_img, cloud, choose, obj, iterations=2, canonical
 
 
 # ------------------------------------------------------------------------------------------ refiner training (a16)
+@_on_tensor_device
 def refine_loss(pred_r, pred_t, model_points, target, points=None, symmetric=None, want_grad=True, want_next=True):
     """Loss_refine forward + backward (lib/loss_refiner.py:12-64) for B objects.  pred_r [B,4], pred_t [B,3],
     model_points / target [B,M,3], points [B,N,3], symmetric [B] bool/uint8 ->
@@ -524,6 +572,7 @@ def refine_loss(pred_r, pred_t, model_points, target, points=None, symmetric=Non
     return dict(dis=dis, d_r=d_r, d_t=d_t, new_points=newp, new_target=newt)
 
 
+@_on_tensor_device
 def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
     """torch.optim.Adam update on flat fp32 device vectors (train.py:149)."""
     require_cuda(params, grads, exp_avg, exp_avg_sq)

@@ -52,3 +52,27 @@ def test_two_rank_allreduced_gradient_equals_whole_batch(tmp_path):
                         '--master-port', '29617', str(script), ROOT], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count('RESULT') == 2
+
+
+def test_kernels_follow_the_tensors_device():
+    """Handles and launches follow the device of their tensors, not the caller's current device (per-device kernel
+    attributes, per-device SM count): the pipeline on cuda:1 while cuda:0 is current gives the bits of cuda:0."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs (gpurun --gpus 2)')
+    import numpy as np
+    from autoposeestimation_b200 import ops, synthetic as synth
+    nobj, B, N = 3, 20, 300
+    sd_e, sd_r = synth.posenet_state_dict(5, nobj), synth.refiner_state_dict(1005, nobj)
+    inp = synth.posenet_inputs(5, N, (40, 60), nobj, batch=B)
+    outs = []
+    for dev in ('cuda:0', 'cuda:1'):
+        torch.cuda.set_device(0)                                  # the current device stays cuda:0 throughout
+        est = ops.NetHandle(ops.NET_POSENET, sd_e, nobj, B, N, device=dev)
+        ref = ops.NetHandle(ops.NET_REFINER, sd_r, nobj, B, N, device=dev)
+        d = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in inp]
+        poses, wm = ops.pose_pipeline(est, ref, *d)
+        assert poses.device == torch.device(dev)
+        src = torch.rand((20000, 3), dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(1)) * 80
+        vox, cnt = ops.voxel_down_sample(src, torch.tensor([0, 20000], dtype=torch.int32, device=dev), 2.0)
+        outs.append((poses.cpu(), int(cnt[0])))
+    assert torch.equal(outs[0][0], outs[1][0]) and outs[0][1] > 0 and outs[1][1] > 0
