@@ -121,8 +121,9 @@ class FrameBatchLoader:
     File naming as the reference: `{:06d}.depth.png`, `{:06d}.meta.json` under `data_dir`,
     `{:06d}.{mode}.label.png` under `label_dir` (create_pointcloud.py:237-253)."""
 
-    def __init__(self, data_dir, label_dir, mode='new_pred', height=480, width=640, pin=True):
+    def __init__(self, data_dir, label_dir, mode='new_pred', height=480, width=640, pin=True, workers=None):
         self.data_dir, self.label_dir, self.mode, self.h, self.w, self.pin = data_dir, label_dir, mode, height, width, pin
+        self.workers = workers if workers is not None else min(16, os.cpu_count() or 1)
 
     def load(self, indices):
         import torch
@@ -131,8 +132,8 @@ class FrameBatchLoader:
                                 else torch.empty(shape, dtype=dt))
         depth = mk((F, self.h, self.w), torch.int16); label = mk((F, self.h, self.w), torch.uint8)
         cam = mk((F, 4), torch.float64); r2c = mk((F, 4, 4), torch.float64)
-        metas = []
-        for k, idx in enumerate(indices):
+        def one(k):
+            idx = indices[k]
             m = load_frame_meta(os.path.join(self.data_dir, '{:06d}.meta.json'.format(idx)))
             d = load_depth_png(os.path.join(self.data_dir, '{:06d}.depth.png'.format(idx)))
             lab = load_label_png(os.path.join(self.label_dir, '{:06d}.{}.label.png'.format(idx, self.mode)))
@@ -143,7 +144,15 @@ class FrameBatchLoader:
             intr = m['intr']
             cam[k] = torch.tensor([intr['ppx'], intr['ppy'], intr['fx'], intr['fy']], dtype=torch.float64)
             r2c[k] = torch.from_numpy(m['robot2Cam'])
-            metas.append(m)
+            return m
+        # PNG decoding releases the GIL (OpenCV): decode the frames of a run on a thread pool straight into the pinned buffers
+        workers = min(self.workers, F) if F else 1
+        if workers > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=workers) as ex:
+                metas = list(ex.map(one, range(F)))
+        else:
+            metas = [one(k) for k in range(F)]
         return {'depth': depth, 'label': label, 'cam': cam, 'robot2cam': r2c, 'meta': metas, 'indices': list(indices)}
 
     @staticmethod

@@ -340,6 +340,36 @@ def icp_leg(torch, ops, lib, peaks, steps, rank=0, world=1, sync=None, reduce_ma
     return out
 
 
+def reconstruct_leg(torch, ops, steps):
+    """Extra leg: the SEQUENTIAL object-cloud reconstruction of main.py option 4 (create_pointcloud.py:232-317, "replicas
+    only": each view registers to the cloud built so far): 30 views of one object -> get_surface for all views in one batched
+    pass -> 29 x (voxel grids, one point-to-point ICP, transform, merge, voxel grid).  Latency, not throughput."""
+    from autoposeestimation_b200 import synthetic as synth
+    from autoposeestimation_b200.pc_reconstruction.create_pointcloud import get_surfaces_batch, reconstruct_run
+    dev = torch.device('cuda', torch.cuda.current_device())
+    n_views = 30
+    scene = synth.Scene(5, n_objects=1)
+    poses = scene.camera_poses(21, n_views)
+    lab, dep = scene.render(poses, seed=3, device=dev, only_object=0)
+    cam = torch.tensor([[synth.INTR['ppx'], synth.INTR['ppy'], synth.INTR['fx'], synth.INTR['fy']]], dtype=torch.float64, device=dev).repeat(n_views, 1)
+    r2c = torch.from_numpy(poses).to(dev)
+
+    def run():
+        t0 = time.perf_counter()
+        surfaces = get_surfaces_batch(lab, dep, cam, r2c, 20, 5.0, 20, 2.0)
+        torch.cuda.synchronize(); t1 = time.perf_counter()
+        cloud = reconstruct_run(surfaces, 2.0, 10.0)
+        torch.cuda.synchronize(); t2 = time.perf_counter()
+        return (t1 - t0) * 1e3, (t2 - t1) * 1e3, len(cloud), sum(len(s_) for s_ in surfaces) / n_views
+    run()
+    r = [run() for _ in range(3)]
+    best = min(r, key=lambda x: x[0] + x[1])
+    return dict(views=n_views, surfaces_ms=best[0], register_and_merge_ms=best[1], ms_per_registration=best[1] / (n_views - 1),
+                final_cloud_points=best[2], mean_surface_points=best[3],
+                note='wall clock incl. host synchronisation (the loop is sequential by construction); surfaces = back-projection + voxel grid + '
+                     'radius / statistical outlier filters of all 30 views in batched launches')
+
+
 def c4_leg(torch, ops, peaks, steps, rank=0, world=1, sync=None, reduce_max=None):
     """Extra leg (BASELINE config 4 as written): batch pose-label generation over 10 000 synthetic frames x 5 objects, the
     frames sharded over the ranks (10 000 / world per rank, distinct frames: seeded camera poses on a hemisphere around a
@@ -912,6 +942,11 @@ def run_b200(args):
             extra = dict(extra or {}, live_frame=live_leg(torch, ops, args.steps))
         except Exception as ex:
             extra = dict(extra or {}, live_frame=dict(error=repr(ex)))
+        if not args.no_icp:
+            try:
+                extra = dict(extra or {}, reconstruct_30_views=reconstruct_leg(torch, ops, args.steps))
+            except Exception as ex:
+                extra = dict(extra or {}, reconstruct_30_views=dict(error=repr(ex)))
         if world == 1:
             try:
                 extra = dict(extra or {}, real_pipeline=real_pipeline_leg(torch, args.steps, sd_e, sd_r))
@@ -967,7 +1002,7 @@ def make_summary(line):
                 knn_vs_ref=g(x, 'add_metric', 'knn_vs_reference_kernel', 'speedup'),
                 train_ms=g(x, 'refiner_training', 'ms_per_step'), train_ops=g(x, 'refiner_training', 'objects_per_s'),
                 train_ar_ms=g(x, 'refiner_training', 'allreduce_ms'), train_frac=g(x, 'refiner_training', 'roofline', 'frac'),
-                live_us=g(x, 'live_frame', 'us_per_frame_cuda_graph'))
+                live_us=g(x, 'live_frame', 'us_per_frame_cuda_graph'), recon30_ms=g(x, 'reconstruct_30_views', 'register_and_merge_ms'))
 
 
 def main():
