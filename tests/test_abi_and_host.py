@@ -159,19 +159,21 @@ def test_host_quaternion_helpers(golden_dir):
 
 def test_committed_profiles_feed_the_bench_roofline():
     """bench.py reads roofline.traffic (and the ncu tensor-pipe utilisation) from profiles/traffic.json: the committed file
-    must hold the three kernels the bench line reports, consistent with the committed ncu summaries it was derived from."""
+    must hold the kernels the bench line reports, consistent with the committed ncu summaries it was derived from."""
     import csv
     import json
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     t = json.load(open(os.path.join(root, 'profiles', 'traffic.json')))
-    for k in ('gemm', 'surface_backproject', 'icp_p2p'):
+    for k in ('gemm', 'surface_backproject', 'icp_p2p', 'add_metric'):
         assert t[k]['dram_bytes_per_launch'] > 0 and os.path.exists(os.path.join(root, t[k]['source'].split(' ')[0]))
     assert 40.0 <= t['gemm']['tensor_pipe_active_pct_time_weighted'] <= 100.0      # BASELINE target: >= 40 % tensor-pipe utilisation
     rows = list(csv.reader(open(os.path.join(root, t['gemm']['source'].split(' ')[0]))))
-    assert len(rows) - 1 == t['gemm']['launches_captured'] == 12
+    assert sum('gemm_split' in r[0] for r in rows[1:]) == t['gemm']['launches_captured'] == 12      # one step: 6 PoseNet + 2 x 3 refiner layers
+    assert sum('dense_swapped' in r[0] for r in rows[1:]) == 5                                        # + the 5 per-object dense launches
     import bench
     assert bench.measured_traffic('gemm') == t['gemm']['dram_bytes_per_launch']
+    assert bench.measured_traffic('add_metric') == t['add_metric']['dram_bytes_per_launch']
     assert abs(bench.measured_traffic('icp_p2p', 2 * t['icp_p2p']['registrations_per_launch']) - 2 * t['icp_p2p']['dram_bytes_per_launch']) < 1.0
     # back-projection: measured DRAM traffic must not exceed the algorithmic bytes by more than a few per cent
     # (512 frames x 921 600 B + 24 B per valid pixel ~ 574 MB): no wasted re-reads

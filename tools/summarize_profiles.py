@@ -75,6 +75,7 @@ def traffic(tag):
                            dram_bytes_per_step=sum(b), source='profiles/%s_ncu_gemm.csv (ncu --set full, one bench step: %d GEMM launches)' % (tag, len(b)))
     per = collections.OrderedDict()
     for name in ('label', 'icp'):                      # ncu picks the byte unit per report: one summary file per report
+        per = collections.OrderedDict() if name == 'label' else per
         pl = os.path.join(ROOT, 'profiles', '%s_ncu_%s.csv' % (tag, name))
         if os.path.exists(pl):
             rows = list(csv.reader(open(pl))); hdr = rows[0]
@@ -87,11 +88,21 @@ def traffic(tag):
         if surf:
             out['surface_backproject'] = dict(kernels={k: avg[k] for k in surf}, dram_bytes_per_launch=sum(avg[k] for k in surf),
                                               source='profiles/%s_ncu_label.csv (mask + scan + emit of one 512-frame call)' % tag)
-        icp = [k for k in avg if k.startswith('icp_p2p')]
+        icp = [k for k in avg if 'icp_p2p' in k]
         if icp:
-            out['icp_p2p'] = dict(kernel=icp[0], dram_bytes_per_launch=avg[icp[0]], registrations_per_launch=1184,
-                                  source='profiles/%s_ncu_icp.csv (captured with 1184 registrations per launch; bench.py scales it to '
-                                         'its own launch size)' % tag)
+            nreg = 1184 if tag.startswith('r01') else 3552
+            out['icp_p2p'] = dict(kernel=icp[0], dram_bytes_per_launch=avg[icp[0]], registrations_per_launch=nreg,
+                                  source='profiles/%s_ncu_icp.csv (captured with %d registrations per launch; bench.py scales it to '
+                                         'its own launch size)' % (tag, nreg))
+    pa = os.path.join(ROOT, 'profiles', tag + '_ncu_adds.csv')
+    if os.path.exists(pa):
+        rows = list(csv.reader(open(pa))); hdr = rows[0]
+        b = [_mb(r, hdr, 'dram__bytes_read.sum') + _mb(r, hdr, 'dram__bytes_write.sum') for r in rows[1:] if r and 'add_metric' in r[0]]
+        if b:
+            mixed = b[:-1] if len(b) > 1 else b           # the last captured launch is the all-symmetric run
+            out['add_metric'] = dict(kernel='add_metric_kernel', dram_bytes_per_launch=sum(mixed) / len(mixed), instances_per_launch=12500,
+                                     dram_bytes_per_launch_all_symmetric=b[-1],
+                                     source='profiles/%s_ncu_adds.csv (12 500 instances per launch, dataset mix of symmetric classes; last row: all symmetric)' % tag)
     with open(os.path.join(ROOT, 'profiles', 'traffic.json'), 'w') as f:
         json.dump(out, f, indent=1)
     print('wrote profiles/traffic.json', {k: round(v['dram_bytes_per_launch'] / 1e6, 1) for k, v in out.items()}, 'MB per launch')
