@@ -12,6 +12,7 @@
 // read and share the SMs with the persistent GEMM CTAs; the shared-memory carve-out preference makes no difference), which
 // is why the Runner prefers the host pool while the host keeps up (densefusion/estimate_poses.py).
 #include "ape_common.cuh"
+#include <cstdlib>
 
 namespace ape {
 
@@ -19,9 +20,13 @@ namespace ape {
 // grid = (ceil(N / 128), B, 32 / CH), block = 128.
 template <int CH>
 __global__ void __launch_bounds__(128)
-gather_emb_nchw_kernel(const float* __restrict__ img, int hw, const int64_t* __restrict__ choose, int N, float* __restrict__ emb)
+gather_emb_nchw_kernel(const float* __restrict__ img, int hw, const int64_t* __restrict__ choose, int N, float* __restrict__ emb, int B)
 {
-    const int b = blockIdx.y;
+  // grid.y = min(B, 16): 256 CTAs walk the objects.  Reading a pinned host map, one CTA per (object, point block, channel
+  // block) = 1024 CTAs of waiting loads got in the way of the step's kernels on the other stream (a whole batch through the
+  // zero-copy path: 1.41 ms per step; 16 object rows: 1.27 ms = the gather's stand-alone time, i.e. fully overlapped;
+  // 4 rows: 1.79 ms, too few requests in flight) -- profiles/r02_e2e_diag.txt.
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
     const int n = blockIdx.x * 128 + threadIdx.x;
     const int c0 = blockIdx.z * CH;
     if (n >= N) return;
@@ -34,6 +39,7 @@ gather_emb_nchw_kernel(const float* __restrict__ img, int hw, const int64_t* __r
     float* dst = emb + ((size_t)b * 32 + c0) * N + n;
 #pragma unroll
     for (int j = 0; j < CH; ++j) dst[(size_t)j * N] = e[j];
+  }
 }
 
 // Channels-last map [B,hw,32]: one warp reads 8 points, lane = channel (one 128-byte line per point).
@@ -69,8 +75,10 @@ int ape_gather_emb(const float* out_img, int hw, int layout, const int64_t* choo
     APE_REQUIRE(layout == APE_EMB_NCHW || layout == APE_EMB_NHWC, "ape_gather_emb: layout must be APE_EMB_NCHW or APE_EMB_NHWC");
     cudaStream_t s = (cudaStream_t)stream;
     ape::ProfScope prof_("gather_emb", s);
+    static int max_y = -1;
+    if (max_y < 0) { const char* e = getenv("APE_GATHER_MAX_OBJ_CTAS"); max_y = e ? atoi(e) : 16; }
     if (layout == APE_EMB_NCHW)
-        ape::gather_emb_nchw_kernel<8><<<dim3((N + 127) / 128, B, 4), 128, 0, s>>>(out_img, hw, choose, N, emb);
+        ape::gather_emb_nchw_kernel<8><<<dim3((N + 127) / 128, (max_y > 0 && max_y < B) ? max_y : B, 4), 128, 0, s>>>(out_img, hw, choose, N, emb, B);
     else
         ape::gather_emb_nhwc_kernel<<<dim3((N + 63) / 64, B), 256, 0, s>>>(out_img, hw, choose, N, emb);
     ape::count_launch();

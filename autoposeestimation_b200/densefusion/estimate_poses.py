@@ -45,7 +45,8 @@ class Runner:
         self.transfer, self.zc_fraction, self.host_threads, self.use_graph = transfer, zero_copy_fraction, host_threads, use_graph
         self.dma_fraction = dma_fraction if dma_fraction is not None else (0.0 if zero_copy_fraction is not None else None)
         self.crop_pixels = crop_pixels
-        self.copy_stream = torch.cuda.Stream(device=dev, priority=-1)
+        import os
+        self.copy_stream = torch.cuda.Stream(device=dev, priority=int(os.environ.get('APE_RUNNER_PRIO', '-1')))
         mk = lambda shape, dt: [torch.empty(shape, dtype=dt, device=dev) for _ in range(2)]
         self.d_img = mk((max_batch, 32, crop_pixels), torch.float32) if transfer == 'full' else [None, None]   # 'gather': sized on demand
         self.d_emb = mk((max_batch, 32, n_points), torch.float32)

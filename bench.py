@@ -992,6 +992,7 @@ def make_summary(line):
     x = line.get('extra') or {}
     return dict(n=line['n_gpus'], fps=round(line['value']), ms=round(line['ms_per_step'], 4), e2e_fps=round(line['e2e']['value']),
                 e2e_frac=g(line, 'e2e', 'frac_of_value'), e2e_h2d_gbs=g(line, 'e2e', 'h2d_gbs_per_gpu'),
+                e2e_cl_fps=g(line, 'e2e', 'channels_last', 'value'), e2e_full_fps=g(line, 'e2e', 'full_map', 'value'),
                 gemm_frac=g(line, 'roofline', 'frac'), gemm_exec_frac=g(line, 'roofline', 'executed_frac'),
                 bp_fps=g(x, 'backprojection', 'frames_per_s'), bp_gbs=g(x, 'backprojection', 'roofline', 'achieved'),
                 bp_frac=g(x, 'backprojection', 'roofline', 'frac'),
