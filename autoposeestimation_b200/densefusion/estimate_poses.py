@@ -112,12 +112,14 @@ class Runner:
         # DRAM the pool is hammering, so adding either SLOWS the pool down (16 threads: host only 0.69 ms per step, +23 % of the
         # objects by copy engine 0.85 ms; 12 threads: 0.76 against 0.93) -- they only pay once the host is far behind the
         # device.  Policy: everything through the pool while that keeps the host within 25 % of the device time; otherwise
-        # the zero-copy share that balances host and device time (its kernel costs about half of its stand-alone duration
-        # in device time).  The copy-engine path stays available through `dma_fraction=` but is not chosen automatically.
-        c0, zc_visible = 0.15, 0.5                              # ms of launches / events per step on the host
+        # the zero-copy share that lets the pool and the gather kernel finish together.  The copy-engine path stays
+        # available through `dma_fraction=` but is not chosen automatically.
+        c0 = 0.15                                               # ms of launches / events per step on the host
         f2 = 0.0
         if t_host + c0 > 1.25 * t_gpu:
-            f2 = min(1.0, max(0.0, (t_host + c0 - t_gpu) / (t_host + zc_visible * t_zc)))
+            # host stage (1 - f) t_host + c0 and zero-copy stage f t_zc run side by side (the gather kernel, 256 CTAs, overlaps
+            # the step's kernels fully): balance the two
+            f2 = min(1.0, max(0.0, (t_host + c0) / (t_host + t_zc)))
         self.zc_fraction, self.dma_fraction = f2, 0.0
         self.calibration = dict(zero_copy_ms=t_zc, host_ms=t_host, dma_ms=t_dma, compute_ms=t_gpu, zero_copy_fraction=f2,
                                 dma_fraction=0.0, host_fraction=1.0 - f2)

@@ -26,7 +26,7 @@ for i in range(steps):
     ops.pose_pipeline(est, ref, *dsets[i % 3], out=poses)
 e1.record(); torch.cuda.synchronize()
 print('device-resident: %.4f ms/step' % (e0.elapsed_time(e1) / steps))
-for name, kw in (('zc 1.0', dict(zero_copy_fraction=1.0)), ('zc 0.5 4thr', dict(zero_copy_fraction=0.5, host_threads=4)), ('auto 4thr', dict(host_threads=4))):
+for name, kw in (('auto', {}), ('auto 8thr', dict(host_threads=8)), ('auto 4thr', dict(host_threads=4)), ('auto 2thr', dict(host_threads=2)), ('zc 1.0', dict(zero_copy_fraction=1.0))):
     r = Runner(est, ref, B, N, CROP[0] * CROP[1], **kw)
     for i in range(6):
         r.submit(*sets[i % 3])
