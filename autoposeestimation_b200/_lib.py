@@ -66,6 +66,7 @@ SIGNATURES = {
     'ape_refiner_trainer_step': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     'ape_refiner_trainer_adam': (c_int, [c_vp, c_vp, c_vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_int,
                                          ctypes.c_float, c_vp]),
+    'ape_refiner_trainer_wait_bulk': (c_int, [c_vp, c_vp, c_vp]),
     'ape_refine_loss': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'ape_adam_step': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                               c_int, ctypes.c_float, c_vp]),

@@ -9,23 +9,32 @@
 //               caller all-reduces over NCCL (the only collective of the scope)
 //
 // Flat parameter layout (floats; O = num_obj).  Grouped layers are contiguous so the grouped GEMMs see one matrix:
-//   conv1.w [64,3] | e_conv1.w [64,32] | conv2.w, e_conv2.w [2x128,64] | conv5.w [512,384] | conv6.w [1024,512] |
-//   conv1_r.w, conv1_t.w [2x512,1024] | conv2_r.w, conv2_t.w [2x128,512] | conv3_r.w [4O,128] | conv3_t.w [3O,128] |
-//   biases in the same order.
+//   head block: conv1.w [64,3] | e_conv1.w [64,32] | biases of conv1, e_conv1, conv2|e_conv2, conv5 |
+//               conv2.w, e_conv2.w [2x128,64] | conv5.w [512,384]
+//   tail block: conv6.w [1024,512] | conv1_r.w, conv1_t.w [2x512,1024] | conv2_r.w, conv2_t.w [2x128,512] |
+//               conv3_r.w [4O,128] | conv3_t.w [3O,128] | biases of conv6, conv1_{r,t}, conv2_{r,t}, conv3_r, conv3_t
+//   (ape_refiner_trainer_layout gives every offset by name; the blocks exist for the overlapped all-reduce, see train_layout)
 #include "gemm_train.cuh"
 
 namespace ape {
 
 struct TrainLayout {
-    size_t w1, we1, w2e2, w5, w6, wh1, wh2, w3r, w3t, b1, be1, b2e2, b5, b6, bh1, bh2, b3r, b3t, total;
+    size_t w1, we1, w2e2, w5, w6, wh1, wh2, w3r, w3t, b1, be1, b2e2, b5, b6, bh1, bh2, b3r, b3t, bulk, total;
 };
 static TrainLayout train_layout(int O) {
+    // Two contiguous blocks.  TAIL block [bulk, total): conv6 + the heads, weights AND biases -- 89 % of the vector, and
+    // complete as soon as the LAST iteration's conv6 weight gradient is done, i.e. before the backward pass walks conv5,
+    // conv2 and conv1: its all-reduce overlaps that tail (ape_refiner_trainer_wait_bulk).  HEAD block [0, bulk): the rest.
     TrainLayout L; size_t o = 0;
-    L.w1 = o; o += 64 * 3;      L.we1 = o; o += 64 * 32;   L.w2e2 = o; o += 256 * 64;  L.w5 = o; o += 512 * 384;
+    // (the head block's biases sit in front of its big weights so that conv2|e_conv2 .. conv2_{r,t} stay one contiguous
+    // range across the block boundary: one fp32 -> bf16 refresh launch, ape_refiner_trainer_sync_weights)
+    L.w1 = o; o += 64 * 3;      L.we1 = o; o += 64 * 32;
+    L.b1 = o; o += 64; L.be1 = o; o += 64; L.b2e2 = o; o += 256; L.b5 = o; o += 512;
+    L.w2e2 = o; o += 256 * 64;  L.w5 = o; o += 512 * 384;
+    L.bulk = o;
     L.w6 = o; o += 1024 * 512;  L.wh1 = o; o += 1024 * 1024; L.wh2 = o; o += 256 * 512;
     L.w3r = o; o += (size_t)4 * O * 128; L.w3t = o; o += (size_t)3 * O * 128;
-    L.b1 = o; o += 64; L.be1 = o; o += 64; L.b2e2 = o; o += 256; L.b5 = o; o += 512; L.b6 = o; o += 1024;
-    L.bh1 = o; o += 1024; L.bh2 = o; o += 256; L.b3r = o; o += 4 * O; L.b3t = o; o += 3 * O;
+    L.b6 = o; o += 1024; L.bh1 = o; o += 1024; L.bh2 = o; o += 256; L.b3r = o; o += 4 * O; L.b3t = o; o += 3 * O;
     L.total = o;
     return L;
 }
@@ -151,10 +160,12 @@ constexpr int kW1Part = 64 * 3 + 64 * 32;       // conv1.w | e_conv1.w, contiguo
 __global__ void __launch_bounds__(1024)
 fold_partials_kernel(const float* __restrict__ part_b, const float* __restrict__ part_w1, const float* __restrict__ part6, int tiles,
                      float* __restrict__ g_b5, float* __restrict__ g_b2e2, float* __restrict__ g_b1, float* __restrict__ g_w1,
-                     float* __restrict__ g_b6, float* __restrict__ g_bh1)
+                     float* __restrict__ g_b6, float* __restrict__ g_bh1, int phase /* 0: conv6 / conv1_{r,t} biases (their partials are
+                     complete after the conv6 weight gradient), 1: the rest (end of the backward pass) */)
 {
     __shared__ float s_red[32][33];
     if (blockIdx.x < 32) {
+        if (phase != 0) return;
         // conv6 bias: block = 32 columns x 32 tile segments, 4 loads in flight per thread, fixed-order tree over the segments
         const int cx = threadIdx.x & 31, sg = threadIdx.x >> 5, c = blockIdx.x * 32 + cx;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -175,6 +186,7 @@ fold_partials_kernel(const float* __restrict__ part_b, const float* __restrict__
         return;
     }
     const int i = (blockIdx.x - 32) * 1024 + threadIdx.x;
+    if ((phase == 0) != (i >= 4096)) return;                 // [4096, 5120) = conv1_{r,t} bias: phase 0
     if (i < 896) {
         float s = 0.f;
 #pragma unroll
@@ -291,6 +303,8 @@ struct ape_trainer {
     // scratch of ape_refiner_trainer_step (allocated on first use, sized for max_batch x max(max_points, mesh points))
     float *s_r = nullptr, *s_t = nullptr, *s_dr = nullptr, *s_dt = nullptr, *s_pts[2] = {nullptr, nullptr}, *s_tgt[2] = {nullptr, nullptr};
     int s_mesh = 0;
+    cudaEvent_t bulk_event = nullptr;  // recorded when the tail block of the flat gradient is final (last iteration only)
+    int record_bulk = 0;
 };
 
 static int make_bf_maps(BfMat& m) {
@@ -336,6 +350,7 @@ int ape_refiner_trainer_destroy(ape_trainer* tr)
 {
     if (!tr) return APE_OK;
     for (void* p : tr->net.allocs) cudaFree(p);
+    if (tr->bulk_event) cudaEventDestroy(tr->bulk_event);
     delete tr;
     return APE_OK;
 }
@@ -455,6 +470,7 @@ int ape_refiner_trainer_create(float* params, float* grads, int num_obj, int max
     rc = ape_refiner_trainer_sync_weights(tr, nullptr);
     if (rc) { ape_refiner_trainer_destroy(tr); return rc; }
     APE_CUDA(cudaStreamSynchronize(nullptr));
+    APE_CUDA(cudaEventCreateWithFlags(&tr->bulk_event, cudaEventDisableTiming));
     *out = tr;
     return APE_OK;
 }
@@ -549,6 +565,14 @@ int ape_refiner_trainer_backward(ape_trainer* tr, const float* new_points, const
     memset(&p, 0, sizeof(p));
     p.mode = ape::tr::BWD_WGRAD; p.M = 1024; p.N = 512; p.K = M; p.groups = 1; p.dw = G + L.w6; p.dw_ld = 512;
     if ((rc = run_bwd_gemm(tr->dY6, tr->H5m, nullptr, nullptr, p, s, "gemm.train.wgrad6"))) return rc;
+    {   // the conv6 / conv1_{r,t} bias partials are final too: fold them now, then the whole tail block of the gradient is done
+        ape::ProfScope prof_("train.fold_partials", s);
+        ape::fold_partials_kernel<<<32 + 5, 1024, 0, s>>>(tr->part_b, tr->part_w1, tr->part6, M / 128, G + L.b5, G + L.b2e2,
+                                                       G + L.b1, G + L.w1, G + L.b6, G + L.bh1, 0);
+        ape::count_launch();
+        if ((rc = ape::check_launch("fold_partials (tail block)"))) return rc;
+        if (tr->record_bulk && tr->bulk_event) APE_CUDA(cudaEventRecord(tr->bulk_event, s));
+    }
     memset(&p, 0, sizeof(p));
     p.mode = ape::tr::BWD_DGRAD; p.M = M; p.N = 512; p.K = 1024; p.groups = 1; p.out = tr->dZ5.p; p.o_ld = 512;
     p.mask = tr->H5m.p; p.m_ld = 512; p.bias_grad = tr->part_b; p.bg_stride = ape::kBiasPart;
@@ -583,7 +607,7 @@ int ape_refiner_trainer_backward(ape_trainer* tr, const float* new_points, const
     {
         ape::ProfScope prof_("train.fold_partials", s);
         ape::fold_partials_kernel<<<32 + 5, 1024, 0, s>>>(tr->part_b, tr->part_w1, tr->part6, M / 128, G + L.b5, G + L.b2e2,
-                                                       G + L.b1, G + L.w1, G + L.b6, G + L.bh1);
+                                                       G + L.b1, G + L.w1, G + L.b6, G + L.bh1, 1);
         ape::count_launch();
         if ((rc = ape::check_launch("fold_partials"))) return rc;
     }
@@ -648,10 +672,26 @@ int ape_refiner_trainer_step(ape_trainer* tr, const float* points, const float* 
         rc = ape_refine_loss(tr->s_r, tr->s_t, model_points, t_cur, n_mesh, p_cur, N, symmetric, B, dis + (size_t)it * B, tr->s_dr, tr->s_dt,
                              p_nxt, t_nxt, stream);
         if (rc) return rc;
+        tr->record_bulk = last ? 1 : 0;                     // the tail block is final after the LAST iteration's conv6 weight gradient
         rc = ape_refiner_trainer_backward(tr, p_cur, emb, obj, B, N, tr->s_dr, tr->s_dt, stream);
+        tr->record_bulk = 0;
         if (rc) return rc;
         if (!last) { p_cur = p_nxt; t_cur = t_nxt; }
     }
+    return APE_OK;
+}
+
+// Data-parallel overlap: [bulk_begin, total) of the flat gradient (conv6 + heads: 89 %) is final when the last iteration's
+// conv6 weight gradient has been written, before the backward pass walks conv5 / conv2 / conv1.  ape_refiner_trainer_step
+// records an event there; ape_refiner_trainer_wait_bulk makes `side_stream` wait for it, so that the caller's all-reduce of
+// the tail block on that stream overlaps the rest of the backward pass (the head block follows on the main stream).
+extern "C" __attribute__((visibility("default")))
+int ape_refiner_trainer_wait_bulk(ape_trainer* tr, void* side_stream, int64_t* bulk_begin)
+{
+    APE_REQUIRE(tr, "ape_refiner_trainer_wait_bulk: null handle");
+    if (bulk_begin) *bulk_begin = (int64_t)tr->L.bulk;
+    APE_REQUIRE(tr->bulk_event, "ape_refiner_trainer_wait_bulk: trainer without event");
+    APE_CUDA(cudaStreamWaitEvent((cudaStream_t)side_stream, tr->bulk_event, 0));     // never recorded yet: a no-op
     return APE_OK;
 }
 

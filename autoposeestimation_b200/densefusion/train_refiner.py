@@ -32,6 +32,7 @@ class RefinerTrainer:
         self.lr, self.betas, self.eps, self.iterations = lr, betas, eps, iterations
         self.step_count = 0
         self.num_obj = num_obj
+        self._side = None
 
     # -- pieces (also used by the autograd drop-in in network.py)
     def zero_grad(self):
@@ -62,16 +63,36 @@ class RefinerTrainer:
         """Sum the flat gradient over ranks (NCCL on the GPU box; identity for a single process)."""
         sharding.allreduce_gradient(self.h.grads)
 
+    def allreduce_gradient_overlapped(self):
+        """After `self.h.step(...)`: all-reduce the tail block of the gradient (conv6 + heads, 89 %; final once the last
+        iteration's conv6 weight gradient is written) on a side stream while the backward pass still walks conv5 / conv2 /
+        conv1, the head block on the main stream afterwards; the streams are joined before the optimizer."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.h.device)
+        main = torch.cuda.current_stream(self.h.device)
+        lo = self.h.wait_bulk(self._side)
+        with torch.cuda.stream(self._side):
+            dist.all_reduce(self.h.grads[lo:], op=dist.ReduceOp.SUM)
+        dist.all_reduce(self.h.grads[:lo], op=dist.ReduceOp.SUM)
+        main.wait_stream(self._side)
+
     def optimizer_step(self):
         self.step_count += 1
         self.h.adam(self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.betas, self.eps)
 
-    def train_step(self, points, emb, idx, target, model_points):
+    def train_step(self, points, emb, idx, target, model_points, overlap=True):
         """One optimizer step over this rank's shard of the batch (train.py:215-233).  Returns dis [iterations, B].
-        Three host calls per step: the whole accumulation phase (ape_refiner_trainer_step), the NCCL all-reduce of the
-        flat gradient, Adam + weight refresh -- so the step stays GPU-bound when the per-rank batch gets small."""
+        Host calls per step: the whole accumulation phase (ape_refiner_trainer_step), the NCCL all-reduce of the flat
+        gradient in two blocks (the tail block overlapped with the end of the backward pass), Adam + weight refresh -- so
+        the step stays GPU-bound when the per-rank batch gets small."""
         dis = self.h.step(points, emb, idx, target, model_points, self.symmetric_flags(idx), self.iterations, zero_grad=True)
-        self.allreduce_gradient()
+        if overlap:
+            self.allreduce_gradient_overlapped()
+        else:
+            self.allreduce_gradient()
         self.optimizer_step()
         return dis
 

@@ -672,6 +672,14 @@ class RefinerTrainerHandle:
               'ape_refiner_trainer_step')
         return dis
 
+    def wait_bulk(self, side_stream):
+        """Make `side_stream` (torch.cuda.Stream) wait until the tail block grads[bulk_begin:] of the step just enqueued is
+        final (conv6 + heads, 89 % of the vector); returns bulk_begin."""
+        import ctypes
+        lo = ctypes.c_int64(0)
+        check(_lib.load().ape_refiner_trainer_wait_bulk(self._h, side_stream.cuda_stream, ctypes.byref(lo)), 'ape_refiner_trainer_wait_bulk')
+        return int(lo.value)
+
     def adam(self, exp_avg, exp_avg_sq, step, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
         """Adam on the flat vectors + refresh of the bf16 weight copies (one C call)."""
         check(_lib.load().ape_refiner_trainer_adam(self._h, ptr(exp_avg), ptr(exp_avg_sq), float(lr), float(betas[0]), float(betas[1]),

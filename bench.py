@@ -717,6 +717,19 @@ def train_leg(torch, dist, lib, peaks, world, rank, dev, steps):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms)
     ar_ms = 0.0
+    ms_serial = None
+    if world > 1:                                            # the same step with ONE all-reduce after the whole backward pass
+        for _ in range(2):
+            trainer.train_step(pts, emb, idx, target, model, overlap=False)
+        dist.barrier(); torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(n):
+            trainer.train_step(pts, emb, idx, target, model, overlap=False)
+        s1.record(); dist.barrier(); torch.cuda.synchronize()
+        t_s = torch.tensor([s0.elapsed_time(s1) / n], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_s, op=dist.ReduceOp.MAX)
+        ms_serial = float(t_s)
     if world > 1:                                            # the collective on its own (flat fp32 gradient, NCCL sum)
         gbuf = trainer.h.grads
         for _ in range(3):
@@ -744,7 +757,11 @@ def train_leg(torch, dist, lib, peaks, world, rank, dev, steps):
         gemm_ms = sum(v for k, v in kern.items() if k.startswith('gemm.'))
         out = dict(objects_per_s=TRAIN_BATCH / ms * 1e3, ms_per_step=ms, global_batch=TRAIN_BATCH, batch_per_gpu=B, points=NPTS,
                    iterations=TRAIN_ITERS, dtype='bf16 operands, fp32 accumulate / master weights / gradients',
-                   allreduce_bytes=int(trainer.h.grads.numel() * 4) if world > 1 else 0, allreduce_ms=ar_ms, gpu_launches_per_step=launches / n,
+                   allreduce_bytes=int(trainer.h.grads.numel() * 4) if world > 1 else 0, allreduce_ms=ar_ms,
+                   ms_per_step_serial_allreduce=ms_serial,
+                   allreduce='two blocks: conv6 + heads (89 %) on a side stream as soon as the last conv6 weight gradient is written, '
+                             'conv1..conv5 after the backward pass' if world > 1 else 'none (one rank)',
+                   gpu_launches_per_step=launches / n,
                    mean_dis=float(dis.mean()),
                    roofline=dict(bound='tensor', achieved=flops / ms / 1e9, peak=peaks['bf16'] * world, unit='TFLOP/s',
                                  frac=flops / ms / 1e9 / (peaks['bf16'] * world), algorithmic_flops_per_step=flops,

@@ -365,6 +365,13 @@ int ape_refiner_trainer_step(ape_trainer* tr, const float* points, const float* 
                              int n_mesh, int iterations, int zero_grad, float* dis, void* stream);
 int ape_refiner_trainer_adam(ape_trainer* tr, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2,
                              float eps, int step, float grad_scale, void* stream);
+/* Data-parallel overlap.  The flat vectors are laid out in two contiguous blocks: [0, bulk_begin) = conv1 .. conv5 (weights
+ * and biases) and [bulk_begin, total) = conv6 + the heads (89 % of the parameters).  The tail block of the gradient is
+ * final as soon as the LAST iteration's conv6 weight gradient has been written; ape_refiner_trainer_step records an event
+ * at that point and this call makes `side_stream` wait for it, so the caller's all-reduce of grads[bulk_begin:] issued on
+ * that stream overlaps the rest of the backward pass (all-reduce grads[:bulk_begin] on the step's stream afterwards and
+ * join the streams before ape_refiner_trainer_adam).  Not for use with a graph-captured step.                        */
+int ape_refiner_trainer_wait_bulk(ape_trainer* tr, void* side_stream, int64_t* bulk_begin /* out, may be NULL */);
 /* Loss_refine forward + backward for B objects (lib/loss_refiner.py:12-64):
  *   quat [B,4], trans [B,3], model_points [B,M,3], target [B,M,3], points [B,N,3], symmetric [B] u8 or NULL
  *   dis [B] out; d_r [B,4], d_t [B,3] = d dis[b] / d (quat, trans) out (NULL to skip);
