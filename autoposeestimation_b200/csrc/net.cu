@@ -14,6 +14,7 @@
 #include "gemm_tc3.cuh"
 #include "gemm_tc4.cuh"
 #include "gemm_dense.cuh"
+#include "gemm_tail.cuh"
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -843,6 +844,55 @@ static const int* ape_net_masks(const ape_net* net, int N) {
 
 // PoseNet: `choose` != NULL gathers from the encoder map (hw > 0: [B,32,hw]; hw < 0: channels-last [B,-hw,32]);
 // `choose` == NULL: feat_src is the already gathered emb [B,32,N] (as for the refiner).
+// Per-object dense layer on the tensor cores (gemm_dense.cuh) for batches the warp-per-output GEMV does not cover.
+static bool dense_on_tensor_cores(const ape_net* net, int B) {
+    return !net->train && (net->gemm_impl == APE_GEMM_TCGEN05 || net->gemm_impl == APE_GEMM_TCGEN05_B2B) && B > ape::kGemvMaxB && B <= 256;
+}
+
+// PoseRefineNet's pooled tail in one cluster launch (gemm_tail.cuh).  Cluster size: 16 CTAs (non-portable size, one K = 64
+// stage per CTA) when the device can place such a cluster with 205 KB of shared memory per CTA, else 8 (two stages);
+// APE_REFINER_TAIL=0 | 8 | 16 overrides (0: the separate pool_finish / dense / refiner_out launches).
+template <int CL>
+static bool tail_probe() {
+    auto kern = ape::tail::refiner_tail_kernel<CL>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ape::tail::Cfg<CL>::kSmem) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (CL > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return false; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL, 2, 1); cfg.blockDim = dim3(ape::tail::kThreadsT); cfg.dynamicSmemBytes = ape::tail::Cfg<CL>::kSmem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
+    return n >= 2;                                   // the two branches of a chunk run side by side
+}
+static int tail_cluster_size() {
+    static int cl[64];
+    static ape::PerDevice probed;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (probed.first()) {
+        const char* e = getenv("APE_REFINER_TAIL");
+        const int want = e ? atoi(e) : 16;
+        int got = 0;
+        if (want >= 16 && tail_probe<16>()) got = 16;
+        else if (want >= 8 && tail_probe<8>()) got = 8;
+        cl[dev] = got;
+    }
+    return cl[dev];
+}
+static int tail_min_batch() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("APE_REFINER_TAIL_MINB"); v = e ? atoi(e) : 1; }
+    return v;
+}
+static bool refiner_tail_on(const ape_net* net, int B) {
+    return net->kind == APE_NET_REFINER && !net->train && (net->gemm_impl == APE_GEMM_TCGEN05 || net->gemm_impl == APE_GEMM_TCGEN05_B2B) &&
+           B >= tail_min_batch() && B <= 256 && tail_cluster_size() > 0;
+}
+
 static int run_trunk(ape_net* net, const float* feat_src, int hw, const float* cloud, const int64_t* choose, int B, int N,
                      float* emb_out, cudaStream_t s)
 {
@@ -878,6 +928,7 @@ static int run_trunk(ape_net* net, const float* feat_src, int hw, const float* c
     if (net->train) { p.passes = 1; p.relu_bits = net->relu_bits; }
     else p.pass_mask = pm[2];
     if ((rc = run_gemm(net, net->H5, net->W_c6, nullptr, p, wide_layer(2), s, pn ? "gemm.pn.conv6" : "gemm.rf.conv6"))) return rc;
+    if (refiner_tail_on(net, B)) return APE_OK;      // the fused tail kernel finishes the pooling itself (gemm_tail.cuh)
     dim3 gp(1024 / 256, B);
     ape::ProfScope prof_("pool_finish", s);
     APE_CUDA(ape::launch_pdl(ape::pool_finish_kernel, gp, dim3(256), 0, s, net->CS.p, Np / 128, 1024, (float)N, net->AP.p, net->train ? net->APb.hi : net->APs.hi,
@@ -911,10 +962,6 @@ static int dense(const float* in, int in_ld, int in_gs, const DevF32& W, const D
     return ape::check_launch("dense_batch");
 }
 
-// Per-object dense layer on the tensor cores (gemm_dense.cuh) for batches the warp-per-output GEMV does not cover.
-static bool dense_on_tensor_cores(const ape_net* net, int B) {
-    return !net->train && (net->gemm_impl == APE_GEMM_TCGEN05 || net->gemm_impl == APE_GEMM_TCGEN05_B2B) && B > ape::kGemvMaxB && B <= 256;
-}
 static int dense_tc(ape_net* net, const SplitMat& X, int x_kg, int rows_per_group, const SplitMat& W, const float* bias, int relu,
                     float* out, int out_ld, int B, int K, int n_out, const SplitMat* xo, cudaStream_t s)
 {
@@ -940,6 +987,40 @@ static int dense_tc(ape_net* net, const SplitMat& X, int x_kg, int rows_per_grou
     return ape::check_launch("dense_tc");
 }
 
+template <int CL>
+static int refiner_tail_launch(ape_net* net, const ape::tail::TailParams& p, int B, cudaStream_t s)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL, 2, (B + ape::tail::kObj - 1) / ape::tail::kObj); cfg.blockDim = dim3(ape::tail::kThreadsT);
+    cfg.dynamicSmemBytes = ape::tail::Cfg<CL>::kSmem; cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;          // the K slices of a (branch, object chunk) reduce through DSMEM
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = ape::pdl_enabled() ? 2 : 1;
+    ape::ProfScope prof_("refiner_tail", s);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, ape::tail::refiner_tail_kernel<CL>, net->Wd_r1.map_hi, net->Wd_r1.map_lo, p);
+    if (le != cudaSuccess) { ape::set_error("refiner_tail launch failed: %s", cudaGetErrorString(le)); return APE_ERR_CUDA; }
+    ape::count_launch();
+    return ape::check_launch("refiner_tail");
+}
+static int refiner_tail(ape_net* net, const int64_t* obj, int B, int N, float* r2, float* t2, cudaStream_t s)
+{
+    ape::tail::TailParams p;
+    memset(&p, 0, sizeof(p));
+    p.cs = net->CS.p; p.tiles_per_obj = (N + 127) / 128; p.n_points = (float)N;
+    p.b1 = net->br1.p; p.w2 = net->Wr2.p; p.b2 = net->br2.p;
+    p.w3r = net->w3r.p; p.b3r = net->b3r.p; p.w3t = net->w3t.p; p.b3t = net->b3t.p;
+    p.obj = obj; p.num_obj = net->num_obj; p.batch = B; p.r2 = r2; p.t2 = t2;
+    return tail_cluster_size() == 16 ? refiner_tail_launch<16>(net, p, B, s) : refiner_tail_launch<8>(net, p, B, s);
+}
+
+#ifdef APE_TAIL_TIMING   // developer aid (tools/tail_phases.py): per-CTA clock64 stamps of the tail kernel's phases
+extern "C" __attribute__((visibility("default"))) int ape_debug_tail(unsigned long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, ape::tail::g_tail_dbg, sizeof(unsigned long long) * 64 * 16);
+}
+#endif
 // emb_layout: APE_EMB_NCHW  out_img [B,32,hw] (the encoder's own layout), gathered at `choose` (network.py:100-102);
 //             APE_EMB_NHWC  out_img [B,hw,32] (torch channels_last memory format of the same tensor);
 //             APE_EMB_GATHERED  out_img is emb [B,32,N] already gathered (ape_gather_emb / ape_host_gather_*): hw and
@@ -1043,6 +1124,8 @@ int ape_refiner_forward(ape_net* net, const float* new_points, const float* emb,
         p = split_layer(Bp, 128, 512, 2, 0, 512, net->br2.p, net->G2b, 0);
         p.passes = 1; p.hi_only = 1;
         if ((rc = run_gemm(net, net->G1b, net->Wh2b, &net->G2b, p, false, s, "gemm.rf.head2"))) return rc;
+    } else if (refiner_tail_on(net, B)) {
+        return refiner_tail(net, obj, B, N, r2, t2, s);          // pooling finish + conv1 .. conv3 in one cluster launch
     } else if (dense_on_tensor_cores(net, B)) {
         if ((rc = dense_tc(net, net->APs, 0, 0, net->Wd_r1, net->br1.p, 1, net->G1.p, 1024, B, 1024, 1024, &net->G1s, s))) return rc;   // conv1_{r,t}
         if ((rc = dense_tc(net, net->G1s, 512, 128, net->Wd_r2, net->br2.p, 1, net->G2.p, 256, B, 512, 256, nullptr, s))) return rc;   // conv2_{r,t}

@@ -177,3 +177,56 @@ def test_net_errors_are_loud():
         est.posenet_forward(_dev(out_img), _dev(cloud), _dev(choose), _dev(idx))      # N exceeds the workspace
     with pytest.raises(_lib.ApeError):
         ref.posenet_forward(_dev(out_img[:, :, :4, :32]), _dev(cloud[:, :128]), _dev(choose[:, :, :128]), _dev(idx))   # wrong kind
+
+
+_TAIL_WORKER = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+from autoposeestimation_b200 import ops
+from oracle import synth
+out = {}
+for B, N in ((1, 500), (5, 300), (64, 500), (65, 256), (200, 128)):
+    nobj = 4
+    ref = ops.NetHandle(ops.NET_REFINER, synth.refiner_state_dict(300 + B, nobj), nobj, B, N)
+    rng = np.random.RandomState(B)
+    pts = torch.from_numpy((rng.randn(B, N, 3) * 0.05).astype(np.float32)).cuda()
+    emb = torch.from_numpy(rng.randn(B, 32, N).astype(np.float32)).cuda()
+    idx = torch.from_numpy(rng.randint(0, nobj, (B,)).astype(np.int64)).cuda()
+    r2, t2 = ref.refiner_forward(pts, emb, idx)
+    r2b, t2b = ref.refiner_forward(pts, emb, idx)
+    assert torch.equal(r2, r2b) and torch.equal(t2, t2b)          # deterministic (fixed reduction order)
+    out['r%d' % B] = r2.cpu().numpy(); out['t%d' % B] = t2.cpu().numpy()
+np.savez(sys.argv[2], **out)
+'''
+
+
+def test_refiner_tail_cluster_kernel_vs_separate_launches_and_oracle(tmp_path):
+    """The one-launch PoseRefineNet tail (gemm_tail.cuh: pooling finish + conv1..conv3 in a 16- or 8-CTA cluster) against
+    the separate pool_finish / dense / refiner_out launches (APE_REFINER_TAIL=0) and against the oracle's fp32 refiner,
+    at batch sizes around the 64-object chunk (1, 5, 64, 65, 200); r2 / t2 are deterministic run to run."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / 'tail_worker.py'
+    script.write_text(_TAIL_WORKER)
+    res = {}
+    for mode in ('0', '8', '16'):
+        env = dict(os.environ, APE_REFINER_TAIL=mode, PYTHONPATH=root)
+        out = tmp_path / ('tail_%s.npz' % mode)
+        r = subprocess.run([sys.executable, str(script), root, str(out)], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        res[mode] = np.load(out)
+    for key in res['0'].files:
+        a = res['0'][key]
+        for mode in ('8', '16'):
+            assert np.abs(res[mode][key] - a).max() < 2e-5 * max(1.0, np.abs(a).max()), (key, mode)
+    # and the oracle (per-sample fp32 restatement of network.py:187-204) on a few objects of the 65-object case
+    B, N, nobj = 65, 256, 4
+    sd = synth.to_torch(synth.refiner_state_dict(300 + B, nobj))
+    rng = np.random.RandomState(B)
+    pts = (rng.randn(B, N, 3) * 0.05).astype(np.float32); emb = rng.randn(B, 32, N).astype(np.float32)
+    idx = rng.randint(0, nobj, (B,)).astype(np.int64)
+    for b in (0, 63, 64):
+        r, t = odf.refiner_forward(sd, torch.from_numpy(pts[b:b + 1]), torch.from_numpy(emb[b:b + 1]), torch.from_numpy(idx[b:b + 1]).view(1, 1), nobj)
+        assert np.abs(res['16']['r65'][b] - r[0].detach().numpy()).max() < 2e-4
+        assert np.abs(res['16']['t65'][b] - t[0].detach().numpy()).max() < 2e-4
