@@ -27,6 +27,8 @@ SIGNATURES = {
     'ape_add_metric': (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),
     'ape_add_metric_std': (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),
     'ape_icp_work_bytes': (c_sz, [c_int, c_int]),
+    'ape_reconstruct_work_bytes': (c_sz, [c_int]),
+    'ape_reconstruct_run': (c_int, [c_vp, c_vp, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'ape_icp_p2p': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_dbl, c_dbl, c_dbl, c_int,
                             c_vp, c_vp, c_vp, c_vp, c_vp]),
     'ape_icp_p2p_ex': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_dbl, c_dbl, c_dbl, c_int,

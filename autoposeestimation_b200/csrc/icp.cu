@@ -40,7 +40,7 @@ constexpr int kIcpMaxCells = 4096;
 // partner: -2 %; 8 CTAs per SM at 64 registers: +1 %.)
 struct IcpSmem {
     int cell_start[kIcpMaxCells + 2];        // [c] = first cell-sorted position of cell c, [c + 1] = one past its last
-    double red[8][12];                       // up to 8 warps per CTA
+    double red[32][12];                      // up to 32 warps per CTA
     double out[12];
     double U[12];          // current update (3x4 row-major)
     double T[12];          // accumulated transform (3x4 row-major)
@@ -525,6 +525,25 @@ extern "C" __attribute__((visibility("default"))) int ape_icp_p2p_ex(const doubl
     // registration: pick the one with the shorter makespan for this batch (1184 registrations: 2 rounds of 4 per SM beat
     // 1.33 -> 2 rounds of 6 per SM).
     const int sms = ape::sm_count();
+    // Few registrations (the sequential reconstruction loop registers ONE view at a time): a CTA per registration leaves
+    // the GPU empty, so the CTA is made 512 threads wide -- the searches of one registration run 4x as parallel; the
+    // fixed-tree reductions then sum in a different (still fixed) order than the 128-thread kernel.  APE_ICP_WIDE=0 disables.
+    // Measured on the 30-view reconstruction loop (29 registrations of ~800 against ~1800 points, 10 iterations on average,
+    // tools/recon_profile.py): 1099 us per registration with 128 threads, 771 with 256, 632 with 512, 619 with 1024 -- what
+    // is left is the latency of one query's grid walk plus the one-thread SVD (tools/icp_latency.py: 55-67 us set-up and
+    // first search, 40 us per iteration far from convergence, 16 us near it).
+    static int wide = -1;
+    if (wide < 0) { const char* e = getenv("APE_ICP_WIDE"); wide = e ? atoi(e) : 1; }
+    if (wide && n_reg <= sms) {
+        static ape::PerDevice attr_w;
+        if (attr_w.first()) APE_CUDA(cudaFuncSetAttribute(ape::icp_p2p_kernel<1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ape::ProfScope prof_("icp_p2p", (cudaStream_t)stream);
+        ape::icp_p2p_kernel<1, 512><<<n_reg, 512, smem, (cudaStream_t)stream>>>(
+            source, src_offset, src_count, target, tgt_offset, n_reg, threshold, rel_fitness, rel_rmse, max_iter, init, transform, info,
+            wsrc, wtgt, worig, wcorr);
+        ape::count_launch();
+        return ape::check_launch("ape_icp_p2p (wide)");
+    }
     const double t4 = (double)((n_reg + 4 * sms - 1) / (4 * sms)), t6 = 1.30 * (double)((n_reg + 6 * sms - 1) / (6 * sms));
     const int minb = (n_reg > 4 * sms && t6 < t4) ? 6 : 4;
     const int grid = n_reg < sms * minb ? n_reg : sms * minb;

@@ -245,6 +245,32 @@ def icp_p2p(source, src_offset, target, tgt_offset, threshold, rel_fitness=1e-2,
     return tf, info
 
 
+def reconstruct_run(points, offset_host, voxel_size, threshold, rel_fitness=1e-2, rel_rmse=1e-2, max_iter=100):
+    """The sequential register-and-merge loop of create_pointcloud.py:286-312 in ONE call without a host synchronisation.
+    points [P,3] fp64 (the views' surfaces packed), offset_host [V+1] numpy int32 -> (cloud [P,3] fp64, count [1] int32,
+    status [1] int32), the cloud occupies cloud[:count]; status != 0: an intermediate cloud was too large for the batched
+    voxel kernel (run the loop view by view instead)."""
+    import numpy as np
+    require_cuda(points)
+    points = _c(points, torch.float64)
+    oh = np.ascontiguousarray(offset_host, dtype=np.int32)
+    V = oh.size - 1
+    if V < 0 or int(oh[-1]) != points.shape[0]:
+        raise ValueError('reconstruct_run: offset_host must be [n_views + 1] and end at the number of points')
+    dev = points.device
+    lib = _lib.load()
+    P = points.shape[0]
+    work = torch.empty((int(lib.ape_reconstruct_work_bytes(P)) + 7) // 8, dtype=torch.float64, device=dev)
+    out = torch.empty((P, 3), dtype=torch.float64, device=dev)
+    cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+    status = torch.empty((1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.ape_reconstruct_run(ptr(points), oh.ctypes.data, V, float(voxel_size), float(threshold), float(rel_fitness),
+                                      float(rel_rmse), int(max_iter), ptr(out), ptr(cnt), ptr(status), ptr(work), stream_ptr()),
+              'ape_reconstruct_run')
+    return out, cnt, status
+
+
 VOXEL_MAX_POINTS = 16384
 
 

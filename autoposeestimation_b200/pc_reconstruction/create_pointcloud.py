@@ -61,9 +61,20 @@ def get_surfaces_batch(label, depth, cam, robot2cam, min_friends, min_dist, nb_n
     return [PointCloud(flat[off[v]:off[v + 1]].clone()) for v in range(V)]
 
 
-def reconstruct_run(surfaces, voxel_size, threshold, global_regression=False, icp_point2point=True, icp_point2plane=False):
+def reconstruct_run(surfaces, voxel_size, threshold, global_regression=False, icp_point2point=True, icp_point2plane=False,
+                    device_loop=True):
     """create_pointcloud.py:286-312: first non-empty surface starts the cloud; every further one is registered to it
     (`icp_regression`), transformed, concatenated IN FRONT of the target and voxel-down-sampled."""
+    live = [s for s in surfaces if len(s) > 0]
+    if device_loop and len(live) >= 2 and icp_point2point and not global_regression and not icp_point2plane:
+        # the whole loop in one C call, sizes on the device, ONE synchronisation at the end (csrc/reconstruct.cu)
+        off = np.zeros(len(live) + 1, np.int32)
+        off[1:] = np.cumsum([len(s) for s in live])
+        out, cnt, status = ops.reconstruct_run(torch.cat([s.points for s in live]), off, voxel_size, threshold)
+        c, st = (int(v) for v in torch.cat((cnt, status)).cpu())
+        if st == 0:
+            return PointCloud(out[:c].clone())
+        # an intermediate cloud outgrew the batched voxel kernel: view by view below (large clouds take the global-memory path)
     cloud = None
     for source in surfaces:
         if len(source) == 0:

@@ -364,10 +364,19 @@ def reconstruct_leg(torch, ops, steps):
     run()
     r = [run() for _ in range(3)]
     best = min(r, key=lambda x: x[0] + x[1])
+    # the same loop driven view by view from Python (round-1 form: ~6 host round trips per view)
+    surfaces = get_surfaces_batch(lab, dep, cam, r2c, 20, 5.0, 20, 2.0)
+    host_ms = []
+    for _ in range(2):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        hc = reconstruct_run(surfaces, 2.0, 10.0, device_loop=False)
+        torch.cuda.synchronize(); host_ms.append((time.perf_counter() - t0) * 1e3)
     return dict(views=n_views, surfaces_ms=best[0], register_and_merge_ms=best[1], ms_per_registration=best[1] / (n_views - 1),
                 final_cloud_points=best[2], mean_surface_points=best[3],
+                register_and_merge_ms_host_driven_loop=min(host_ms), final_cloud_points_host_driven_loop=len(hc),
                 note='wall clock incl. host synchronisation (the loop is sequential by construction); surfaces = back-projection + voxel grid + '
-                     'radius / statistical outlier filters of all 30 views in batched launches')
+                     'radius / statistical outlier filters of all 30 views in batched launches; register_and_merge = ape_reconstruct_run '
+                     '(one call, sizes on the device, 512-thread ICP CTA per registration)')
 
 
 def c4_leg(torch, ops, peaks, steps, rank=0, world=1, sync=None, reduce_max=None):

@@ -167,6 +167,20 @@ int ape_icp_p2p_ex(const double* source, const int32_t* src_offset, const int32_
                    double threshold, double rel_fitness, double rel_rmse, int max_iter,
                    const double* init, double* transform, double* info, void* work, void* stream);
 
+/* The sequential register-and-merge loop of the object-cloud reconstruction in one call, no host synchronisation.
+ * Replaces the loop body of pc_reconstruction/create_pointcloud.py:286-312 (per further non-empty view: icp_regression =
+ * voxel grid on both clouds + point-to-point ICP, open3d_utils.py:63-104; transform; concatenate source-first; voxel grid).
+ *   points [offset_host[n_views], 3] fp64 (device): the views' surfaces packed; offset_host [n_views + 1] int32 (HOST: the
+ *   surface sizes are known when the surfaces are made); empty views are skipped, the first non-empty one starts the cloud.
+ *   out_points [offset_host[n_views], 3] fp64, out_count [1] int32 (device): the reconstructed cloud;
+ *   out_status [1] int32 (device): 0, or the voxel grid's negative status when an intermediate cloud exceeded
+ *   APE_VOXEL_MAX_POINTS (the caller then runs the loop view by view through ape_voxel_down_sample_large);
+ *   work: ape_reconstruct_work_bytes(offset_host[n_views]) bytes, 8-byte aligned.                                      */
+size_t ape_reconstruct_work_bytes(int total_points);
+int ape_reconstruct_run(const double* points, const int32_t* offset_host, int n_views, double voxel_size, double threshold,
+                        double rel_fitness, double rel_rmse, int max_iter, double* out_points, int32_t* out_count,
+                        int32_t* out_status, void* work, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a5/a6. Voxel-grid down-sampling (open3d 0.9 PointCloud::voxel_down_sample semantics; output
  * sorted by voxel index instead of hash-map order).  Replaces pcd.voxel_down_sample(voxel_size)

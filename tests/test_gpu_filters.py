@@ -144,6 +144,19 @@ def test_get_surfaces_batch_and_reconstruct_run():
     td, sd, T = oicp.icp_regression(a, b.numpy(), voxel_size=2.0, threshold=10.0)
     want = oicp.voxel_down_sample(np.concatenate((sd @ T[:3, :3].T + T[:3, 3], td)), 2.0)
     assert len(cloud) == len(want) and np.allclose(cloud.numpy(), want, atol=1e-6)
+    # the device-resident loop (csrc/reconstruct.cu: one call, sizes on the device) against the view-by-view loop, on a
+    # longer sequence with an empty view in front and in the middle
+    views = [surfs[1], surfs[0], b, surfs[1]]
+    rng = np.random.RandomState(8)
+    for k in range(4):
+        Rk = synth.random_rotation(rng, 0.02); tk = rng.uniform(-1.5, 1.5, size=3)
+        sub = a[rng.rand(len(a)) < 0.8]                                           # partial overlap
+        views.append(PointCloud((sub - a.mean(0)) @ Rk.T + a.mean(0) + tk))
+    dev_cloud = reconstruct_run(views, voxel_size=2.0, threshold=10.0)
+    host_cloud = reconstruct_run(views, voxel_size=2.0, threshold=10.0, device_loop=False)
+    assert len(dev_cloud) == len(host_cloud) and np.allclose(dev_cloud.numpy(), host_cloud.numpy(), atol=1e-6)
+    assert len(cloud) == len(reconstruct_run([surfs[0], surfs[1], b], voxel_size=2.0, threshold=10.0, device_loop=False))
+    assert len(reconstruct_run([surfs[1], surfs[1]], 2.0, 10.0)) == 0 and len(reconstruct_run([surfs[1], b], 2.0, 10.0)) == len(b)
     c0 = cloud.numpy().mean(0)
     rot = rotate_about_center(cloud, R)
     assert np.allclose(rot.numpy().mean(0), c0, atol=1e-9)

@@ -147,6 +147,25 @@ def test_icp_batch_property_identical_registrations(R):
     assert np.abs(T[0].cpu().numpy() - T_ref).max() < 1e-5
 
 
+def test_icp_wide_cta_matches_narrow_kernel():
+    """Launches of at most one registration per SM run a 512-thread CTA per registration (the sequential reconstruction
+    loop registers one view at a time); the same registrations inside a batch larger than the SM count run the
+    128-thread kernel: same iteration and correspondence counts, transforms equal to 1e-9 (the fixed reduction trees
+    differ), both inside the parity gate against the oracle."""
+    from autoposeestimation_b200 import ops
+    probs = [_surface(s) for s in (0, 3, 5)]
+    S, so = _ragged([p[0] for p in probs]); Tg, to = _ragged([p[1] for p in probs])
+    Tw, iw = ops.icp_p2p(_dev(S), _dev(so), _dev(Tg), _dev(to), 10.0)                      # 3 registrations: wide CTAs
+    reps = 60                                                                                # 180 registrations: 128-thread kernel
+    Sn, son = _ragged([p[0] for p in probs] * reps); Tn_, ton = _ragged([p[1] for p in probs] * reps)
+    Tn, inn = ops.icp_p2p(_dev(Sn), _dev(son), _dev(Tn_), _dev(ton), 10.0)
+    Tw, iw, Tn, inn = (x.cpu().numpy() for x in (Tw, iw, Tn, inn))
+    for k, (src, tgt) in enumerate(probs):
+        assert np.array_equal(iw[k, 2:], inn[k, 2:]) and np.array_equal(inn[k], inn[k + 3 * (reps - 1)])
+        assert np.abs(Tw[k] - Tn[k]).max() < 1e-9 and abs(iw[k, 1] - inn[k, 1]) < 1e-9
+        assert np.abs(Tw[k] - oicp.registration_icp_p2p(src, tgt, 10.0)).max() < 1e-5
+
+
 @pytest.mark.parametrize('voxel', [2.0, 5.0])
 def test_voxel_down_sample_exact(voxel):
     from autoposeestimation_b200 import ops
