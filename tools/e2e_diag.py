@@ -40,5 +40,5 @@ for name, kw in (('auto', {}), ('auto 8thr', dict(host_threads=8)), ('auto 4thr'
     r.drain()
     e1.record(); torch.cuda.synchronize()
     print('%-14s %.4f ms/step (cpu submit %.4f ms/step) cal=%s cpu phases: %s' % (
-        name, e0.elapsed_time(e1) / steps, t_sub / steps * 1e3, r.calibration and {k: round(v, 3) for k, v in r.calibration.items()},
+        name, e0.elapsed_time(e1) / steps, t_sub / steps * 1e3, r.calibration and {k: (round(v, 3) if not isinstance(v, dict) else {a: round(b, 3) for a, b in v.items()}) for k, v in r.calibration.items()},
         {k: round(v / steps, 4) for k, v in r.cpu_ms.items()}), flush=True)
