@@ -519,6 +519,8 @@ extern "C" __attribute__((visibility("default"))) int ape_icp_p2p_ex(const doubl
         APE_CUDA(cudaFuncSetAttribute(ape::icp_p2p_kernel<4, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         APE_CUDA(cudaFuncSetAttribute(ape::icp_p2p_kernel<6, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
+    // (Measured and dropped: CTAs drawing registrations from an atomic counter instead of a fixed share -- 535 k against
+    // 557 k registrations/s on 3552 problems; co-resident CTAs already absorb each other's idle time.)
     // Resident CTAs per SM: 4 (128 registers, no spills) or 6 (80 registers, a few spills).  The search is latency-bound
     // (fixed-latency fp64 chains, 4 warps per scheduler), so 6 per SM deliver 15 % more registrations per second when the
     // grid stays full (measured: 3552 registrations, 245 k/s against 213 k/s), but a CTA then takes 1.3x as long per

@@ -379,7 +379,7 @@ def reconstruct_leg(torch, ops, steps):
                      '(one call, sizes on the device, 512-thread ICP CTA per registration)')
 
 
-def c4_leg(torch, ops, peaks, steps, rank=0, world=1, sync=None, reduce_max=None):
+def c4_leg(torch, ops, peaks, steps, rank=0, world=1, sync=None, reduce_max=None, lib=None):
     """Extra leg (BASELINE config 4 as written): batch pose-label generation over 10 000 synthetic frames x 5 objects, the
     frames sharded over the ranks (10 000 / world per rank, distinct frames: seeded camera poses on a hemisphere around a
     5-object scene), no collective.  Per chunk of frames, with NO host synchronisation: one-pass multi-label
@@ -389,7 +389,9 @@ def c4_leg(torch, ops, peaks, steps, rank=0, world=1, sync=None, reduce_max=None
     sync = sync or torch.cuda.synchronize
     reduce_max = reduce_max or (lambda v: v)
     dev = torch.device('cuda', torch.cuda.current_device())
-    n_frames_job, L, chunk = 10000, 5, 250
+    # chunk: 710 frames = 3550 registrations = 4 rounds of 6 resident ICP CTAs on each of the 148 SMs (the last chunk of a
+    # rank is whatever is left)
+    n_frames_job, L, chunk = 10000, 5, 710
     per_rank = n_frames_job // world
     scene = synth.Scene(3)
     poses = scene.camera_poses(1000 + rank, per_rank)
@@ -408,36 +410,48 @@ def c4_leg(torch, ops, peaks, steps, rank=0, world=1, sync=None, reduce_max=None
     results = []
 
     def run_chunk(c0):
-        sl = slice(c0, c0 + chunk)
-        out = ops.surface_backproject_multi(labels[sl], depths[sl], cam[sl], r2c[sl], [1, 2, 3, 4, 5], total_capacity=cap_total)
+        n = min(chunk, per_rank - c0)
+        sl = slice(c0, c0 + n)
+        out = ops.surface_backproject_multi(labels[sl], depths[sl], cam[sl], r2c[sl], [1, 2, 3, 4, 5], total_capacity=n * L * 10240)
         vox, vc = ops.voxel_down_sample(out['points'], out['offsets'], 2.0, max_cloud_points=10240)   # an object covers < 10 k pixels here
-        T, info = ops.icp_p2p(vox, out['offsets'], tgt, to, 10.0, src_count=vc)
+        T, info = ops.icp_p2p(vox, out['offsets'], tgt[:n * L * 2000], to[:n * L + 1], 10.0, src_count=vc)
         return out, vc, T, info
 
-    n_chunks = per_rank // chunk
+    starts = list(range(0, per_rank, chunk))
+    n_chunks = len(starts)
     out, vc, T, info = run_chunk(0)                             # warm-up
+    if starts[-1] != 0:
+        run_chunk(starts[-1])
     sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for c in range(n_chunks):
-        out, vc, T, info = run_chunk(c * chunk)
+    for c0 in starts:
+        out, vc, T, info = run_chunk(c0)
         results.append((out['offsets'][-1:], vc, info))
     e1.record(); sync()
     ms = reduce_max([e0.elapsed_time(e1)])[0]
     n_valid = int(sum(int(r[0]) for r in results))
     infos = torch.cat([r[2] for r in results])
     vcs = torch.cat([r[1] for r in results])
-    frames = n_chunks * chunk
+    frames = per_rank
     # back-projection alone on the same frames (multi-label, packed)
     e0.record()
-    for c in range(n_chunks):
-        sl = slice(c * chunk, (c + 1) * chunk)
+    for c0 in starts:
+        sl = slice(c0, min(c0 + chunk, per_rank))
         ops.surface_backproject_multi(labels[sl], depths[sl], cam[sl], r2c[sl], [1, 2, 3, 4, 5], total_capacity=cap_total)
     e1.record(); sync()
+    kern = None
+    if rank == 0 and lib is not None:                           # where a chunk's time goes (CUDA events around every launch)
+        lib.ape_profile_enable(1)
+        run_chunk(0)
+        sync()
+        kern = {k: v[1] for k, v in profile_report(lib).items()}
+        lib.ape_profile_enable(0)
     ms_bp = reduce_max([e0.elapsed_time(e1)])[0]
     bytes_bp = frames * H * W * 3 + n_valid * 24
     return dict(frames_per_s=world * frames / ms * 1e3, registrations_per_s=world * frames * L / ms * 1e3, ms_total=ms,
                 frames_per_rank=frames, objects_per_frame=L, registrations_per_rank=frames * L, n_gpus=world, chunk_frames=chunk,
+                rank0_kernel_ms_first_chunk=kern,
                 mean_source_points=float(vcs.float().mean()), mean_valid_pixels_per_view=n_valid / (frames * L),
                 mean_iterations=float(infos[:, 2].mean()), mean_fitness=float(infos[:, 0].mean()), mean_rmse_mm=float(infos[:, 1].mean()),
                 converged_fraction=float((infos[:, 0] > 0.9).double().mean()),
@@ -901,11 +915,11 @@ def run_b200(args):
             pass
         elif world == 1:
             try:
-                label_leg = dict(label_leg, label_c4=c4_leg(torch, ops, peaks, args.steps, 0, 1, barrier, reduce_max))
+                label_leg = dict(label_leg, label_c4=c4_leg(torch, ops, peaks, args.steps, 0, 1, barrier, reduce_max, lib))
             except Exception as ex:
                 label_leg = dict(label_leg, label_c4=dict(error=repr(ex)))
         else:
-            label_leg = dict(label_leg, label_c4=c4_leg(torch, ops, peaks, args.steps, rank, world, barrier, reduce_max))
+            label_leg = dict(label_leg, label_c4=c4_leg(torch, ops, peaks, args.steps, rank, world, barrier, reduce_max, lib))
         torch.cuda.empty_cache()
         # ---- ADD / ADD-S evaluation (BASELINE config 3), same sharding rule
         if args.no_adds:

@@ -181,6 +181,31 @@ def test_voxel_down_sample_exact(voxel):
         assert np.array_equal(out[off[c]:off[c] + cnt[c]], want)               # same order, same bits as the oracle
 
 
+def test_voxel_big_batch_mixed_sizes():
+    """A batch of several hundred clouds of mixed sizes (empty, 1 point, around the powers of two the in-CTA sort pads to,
+    the 16 384-point limit and one cloud above it, flagged -1): every cloud's output has the bits it has in a small batch
+    and, for sampled clouds, the oracle's."""
+    from autoposeestimation_b200 import ops
+    rng = np.random.RandomState(11)
+    sizes = [0, 1, 4095, 4096, 4097, 8191, 8192, 8193, 16384, 16385] + list(rng.randint(1, 12000, size=330))
+    clouds = [rng.uniform(-40, 40, size=(n, 3)) for n in sizes]
+    P, off = _ragged(clouds)
+    out, cnt = ops.voxel_down_sample(_dev(P), _dev(off), 3.0, max_cloud_points=16384)       # 340 clouds in one launch
+    out = out.cpu().numpy(); cnt = cnt.cpu().numpy()
+    assert cnt[0] == 0 and cnt[9] == -1
+    for lo in range(0, len(clouds), 100):                                                   # the same clouds, 100 per launch
+        sub = clouds[lo:lo + 100]
+        Ps, offs = _ragged(sub)
+        o2, c2 = ops.voxel_down_sample(_dev(Ps), _dev(offs), 3.0, max_cloud_points=16384)
+        o2 = o2.cpu().numpy(); c2 = c2.cpu().numpy()
+        for k in range(len(sub)):
+            assert c2[k] == cnt[lo + k]
+            if c2[k] > 0:
+                assert np.array_equal(o2[offs[k]:offs[k] + c2[k]], out[off[lo + k]:off[lo + k] + c2[k]])
+    for k in (2, 4, 7, 8):
+        assert np.array_equal(out[off[k]:off[k] + cnt[k]], oicp.voxel_down_sample(clouds[k], 3.0))
+
+
 def test_voxel_batched_entry_flags_oversize_clouds():
     """The batched C entry itself does not process a cloud above 16 384 points: it flags it with out_counts = -1 (header
     contract) and ops.voxel_down_sample then routes it through the large path; when the caller vouches for the sizes
