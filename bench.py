@@ -947,10 +947,13 @@ def run_b200(args):
         gemm_ms = sum(v[1] for k, v in rep.items() if k.startswith('gemm.')) / args.steps
         all_ms = sum(v[1] for v in rep.values()) / args.steps
         refine = {k: (REFINE_ITERS if k.startswith('gemm.rf') else 1) for k in GEMM_FLOPS_PER_PT}
-        alg = sum(GEMM_FLOPS_PER_PT[k] * refine[k] for k in GEMM_FLOPS_PER_PT) * BATCH * NPTS
+        # only the layers the GEMM kernel actually ran count (conv2 | e_conv2 are computed inside the front-end kernel,
+        # frontend_tc.cuh: neither their FLOPs nor their time are in this figure)
+        in_gemm = [k for k in GEMM_FLOPS_PER_PT if k in rep or k in ('gemm.pn.heads1', 'gemm.pn.heads2') and 'gemm.pn.heads12' in rep]
+        alg = sum(GEMM_FLOPS_PER_PT[k] * refine[k] for k in in_gemm) * BATCH * NPTS
         rows = BATCH * ((NPTS + 127) // 128 * 128)
         epr = gemm_exec_per_row(est, ref)
-        exe = sum(epr[k] * refine[k] for k in epr) * rows
+        exe = sum(epr[k] * refine[k] for k in in_gemm) * rows
         fpt = dict(GEMM_FLOPS_PER_PT)
         # the back-to-back heads kernel (gemm_tc4.cuh) does the work of two layers in one launch
         fpt['gemm.pn.heads12'] = fpt['gemm.pn.heads1'] + fpt['gemm.pn.heads2']
@@ -964,7 +967,9 @@ def run_b200(args):
             achieved=alg / gemm_ms / 1e9, peak=peaks['bf16'], unit='TFLOP/s', frac=alg / gemm_ms / 1e9 / peaks['bf16'],
             traffic=measured_traffic('gemm'), traffic_source='profiles/traffic.json (ncu --set full, bytes per GEMM launch)',
             peak_source=peaks['src'] + ' bf16_tflops_sustained',
-            algorithmic_flops_per_step=alg, executed_bf16_tflops=exe / gemm_ms / 1e9,
+            algorithmic_flops_per_step=alg, layers_in_gemm_kernel=sorted(in_gemm),
+            layers_fused_elsewhere=sorted(k for k in GEMM_FLOPS_PER_PT if k not in in_gemm),
+            executed_bf16_tflops=exe / gemm_ms / 1e9,
             executed_frac=exe / gemm_ms / 1e9 / peaks['bf16'], gemm_ms_per_step=gemm_ms, all_kernels_ms_per_step=all_ms,
             gemm_share_of_kernel_time=gemm_ms / all_ms, layers=layers,
             other_kernels_ms_per_step={k: v[1] / args.steps for k, v in rep.items() if not k.startswith('gemm.')},
