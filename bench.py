@@ -441,10 +441,10 @@ def c4_leg(torch, ops, peaks, steps, rank=0, world=1, sync=None, reduce_max=None
         ops.surface_backproject_multi(labels[sl], depths[sl], cam[sl], r2c[sl], [1, 2, 3, 4, 5], total_capacity=cap_total)
     e1.record(); sync()
     kern = None
-    if rank == 0 and lib is not None:                           # where a chunk's time goes (CUDA events around every launch)
-        lib.ape_profile_enable(1)
-        run_chunk(0)
-        sync()
+    if world == 1 and lib is not None:                          # where a chunk's time goes (CUDA events around every launch);
+        lib.ape_profile_enable(1)                               # single process only: `sync` is a BARRIER under torchrun and
+        run_chunk(0)                                            # nothing rank-dependent may call it
+        torch.cuda.synchronize()
         kern = {k: v[1] for k, v in profile_report(lib).items()}
         lib.ape_profile_enable(0)
     ms_bp = reduce_max([e0.elapsed_time(e1)])[0]
@@ -947,8 +947,8 @@ def run_b200(args):
         gemm_ms = sum(v[1] for k, v in rep.items() if k.startswith('gemm.')) / args.steps
         all_ms = sum(v[1] for v in rep.values()) / args.steps
         refine = {k: (REFINE_ITERS if k.startswith('gemm.rf') else 1) for k in GEMM_FLOPS_PER_PT}
-        # only the layers the GEMM kernel actually ran count (conv2 | e_conv2 are computed inside the front-end kernel,
-        # frontend_tc.cuh: neither their FLOPs nor their time are in this figure)
+        # only the layers the GEMM kernel actually ran count (a layer fused into another kernel contributes neither FLOPs nor
+        # time to this figure)
         in_gemm = [k for k in GEMM_FLOPS_PER_PT if k in rep or k in ('gemm.pn.heads1', 'gemm.pn.heads2') and 'gemm.pn.heads12' in rep]
         alg = sum(GEMM_FLOPS_PER_PT[k] * refine[k] for k in in_gemm) * BATCH * NPTS
         rows = BATCH * ((NPTS + 127) // 128 * 128)

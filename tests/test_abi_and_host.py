@@ -178,3 +178,25 @@ def test_committed_profiles_feed_the_bench_roofline():
     # back-projection: measured DRAM traffic must not exceed the algorithmic bytes by more than a few per cent
     # (512 frames x 921 600 B + 24 B per valid pixel ~ 574 MB): no wasted re-reads
     assert t['surface_backproject']['dram_bytes_per_launch'] < 1.05 * 574e6
+
+
+def test_bench_has_no_collective_inside_rank_dependent_branches():
+    """bench.py runs one process per GPU under torchrun: a barrier / all-reduce that only SOME ranks reach hangs the job
+    (it happened once: a rank-0-only profiling block called the leg's `sync`, which is a barrier there).  Static guard: no
+    call to a collective or to the legs' `sync` / `barrier` / `reduce_max` helpers inside an `if` whose condition reads
+    `rank`."""
+    import ast
+    src = open(os.path.join(ROOT, 'bench.py')).read()
+    tree = ast.parse(src)
+    collective = {'sync', 'barrier', 'reduce_max', 'all_reduce', 'broadcast', 'all_gather', 'reduce_scatter', 'allreduce_gradient',
+                  'allreduce_gradient_overlapped', 'train_step'}
+    bad = []
+    for node in ast.walk(tree):
+        if isinstance(node, ast.If) and any(isinstance(n, ast.Name) and n.id == 'rank' for n in ast.walk(node.test)):
+            for sub in node.body + node.orelse:
+                for c in ast.walk(sub):
+                    if isinstance(c, ast.Call):
+                        name = c.func.id if isinstance(c.func, ast.Name) else (c.func.attr if isinstance(c.func, ast.Attribute) else None)
+                        if name in collective:
+                            bad.append((node.lineno, c.lineno, name))
+    assert not bad, 'collective calls inside rank-dependent branches of bench.py: %s' % bad
