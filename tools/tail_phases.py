@@ -1,5 +1,11 @@
+"""Developer aid: clock64 stamps of the phases of refiner_tail_kernel (gemm_tail.cuh), median / max over the CTAs of one launch.
+Needs a TIMING build of the library: add `#define APE_TAIL_TIMING` in front of `#include "gemm_tail.cuh"` in csrc/net.cu,
+rebuild (python -m autoposeestimation_b200.build), run this on the GPU box, then remove the define again (the timing build
+exports an extra symbol, ape_debug_tail, that include/ape_b200.h does not declare).
+Stamps: 0 start, 1 weights issued, 2 after the dependency wait, 3 pooled operand built, 4 MMAs retired, 5 partial tile written,
+6 barrier, 7 conv1 reduced, 8 conv2 partials, 9 barrier, 10 conv2 reduced, 11 conv3 partials pushed, 12 barrier, 13 done."""
 import ctypes, sys, numpy as np, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from autoposeestimation_b200 import ops, _lib, synthetic as synth
 
 
